@@ -1,0 +1,556 @@
+// hy_cuda.cu - C ABI of libhy_cuda (see include/hy_cuda.h) over the sm_100a
+// kernels in hy_kernels.cuh.  No CPU fallback exists: every entry point needs
+// a CUDA device and fails loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hy_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string &msg)
+{
+    g_err = msg;
+    return 1;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +     \
+                        std::to_string(__LINE__) + ")");                                                 \
+    } while (0)
+
+} // namespace
+
+struct hy_ctx {
+    int device = 0;
+    int fp_bits = 64;
+    size_t rb = 8; // bytes per real
+    hy_dims d{};
+    uint32_t B = 0;
+    double tol = 0;
+    int high_accuracy = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // tape (device)
+    hy_op *d_ops = nullptr;
+    hy_term *d_terms = nullptr;
+    uint32_t *d_levels = nullptr;
+    uint32_t *d_ev = nullptr;
+    // lanes (device)
+    void *d_state = nullptr, *d_pars = nullptr, *d_thi = nullptr, *d_tlo = nullptr, *d_lasth = nullptr;
+    void *d_tf = nullptr, *d_mdt = nullptr, *d_minh = nullptr, *d_maxh = nullptr, *d_tc = nullptr;
+    long long *d_outcome = nullptr;
+    unsigned long long *d_nsteps = nullptr;
+    unsigned int *d_counter = nullptr;
+    void *d_gws = nullptr;
+    // launch geometry
+    hy_launch_info li{};
+    uint32_t TS = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0;
+    uint64_t last_launches = 0;
+};
+
+namespace {
+
+template <typename R, int G> cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+{
+    auto kern = hy::propagate_kernel<R, G>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+{
+    switch (li.group) {
+    case 1: return launch_g<R, 1>(P, li, s);
+    case 2: return launch_g<R, 2>(P, li, s);
+    case 4: return launch_g<R, 4>(P, li, s);
+    case 8: return launch_g<R, 8>(P, li, s);
+    case 16: return launch_g<R, 16>(P, li, s);
+    case 32: return launch_g<R, 32>(P, li, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename R, int G> int regs_of()
+{
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, hy::propagate_kernel<R, G>) != cudaSuccess) return 0;
+    return a.numRegs;
+}
+
+template <typename R> int regs_for_group(uint32_t g)
+{
+    switch (g) {
+    case 1: return regs_of<R, 1>();
+    case 2: return regs_of<R, 2>();
+    case 4: return regs_of<R, 4>();
+    case 8: return regs_of<R, 8>();
+    case 16: return regs_of<R, 16>();
+    default: return regs_of<R, 32>();
+    }
+}
+
+uint32_t env_u32(const char *name, uint32_t dflt)
+{
+    const char *v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)std::strtoul(v, nullptr, 10);
+}
+
+// Choose the launch geometry for a tape: group size G, trajectories per CTA T.
+int choose_geometry(hy_ctx *c)
+{
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    int smem_optin = 0;
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const hy_dims &d = c->d;
+    const uint32_t rows = d.n_rows + d.n_par;
+    const uint32_t max_threads = 512;
+
+    // Widest dependency level bounds the useful group size.
+    std::vector<uint32_t> ls(d.n_levels + 1);
+    CU(cudaMemcpy(ls.data(), c->d_levels, ls.size() * 4, cudaMemcpyDeviceToHost));
+    uint32_t widest = 1;
+    for (uint32_t i = 0; i < d.n_levels; ++i) widest = std::max(widest, ls[i + 1] - ls[i]);
+
+    hy::SmemLayout L0 = hy::make_layout(d, 1, (uint32_t)c->rb, 0);
+    const uint32_t fixed = L0.total + 64;
+    const uint32_t budget = (uint32_t)smem_optin > fixed ? (uint32_t)smem_optin - fixed : 0;
+    uint32_t Tfit = budget / (rows * (uint32_t)c->rb);
+    hy_launch_info &li = c->li;
+    li.n_sm = (uint32_t)prop.multiProcessorCount;
+
+    uint32_t G = env_u32("HY_CUDA_GROUP", 0);
+    uint32_t T;
+    if (Tfit >= 1) {
+        li.ws_in_smem = 1;
+        if (G == 0) {
+            // Smallest power of two that brings the CTA to >= 256 threads,
+            // not wider than the widest level (rounded up to a power of two).
+            uint32_t wcap = 1;
+            while (wcap < widest && wcap < 32) wcap <<= 1;
+            G = 1;
+            while (G < wcap && Tfit * G < 256) G <<= 1;
+        }
+        T = std::min(Tfit, max_threads / G);
+    } else {
+        // Jets do not fit in shared memory: global-memory workspace (L1/L2).
+        li.ws_in_smem = 0;
+        if (G == 0) G = 1;
+        T = 128 / G;
+    }
+    uint32_t Tenv = env_u32("HY_CUDA_TRAJ_PER_CTA", 0);
+    if (Tenv) T = std::min(Tenv, li.ws_in_smem ? Tfit : 512u);
+    if (T == 0) T = 1;
+    // Do not keep more trajectories resident than the batch can feed.
+    uint32_t per_cta_needed = (c->B + li.n_sm - 1) / li.n_sm;
+    if (per_cta_needed == 0) per_cta_needed = 1;
+    T = std::min(T, per_cta_needed);
+    // Shrink the row stride to what is used, keep it odd (bank-conflict-free
+    // 64-bit column accesses).
+    uint32_t TS = T | 1u;
+    if (li.ws_in_smem && (uint64_t)rows * TS * c->rb > budget) TS = T; // T already odd or it would not fit
+    li.group = G;
+    li.traj_per_cta = T;
+    li.threads = ((T * G + 31) / 32) * 32;
+    uint32_t ctas = (c->B + T - 1) / T;
+    li.ctas = std::max(1u, std::min(ctas, li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
+    c->TS = TS;
+    hy::SmemLayout L = hy::make_layout(d, TS, (uint32_t)c->rb, (int)li.ws_in_smem);
+    li.smem_bytes = L.total;
+    if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
+    li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G) : regs_for_group<float>(G));
+    if (!li.ws_in_smem) {
+        if (c->d_gws) cudaFree(c->d_gws);
+        CU(cudaMalloc(&c->d_gws, (size_t)li.ctas * rows * TS * c->rb));
+    }
+    return 0;
+}
+
+template <typename R>
+hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc)
+{
+    hy::KParams<R> P{};
+    P.d = c->d;
+    P.ops = c->d_ops;
+    P.terms = c->d_terms;
+    P.level_start = c->d_levels;
+    P.ev_ref = c->d_ev;
+    P.state = (R *)c->d_state;
+    P.pars = (const R *)c->d_pars;
+    P.t_hi = (R *)c->d_thi;
+    P.t_lo = (R *)c->d_tlo;
+    P.last_h = (R *)c->d_lasth;
+    P.tf = (const R *)c->d_tf;
+    P.mdt = have_mdt ? (const R *)c->d_mdt : nullptr;
+    P.outcome = c->d_outcome;
+    P.min_h = (R *)c->d_minh;
+    P.max_h = (R *)c->d_maxh;
+    P.n_steps = c->d_nsteps;
+    P.tc = (R *)c->d_tc;
+    P.counter = c->d_counter;
+    P.gws = (R *)c->d_gws;
+    P.B = c->B;
+    P.T = c->li.traj_per_cta;
+    P.TS = c->TS;
+    P.max_steps = max_steps;
+    P.mode = mode;
+    P.backward = backward;
+    P.write_tc = write_tc;
+    P.high_accuracy = c->high_accuracy;
+    P.ws_in_smem = (int)c->li.ws_in_smem;
+    const double p = (double)c->d.order;
+    P.rhofac = (R)(std::exp(-7.0 / (10.0 * (p - 1.0))) / (M_E * M_E));
+    P.inv_p = (R)(1.0 / p);
+    P.inv_pm1 = (R)(1.0 / (p - 1.0));
+    return P;
+}
+
+int ensure_tc(hy_ctx *c)
+{
+    if (!c->d_tc) {
+        size_t bytes = (size_t)c->d.n_state * (c->d.order + 1) * c->B * c->rb;
+        CU(cudaMalloc(&c->d_tc, bytes ? bytes : 8));
+        CU(cudaMemsetAsync(c->d_tc, 0, bytes, c->stream));
+    }
+    return 0;
+}
+
+int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc)
+{
+    if (c->B == 0) {
+        c->last_ms = 0;
+        c->last_launches = 0;
+        return 0;
+    }
+    if (write_tc && ensure_tc(c)) return 1;
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    cudaError_t e;
+    if (c->fp_bits == 64)
+        e = launch<double>(make_params<double>(c, mode, backward, max_steps, have_mdt, write_tc), c->li, c->stream);
+    else
+        e = launch<float>(make_params<float>(c, mode, backward, max_steps, have_mdt, write_tc), c->li, c->stream);
+    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+    c->last_launches = 1;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *hy_last_error(void) { return g_err.c_str(); }
+
+int hy_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return 0;
+}
+
+int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const hy_op *ops, const hy_term *terms,
+              const uint32_t *level_start, const uint32_t *ev_ref, const int32_t *ev_dir, const double *ev_cooldown,
+              double tol, int high_accuracy, uint32_t batch)
+{
+    (void)ev_dir;
+    (void)ev_cooldown;
+    if (!out || !dims || !ops || !level_start) return fail("hy_create: null argument");
+    if (fp_bits != 32 && fp_bits != 64) return fail("hy_create: fp_bits must be 32 or 64");
+    if (dims->order < 2 || dims->order > 62) return fail("hy_create: unsupported Taylor order");
+    int ndev = 0;
+    if (hy_device_count(&ndev)) return 1;
+    if (ndev == 0) return fail("hy_create: no CUDA device is visible (libhy_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("hy_create: invalid device index");
+    CU(cudaSetDevice(device));
+    hy_ctx *c = new hy_ctx();
+    c->device = device;
+    c->fp_bits = fp_bits;
+    c->rb = fp_bits / 8;
+    c->d = *dims;
+    c->B = batch;
+    c->tol = tol;
+    c->high_accuracy = high_accuracy;
+    *out = c;
+    const hy_dims &d = c->d;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->d_ops, std::max<size_t>(1, d.n_ops) * sizeof(hy_op)));
+    CU(cudaMemcpy(c->d_ops, ops, d.n_ops * sizeof(hy_op), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_terms, std::max<size_t>(1, d.n_terms) * sizeof(hy_term)));
+    if (d.n_terms) CU(cudaMemcpy(c->d_terms, terms, d.n_terms * sizeof(hy_term), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_levels, (d.n_levels + 1) * 4));
+    CU(cudaMemcpy(c->d_levels, level_start, (d.n_levels + 1) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_ev, std::max<size_t>(1, d.n_events) * 4));
+    if (d.n_events) CU(cudaMemcpy(c->d_ev, ev_ref, d.n_events * 4, cudaMemcpyHostToDevice));
+    const size_t B = std::max<size_t>(1, batch), rb = c->rb;
+    CU(cudaMalloc(&c->d_state, B * d.n_state * rb));
+    CU(cudaMalloc(&c->d_pars, B * std::max<size_t>(1, d.n_par) * rb));
+    CU(cudaMalloc(&c->d_thi, B * rb));
+    CU(cudaMalloc(&c->d_tlo, B * rb));
+    CU(cudaMalloc(&c->d_lasth, B * rb));
+    CU(cudaMalloc(&c->d_tf, B * rb));
+    CU(cudaMalloc(&c->d_mdt, B * rb));
+    CU(cudaMalloc(&c->d_minh, B * rb));
+    CU(cudaMalloc(&c->d_maxh, B * rb));
+    CU(cudaMalloc(&c->d_outcome, B * sizeof(long long)));
+    CU(cudaMalloc(&c->d_nsteps, B * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+    CU(cudaMemset(c->d_state, 0, B * d.n_state * rb));
+    CU(cudaMemset(c->d_pars, 0, B * std::max<size_t>(1, d.n_par) * rb));
+    CU(cudaMemset(c->d_thi, 0, B * rb));
+    CU(cudaMemset(c->d_tlo, 0, B * rb));
+    CU(cudaMemset(c->d_lasth, 0, B * rb));
+    if (choose_geometry(c)) return 1;
+    return 0;
+}
+
+int hy_destroy(hy_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->d_ops,  c->d_terms, c->d_levels, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
+                    c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
+                    c->d_counter, c->d_gws};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int hy_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail("null argument");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 8, cudaHostAllocPortable));
+    std::memset(*ptr, 0, bytes ? bytes : 8);
+    return 0;
+}
+
+int hy_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+int hy_set_stream(hy_ctx *c, void *cuda_stream)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    if (c->own_stream && c->stream) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamDestroy(c->stream));
+    }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return 0;
+}
+
+int hy_upload(hy_ctx *c, const void *state, const void *pars, const void *t_hi, const void *t_lo)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb;
+    if (B == 0) return 0;
+    if (state) CU(cudaMemcpyAsync(c->d_state, state, B * c->d.n_state * rb, cudaMemcpyHostToDevice, c->stream));
+    if (pars && c->d.n_par) CU(cudaMemcpyAsync(c->d_pars, pars, B * c->d.n_par * rb, cudaMemcpyHostToDevice, c->stream));
+    if (t_hi) CU(cudaMemcpyAsync(c->d_thi, t_hi, B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (t_lo) CU(cudaMemcpyAsync(c->d_tlo, t_lo, B * rb, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_download(hy_ctx *c, void *state, void *t_hi, void *t_lo, void *last_h)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb;
+    if (B == 0) return 0;
+    if (state) CU(cudaMemcpyAsync(state, c->d_state, B * c->d.n_state * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (t_hi) CU(cudaMemcpyAsync(t_hi, c->d_thi, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (t_lo) CU(cudaMemcpyAsync(t_lo, c->d_tlo, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (last_h) CU(cudaMemcpyAsync(last_h, c->d_lasth, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_upload_dev(hy_ctx *c, const void *d_state, const void *d_pars, const void *d_t_hi, const void *d_t_lo)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb;
+    if (B == 0) return 0;
+    if (d_state) CU(cudaMemcpyAsync(c->d_state, d_state, B * c->d.n_state * rb, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_pars && c->d.n_par)
+        CU(cudaMemcpyAsync(c->d_pars, d_pars, B * c->d.n_par * rb, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_t_hi) CU(cudaMemcpyAsync(c->d_thi, d_t_hi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_t_lo) CU(cudaMemcpyAsync(c->d_tlo, d_t_lo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_state_dev(hy_ctx *c, void **d_state, void **d_t_hi, void **d_t_lo)
+{
+    if (!c) return fail("null ctx");
+    if (d_state) *d_state = c->d_state;
+    if (d_t_hi) *d_t_hi = c->d_thi;
+    if (d_t_lo) *d_t_lo = c->d_tlo;
+    return 0;
+}
+
+static int fetch_results(hy_ctx *c, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
+{
+    const size_t B = c->B, rb = c->rb;
+    if (B == 0) return 0;
+    if (outcome) CU(cudaMemcpyAsync(outcome, c->d_outcome, B * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (min_h) CU(cudaMemcpyAsync(min_h, c->d_minh, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (max_h) CU(cudaMemcpyAsync(max_h, c->d_maxh, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (n_steps) CU(cudaMemcpyAsync(n_steps, c->d_nsteps, B * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_step(hy_ctx *c, const void *max_delta_t, int backward, int write_tc, int64_t *outcome, void *h)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb;
+    if (max_delta_t && B) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (run_kernel(c, hy::MODE_STEP, backward, 1, max_delta_t != nullptr, write_tc)) return 1;
+    if (fetch_results(c, outcome, nullptr, nullptr, nullptr)) return 1;
+    if (h && B) {
+        CU(cudaMemcpyAsync(h, c->d_lasth, B * rb, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int hy_propagate(hy_ctx *c, const void *t, int is_delta, uint64_t max_steps, const void *max_delta_t, int write_tc,
+                 int c_output, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
+{
+    if (!c) return fail("null ctx");
+    if (c_output) return fail("hy_propagate: c_output is not implemented yet");
+    if (!t && c->B) return fail("hy_propagate: null time array");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb;
+    if (B) CU(cudaMemcpyAsync(c->d_tf, t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (max_delta_t && B) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (run_kernel(c, is_delta ? hy::MODE_FOR : hy::MODE_UNTIL, 0, max_steps, max_delta_t != nullptr, write_tc))
+        return 1;
+    return fetch_results(c, outcome, min_h, max_h, n_steps);
+}
+
+int hy_propagate_grid(hy_ctx *, const void *, size_t, uint64_t, const void *, void *, int64_t *, void *, void *,
+                      uint64_t *)
+{
+    return fail("hy_propagate_grid: not implemented yet");
+}
+
+int hy_last_timing(hy_ctx *c, double *kernel_ms, uint64_t *launches)
+{
+    if (!c) return fail("null ctx");
+    if (kernel_ms) *kernel_ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    return 0;
+}
+
+int hy_get_tc(hy_ctx *c, void *tc)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    if (ensure_tc(c)) return 1;
+    size_t bytes = (size_t)c->d.n_state * (c->d.order + 1) * c->B * c->rb;
+    if (bytes) CU(cudaMemcpyAsync(tc, c->d_tc, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_dense_eval(hy_ctx *, const void *, int, void *) { return fail("hy_dense_eval: not implemented yet"); }
+int hy_cout_info(hy_ctx *, uint64_t *, uint64_t *) { return fail("hy_cout_info: not implemented yet"); }
+int hy_cout_get(hy_ctx *, void *, void *, void *, uint64_t) { return fail("hy_cout_get: not implemented yet"); }
+int hy_cout_eval(hy_ctx *, const void *, size_t, void *) { return fail("hy_cout_eval: not implemented yet"); }
+int hy_events_count(hy_ctx *, uint64_t *n)
+{
+    if (n) *n = 0;
+    return 0;
+}
+int hy_events_drain(hy_ctx *, hy_event_rec *, uint64_t, uint64_t *n)
+{
+    if (n) *n = 0;
+    return 0;
+}
+int hy_get_cooldowns(hy_ctx *, void *, void *) { return fail("hy_get_cooldowns: not implemented yet"); }
+int hy_reset_cooldowns(hy_ctx *, int64_t) { return 0; }
+
+int hy_get_launch_info(hy_ctx *c, hy_launch_info *info)
+{
+    if (!c || !info) return fail("null argument");
+    *info = c->li;
+    return 0;
+}
+
+int hy_measure_fma_peak(int device, int fp_bits, double *tflops)
+{
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 4096;
+    void *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)threads * blocks * 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0));
+        if (fp_bits == 64)
+            hy::fma_peak_kernel<double><<<blocks, threads>>>((double *)out, iters);
+        else
+            hy::fma_peak_kernel<float><<<blocks, threads>>>((float *)out, iters);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    CU(cudaFree(out));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+}
+
+} // extern "C"

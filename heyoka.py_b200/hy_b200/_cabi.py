@@ -1,0 +1,297 @@
+"""ctypes binding of libhy_cuda (include/hy_cuda.h).
+
+This is the reference-side binding a maintainer would add in place of the
+heyoka C++ calls made from expose_batch_integrators.cpp.
+There is NO CPU fallback: if the shared library or a CUDA device is missing,
+every entry point raises.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "csrc", "libhy_cuda.so")
+
+_lib = None
+
+
+class HyCudaError(RuntimeError):
+    pass
+
+
+class dims_t(C.Structure):
+    _fields_ = [
+        (k, C.c_uint32)
+        for k in (
+            "n_state",
+            "n_par",
+            "order",
+            "n_rows",
+            "n_ops",
+            "n_terms",
+            "n_levels",
+            "n_events",
+            "n_tevents",
+        )
+    ]
+
+
+class launch_info_t(C.Structure):
+    _fields_ = [
+        (k, C.c_uint32)
+        for k in (
+            "group",
+            "traj_per_cta",
+            "threads",
+            "ctas",
+            "smem_bytes",
+            "ws_in_smem",
+            "n_sm",
+            "regs_per_thread",
+        )
+    ]
+
+
+class event_rec_t(C.Structure):
+    _fields_ = [
+        ("lane", C.c_uint32),
+        ("ev_idx", C.c_uint32),
+        ("d_sgn", C.c_int32),
+        ("step", C.c_uint32),
+        ("t", C.c_double),
+    ]
+
+
+event_rec_dtype = np.dtype(
+    [("lane", "<u4"), ("ev_idx", "<u4"), ("d_sgn", "<i4"), ("step", "<u4"), ("t", "<f8")]
+)
+
+# Every symbol include/hy_cuda.h declares (checked by tests/test_cabi_symbols.py).
+SYMBOLS = [
+    "hy_last_error",
+    "hy_device_count",
+    "hy_create",
+    "hy_destroy",
+    "hy_host_alloc",
+    "hy_host_free",
+    "hy_set_stream",
+    "hy_upload",
+    "hy_download",
+    "hy_upload_dev",
+    "hy_state_dev",
+    "hy_step",
+    "hy_propagate",
+    "hy_propagate_grid",
+    "hy_last_timing",
+    "hy_get_tc",
+    "hy_dense_eval",
+    "hy_cout_info",
+    "hy_cout_get",
+    "hy_cout_eval",
+    "hy_events_count",
+    "hy_events_drain",
+    "hy_get_cooldowns",
+    "hy_reset_cooldowns",
+    "hy_get_launch_info",
+    "hy_measure_fma_peak",
+]
+
+
+def lib():
+    """Load libhy_cuda.so (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        path = os.path.abspath(LIB_PATH)
+        if not os.path.exists(path):
+            raise HyCudaError(
+                "libhy_cuda.so not found at {}: build it with `python -c 'import "
+                "__graft_entry__ as g; g.build()'` (there is no CPU fallback)".format(path)
+            )
+        _lib = C.CDLL(path)
+        _lib.hy_last_error.restype = C.c_char_p
+        for s in SYMBOLS:
+            if s != "hy_last_error":
+                getattr(_lib, s).restype = C.c_int
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().hy_last_error()
+        raise HyCudaError(msg.decode() if msg else "libhy_cuda failure")
+
+
+def ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().hy_device_count(C.byref(n))
+    if rc != 0:
+        return 0
+    return n.value
+
+
+class PinnedArray:
+    """numpy array over cudaHostAlloc'ed memory."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in shape)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._p = C.c_void_p()
+        check(lib().hy_host_alloc(C.byref(self._p), C.c_size_t(nbytes)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(
+            self.shape
+        )
+
+    def __del__(self):
+        try:
+            if self._p and self._p.value:
+                lib().hy_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class Context:
+    """Owner of one hy_ctx."""
+
+    def __init__(self, dc, fp_bits, batch, tol, high_accuracy, device=0, n_tevents=0,
+                 ev_dir=None, ev_cooldown=None):
+        self._ctx = C.c_void_p()
+        self.dims = dims_t(
+            dc.n_state,
+            dc.n_par,
+            dc.order,
+            dc.n_rows,
+            len(dc.ops),
+            len(dc.terms),
+            len(dc.level_start) - 1,
+            dc.n_events,
+            n_tevents,
+        )
+        self._keep = (dc.ops, dc.terms, dc.level_start, dc.ev_ref)
+        evd = None if ev_dir is None else np.ascontiguousarray(ev_dir, dtype=np.int32)
+        evc = None if ev_cooldown is None else np.ascontiguousarray(ev_cooldown, dtype=np.float64)
+        check(
+            lib().hy_create(
+                C.byref(self._ctx),
+                C.c_int(device),
+                C.c_int(fp_bits),
+                C.byref(self.dims),
+                ptr(dc.ops),
+                ptr(dc.terms),
+                ptr(dc.level_start),
+                ptr(dc.ev_ref),
+                ptr(evd),
+                ptr(evc),
+                C.c_double(tol),
+                C.c_int(int(high_accuracy)),
+                C.c_uint32(batch),
+            )
+        )
+        self.batch = batch
+        self.fp_bits = fp_bits
+
+    def close(self):
+        if self._ctx is not None and self._ctx.value:
+            lib().hy_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(lib().hy_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def upload(self, state=None, pars=None, t_hi=None, t_lo=None):
+        check(lib().hy_upload(self._ctx, ptr(state), ptr(pars), ptr(t_hi), ptr(t_lo)))
+
+    def download(self, state=None, t_hi=None, t_lo=None, last_h=None):
+        check(lib().hy_download(self._ctx, ptr(state), ptr(t_hi), ptr(t_lo), ptr(last_h)))
+
+    def step(self, max_delta_t, backward, write_tc, outcome, h):
+        check(
+            lib().hy_step(
+                self._ctx, ptr(max_delta_t), C.c_int(int(backward)), C.c_int(int(write_tc)),
+                ptr(outcome), ptr(h),
+            )
+        )
+
+    def propagate(self, t, is_delta, max_steps, max_delta_t, write_tc, c_output, outcome,
+                  min_h, max_h, n_steps):
+        check(
+            lib().hy_propagate(
+                self._ctx, ptr(t), C.c_int(int(is_delta)), C.c_uint64(int(max_steps)),
+                ptr(max_delta_t), C.c_int(int(write_tc)), C.c_int(int(c_output)), ptr(outcome),
+                ptr(min_h), ptr(max_h), ptr(n_steps),
+            )
+        )
+
+    def propagate_grid(self, grid, k, max_steps, max_delta_t, out, outcome, min_h, max_h, n_steps):
+        check(
+            lib().hy_propagate_grid(
+                self._ctx, ptr(grid), C.c_size_t(int(k)), C.c_uint64(int(max_steps)),
+                ptr(max_delta_t), ptr(out), ptr(outcome), ptr(min_h), ptr(max_h), ptr(n_steps),
+            )
+        )
+
+    def last_timing(self):
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        check(lib().hy_last_timing(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def get_tc(self, tc):
+        check(lib().hy_get_tc(self._ctx, ptr(tc)))
+
+    def dense_eval(self, t, rel_time, out):
+        check(lib().hy_dense_eval(self._ctx, ptr(t), C.c_int(int(rel_time)), ptr(out)))
+
+    def cout_info(self, n_steps):
+        mx = C.c_uint64(0)
+        check(lib().hy_cout_info(self._ctx, ptr(n_steps), C.byref(mx)))
+        return mx.value
+
+    def cout_get(self, tcs, thi, tlo, S):
+        check(lib().hy_cout_get(self._ctx, ptr(tcs), ptr(thi), ptr(tlo), C.c_uint64(int(S))))
+
+    def cout_eval(self, t, k, out):
+        check(lib().hy_cout_eval(self._ctx, ptr(t), C.c_size_t(int(k)), ptr(out)))
+
+    def events_drain(self):
+        n = C.c_uint64(0)
+        check(lib().hy_events_count(self._ctx, C.byref(n)))
+        recs = np.zeros(n.value, dtype=event_rec_dtype)
+        if n.value:
+            m = C.c_uint64(0)
+            check(lib().hy_events_drain(self._ctx, ptr(recs), C.c_uint64(n.value), C.byref(m)))
+            recs = recs[: m.value]
+        return recs
+
+    def get_cooldowns(self, elapsed, total):
+        check(lib().hy_get_cooldowns(self._ctx, ptr(elapsed), ptr(total)))
+
+    def reset_cooldowns(self, lane=-1):
+        check(lib().hy_reset_cooldowns(self._ctx, C.c_int64(int(lane))))
+
+    def launch_info(self):
+        li = launch_info_t()
+        check(lib().hy_get_launch_info(self._ctx, C.byref(li)))
+        return {k: getattr(li, k) for k, _ in launch_info_t._fields_}
+
+
+def measure_fma_peak(device=0, fp_bits=64):
+    tf = C.c_double(0)
+    check(lib().hy_measure_fma_peak(C.c_int(device), C.c_int(fp_bits), C.byref(tf)))
+    return tf.value

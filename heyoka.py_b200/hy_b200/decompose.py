@@ -23,7 +23,7 @@ import math
 
 import numpy as np
 
-from . import expression as E
+from . import _expression as E
 
 # Opcodes: keep in sync with include/hy_cuda.h.
 OP_LINCOMB, OP_MUL, OP_SQUARE, OP_DIV, OP_POW, OP_SQRT, OP_EXP, OP_LOG = range(8)

@@ -1,0 +1,151 @@
+"""Event classes of the batch integrator.
+
+Mirror of /root/reference/heyoka/taylor_expose_events.cpp:185-317 (classes)
+and :78-182 (callback wrapper): non-terminal callbacks have signature
+``(ta, t, d_sgn, batch_idx) -> None``, terminal ones
+``(ta, d_sgn, batch_idx) -> bool``; callbacks are deep-copied on event
+construction (:83).  Detection itself happens on the device
+(hy_kernels.cuh); the host replays the drained event log through the
+callbacks in chronological order per lane.
+"""
+
+import copy as _copy
+
+import numpy as np
+
+from . import _expression as _E
+from .enums import event_direction
+
+
+def _check_dir(direction):
+    if not isinstance(direction, event_direction):
+        try:
+            direction = event_direction(direction)
+        except Exception:
+            raise ValueError(
+                "Invalid value selected for the direction of an event: the value must be one of "
+                "'event_direction.any', 'event_direction.positive' or 'event_direction.negative'"
+            )
+    return direction
+
+
+class nt_event_batch_impl:
+    _fp = np.float64
+
+    def __init__(self, ex, callback, direction=event_direction.any):
+        if not isinstance(ex, _E.expression):
+            raise TypeError("An event needs an expression as first argument")
+        if callback is None or not callable(callback):
+            raise TypeError(
+                "An object of type '{}' cannot be used as an event callback because it is not "
+                "callable".format(type(callback).__name__)
+            )
+        self.expression = ex
+        self.callback = _copy.deepcopy(callback)
+        self.direction = _check_dir(direction)
+
+    def __repr__(self):
+        return (
+            "C++ datatype   : {}\nEvent type     : non-terminal\nEvent direction: "
+            "event_direction::{}\nBatch mode     : true\n".format(
+                "double" if self._fp == np.float64 else "float", self.direction.name
+            )
+        )
+
+    def __deepcopy__(self, memo):
+        return type(self)(self.expression, self.callback, direction=self.direction)
+
+    def __copy__(self):
+        return self.__deepcopy__({})
+
+
+class t_event_batch_impl:
+    _fp = np.float64
+
+    def __init__(self, ex, callback=None, direction=event_direction.any, cooldown=-1):
+        if not isinstance(ex, _E.expression):
+            raise TypeError("An event needs an expression as first argument")
+        if callback is not None and not callable(callback):
+            raise TypeError(
+                "An object of type '{}' cannot be used as an event callback because it is not "
+                "callable".format(type(callback).__name__)
+            )
+        self.expression = ex
+        self.callback = _copy.deepcopy(callback) if callback is not None else None
+        self.direction = _check_dir(direction)
+        cd = float(cooldown)
+        if cd != cd or cd in (float("inf"), float("-inf")):
+            raise ValueError("Cannot set a non-finite cooldown value for a terminal event")
+        self.cooldown = self._fp(cd)
+
+    def __repr__(self):
+        return (
+            "C++ datatype   : {}\nEvent type     : terminal\nEvent direction: "
+            "event_direction::{}\nWith callback  : {}\nCooldown       : {}\nBatch mode     : true\n".format(
+                "double" if self._fp == np.float64 else "float", self.direction.name,
+                "yes" if self.callback is not None else "no",
+                "auto" if self.cooldown < 0 else self.cooldown,
+            )
+        )
+
+    def __deepcopy__(self, memo):
+        return type(self)(self.expression, self.callback, direction=self.direction,
+                          cooldown=self.cooldown)
+
+    def __copy__(self):
+        return self.__deepcopy__({})
+
+
+class nt_event_batch_dbl(nt_event_batch_impl):
+    _fp = np.float64
+
+
+class nt_event_batch_flt(nt_event_batch_impl):
+    _fp = np.float32
+
+
+class t_event_batch_dbl(t_event_batch_impl):
+    _fp = np.float64
+
+
+class t_event_batch_flt(t_event_batch_impl):
+    _fp = np.float32
+
+
+def dispatch(ta):
+    """Drain the device event log of ``ta`` and run the callbacks.
+
+    Returns a boolean mask of lanes stopped by a terminal-event callback that
+    returned False (or None when nothing happened)."""
+    recs = ta._ctx.events_drain()
+    if len(recs) == 0:
+        return None
+    nte = len(ta._t_events)
+    order = np.lexsort((recs["t"], recs["step"], recs["lane"]))
+    stop = np.zeros(ta._B, dtype=bool)
+    for r in recs[order]:
+        ev = int(r["ev_idx"])
+        lane = int(r["lane"])
+        if ev >= nte:
+            cb = ta._nt_events[ev - nte].callback
+            try:
+                cb(ta, ta._fp(r["t"]), int(r["d_sgn"]), lane)
+            except TypeError as e:
+                raise TypeError(
+                    "The call operator of a non-terminal event callback has an incompatible "
+                    "signature: {}".format(e)
+                )
+        else:
+            cb = ta._t_events[ev].callback
+            if cb is not None:
+                ret = cb(ta, int(r["d_sgn"]), lane)
+                if not isinstance(ret, (bool, np.bool_)):
+                    raise TypeError(
+                        "The call operator of a terminal event callback is expected to return a "
+                        "boolean, but a value of type \"{}\" was returned instead".format(
+                            type(ret).__name__
+                        )
+                    )
+                if not ret:
+                    stop[lane] = True
+    return stop

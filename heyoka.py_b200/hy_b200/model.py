@@ -7,7 +7,7 @@ models BASELINE.json's configs use (/root/reference/heyoka/expose_models.cpp:
 /root/reference/heyoka/_test_model.py:153-278).
 """
 
-from . import expression as E
+from . import _expression as E
 
 __all__ = [
     "pendulum",

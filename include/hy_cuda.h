@@ -130,6 +130,12 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
               uint32_t batch);
 int hy_destroy(hy_ctx *ctx);
 
+/* Page-locked host buffers for the numpy mirrors of state/pars/time (the
+ * reference's views alias integrator memory, expose_batch_integrators.cpp:
+ * 394-518; here they alias pinned memory the DMA engines can reach). */
+int hy_host_alloc(void **ptr, size_t bytes);
+int hy_host_free(void *ptr);
+
 /* Use an externally owned CUDA stream (cudaStream_t) for all work of ctx. */
 int hy_set_stream(hy_ctx *ctx, void *cuda_stream);
 
