@@ -43,9 +43,12 @@ struct hy_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // tape (device)
-    hy_op *d_ops = nullptr;
-    hy_term *d_terms = nullptr;
-    uint32_t *d_levels = nullptr;
+    std::vector<hy_op> h_ops; // the ABI tape (kept for re-scheduling)
+    std::vector<hy_term> h_terms;
+    std::vector<uint32_t> h_levels;
+    hy::Program prog;
+    void *d_prog = nullptr; // [ops | terms | imm]
+    uint32_t *d_phase = nullptr;
     uint32_t *d_ev = nullptr;
     // lanes (device)
     void *d_state = nullptr, *d_pars = nullptr, *d_thi = nullptr, *d_tlo = nullptr, *d_lasth = nullptr;
@@ -65,9 +68,10 @@ struct hy_ctx {
 
 namespace {
 
-template <typename R, int G> cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+template <typename R, int G, bool SMEM>
+cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
 {
-    auto kern = hy::propagate_kernel<R, G>;
+    auto kern = hy::propagate_kernel<R, G, SMEM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
@@ -76,33 +80,43 @@ template <typename R, int G> cudaError_t launch_g(const hy::KParams<R> &P, const
 
 template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
 {
+    if (li.ws_in_smem) {
+        switch (li.group) {
+        case 1: return launch_g<R, 1, true>(P, li, s);
+        case 2: return launch_g<R, 2, true>(P, li, s);
+        case 4: return launch_g<R, 4, true>(P, li, s);
+        case 8: return launch_g<R, 8, true>(P, li, s);
+        case 16: return launch_g<R, 16, true>(P, li, s);
+        case 32: return launch_g<R, 32, true>(P, li, s);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    // Global-memory workspace fallback (jets too large for shared memory).
     switch (li.group) {
-    case 1: return launch_g<R, 1>(P, li, s);
-    case 2: return launch_g<R, 2>(P, li, s);
-    case 4: return launch_g<R, 4>(P, li, s);
-    case 8: return launch_g<R, 8>(P, li, s);
-    case 16: return launch_g<R, 16>(P, li, s);
-    case 32: return launch_g<R, 32>(P, li, s);
+    case 1: return launch_g<R, 1, false>(P, li, s);
+    case 8: return launch_g<R, 8, false>(P, li, s);
+    case 32: return launch_g<R, 32, false>(P, li, s);
     default: return cudaErrorInvalidValue;
     }
 }
 
-template <typename R, int G> int regs_of()
+template <typename R, int G, bool SMEM> int regs_of()
 {
     cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, hy::propagate_kernel<R, G>) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&a, hy::propagate_kernel<R, G, SMEM>) != cudaSuccess) return 0;
     return a.numRegs;
 }
 
-template <typename R> int regs_for_group(uint32_t g)
+template <typename R> int regs_for_group(uint32_t g, bool smem)
 {
+    if (!smem) return g == 1 ? regs_of<R, 1, false>() : (g == 8 ? regs_of<R, 8, false>() : regs_of<R, 32, false>());
     switch (g) {
-    case 1: return regs_of<R, 1>();
-    case 2: return regs_of<R, 2>();
-    case 4: return regs_of<R, 4>();
-    case 8: return regs_of<R, 8>();
-    case 16: return regs_of<R, 16>();
-    default: return regs_of<R, 32>();
+    case 1: return regs_of<R, 1, true>();
+    case 2: return regs_of<R, 2, true>();
+    case 4: return regs_of<R, 4, true>();
+    case 8: return regs_of<R, 8, true>();
+    case 16: return regs_of<R, 16, true>();
+    default: return regs_of<R, 32, true>();
     }
 }
 
@@ -113,7 +127,14 @@ uint32_t env_u32(const char *name, uint32_t dflt)
     return (uint32_t)std::strtoul(v, nullptr, 10);
 }
 
-// Choose the launch geometry for a tape: group size G, trajectories per CTA T.
+hy::ProgDims prog_dims(const hy::Program &p)
+{
+    return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases};
+}
+
+// Choose the launch geometry for a tape: group size G (threads cooperating on
+// one trajectory), trajectories per CTA T; schedule the tape for that G and
+// upload the program.
 int choose_geometry(hy_ctx *c)
 {
     cudaDeviceProp prop{};
@@ -121,65 +142,79 @@ int choose_geometry(hy_ctx *c)
     int smem_optin = 0;
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const hy_dims &d = c->d;
-    const uint32_t rows = d.n_rows + d.n_par;
     const uint32_t max_threads = 512;
-
-    // Widest dependency level bounds the useful group size.
-    std::vector<uint32_t> ls(d.n_levels + 1);
-    CU(cudaMemcpy(ls.data(), c->d_levels, ls.size() * 4, cudaMemcpyDeviceToHost));
-    uint32_t widest = 1;
-    for (uint32_t i = 0; i < d.n_levels; ++i) widest = std::max(widest, ls[i + 1] - ls[i]);
-
-    hy::SmemLayout L0 = hy::make_layout(d, 1, (uint32_t)c->rb, 0);
-    const uint32_t fixed = L0.total + 64;
-    const uint32_t budget = (uint32_t)smem_optin > fixed ? (uint32_t)smem_optin - fixed : 0;
-    uint32_t Tfit = budget / (rows * (uint32_t)c->rb);
+    // Per-trajectory workspace column, padded to an odd element count so that
+    // lanes working on different trajectories hit different banks.
+    const uint32_t RS = hy::ws_rows(d) | 1u;
     hy_launch_info &li = c->li;
     li.n_sm = (uint32_t)prop.multiProcessorCount;
+    const bool force_global = env_u32("HY_CUDA_FORCE_GLOBAL_WS", 0) != 0;
+    const uint32_t Genv = env_u32("HY_CUDA_GROUP", 0);
 
-    uint32_t G = env_u32("HY_CUDA_GROUP", 0);
-    uint32_t T;
-    if (Tfit >= 1) {
-        li.ws_in_smem = 1;
-        if (G == 0) {
-            // Smallest power of two that brings the CTA to >= 256 threads,
-            // not wider than the widest level (rounded up to a power of two).
-            uint32_t wcap = 1;
-            while (wcap < widest && wcap < 32) wcap <<= 1;
-            G = 1;
-            while (G < wcap && Tfit * G < 256) G <<= 1;
+    double best_score = -1;
+    uint32_t bestG = 0, bestT = 0;
+    bool best_smem = false;
+    hy::Program best;
+    for (uint32_t G = 1; G <= 32; G <<= 1) {
+        if (Genv && G != Genv) continue;
+        hy::Program pr;
+        std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), G, pr);
+        if (!err.empty()) return fail("hy_create: " + err);
+        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), G, 0, RS, (uint32_t)c->rb, 0);
+        const uint32_t fixed = L0.total + 64;
+        if (fixed > (uint32_t)smem_optin) continue;
+        const uint32_t budget = (uint32_t)smem_optin - fixed;
+        uint32_t Tfit = budget / (RS * (uint32_t)c->rb);
+        bool smem = Tfit >= 1 && !force_global;
+        if (!smem && G != 1 && G != 8 && G != 32) continue; // fallback kernels exist for these only
+        uint32_t T = smem ? std::min(Tfit, max_threads / G) : std::max(1u, 256u / G);
+        const double threads = std::min<double>((double)T * G, max_threads);
+        const double score = pr.lane_utilisation * threads * (smem ? 1.0 : 0.05);
+        if (score > best_score * 1.02) {
+            best_score = score;
+            bestG = G;
+            bestT = T;
+            best_smem = smem;
+            best = pr;
         }
-        T = std::min(Tfit, max_threads / G);
-    } else {
-        // Jets do not fit in shared memory: global-memory workspace (L1/L2).
-        li.ws_in_smem = 0;
-        if (G == 0) G = 1;
-        T = 128 / G;
     }
+    if (!bestG) return fail("hy_create: the program does not fit in shared memory for any group size");
+    uint32_t G = bestG, T = bestT;
+    li.ws_in_smem = best_smem ? 1 : 0;
     uint32_t Tenv = env_u32("HY_CUDA_TRAJ_PER_CTA", 0);
-    if (Tenv) T = std::min(Tenv, li.ws_in_smem ? Tfit : 512u);
-    if (T == 0) T = 1;
+    if (Tenv) T = std::min(Tenv, T);
     // Do not keep more trajectories resident than the batch can feed.
-    uint32_t per_cta_needed = (c->B + li.n_sm - 1) / li.n_sm;
-    if (per_cta_needed == 0) per_cta_needed = 1;
-    T = std::min(T, per_cta_needed);
-    // Shrink the row stride to what is used, keep it odd (bank-conflict-free
-    // 64-bit column accesses).
-    uint32_t TS = T | 1u;
-    if (li.ws_in_smem && (uint64_t)rows * TS * c->rb > budget) TS = T; // T already odd or it would not fit
+    uint32_t per_cta_needed = std::max(1u, (c->B + li.n_sm - 1) / li.n_sm);
+    T = std::max(1u, std::min(T, per_cta_needed));
     li.group = G;
     li.traj_per_cta = T;
     li.threads = ((T * G + 31) / 32) * 32;
     uint32_t ctas = (c->B + T - 1) / T;
     li.ctas = std::max(1u, std::min(ctas, li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
-    c->TS = TS;
-    hy::SmemLayout L = hy::make_layout(d, TS, (uint32_t)c->rb, (int)li.ws_in_smem);
+    c->TS = RS;
+    c->prog = best;
+    hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
     li.smem_bytes = L.total;
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
-    li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G) : regs_for_group<float>(G));
+    li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G, li.ws_in_smem)
+                                                     : regs_for_group<float>(G, li.ws_in_smem));
+    // Upload the program blob [ops | terms | imm] (same layout as in shared memory).
+    {
+        std::vector<unsigned char> blob(L.off_phase, 0);
+        std::memcpy(blob.data() + L.off_ops, c->prog.ops.data(), c->prog.ops.size() * sizeof(hy::DOp));
+        if (!c->prog.terms.empty())
+            std::memcpy(blob.data() + L.off_terms, c->prog.terms.data(), c->prog.terms.size() * sizeof(hy::DTerm));
+        std::memcpy(blob.data() + L.off_imm, c->prog.imm.data(), c->prog.imm.size() * 8);
+        if (c->d_prog) cudaFree(c->d_prog);
+        CU(cudaMalloc(&c->d_prog, std::max<size_t>(16, blob.size())));
+        CU(cudaMemcpy(c->d_prog, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        if (c->d_phase) cudaFree(c->d_phase);
+        CU(cudaMalloc(&c->d_phase, c->prog.phase_slot.size() * 4));
+        CU(cudaMemcpy(c->d_phase, c->prog.phase_slot.data(), c->prog.phase_slot.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (!li.ws_in_smem) {
         if (c->d_gws) cudaFree(c->d_gws);
-        CU(cudaMalloc(&c->d_gws, (size_t)li.ctas * rows * TS * c->rb));
+        CU(cudaMalloc(&c->d_gws, (size_t)li.ctas * T * RS * c->rb));
     }
     return 0;
 }
@@ -189,10 +224,10 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
 {
     hy::KParams<R> P{};
     P.d = c->d;
-    P.ops = c->d_ops;
-    P.terms = c->d_terms;
-    P.level_start = c->d_levels;
+    P.prog = c->d_prog;
+    P.phase_slot = c->d_phase;
     P.ev_ref = c->d_ev;
+    P.pd = prog_dims(c->prog);
     P.state = (R *)c->d_state;
     P.pars = (const R *)c->d_pars;
     P.t_hi = (R *)c->d_thi;
@@ -304,12 +339,9 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
     c->own_stream = true;
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
-    CU(cudaMalloc(&c->d_ops, std::max<size_t>(1, d.n_ops) * sizeof(hy_op)));
-    CU(cudaMemcpy(c->d_ops, ops, d.n_ops * sizeof(hy_op), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_terms, std::max<size_t>(1, d.n_terms) * sizeof(hy_term)));
-    if (d.n_terms) CU(cudaMemcpy(c->d_terms, terms, d.n_terms * sizeof(hy_term), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_levels, (d.n_levels + 1) * 4));
-    CU(cudaMemcpy(c->d_levels, level_start, (d.n_levels + 1) * 4, cudaMemcpyHostToDevice));
+    c->h_ops.assign(ops, ops + d.n_ops);
+    if (d.n_terms) c->h_terms.assign(terms, terms + d.n_terms);
+    c->h_levels.assign(level_start, level_start + d.n_levels + 1);
     CU(cudaMalloc(&c->d_ev, std::max<size_t>(1, d.n_events) * 4));
     if (d.n_events) CU(cudaMemcpy(c->d_ev, ev_ref, d.n_events * 4, cudaMemcpyHostToDevice));
     const size_t B = std::max<size_t>(1, batch), rb = c->rb;
@@ -338,7 +370,7 @@ int hy_destroy(hy_ctx *c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_ops,  c->d_terms, c->d_levels, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
+    void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
                     c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
                     c->d_counter, c->d_gws};
     for (void *p : ptrs)

@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "../../include/hy_cuda.h"
+#include "hy_schedule.hpp"
 
 namespace hy {
 
@@ -58,12 +59,16 @@ template <typename R> __device__ __forceinline__ R nan_max(R m, R a) { return (a
 
 enum { MODE_UNTIL = 0, MODE_FOR = 1, MODE_STEP = 2 };
 
+struct ProgDims {
+    uint32_t n_slots, n_tslots, n_imm, n_phases;
+};
+
 template <typename R> struct KParams {
     hy_dims d;
-    const hy_op *ops;
-    const hy_term *terms;
-    const uint32_t *level_start;
+    const void *prog;            // [ops | terms | imm] in the smem layout
+    const uint32_t *phase_slot;  // [n_phases + 1]
     const uint32_t *ev_ref;
+    ProgDims pd;
     R *state;      // [n][B]
     const R *pars; // [m][B]
     R *t_hi, *t_lo, *last_h;
@@ -81,8 +86,19 @@ template <typename R> struct KParams {
     R rhofac, inv_p, inv_pm1;
 };
 
-// Row reference -> row index at order k.
-__device__ __forceinline__ uint32_t ref_row(uint32_t ref, uint32_t k) { return (ref & 0x7fffffffu) + (ref >> 31) * k; }
+// ---------------------------------------------------------------------------
+// Device-side program (built by hy_schedule.hpp): per-lane op streams in a
+// lane-interleaved layout, 16-byte ops, 16-byte terms.
+//
+// Workspace of ONE trajectory (contiguous, RS elements, RS odd):
+//   [0, n_rows)                 jets / cur rows of the u-variables
+//   [n_rows, n_rows+n_par)      runtime parameters
+//   [n_rows+n_par, +P1)         unit jet [1, 0, ..., 0]   (also "par = 1.0")
+// Orders of a jet are contiguous, so a convolution walks a[+j], b[-j] with
+// immediate offsets.  Trajectory t of the CTA lives at ws + t*RS.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t roff(uint32_t ref, uint32_t k) { return (ref & 0x7fffffffu) + ((ref >> 31) ? k : 0u); }
+__device__ __forceinline__ uint32_t rbase(uint32_t ref) { return ref & 0x7fffffffu; }
 
 template <typename R> __device__ __forceinline__ R pow0(R x, double alpha)
 {
@@ -94,150 +110,214 @@ template <typename R> __device__ __forceinline__ R pow0(R x, double alpha)
     return r_pow(x, (R)alpha);
 }
 
-// One op of the tape at order k for the trajectory whose column is `w`
-// (w = ws + t; element of row r is w[r * TS]).
-template <typename R>
-__device__ __forceinline__ void exec_op(const hy_op &o, const hy_term *__restrict__ terms, R *w, const uint32_t TS,
-                                        const R *__restrict__ rk, const uint32_t k, const R tm, const uint32_t par_row)
+// sum_{j=0}^{n-1} pa[j] * pb[-j]; two accumulators, unrolled by 4.
+template <typename R> __device__ __forceinline__ R conv(const R *__restrict__ pa, const R *__restrict__ pb, int n)
 {
-#define ROW(r) w[(size_t)(r) * TS]
+    R s0 = 0, s1 = 0;
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+        const R a0 = pa[j], a1 = pa[j + 1], a2 = pa[j + 2], a3 = pa[j + 3];
+        const R b0 = pb[-j], b1 = pb[-j - 1], b2 = pb[-j - 2], b3 = pb[-j - 3];
+        s0 = r_fma(a0, b0, s0);
+        s1 = r_fma(a1, b1, s1);
+        s0 = r_fma(a2, b2, s0);
+        s1 = r_fma(a3, b3, s1);
+    }
+    for (; j < n; ++j) s0 = r_fma(pa[j], pb[-j], s0);
+    return s0 + s1;
+}
+
+// One op of the program at order k on the trajectory column `w`.  `lt` is the
+// lane's term stream (term c at lt[c * G]).
+template <typename R, int G>
+__device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ lt, R *__restrict__ w,
+                                        const R *__restrict__ rk, const double *__restrict__ s_imm, const uint32_t k,
+                                        const R tm)
+{
+    const uint32_t ka = (o.flags & DF_JA) ? k : 0u, kb = (o.flags & DF_JB) ? k : 0u;
+    const uint32_t kd = (o.flags & DF_JDST) ? k : 0u;
     switch (o.opcode) {
     case HY_OP_LINCOMB: {
         R acc = 0;
-        const hy_term *t = terms + o.b;
-        for (uint32_t i = 0; i < o.n; ++i) {
-            R c = (R)t[i].coef;
-            if (t[i].par >= 0) c = c * ROW(par_row + t[i].par);
-            const uint32_t src = t[i].src;
-            R v = (src == HY_REF_ONE) ? (k == 0 ? (R)1 : (R)0) : ROW(ref_row(src, k));
-            acc = r_fma(c, v, acc);
+        const DTerm *t = lt + (uint32_t)o.b * G;
+        const uint32_t n = o.n;
+        for (uint32_t i = 0; i < n; ++i) {
+            const DTerm tt = t[i * G];
+            const R c = (R)tt.coef * w[tt.aux];
+            acc = r_fma(c, w[roff(tt.src, k)], acc);
         }
-        ROW(ref_row(o.dst, k)) = acc;
+        if (o.flags & HY_OPF_SVD)
+            w[o.dst + k + 1] = acc * rk[k + 1];
+        else
+            w[o.dst + kd] = acc;
+    } break;
+    case HY_OP_ADDSUB: {
+        R a = w[o.a + ka], b = w[o.b + kb];
+        if (o.flags & HY_OPF_NEGA) a = -a;
+        if (o.flags & HY_OPF_NEGB) b = -b;
+        const R acc = a + b;
+        if (o.flags & HY_OPF_SVD)
+            w[o.dst + k + 1] = acc * rk[k + 1];
+        else
+            w[o.dst + kd] = acc;
     } break;
     case HY_OP_MUL: {
-        const R *a = &ROW(o.a & 0x7fffffffu), *b = &ROW((o.b & 0x7fffffffu) + k);
-        R acc = 0;
-        for (uint32_t j = 0; j <= k; ++j) acc = r_fma(a[(size_t)j * TS], b[-(ptrdiff_t)((size_t)j * TS)], acc);
-        ROW(ref_row(o.dst, k)) = acc;
+        w[o.dst + kd] = conv<R>(w + o.a, w + o.b + k, (int)k + 1);
     } break;
     case HY_OP_SQUARE: {
-        const R *a = &ROW(o.a & 0x7fffffffu), *b = a + (size_t)k * TS;
-        R acc = 0;
-        const uint32_t half = (k + 1) >> 1;
-        for (uint32_t j = 0; j < half; ++j) acc = r_fma(a[(size_t)j * TS], b[-(ptrdiff_t)((size_t)j * TS)], acc);
+        const R *a = w + o.a;
+        R acc = conv<R>(a, a + k, (int)((k + 1) >> 1));
         acc = acc + acc;
         if ((k & 1u) == 0) {
-            R m = a[(size_t)(k >> 1) * TS];
+            const R m = a[k >> 1];
             acc = r_fma(m, m, acc);
         }
-        ROW(ref_row(o.dst, k)) = acc;
+        w[o.dst + kd] = acc;
     } break;
     case HY_OP_SUMSQ: {
-        R acc = 0;
-        const uint32_t half = (k + 1) >> 1;
-        const hy_term *t = terms + o.b;
-        for (uint32_t i = 0; i < o.n; ++i) {
-            const R *a = &ROW(t[i].src & 0x7fffffffu), *b = a + (size_t)k * TS;
-            for (uint32_t j = 0; j < half; ++j)
-                acc = r_fma(a[(size_t)j * TS], b[-(ptrdiff_t)((size_t)j * TS)], acc);
-        }
-        acc = acc + acc;
-        if ((k & 1u) == 0)
-            for (uint32_t i = 0; i < o.n; ++i) {
-                R m = ROW((t[i].src & 0x7fffffffu) + (k >> 1));
-                acc = r_fma(m, m, acc);
+        R s0 = 0, s1 = 0;
+        const int half = (int)((k + 1) >> 1);
+        const DTerm *t = lt + (uint32_t)o.b * G;
+        const uint32_t n = o.n;
+        R acc2 = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const R *a = w + rbase(t[i * G].src);
+            const R *b = a + k;
+            int j = 0;
+            for (; j + 2 <= half; j += 2) {
+                const R a0 = a[j], a1 = a[j + 1], b0 = b[-j], b1 = b[-j - 1];
+                s0 = r_fma(a0, b0, s0);
+                s1 = r_fma(a1, b1, s1);
             }
-        ROW(ref_row(o.dst, k)) = acc;
+            if (j < half) s0 = r_fma(a[j], b[-j], s0);
+            if ((k & 1u) == 0) {
+                const R m = a[k >> 1];
+                acc2 = r_fma(m, m, acc2);
+            }
+        }
+        R acc = s0 + s1;
+        w[o.dst + kd] = (acc + acc) + acc2;
     } break;
     case HY_OP_MULSH: {
-        const R *b = &ROW((o.a & 0x7fffffffu) + k);
-        const hy_term *t = terms + o.b;
-        for (uint32_t i = 0; i < o.n; ++i) {
-            const R *a = &ROW(t[i].src & 0x7fffffffu);
-            R acc = 0;
-            for (uint32_t j = 0; j <= k; ++j)
-                acc = r_fma(a[(size_t)j * TS], b[-(ptrdiff_t)((size_t)j * TS)], acc);
-            ROW(ref_row(t[i].dst, k)) = acc;
+        const R *b = w + o.a + k;
+        const DTerm *t = lt + (uint32_t)o.b * G;
+        const int n = (int)k + 1;
+        if (o.n == 3) {
+            const DTerm t0 = t[0], t1 = t[G], t2 = t[2 * G];
+            const R *a0 = w + rbase(t0.src), *a1 = w + rbase(t1.src), *a2 = w + rbase(t2.src);
+            R s0 = 0, s1 = 0, s2 = 0;
+            int j = 0;
+            for (; j + 2 <= n; j += 2) {
+                const R b0 = b[-j], b1 = b[-j - 1];
+                const R x0 = a0[j], x1 = a1[j], x2 = a2[j];
+                const R y0 = a0[j + 1], y1 = a1[j + 1], y2 = a2[j + 1];
+                s0 = r_fma(x0, b0, s0);
+                s1 = r_fma(x1, b0, s1);
+                s2 = r_fma(x2, b0, s2);
+                s0 = r_fma(y0, b1, s0);
+                s1 = r_fma(y1, b1, s1);
+                s2 = r_fma(y2, b1, s2);
+            }
+            if (j < n) {
+                const R b0 = b[-j];
+                s0 = r_fma(a0[j], b0, s0);
+                s1 = r_fma(a1[j], b0, s1);
+                s2 = r_fma(a2[j], b0, s2);
+            }
+            w[roff(t0.aux, k)] = s0;
+            w[roff(t1.aux, k)] = s1;
+            w[roff(t2.aux, k)] = s2;
+        } else {
+            for (uint32_t i = 0; i < o.n; ++i) {
+                const DTerm ti = t[i * G];
+                w[roff(ti.aux, k)] = conv<R>(w + rbase(ti.src), b, n);
+            }
         }
     } break;
     case HY_OP_DIV: {
-        const R *b = &ROW(o.b & 0x7fffffffu);
-        R *c = &ROW(o.dst & 0x7fffffffu);
-        if (k == 0) ROW(o.dst2) = (R)1 / b[0];
-        R acc = ROW(ref_row(o.a, k));
-        for (uint32_t j = 1; j <= k; ++j) acc = r_fma(-b[(size_t)j * TS], c[(size_t)(k - j) * TS], acc);
-        c[(size_t)k * TS] = acc * ROW(o.dst2);
+        const R *b = w + o.b;
+        R *c = w + o.dst;
+        if (k == 0) w[o.dst2] = (R)1 / b[0];
+        R acc = w[o.a + ka];
+        for (uint32_t j = 1; j <= k; ++j) acc = r_fma(-b[j], c[k - j], acc);
+        c[k] = acc * w[o.dst2];
     } break;
     case HY_OP_POW:
     case HY_OP_SQRT: {
-        const R *a = &ROW(o.a & 0x7fffffffu);
-        R *c = &ROW(o.dst & 0x7fffffffu);
-        const double alpha = o.opcode == HY_OP_SQRT ? 0.5 : o.imm;
+        const R *a = w + o.a;
+        R *c = w + o.dst;
+        const double alpha = o.opcode == HY_OP_SQRT ? 0.5 : s_imm[o.imm];
         if (k == 0) {
-            ROW(o.dst2) = (R)1 / a[0];
+            w[o.dst2] = (R)1 / a[0];
             c[0] = o.opcode == HY_OP_SQRT ? r_sqrt(a[0]) : pow0<R>(a[0], alpha);
         } else {
-            const R al = (R)alpha, al1 = (R)(alpha + 1.0), kal = (R)k * al;
-            R acc = 0;
-            const R *ak = a + (size_t)k * TS;
-            for (uint32_t j = 0; j < k; ++j) {
-                const R wgt = r_fma(-(R)j, al1, kal);
-                acc = r_fma(wgt * ak[-(ptrdiff_t)((size_t)j * TS)], c[(size_t)j * TS], acc);
+            const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;
+            R s0 = 0, s1 = 0, jr = 0;
+            const R *ak = a + k;
+            int j = 0;
+            const int n = (int)k;
+            for (; j + 2 <= n; j += 2) {
+                const R a0 = ak[-j], a1 = ak[-j - 1], c0 = c[j], c1 = c[j + 1];
+                const R w0 = r_fma(-jr, al1, kal);
+                const R w1 = r_fma(-(jr + (R)1), al1, kal);
+                jr += (R)2;
+                s0 = r_fma(w0 * a0, c0, s0);
+                s1 = r_fma(w1 * a1, c1, s1);
             }
-            c[(size_t)k * TS] = (acc * rk[k]) * ROW(o.dst2);
+            if (j < n) s0 = r_fma(r_fma(-jr, al1, kal) * ak[-j], c[j], s0);
+            c[k] = ((s0 + s1) * rk[k]) * w[o.dst2];
         }
     } break;
     case HY_OP_EXP: {
-        const R *a = &ROW(o.a & 0x7fffffffu);
-        R *c = &ROW(o.dst & 0x7fffffffu);
+        const R *a = w + o.a;
+        R *c = w + o.dst;
         if (k == 0) {
             c[0] = r_exp(a[0]);
         } else {
-            R acc = 0;
-            for (uint32_t j = 1; j <= k; ++j) acc = r_fma((R)j * a[(size_t)j * TS], c[(size_t)(k - j) * TS], acc);
-            c[(size_t)k * TS] = acc * rk[k];
+            R acc = 0, jr = 1;
+            for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * a[j], c[k - j], acc);
+            c[k] = acc * rk[k];
         }
     } break;
     case HY_OP_LOG: {
-        const R *a = &ROW(o.a & 0x7fffffffu);
-        R *c = &ROW(o.dst & 0x7fffffffu);
+        const R *a = w + o.a;
+        R *c = w + o.dst;
         if (k == 0) {
-            ROW(o.dst2) = (R)1 / a[0];
+            w[o.dst2] = (R)1 / a[0];
             c[0] = r_log(a[0]);
         } else {
-            R acc = 0;
-            for (uint32_t j = 1; j < k; ++j) acc = r_fma((R)j * c[(size_t)j * TS], a[(size_t)(k - j) * TS], acc);
-            c[(size_t)k * TS] = r_fma(-acc, rk[k], a[(size_t)k * TS]) * ROW(o.dst2);
+            R acc = 0, jr = 1;
+            for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * c[j], a[k - j], acc);
+            c[k] = r_fma(-acc, rk[k], a[k]) * w[o.dst2];
         }
     } break;
     case HY_OP_SINCOS: {
-        const R *a = &ROW(o.a & 0x7fffffffu);
-        R *s = &ROW(o.dst & 0x7fffffffu), *c = &ROW(o.dst2 & 0x7fffffffu);
+        const R *a = w + o.a;
+        R *s = w + o.dst, *c = w + o.dst2;
         if (k == 0) {
             R sv, cv;
             r_sincos(a[0], &sv, &cv);
             s[0] = sv;
             c[0] = cv;
         } else {
-            R sa = 0, ca = 0;
-            for (uint32_t j = 1; j <= k; ++j) {
-                const R ja = (R)j * a[(size_t)j * TS];
-                sa = r_fma(ja, c[(size_t)(k - j) * TS], sa);
-                ca = r_fma(ja, s[(size_t)(k - j) * TS], ca);
+            R sa = 0, ca = 0, jr = 1;
+            for (uint32_t j = 1; j <= k; ++j, jr += (R)1) {
+                const R ja = jr * a[j];
+                sa = r_fma(ja, c[k - j], sa);
+                ca = r_fma(ja, s[k - j], ca);
             }
-            s[(size_t)k * TS] = sa * rk[k];
-            c[(size_t)k * TS] = -(ca * rk[k]);
+            s[k] = sa * rk[k];
+            c[k] = -(ca * rk[k]);
         }
     } break;
     case HY_OP_TIME: {
-        ROW((o.dst & 0x7fffffffu) + k) = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);
+        w[o.dst + k] = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);
     } break;
     case HY_OP_SVD: {
-        ROW((o.dst & 0x7fffffffu) + k + 1) = ROW(ref_row(o.a, k)) * rk[k + 1];
+        w[o.dst + k + 1] = w[o.a + ka] * rk[k + 1];
     } break;
-    default: break;
+    default: break; // OP_NOP
     }
-#undef ROW
 }
 
 // Error-free time arithmetic.  __dadd_rn & co. forbid
@@ -268,75 +348,81 @@ template <typename R> __device__ __forceinline__ R time_sub(R ahi, R alo, R bhi,
 }
 
 // Shared-memory carve-up (dynamic smem):
-//   [ops | terms | level_start | ev_ref | rk | ws]
+//   [ops | terms | imm | phase_slot | ev_ref | rk | ws]
 struct SmemLayout {
-    uint32_t off_ops, off_terms, off_levels, off_ev, off_rk, off_ws, total;
+    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_rk, off_ws, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(const hy_dims &d, uint32_t TS, uint32_t real_bytes, int ws_in_smem)
+// Elements of one trajectory's workspace column (before padding to odd).
+__host__ __device__ inline uint32_t ws_rows(const hy_dims &d) { return d.n_rows + d.n_par + d.order + 1; }
+
+__host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDims &pd, uint32_t G, uint32_t T,
+                                                  uint32_t RS, uint32_t real_bytes, int ws_in_smem)
 {
     SmemLayout L;
     uint32_t o = 0;
     L.off_ops = o;
-    o += d.n_ops * (uint32_t)sizeof(hy_op);
+    o += pd.n_slots * G * 16u;
     L.off_terms = o;
-    o += d.n_terms * (uint32_t)sizeof(hy_term);
-    o = align_up(o, 8);
-    L.off_levels = o;
-    o += (d.n_levels + 1) * 4;
+    o += pd.n_tslots * G * 16u;
+    L.off_imm = o;
+    o += pd.n_imm * 8u;
+    L.off_phase = o;
+    o += (pd.n_phases + 1) * 4u;
     L.off_ev = o;
-    o += d.n_events * 4;
+    o += d.n_events * 4u;
     o = align_up(o, 8);
     L.off_rk = o;
     o += (d.order + 2) * real_bytes;
     o = align_up(o, 16);
     L.off_ws = o;
-    if (ws_in_smem) o += (d.n_rows + d.n_par) * TS * real_bytes;
+    if (ws_in_smem) o += T * RS * real_bytes;
     L.total = o;
     return L;
 }
 
-template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate_kernel(const KParams<R> P)
+template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
-    const SmemLayout L = make_layout(d, P.TS, sizeof(R), P.ws_in_smem);
-    hy_op *s_ops = reinterpret_cast<hy_op *>(smem_raw + L.off_ops);
-    hy_term *s_terms = reinterpret_cast<hy_term *>(smem_raw + L.off_terms);
-    uint32_t *s_levels = reinterpret_cast<uint32_t *>(smem_raw + L.off_levels);
+    const SmemLayout L = make_layout(d, P.pd, G, P.T, P.TS, sizeof(R), SMEM ? 1 : 0);
+    DOp *s_ops = reinterpret_cast<DOp *>(smem_raw + L.off_ops);
+    DTerm *s_terms = reinterpret_cast<DTerm *>(smem_raw + L.off_terms);
+    double *s_imm = reinterpret_cast<double *>(smem_raw + L.off_imm);
+    uint32_t *s_phase = reinterpret_cast<uint32_t *>(smem_raw + L.off_phase);
     uint32_t *s_ev = reinterpret_cast<uint32_t *>(smem_raw + L.off_ev);
     R *s_rk = reinterpret_cast<R *>(smem_raw + L.off_rk);
-    R *ws = P.ws_in_smem ? reinterpret_cast<R *>(smem_raw + L.off_ws)
-                         : P.gws + (size_t)blockIdx.x * (d.n_rows + d.n_par) * P.TS;
+    const uint32_t RS = P.TS; // workspace stride between trajectories (odd)
 
-    // ---- stage the tape ----
+    // ---- stage the program ----
     {
-        const uint32_t nw_ops = d.n_ops * (uint32_t)sizeof(hy_op) / 4;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.ops);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_ops);
-        for (uint32_t i = threadIdx.x; i < nw_ops; i += blockDim.x) dst[i] = src[i];
-        const uint32_t nw_t = d.n_terms * (uint32_t)sizeof(hy_term) / 4;
-        src = reinterpret_cast<const uint32_t *>(P.terms);
-        dst = reinterpret_cast<uint32_t *>(s_terms);
-        for (uint32_t i = threadIdx.x; i < nw_t; i += blockDim.x) dst[i] = src[i];
-        for (uint32_t i = threadIdx.x; i <= d.n_levels; i += blockDim.x) s_levels[i] = P.level_start[i];
+        const uint32_t nw = L.off_phase / 4; // ops + terms + imm are contiguous
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.prog);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i <= P.pd.n_phases; i += blockDim.x) s_phase[i] = P.phase_slot[i];
         for (uint32_t i = threadIdx.x; i < d.n_events; i += blockDim.x) s_ev[i] = P.ev_ref[i];
         for (uint32_t i = threadIdx.x; i < d.order + 2; i += blockDim.x)
             s_rk[i] = i == 0 ? (R)0 : (R)(1.0 / (double)i);
     }
     __syncthreads();
 
-    const uint32_t TS = P.TS;
     const uint32_t p = d.order, P1 = p + 1, n = d.n_state;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t sub = threadIdx.x & (G - 1);
     const uint32_t slot = threadIdx.x / G; // trajectory slot in this CTA
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
-    const uint32_t par_row = d.n_rows;
+    const uint32_t par_off = d.n_rows, one_off = d.n_rows + d.n_par;
     if (slot >= P.T) return; // whole groups only: safe w.r.t. group-mask syncs
-    R *w = ws + slot;
+    R *w;
+    if (SMEM)
+        w = reinterpret_cast<R *>(smem_raw + L.off_ws) + (size_t)slot * RS;
+    else
+        w = P.gws + ((size_t)blockIdx.x * P.T + slot) * RS;
+    // unit jet [1, 0, ..., 0] (never changes)
+    for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
 
     for (;;) {
         // ---- fetch the next trajectory for this group ----
@@ -345,8 +431,8 @@ template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate
         if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
         if (traj >= P.B) break;
 
-        for (uint32_t i = sub; i < n; i += G) w[(size_t)(i * P1) * TS] = P.state[(size_t)i * P.B + traj];
-        for (uint32_t i = sub; i < d.n_par; i += G) w[(size_t)(par_row + i) * TS] = P.pars[(size_t)i * P.B + traj];
+        for (uint32_t i = sub; i < n; i += G) w[i * P1] = P.state[(size_t)i * P.B + traj];
+        for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i] = P.pars[(size_t)i * P.B + traj];
         R hi = P.t_hi[traj], lo = P.t_lo[traj];
         R mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
         R tf_hi = 0, tf_lo = 0;
@@ -376,21 +462,26 @@ template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate
                 lim = r_abs(rem) < mdt ? rem : r_copysign(mdt, rem);
             }
 
-            // ---- jets: orders 0..p-1 of every op, then x[k+1] ----
+            // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
+            const DOp *lops = s_ops + sub;
+            const DTerm *lterms = s_terms + sub;
+            const uint32_t n_ph = P.pd.n_phases;
             for (uint32_t k = 0; k < p; ++k) {
-                for (uint32_t lv = 0; lv < d.n_levels; ++lv) {
-                    const uint32_t e = s_levels[lv + 1];
-                    for (uint32_t i = s_levels[lv] + sub; i < e; i += G)
-                        exec_op<R>(s_ops[i], s_terms, w, TS, s_rk, k, hi, par_row);
+                for (uint32_t ph = 0; ph < n_ph; ++ph) {
+                    const uint32_t e = s_phase[ph + 1];
+                    for (uint32_t i = s_phase[ph]; i < e; ++i)
+                        exec_op<R, G>(lops[i * G], lterms, w, s_rk, s_imm, k, hi);
                     if (G > 1) __syncwarp(gmask);
                 }
             }
             if (d.n_events) {
-                for (uint32_t lv = 0; lv < d.n_levels; ++lv) {
-                    const uint32_t e = s_levels[lv + 1];
-                    for (uint32_t i = s_levels[lv] + sub; i < e; i += G)
-                        if ((s_ops[i].flags & HY_OPF_EVENT) && s_ops[i].opcode != HY_OP_SVD)
-                            exec_op<R>(s_ops[i], s_terms, w, TS, s_rk, p, hi, par_row);
+                for (uint32_t ph = 0; ph < n_ph; ++ph) {
+                    const uint32_t e = s_phase[ph + 1];
+                    for (uint32_t i = s_phase[ph]; i < e; ++i) {
+                        const DOp o = lops[i * G];
+                        if ((o.flags & HY_OPF_EVENT) && !(o.flags & HY_OPF_SVD) && o.opcode != HY_OP_SVD)
+                            exec_op<R, G>(o, lterms, w, s_rk, s_imm, p, hi);
+                    }
                     if (G > 1) __syncwarp(gmask);
                 }
             }
@@ -398,10 +489,10 @@ template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
             for (uint32_t i = sub; i < n + d.n_events; i += G) {
-                const R *x = i < n ? &w[(size_t)(i * P1) * TS] : &w[(size_t)(s_ev[i - n] & 0x7fffffffu) * TS];
+                const R *x = i < n ? &w[i * P1] : &w[rbase(s_ev[i - n])];
                 n0 = nan_max(n0, r_abs(x[0]));
-                n1 = nan_max(n1, r_abs(x[(size_t)(p - 1) * TS]));
-                n2 = nan_max(n2, r_abs(x[(size_t)p * TS]));
+                n1 = nan_max(n1, r_abs(x[p - 1]));
+                n2 = nan_max(n2, r_abs(x[p]));
             }
 #pragma unroll
             for (int m = G >> 1; m > 0; m >>= 1) {
@@ -426,20 +517,20 @@ template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate
 
             // ---- optional tc write, then the state update ----
             if (P.write_tc && P.tc) {
-                for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = w[(size_t)i * TS];
+                for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = w[i];
                 if (G > 1) __syncwarp(gmask);
             }
             bool finite = true;
             for (uint32_t i = sub; i < n; i += G) {
-                R *x = &w[(size_t)(i * P1) * TS];
+                R *x = &w[i * P1];
                 R acc;
                 if (!P.high_accuracy) {
-                    acc = x[(size_t)p * TS];
-                    for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[(size_t)k * TS]);
+                    acc = x[p];
+                    for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[k]);
                 } else {
                     R sum = x[0], comp = 0, hk = h;
                     for (uint32_t k = 1; k <= p; ++k) {
-                        const R term = x[(size_t)k * TS] * hk; // single rounding (no fma partner)
+                        const R term = x[k] * hk;
                         const R y = ef_sub(term, comp);
                         const R tt = ef_add(sum, y);
                         comp = ef_sub(ef_sub(tt, sum), y);
@@ -484,7 +575,7 @@ template <typename R, int G> __global__ void __launch_bounds__(512, 1) propagate
 
         // ---- retire the trajectory ----
         if (G > 1) __syncwarp(gmask);
-        for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[(size_t)(i * P1) * TS];
+        for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[i * P1];
         if (sub == 0) {
             P.t_hi[traj] = hi;
             P.t_lo[traj] = lo;

@@ -1,0 +1,351 @@
+// hy_schedule.hpp - host-side scheduling of the ABI tape into per-lane programs.
+//
+// The ABI tape (include/hy_cuda.h) lists the elementary ops of one order sweep
+// in dependency order.  A group of G lanes cooperates on one trajectory, so the
+// ops must be distributed over the lanes with as few group synchronisations as
+// possible.  This file
+//   1. finds the same-sweep dependencies between ops,
+//   2. merges every op whose consumers all live in one cluster into that
+//      cluster (a cluster is executed start-to-end by ONE lane, so its internal
+//      dependencies need no synchronisation; for the N-body problem a cluster is
+//      one body pair: 3 differences, sum of squares, pow(-3/2), 3 products),
+//   3. levels the cluster DAG into PHASES (one group sync per phase),
+//   4. packs clusters with identical opcode signatures into rows of G lanes so
+//      that the lanes of a warp run the same opcode at the same time,
+//   5. emits the program in a lane-interleaved (ELL) layout: op slot j of lane s
+//      sits at ops[(slot)*G + s] and term c of lane s at terms[c*G + s], so every
+//      tape access of a warp is bank-conflict free (or a broadcast).
+//
+// This replaces the instruction scheduling LLVM performs for the reference's
+// JIT-compiled stepper ([UPSTREAM] heyoka taylor_adaptive_batch ctor, called
+// from /root/reference/heyoka/expose_batch_integrators.cpp:166-208).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/hy_cuda.h"
+
+namespace hy {
+
+// Device op: 16 bytes, one LDS.128.
+struct DOp {
+    uint8_t opcode; // hy_opcode, or OP_NOP
+    uint8_t flags;  // bits 0-3: HY_OPF_*; bits 4-7: jet flag of dst, dst2, a, b
+    uint16_t n;     // number of terms
+    uint16_t dst, dst2;
+    uint16_t a, b; // operand offsets; for term ops b = first term position in the lane's stream
+    uint16_t imm;  // index into the immediate table
+    uint16_t pad;
+};
+static_assert(sizeof(DOp) == 16, "DOp must be 16 bytes");
+// Device term: 16 bytes.
+struct DTerm {
+    double coef;
+    uint32_t src; // offset | bit 31 = jet
+    uint32_t aux; // LINCOMB: offset of the multiplier (parameter row or 1.0); MULSH: dst ref
+};
+static_assert(sizeof(DTerm) == 16, "DTerm must be 16 bytes");
+
+enum : uint8_t { OP_NOP = 255 };
+enum : uint8_t { DF_JDST = 0x10, DF_JDST2 = 0x20, DF_JA = 0x40, DF_JB = 0x80 };
+
+struct Program {
+    uint32_t G = 1;
+    uint32_t n_phases = 0;
+    std::vector<uint32_t> phase_slot; // [n_phases + 1] slot ranges
+    std::vector<DOp> ops;             // [n_slots * G]
+    std::vector<DTerm> terms;         // [n_tslots * G]
+    std::vector<double> imm;          // immediates
+    uint32_t n_slots = 0, n_tslots = 0;
+    // statistics
+    uint32_t n_clusters = 0;
+    double lane_utilisation = 0; // useful op slots / (slots * G), cost weighted
+};
+
+namespace detail {
+
+inline bool is_term_op(uint16_t oc) { return oc == HY_OP_LINCOMB || oc == HY_OP_SUMSQ || oc == HY_OP_MULSH; }
+
+// Rough relative cost of an op at a mid order (used only for balancing).
+inline double op_cost(const hy_op &o)
+{
+    const double k = 10;
+    switch (o.opcode) {
+    case HY_OP_LINCOMB: return 4 + 3.0 * o.n;
+    case HY_OP_ADDSUB: return 5;
+    case HY_OP_MUL: return 8 + 3 * k;
+    case HY_OP_SQUARE: return 8 + 1.5 * k;
+    case HY_OP_SUMSQ: return 8 + 1.5 * k * o.n;
+    case HY_OP_MULSH: return 8 + (1.0 + o.n) * k + o.n * k * 0.5;
+    case HY_OP_DIV: return 10 + 3 * k;
+    case HY_OP_POW:
+    case HY_OP_SQRT: return 12 + 5 * k;
+    case HY_OP_EXP:
+    case HY_OP_LOG: return 10 + 4 * k;
+    case HY_OP_SINCOS: return 12 + 6 * k;
+    case HY_OP_TIME: return 3;
+    case HY_OP_SVD: return 4;
+    default: return 1;
+    }
+}
+
+struct UF {
+    std::vector<int> p;
+    explicit UF(int n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+    int find(int x)
+    {
+        while (p[x] != x) x = p[x] = p[p[x]];
+        return x;
+    }
+};
+
+} // namespace detail
+
+// Build the per-lane program.  Returns an empty string on success, else an
+// error message.
+inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_term *terms, uint32_t G, Program &out)
+{
+    using namespace detail;
+    const uint32_t n_ops = d.n_ops;
+    const uint32_t par_off = d.n_rows, one_off = d.n_rows + d.n_par;
+    const uint32_t ws_len = d.n_rows + d.n_par + d.order + 1;
+    if (ws_len > 65535u) return "the system is too large: more than 65535 workspace rows per trajectory";
+    const uint32_t P1 = d.order + 1;
+
+    // ---- 1. producers of rows written in the same sweep ----
+    std::map<uint32_t, int> prod; // row base -> op
+    auto base_of = [](uint32_t ref) { return ref & 0x7fffffffu; };
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const hy_op &o = ops[i];
+        if (o.opcode >= HY_OP_COUNT) return "invalid opcode in the tape";
+        if (o.opcode == HY_OP_SVD || (o.flags & HY_OPF_SVD)) continue; // writes order k+1: next sweep
+        if (o.opcode == HY_OP_MULSH) {
+            for (uint32_t j = 0; j < o.n; ++j) prod[base_of(terms[o.b + j].dst)] = (int)i;
+        } else {
+            prod[base_of(o.dst)] = (int)i;
+            if (o.opcode == HY_OP_SINCOS) prod[base_of(o.dst2)] = (int)i;
+        }
+    }
+    std::vector<std::vector<int>> deps(n_ops), cons(n_ops);
+    auto add_dep = [&](uint32_t i, uint32_t ref) {
+        if (ref == HY_REF_ONE) return;
+        auto it = prod.find(base_of(ref));
+        if (it != prod.end() && it->second != (int)i) {
+            if (std::find(deps[i].begin(), deps[i].end(), it->second) == deps[i].end()) {
+                deps[i].push_back(it->second);
+                cons[it->second].push_back((int)i);
+            }
+        }
+    };
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const hy_op &o = ops[i];
+        if (is_term_op(o.opcode)) {
+            if ((uint64_t)o.b + o.n > d.n_terms) return "term range out of bounds";
+            for (uint32_t j = 0; j < o.n; ++j) add_dep(i, terms[o.b + j].src);
+            if (o.opcode == HY_OP_MULSH) add_dep(i, o.a);
+        } else if (o.opcode != HY_OP_TIME) {
+            add_dep(i, o.a);
+            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB) add_dep(i, o.b);
+        }
+    }
+    for (uint32_t i = 0; i < n_ops; ++i)
+        for (int j : deps[i])
+            if (j > (int)i) return "the tape is not in dependency order";
+
+    // ---- 2. clusters ----
+    UF uf((int)n_ops);
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (uint32_t j = 0; j < n_ops; ++j) {
+            if (cons[j].empty()) continue;
+            const int c0 = uf.find(cons[j][0]);
+            bool same = true;
+            for (int c : cons[j]) same = same && uf.find(c) == c0;
+            if (same && uf.find((int)j) != c0) {
+                uf.p[uf.find((int)j)] = c0;
+                changed = true;
+            }
+        }
+    }
+    std::map<int, std::vector<int>> members; // root -> ops in tape order
+    for (uint32_t i = 0; i < n_ops; ++i) members[uf.find((int)i)].push_back((int)i);
+    std::vector<std::vector<int>> clusters;
+    std::vector<int> cl_of(n_ops);
+    for (auto &kv : members) {
+        for (int i : kv.second) cl_of[i] = (int)clusters.size();
+        clusters.push_back(kv.second);
+    }
+    const int NC = (int)clusters.size();
+
+    // ---- 3. phases = levels of the cluster DAG ----
+    std::vector<int> lvl(NC, 0);
+    std::vector<char> has_pred(NC, 0), has_succ(NC, 0);
+    // clusters are numbered by their root op id, not topologically: iterate to a fixed point
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (uint32_t i = 0; i < n_ops; ++i)
+            for (int j : deps[i]) {
+                const int ci = cl_of[i], cj = cl_of[j];
+                if (ci == cj) continue;
+                has_pred[ci] = 1;
+                has_succ[cj] = 1;
+                if (lvl[ci] < lvl[cj] + 1) {
+                    lvl[ci] = lvl[cj] + 1;
+                    changed = true;
+                }
+            }
+    }
+    int n_ph = 0;
+    for (int c = 0; c < NC; ++c) n_ph = std::max(n_ph, lvl[c] + 1);
+    // Isolated clusters (e.g. x' = v recurrences) go where they disturb least: the last phase.
+    for (int c = 0; c < NC; ++c)
+        if (!has_pred[c] && !has_succ[c]) lvl[c] = n_ph - 1;
+
+    // ---- 4. rows of equal-signature clusters ----
+    auto signature = [&](int c) {
+        std::vector<uint32_t> s;
+        for (int i : clusters[c]) s.push_back(((uint32_t)ops[i].opcode << 16) | (ops[i].n & 0xffffu));
+        return s;
+    };
+    auto cl_cost = [&](int c) {
+        double t = 0;
+        for (int i : clusters[c]) t += op_cost(ops[i]);
+        return t;
+    };
+    // lane programs: per phase, per lane, list of op ids (-1 = NOP)
+    std::vector<std::vector<std::vector<int>>> prog(n_ph, std::vector<std::vector<int>>(G));
+    double useful = 0, total = 0;
+    for (int ph = 0; ph < n_ph; ++ph) {
+        std::map<std::vector<uint32_t>, std::vector<int>> groups;
+        for (int c = 0; c < NC; ++c)
+            if (lvl[c] == ph) groups[signature(c)].push_back(c);
+        std::vector<std::pair<double, std::vector<int>>> full_rows;
+        std::vector<int> leftovers;
+        for (auto &kv : groups) {
+            auto &v = kv.second;
+            size_t i = 0;
+            for (; i + G <= v.size(); i += G)
+                full_rows.push_back({cl_cost(v[i]), std::vector<int>(v.begin() + i, v.begin() + i + G)});
+            // A nearly full tail stays a row of its own (no divergence).
+            if (v.size() - i >= (3 * G + 3) / 4) {
+                full_rows.push_back({cl_cost(v[i]), std::vector<int>(v.begin() + i, v.end())});
+            } else {
+                for (; i < v.size(); ++i) leftovers.push_back(v[i]);
+            }
+        }
+        // Heaviest leftovers first, packed into mixed rows.
+        std::sort(leftovers.begin(), leftovers.end(), [&](int a, int b) { return cl_cost(a) > cl_cost(b); });
+        for (size_t i = 0; i < leftovers.size(); i += G)
+            full_rows.push_back({cl_cost(leftovers[i]),
+                                 std::vector<int>(leftovers.begin() + i,
+                                                  leftovers.begin() + std::min(leftovers.size(), i + (size_t)G))});
+        std::stable_sort(full_rows.begin(), full_rows.end(),
+                         [](const auto &a, const auto &b) { return a.first > b.first; });
+        for (auto &row : full_rows) {
+            size_t len = 0;
+            for (int c : row.second) len = std::max(len, clusters[c].size());
+            double rc = 0;
+            for (int c : row.second) rc = std::max(rc, cl_cost(c));
+            for (uint32_t s = 0; s < G; ++s) {
+                auto &lp = prog[ph][s];
+                size_t k = 0;
+                if (s < row.second.size()) {
+                    for (int i : clusters[row.second[s]]) lp.push_back(i), ++k;
+                    useful += cl_cost(row.second[s]);
+                }
+                for (; k < len; ++k) lp.push_back(-1);
+            }
+            total += rc * G;
+        }
+    }
+
+    // ---- 5. emit ----
+    out = Program();
+    out.G = G;
+    out.n_phases = (uint32_t)n_ph;
+    out.n_clusters = (uint32_t)NC;
+    out.lane_utilisation = total > 0 ? useful / total : 1.0;
+    out.phase_slot.push_back(0);
+    uint32_t slots = 0;
+    for (int ph = 0; ph < n_ph; ++ph) {
+        slots += (uint32_t)prog[ph][0].size();
+        out.phase_slot.push_back(slots);
+    }
+    out.n_slots = slots;
+    DOp nop{};
+    nop.opcode = OP_NOP;
+    out.ops.assign((size_t)slots * G, nop);
+    std::vector<std::vector<DTerm>> lane_terms(G);
+    std::map<uint64_t, uint16_t> imm_idx;
+    auto imm_of = [&](double v) {
+        uint64_t key;
+        std::memcpy(&key, &v, 8);
+        auto it = imm_idx.find(key);
+        if (it != imm_idx.end()) return it->second;
+        uint16_t id = (uint16_t)out.imm.size();
+        out.imm.push_back(v);
+        imm_idx[key] = id;
+        return id;
+    };
+    auto fix = [&](uint32_t ref) { return ref == HY_REF_ONE ? (one_off | HY_REF_JET) : ref; };
+    for (int ph = 0; ph < n_ph; ++ph)
+        for (uint32_t s = 0; s < G; ++s) {
+            const auto &lp = prog[ph][s];
+            for (size_t j = 0; j < lp.size(); ++j) {
+                if (lp[j] < 0) continue;
+                const hy_op &o = ops[lp[j]];
+                DOp q{};
+                q.opcode = (uint8_t)o.opcode;
+                q.flags = (uint8_t)(o.flags & 0xf);
+                q.n = (uint16_t)o.n;
+                auto setref = [&](uint32_t ref, uint16_t &field, uint8_t jflag) {
+                    ref = fix(ref);
+                    field = (uint16_t)(ref & 0x7fffffffu);
+                    if (ref & HY_REF_JET) q.flags |= jflag;
+                };
+                if (o.opcode != HY_OP_MULSH) setref(o.dst, q.dst, DF_JDST);
+                if (o.opcode == HY_OP_SINCOS)
+                    setref(o.dst2, q.dst2, DF_JDST2);
+                else
+                    q.dst2 = (uint16_t)o.dst2; // scratch row (DIV/POW/SQRT/LOG)
+                if (o.opcode != HY_OP_TIME) setref(o.a, q.a, DF_JA);
+                if (is_term_op(o.opcode)) {
+                    if (lane_terms[s].size() + o.n > 65535u) return "too many terms per lane";
+                    q.b = (uint16_t)lane_terms[s].size();
+                    for (uint32_t t = 0; t < o.n; ++t) {
+                        const hy_term &ht = terms[o.b + t];
+                        if (ht.par >= (int32_t)d.n_par) return "parameter index out of bounds";
+                        DTerm u{};
+                        u.coef = ht.coef;
+                        u.src = fix(ht.src);
+                        if (o.opcode == HY_OP_MULSH)
+                            u.aux = ht.dst;
+                        else
+                            u.aux = ht.par >= 0 ? par_off + (uint32_t)ht.par : one_off;
+                        lane_terms[s].push_back(u);
+                    }
+                } else {
+                    setref(o.b, q.b, DF_JB);
+                }
+                q.imm = imm_of(o.imm);
+                (void)P1;
+                out.ops[((size_t)out.phase_slot[ph] + j) * G + s] = q;
+            }
+        }
+    size_t tmax = 0;
+    for (auto &v : lane_terms) tmax = std::max(tmax, v.size());
+    out.n_tslots = (uint32_t)tmax;
+    DTerm zt{};
+    zt.aux = one_off;
+    out.terms.assign(tmax * G, zt);
+    for (uint32_t s = 0; s < G; ++s)
+        for (size_t c = 0; c < lane_terms[s].size(); ++c) out.terms[c * G + s] = lane_terms[s][c];
+    if (out.imm.empty()) out.imm.push_back(0.0);
+    return "";
+}
+
+} // namespace hy

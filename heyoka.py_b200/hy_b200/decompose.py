@@ -27,8 +27,8 @@ from . import _expression as E
 
 # Opcodes: keep in sync with include/hy_cuda.h.
 OP_LINCOMB, OP_MUL, OP_SQUARE, OP_DIV, OP_POW, OP_SQRT, OP_EXP, OP_LOG = range(8)
-OP_SINCOS, OP_TIME, OP_SVD, OP_SUMSQ, OP_MULSH = 8, 9, 10, 11, 12
-OPF_EVENT = 0x1
+OP_SINCOS, OP_TIME, OP_SVD, OP_SUMSQ, OP_MULSH, OP_ADDSUB = 8, 9, 10, 11, 12, 13
+OPF_EVENT, OPF_NEGA, OPF_NEGB, OPF_SVD = 0x1, 0x2, 0x4, 0x8
 REF_JET = 0x80000000
 REF_ONE = 0x7FFFFFFF
 
@@ -46,6 +46,7 @@ OP_NAMES = {
     OP_SVD: "svd",
     OP_SUMSQ: "sumsq",
     OP_MULSH: "mulsh",
+    OP_ADDSUB: "addsub",
 }
 
 op_dtype = np.dtype(
@@ -79,7 +80,7 @@ def taylor_order(tol):
 class _UVar:
     __slots__ = (
         "id", "op", "args", "imm", "terms", "jet", "level", "row", "pair", "event", "mterms",
-        "inv_row",
+        "inv_row", "svd_of", "signs",
     )
 
     def __init__(self, uid, op, args=(), imm=0.0, terms=None):
@@ -94,6 +95,8 @@ class _UVar:
         self.pair = None  # SINCOS: id of the partner output (cos)
         self.event = False
         self.inv_row = 0
+        self.svd_of = None  # state index when fused with the state recurrence
+        self.signs = 0
 
 
 class _Lin:
@@ -177,6 +180,9 @@ class Decomposition:
                 if oc == OP_LINCOMB:
                     fl += 2 * n
                     lo += n
+                elif oc == OP_ADDSUB:
+                    fl += 1
+                    lo += 2
                 elif oc == OP_MUL:
                     fl += 2 * (k + 1)
                     lo += 2 * (k + 1)
@@ -458,6 +464,31 @@ def decompose(sys, order, events=(), fuse=True):
         if uv[a].op == "mulsh_out":
             stack.append(uv[a].imm)  # owner op id
 
+    # ---- ADDSUB: two-term +-1 linear combinations need no term records ----
+    if fuse:
+        for u in uv[n:]:
+            if (u.op == OP_LINCOMB and len(u.terms) == 2
+                    and all(t[0] != ONE and t[1] == -1 and t[2] in (1.0, -1.0) for t in u.terms)):
+                u.op = OP_ADDSUB
+                u.args = (u.terms[0][0], u.terms[1][0])
+                u.signs = (OPF_NEGA if u.terms[0][2] < 0 else 0) | (OPF_NEGB if u.terms[1][2] < 0 else 0)
+                u.terms = None
+        # ---- fuse "x_i' = <linear op>" into the linear op itself ----
+        nuse = {}
+        for u in uv:
+            srcs = set(a for a in u.args if a != ONE)
+            if u.terms:
+                srcs |= set(t[0] for t in u.terms if t[0] != ONE)
+            for a in srcs:
+                nuse[a] = nuse.get(a, 0) + 1
+        for a in list(sv_src) + list(ev_u):
+            nuse[a] = nuse.get(a, 0) + 1
+        for i, a in enumerate(sv_src):
+            u = uv[a]
+            if (a >= n and u.op in (OP_LINCOMB, OP_ADDSUB) and not u.jet and not u.event
+                    and nuse.get(a, 0) == 1 and u.svd_of is None):
+                u.svd_of = i
+
     # ---- levels ----
     def deps(u):
         d = [x for x in u.args if x != ONE]
@@ -506,7 +537,7 @@ def decompose(sys, order, events=(), fuse=True):
             u.row = row
             row += P1
     for u in uv[n:]:
-        if u.id in live and not u.jet and u.op != OP_MULSH:
+        if u.id in live and not u.jet and u.op != OP_MULSH and u.svd_of is None:
             u.row = row
             row += 1
     # Scratch rows holding 1/a[0] (computed once per step at order 0).
@@ -530,7 +561,9 @@ def decompose(sys, order, events=(), fuse=True):
     ]
     emit.sort(key=lambda u: (u.level, u.op, u.id))
     n_lev = (max([u.level for u in emit]) if emit else 0) + 1  # + SVD level
-    ops = np.zeros(len(emit) + n, dtype=op_dtype)
+    fused_sv = set(u.svd_of for u in emit if u.svd_of is not None)
+    sv_plain = [i for i in range(n) if i not in fused_sv]
+    ops = np.zeros(len(emit) + len(sv_plain), dtype=op_dtype)
     terms = []
     level_start = [0]
     cur_level = 1
@@ -541,7 +574,10 @@ def decompose(sys, order, events=(), fuse=True):
         o = ops[i]
         o["opcode"] = u.op
         o["flags"] = OPF_EVENT if u.event else 0
-        if u.op != OP_MULSH:
+        if u.svd_of is not None:
+            o["flags"] = int(o["flags"]) | OPF_SVD
+            o["dst"] = ref(u.svd_of)
+        elif u.op != OP_MULSH:
             o["dst"] = ref(u.id)
         o["imm"] = u.imm if u.op == OP_POW else 0.0
         if u.op in (OP_LINCOMB, OP_SUMSQ):
@@ -561,6 +597,10 @@ def decompose(sys, order, events=(), fuse=True):
             o["dst2"] = ref(u.pair)
         elif u.op == OP_TIME:
             pass
+        elif u.op == OP_ADDSUB:
+            o["flags"] = int(o["flags"]) | u.signs
+            o["a"] = ref(u.args[0])
+            o["b"] = ref(u.args[1])
         else:
             o["a"] = ref(u.args[0])
             if len(u.args) > 1:
@@ -571,12 +611,12 @@ def decompose(sys, order, events=(), fuse=True):
         level_start.append(len(emit))
         cur_level += 1
     # SVD level: x_i[k+1] = src_i[k] / (k+1)
-    for i in range(n):
-        o = ops[len(emit) + i]
+    for j, i in enumerate(sv_plain):
+        o = ops[len(emit) + j]
         o["opcode"] = OP_SVD
         o["dst"] = ref(i)
         o["a"] = ref(sv_src[i])
-    level_start.append(len(emit) + n)
+    level_start.append(len(emit) + len(sv_plain))
 
     d = Decomposition()
     d.n_state = n

@@ -58,11 +58,17 @@ enum hy_opcode {
     HY_OP_SVD = 10,    /* state jet: dst[k+1] = a[k] / (k+1)                   */
     HY_OP_SUMSQ = 11,  /* dst[k] = sum_i sum_j a_i[j] a_i[k-j]       (terms)   */
     HY_OP_MULSH = 12,  /* dst_i[k] = sum_j a_i[j] b[k-j], i<n (terms=a_i,dst_i)*/
+    HY_OP_ADDSUB = 13, /* dst[k] = (+-)a[k] (+-)b[k]   (signs: HY_OPF_NEGA/NEGB)  */
     HY_OP_COUNT
 };
 
 /* flags */
 #define HY_OPF_EVENT 0x1u /* needed at order p for the event polynomials */
+#define HY_OPF_NEGA 0x2u  /* ADDSUB: first operand enters with a minus sign  */
+#define HY_OPF_NEGB 0x4u  /* ADDSUB: second operand enters with a minus sign */
+#define HY_OPF_SVD 0x8u   /* LINCOMB/ADDSUB fused with the state recurrence:
+                             dst is a state jet and the op stores
+                             dst[k+1] = value[k] / (k+1) instead of dst[k]   */
 
 typedef struct hy_op {
     uint16_t opcode;

@@ -29,9 +29,7 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libhy_oracle.so")
-        if not os.path.exists(so):
-            build()
+        so = build()  # no-op unless the sources are newer than the library
         _LIB = C.CDLL(so)
     return _LIB
 

@@ -58,7 +58,20 @@ static void FN(exec_op)(const FN(ora_sys) * S, const hy_op *o, REAL *ws, const R
             REAL v = (t->src == HY_REF_ONE) ? (k == 0 ? (REAL)1 : (REAL)0) : FN(ld)(ws, t->src, k);
             acc = R_FMA(c, v, acc);
         }
-        *FN(st)(ws, o->dst, k) = acc;
+        if (o->flags & HY_OPF_SVD)
+            JET(o->dst)[k + 1] = acc * S->rk[k + 1]; /* fused x[k+1] = f[k]/(k+1) */
+        else
+            *FN(st)(ws, o->dst, k) = acc;
+    } break;
+    case HY_OP_ADDSUB: {
+        REAL a = FN(ld)(ws, o->a, k), b = FN(ld)(ws, o->b, k);
+        if (o->flags & HY_OPF_NEGA) a = -a;
+        if (o->flags & HY_OPF_NEGB) b = -b;
+        REAL acc = a + b;
+        if (o->flags & HY_OPF_SVD)
+            JET(o->dst)[k + 1] = acc * S->rk[k + 1];
+        else
+            *FN(st)(ws, o->dst, k) = acc;
     } break;
     case HY_OP_MUL: {
         const REAL *a = JET(o->a), *b = JET(o->b);
@@ -186,7 +199,8 @@ static void FN(build_jets)(const FN(ora_sys) * S, REAL *ws, const REAL *pars, RE
     if (d->n_events) {
         /* Order p of the event functions (and what they depend on). */
         for (uint32_t i = 0; i < d->n_ops; ++i)
-            if ((S->ops[i].flags & HY_OPF_EVENT) && S->ops[i].opcode != HY_OP_SVD)
+            if ((S->ops[i].flags & HY_OPF_EVENT) && S->ops[i].opcode != HY_OP_SVD &&
+                !(S->ops[i].flags & HY_OPF_SVD))
                 FN(exec_op)(S, &S->ops[i], ws, pars, tm, d->order);
     }
 }
