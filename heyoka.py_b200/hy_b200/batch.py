@@ -201,6 +201,7 @@ class taylor_adaptive_batch_impl:
         self._p_thi.array[...] = t_hi
         self._p_tlo.array[...] = t_lo
         self._outcome = np.zeros(B, dtype=np.int64)
+        self._outcome_s = np.zeros(B, dtype=np.int64)
         self._h = np.zeros(B, dtype=fp)
         self._min_h = np.zeros(B, dtype=fp)
         self._max_h = np.zeros(B, dtype=fp)
@@ -346,10 +347,22 @@ class taylor_adaptive_batch_impl:
 
     @property
     def step_res(self):
+        if self._step_res is None:
+            fp = self._fp
+            self._step_res = [
+                (_outcome_from_int(int(o)), fp(h)) for o, h in zip(self._outcome_s, self._h)
+            ]
         return list(self._step_res)
 
     @property
     def propagate_res(self):
+        # Built lazily: a 1M-lane list of tuples costs more than the transfer.
+        if self._prop_res is None:
+            fp = self._fp
+            self._prop_res = [
+                (_outcome_from_int(int(o)), fp(a), fp(b), int(s))
+                for o, a, b, s in zip(self._outcome, self._min_h, self._max_h, self._nsteps)
+            ]
         return list(self._prop_res)
 
     # bulk numpy forms (1M-lane lists of tuples are slow to build)
@@ -467,12 +480,9 @@ class taylor_adaptive_batch_impl:
 
     def _do_step(self, mdt, backward, write_tc):
         self._push()
-        self._ctx.step(mdt, backward, write_tc, self._outcome, self._h)
+        self._ctx.step(mdt, backward, write_tc, self._outcome_s, self._h)
         self._pull()
-        fp = self._fp
-        self._step_res = [
-            (_outcome_from_int(int(o)), fp(h)) for o, h in zip(self._outcome, self._h)
-        ]
+        self._step_res = None
         self._dispatch_events()
 
     # ---- propagate (expose_batch_integrators.cpp:243-314) ----
@@ -509,10 +519,7 @@ class taylor_adaptive_batch_impl:
             self._dispatch_events()
         else:
             self._propagate_host_loop(tt, is_delta, max_steps, mdt, cbs, write_tc, c_output)
-        self._prop_res = [
-            (_outcome_from_int(int(o)), fp(a), fp(b), int(s))
-            for o, a, b, s in zip(self._outcome, self._min_h, self._max_h, self._nsteps)
-        ]
+        self._prop_res = None
         cout = None
         if c_output:
             cout = continuous_output_batch_impl._from_integrator(self)
@@ -649,10 +656,7 @@ class taylor_adaptive_batch_impl:
                                  self._max_h, self._nsteps)
         self._pull()
         self._dispatch_events()
-        self._prop_res = [
-            (_outcome_from_int(int(o)), fp(a), fp(b), int(s))
-            for o, a, b, s in zip(self._outcome, self._min_h, self._max_h, self._nsteps)
-        ]
+        self._prop_res = None
         return (cb_ret, out)
 
     # ---- dense output (expose_batch_integrators.cpp:519-541) ----
@@ -709,8 +713,10 @@ class taylor_adaptive_batch_impl:
             nt_events=self._nt_events,
             llvm_kw=self._llvm_kw,
             device=self._device,
-            step_res=self._step_res,
-            prop_res=self._prop_res,
+            step_res=self.step_res,
+            prop_res=self.propagate_res,
+            outcome_s=self._outcome_s.copy(),
+            h=self._h.copy(),
             res_arrays=(self._outcome.copy(), self._min_h.copy(), self._max_h.copy(),
                         self._nsteps.copy()),
             tc=np.array(self.tc),
@@ -741,6 +747,8 @@ class taylor_adaptive_batch_impl:
         ta._p_lasth.array[...] = sd["last_h"]
         ta._step_res = list(sd["step_res"])
         ta._prop_res = list(sd["prop_res"])
+        ta._outcome_s[...] = sd["outcome_s"]
+        ta._h[...] = sd["h"]
         for dst, src in zip((ta._outcome, ta._min_h, ta._max_h, ta._nsteps), sd["res_arrays"]):
             dst[...] = src
         ta._restore_device_extras(sd)
