@@ -57,6 +57,13 @@ struct hy_ctx {
     unsigned long long *d_nsteps = nullptr;
     unsigned int *d_counter = nullptr;
     void *d_gws = nullptr;
+    // continuous output
+    void *d_cout_tcs = nullptr, *d_cout_thi = nullptr, *d_cout_tlo = nullptr;
+    unsigned long long *d_cout_count = nullptr;
+    uint64_t cout_S = 0; // recorded capacity == max steps over lanes
+    // scratch for grid / dense / cout evaluation
+    void *d_tmp_in = nullptr, *d_tmp_out = nullptr;
+    size_t tmp_in_bytes = 0, tmp_out_bytes = 0;
     // launch geometry
     hy_launch_info li{};
     uint32_t TS = 0;
@@ -240,6 +247,13 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.max_h = (R *)c->d_maxh;
     P.n_steps = c->d_nsteps;
     P.tc = (R *)c->d_tc;
+    P.cout_tcs = nullptr;
+    P.cout_thi = nullptr;
+    P.cout_tlo = nullptr;
+    P.cout_cap = 0;
+    P.grid = nullptr;
+    P.gout = nullptr;
+    P.grid_k = 0;
     P.counter = c->d_counter;
     P.gws = (R *)c->d_gws;
     P.B = c->B;
@@ -268,7 +282,45 @@ int ensure_tc(hy_ctx *c)
     return 0;
 }
 
-int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc)
+struct RunExtras {
+    bool record_cout = false;
+    const void *grid = nullptr;
+    void *gout = nullptr;
+    uint32_t grid_k = 0;
+};
+
+int ensure_tmp(hy_ctx *c, size_t in_bytes, size_t out_bytes)
+{
+    if (in_bytes > c->tmp_in_bytes) {
+        if (c->d_tmp_in) cudaFree(c->d_tmp_in);
+        c->d_tmp_in = nullptr;
+        CU(cudaMalloc(&c->d_tmp_in, in_bytes));
+        c->tmp_in_bytes = in_bytes;
+    }
+    if (out_bytes > c->tmp_out_bytes) {
+        if (c->d_tmp_out) cudaFree(c->d_tmp_out);
+        c->d_tmp_out = nullptr;
+        CU(cudaMalloc(&c->d_tmp_out, out_bytes));
+        c->tmp_out_bytes = out_bytes;
+    }
+    return 0;
+}
+
+template <typename R> void apply_extras(hy_ctx *c, hy::KParams<R> &P, const RunExtras &x)
+{
+    if (x.record_cout) {
+        P.cout_tcs = (R *)c->d_cout_tcs;
+        P.cout_thi = (R *)c->d_cout_thi;
+        P.cout_tlo = (R *)c->d_cout_tlo;
+        P.cout_cap = (uint32_t)c->cout_S;
+    }
+    P.grid = (const R *)x.grid;
+    P.gout = (R *)x.gout;
+    P.grid_k = x.grid_k;
+}
+
+int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc,
+               const RunExtras &x = RunExtras())
 {
     if (c->B == 0) {
         c->last_ms = 0;
@@ -279,10 +331,15 @@ int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
     CU(cudaEventRecord(c->ev0, c->stream));
     cudaError_t e;
-    if (c->fp_bits == 64)
-        e = launch<double>(make_params<double>(c, mode, backward, max_steps, have_mdt, write_tc), c->li, c->stream);
-    else
-        e = launch<float>(make_params<float>(c, mode, backward, max_steps, have_mdt, write_tc), c->li, c->stream);
+    if (c->fp_bits == 64) {
+        auto P = make_params<double>(c, mode, backward, max_steps, have_mdt, write_tc);
+        apply_extras(c, P, x);
+        e = launch<double>(P, c->li, c->stream);
+    } else {
+        auto P = make_params<float>(c, mode, backward, max_steps, have_mdt, write_tc);
+        apply_extras(c, P, x);
+        e = launch<float>(P, c->li, c->stream);
+    }
     if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -294,6 +351,19 @@ int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_
 }
 
 } // namespace
+
+template <typename R> static void cout_transpose(const hy_ctx *c, const std::vector<R> &src,
+                                                 const std::vector<unsigned long long> &cnt, R *dst, uint64_t S)
+{
+    // device layout [S][B][n*P1] -> reference layout [S][n][P1][B], NaN past each lane's count
+    const size_t B = c->B, nP = (size_t)c->d.n_state * (c->d.order + 1);
+    for (uint64_t s = 0; s < S; ++s)
+        for (size_t l = 0; l < B; ++l) {
+            const bool ok = s < cnt[l];
+            const R *p = src.data() + (s * B + l) * nP;
+            for (size_t i = 0; i < nP; ++i) dst[(s * nP + i) * B + l] = ok ? p[i] : (R)NAN;
+        }
+}
 
 extern "C" {
 
@@ -372,7 +442,8 @@ int hy_destroy(hy_ctx *c)
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
                     c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
-                    c->d_counter, c->d_gws};
+                    c->d_counter, c->d_gws, c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo, c->d_cout_count,
+                    c->d_tmp_in, c->d_tmp_out};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -492,21 +563,83 @@ int hy_propagate(hy_ctx *c, const void *t, int is_delta, uint64_t max_steps, con
                  int c_output, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
 {
     if (!c) return fail("null ctx");
-    if (c_output) return fail("hy_propagate: c_output is not implemented yet");
     if (!t && c->B) return fail("hy_propagate: null time array");
     CU(cudaSetDevice(c->device));
     const size_t B = c->B, rb = c->rb;
     if (B) CU(cudaMemcpyAsync(c->d_tf, t, B * rb, cudaMemcpyHostToDevice, c->stream));
     if (max_delta_t && B) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
-    if (run_kernel(c, is_delta ? hy::MODE_FOR : hy::MODE_UNTIL, 0, max_steps, max_delta_t != nullptr, write_tc))
-        return 1;
+    const int mode = is_delta ? hy::MODE_FOR : hy::MODE_UNTIL;
+    if (!c_output || B == 0) {
+        if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, write_tc)) return 1;
+        return fetch_results(c, outcome, min_h, max_h, n_steps);
+    }
+    // Continuous output.  The number of steps is not known in advance and the
+    // stepping is deterministic, so: pass 1 counts the steps on a backup of the
+    // state, pass 2 (on the restored state) records exactly that many.
+    const size_t n = c->d.n_state, P1 = c->d.order + 1;
+    void *bk_state = nullptr, *bk_thi = nullptr, *bk_tlo = nullptr;
+    CU(cudaMalloc(&bk_state, B * n * rb));
+    CU(cudaMalloc(&bk_thi, B * rb));
+    CU(cudaMalloc(&bk_tlo, B * rb));
+    CU(cudaMemcpyAsync(bk_state, c->d_state, B * n * rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(bk_thi, c->d_thi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(bk_tlo, c->d_tlo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, 0)) return 1;
+    double ms1 = c->last_ms;
+    std::vector<unsigned long long> ns(B);
+    CU(cudaMemcpy(ns.data(), c->d_nsteps, B * 8, cudaMemcpyDeviceToHost));
+    uint64_t S = 0;
+    for (auto v : ns) S = std::max<uint64_t>(S, v);
+    for (void *p : {c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo})
+        if (p) cudaFree(p);
+    c->d_cout_tcs = c->d_cout_thi = c->d_cout_tlo = nullptr;
+    if (!c->d_cout_count) CU(cudaMalloc(&c->d_cout_count, B * 8));
+    c->cout_S = S;
+    const size_t tcs_bytes = std::max<size_t>(8, S * B * n * P1 * rb), tm_bytes = (S + 1) * B * rb;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (tcs_bytes + 2 * tm_bytes > free_b)
+        return fail("hy_propagate: continuous output needs " + std::to_string((tcs_bytes + 2 * tm_bytes) >> 20) +
+                    " MiB of device memory but only " + std::to_string(free_b >> 20) + " MiB are free");
+    CU(cudaMalloc(&c->d_cout_tcs, tcs_bytes));
+    CU(cudaMalloc(&c->d_cout_thi, tm_bytes));
+    CU(cudaMalloc(&c->d_cout_tlo, tm_bytes));
+    CU(cudaMemcpyAsync(c->d_state, bk_state, B * n * rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_thi, bk_thi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_tlo, bk_tlo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
+    RunExtras x;
+    x.record_cout = true;
+    if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, 1, x)) return 1;
+    c->last_ms += ms1;
+    c->last_launches = 2;
+    CU(cudaMemcpyAsync(c->d_cout_count, c->d_nsteps, B * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(bk_state);
+    cudaFree(bk_thi);
+    cudaFree(bk_tlo);
     return fetch_results(c, outcome, min_h, max_h, n_steps);
 }
 
-int hy_propagate_grid(hy_ctx *, const void *, size_t, uint64_t, const void *, void *, int64_t *, void *, void *,
-                      uint64_t *)
+int hy_propagate_grid(hy_ctx *c, const void *grid, size_t k, uint64_t max_steps, const void *max_delta_t, void *out,
+                      int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
 {
-    return fail("hy_propagate_grid: not implemented yet");
+    if (!c) return fail("null ctx");
+    if (!grid || !out || k == 0) return fail("hy_propagate_grid: null/empty grid");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
+    if (B == 0) return 0;
+    if (ensure_tmp(c, k * B * rb, k * n * B * rb)) return 1;
+    CU(cudaMemcpyAsync(c->d_tmp_in, grid, k * B * rb, cudaMemcpyHostToDevice, c->stream));
+    // NaN-fill: grid points past an early exit stay NaN (reference behaviour).
+    CU(cudaMemsetAsync(c->d_tmp_out, 0xff, k * n * B * rb, c->stream));
+    if (max_delta_t) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    RunExtras x;
+    x.grid = c->d_tmp_in;
+    x.gout = c->d_tmp_out;
+    x.grid_k = (uint32_t)k;
+    if (run_kernel(c, hy::MODE_GRID, 0, max_steps, max_delta_t != nullptr, 1, x)) return 1;
+    CU(cudaMemcpyAsync(out, c->d_tmp_out, k * n * B * rb, cudaMemcpyDeviceToHost, c->stream));
+    return fetch_results(c, outcome, min_h, max_h, n_steps);
 }
 
 int hy_last_timing(hy_ctx *c, double *kernel_ms, uint64_t *launches)
@@ -528,10 +661,108 @@ int hy_get_tc(hy_ctx *c, void *tc)
     return 0;
 }
 
-int hy_dense_eval(hy_ctx *, const void *, int, void *) { return fail("hy_dense_eval: not implemented yet"); }
-int hy_cout_info(hy_ctx *, uint64_t *, uint64_t *) { return fail("hy_cout_info: not implemented yet"); }
-int hy_cout_get(hy_ctx *, void *, void *, void *, uint64_t) { return fail("hy_cout_get: not implemented yet"); }
-int hy_cout_eval(hy_ctx *, const void *, size_t, void *) { return fail("hy_cout_eval: not implemented yet"); }
+int hy_dense_eval(hy_ctx *c, const void *t, int rel_time, void *out)
+{
+    if (!c || !t || !out) return fail("hy_dense_eval: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
+    if (B == 0) return 0;
+    if (ensure_tc(c)) return 1;
+    if (ensure_tmp(c, B * rb, n * B * rb)) return 1;
+    CU(cudaMemcpyAsync(c->d_tmp_in, t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    const unsigned th = 128, bl = (unsigned)((B + th - 1) / th);
+    if (c->fp_bits == 64)
+        hy::dense_eval_kernel<double><<<bl, th, 0, c->stream>>>(
+            (const double *)c->d_tc, (const double *)c->d_thi, (const double *)c->d_tlo, (const double *)c->d_lasth,
+            (const double *)c->d_tmp_in, rel_time, (double *)c->d_tmp_out, (uint32_t)n, c->d.order, (uint32_t)B);
+    else
+        hy::dense_eval_kernel<float><<<bl, th, 0, c->stream>>>(
+            (const float *)c->d_tc, (const float *)c->d_thi, (const float *)c->d_tlo, (const float *)c->d_lasth,
+            (const float *)c->d_tmp_in, rel_time, (float *)c->d_tmp_out, (uint32_t)n, c->d.order, (uint32_t)B);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_tmp_out, n * B * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_cout_info(hy_ctx *c, uint64_t *n_steps, uint64_t *max_steps)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    if (max_steps) *max_steps = c->d_cout_tcs ? c->cout_S : 0;
+    if (n_steps && c->B) {
+        if (!c->d_cout_count) {
+            std::memset(n_steps, 0, c->B * 8);
+        } else {
+            CU(cudaMemcpy(n_steps, c->d_cout_count, c->B * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
+int hy_cout_get(hy_ctx *c, void *tcs, void *times_hi, void *times_lo, uint64_t S)
+{
+    if (!c) return fail("null ctx");
+    if (!c->d_cout_tcs) return fail("hy_cout_get: no continuous output was recorded");
+    if (S != c->cout_S) return fail("hy_cout_get: S does not match the recorded number of steps");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb, nP = (size_t)c->d.n_state * (c->d.order + 1);
+    std::vector<unsigned long long> cnt(B);
+    CU(cudaMemcpy(cnt.data(), c->d_cout_count, B * 8, cudaMemcpyDeviceToHost));
+    if (tcs && S) {
+        if (c->fp_bits == 64) {
+            std::vector<double> tmp(S * B * nP);
+            CU(cudaMemcpy(tmp.data(), c->d_cout_tcs, tmp.size() * rb, cudaMemcpyDeviceToHost));
+            cout_transpose<double>(c, tmp, cnt, (double *)tcs, S);
+        } else {
+            std::vector<float> tmp(S * B * nP);
+            CU(cudaMemcpy(tmp.data(), c->d_cout_tcs, tmp.size() * rb, cudaMemcpyDeviceToHost));
+            cout_transpose<float>(c, tmp, cnt, (float *)tcs, S);
+        }
+    }
+    for (int which = 0; which < 2; ++which) {
+        void *dst = which ? times_lo : times_hi;
+        if (!dst) continue;
+        CU(cudaMemcpy(dst, which ? c->d_cout_tlo : c->d_cout_thi, (S + 1) * B * rb, cudaMemcpyDeviceToHost));
+        for (uint64_t s = 0; s <= S; ++s)
+            for (size_t l = 0; l < B; ++l)
+                if (s > cnt[l]) {
+                    if (c->fp_bits == 64)
+                        ((double *)dst)[s * B + l] = NAN;
+                    else
+                        ((float *)dst)[s * B + l] = NAN;
+                }
+    }
+    return 0;
+}
+
+int hy_cout_eval(hy_ctx *c, const void *t, size_t k, void *out)
+{
+    if (!c || !t || !out) return fail("hy_cout_eval: null argument");
+    if (!c->d_cout_tcs) return fail("hy_cout_eval: no continuous output was recorded");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
+    if (B == 0 || k == 0) return 0;
+    if (ensure_tmp(c, k * B * rb, k * n * B * rb)) return 1;
+    CU(cudaMemcpyAsync(c->d_tmp_in, t, k * B * rb, cudaMemcpyHostToDevice, c->stream));
+    const unsigned th = 128;
+    const unsigned bl = (unsigned)((k * B + th - 1) / th);
+    if (c->fp_bits == 64)
+        hy::cout_eval_kernel<double><<<bl, th, 0, c->stream>>>(
+            (const double *)c->d_cout_tcs, (const double *)c->d_cout_thi, (const double *)c->d_cout_tlo,
+            c->d_cout_count, (const double *)c->d_tmp_in, (double *)c->d_tmp_out, (uint32_t)n, c->d.order,
+            (uint32_t)B, (uint32_t)k);
+    else
+        hy::cout_eval_kernel<float><<<bl, th, 0, c->stream>>>(
+            (const float *)c->d_cout_tcs, (const float *)c->d_cout_thi, (const float *)c->d_cout_tlo,
+            c->d_cout_count, (const float *)c->d_tmp_in, (float *)c->d_tmp_out, (uint32_t)n, c->d.order, (uint32_t)B,
+            (uint32_t)k);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_tmp_out, k * n * B * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int hy_events_count(hy_ctx *, uint64_t *n)
 {
     if (n) *n = 0;

@@ -57,7 +57,7 @@ template <> __device__ __forceinline__ float shfl_xor<float>(unsigned mask, floa
 // NaN-propagating max (once NaN, stays NaN).
 template <typename R> __device__ __forceinline__ R nan_max(R m, R a) { return (a > m || a != a) ? a : m; }
 
-enum { MODE_UNTIL = 0, MODE_FOR = 1, MODE_STEP = 2 };
+enum { MODE_UNTIL = 0, MODE_FOR = 1, MODE_STEP = 2, MODE_GRID = 3 };
 
 struct ProgDims {
     uint32_t n_slots, n_tslots, n_imm, n_phases;
@@ -78,6 +78,13 @@ template <typename R> struct KParams {
     R *min_h, *max_h;
     unsigned long long *n_steps;
     R *tc; // [n][p+1][B] or nullptr
+    // continuous output recording (device layout: tcs [S][B][n*(p+1)], times [S+1][B])
+    R *cout_tcs, *cout_thi, *cout_tlo;
+    uint32_t cout_cap;
+    // propagate_grid: grid [K][B] in, gout [K][n][B] out
+    const R *grid;
+    R *gout;
+    uint32_t grid_k;
     unsigned int *counter;
     R *gws; // global workspace fallback (ws_in_smem == 0)
     uint32_t B, T, TS;
@@ -442,6 +449,26 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             time_add(tf_hi, tf_lo, P.tf[traj]);
         } else if (P.mode == MODE_UNTIL) {
             tf_hi = P.tf[traj];
+        } else if (P.mode == MODE_GRID) {
+            tf_hi = P.grid[(size_t)(P.grid_k - 1) * P.B + traj];
+        }
+        uint32_t gi = 0;   // next grid point to emit (MODE_GRID)
+        uint32_t cc = 0;   // recorded continuous-output steps
+        if (P.mode == MODE_GRID) {
+            // Grid points at (or before) the starting time take the current state.
+            const R dir = tf_hi - hi;
+            while (gi < P.grid_k) {
+                const R g = P.grid[(size_t)gi * P.B + traj];
+                const R dg = (g - hi) - lo;
+                if ((dir >= (R)0 && dg > (R)0) || (dir < (R)0 && dg < (R)0)) break;
+                for (uint32_t i = sub; i < n; i += G)
+                    P.gout[((size_t)gi * n + i) * P.B + traj] = w[i * P1];
+                ++gi;
+            }
+        }
+        if (P.cout_tcs && sub == 0) {
+            P.cout_thi[traj] = hi;
+            P.cout_tlo[traj] = lo;
         }
         if (P.mode != MODE_STEP) mdt = r_abs(mdt);
         long long oc = HY_OUTCOME_TIME_LIMIT;
@@ -520,6 +547,26 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                 for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = w[i];
                 if (G > 1) __syncwarp(gmask);
             }
+            if (P.cout_tcs && cc < P.cout_cap) {
+                R *dstc = P.cout_tcs + ((size_t)cc * P.B + traj) * (size_t)(n * P1);
+                for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = w[i];
+            }
+            if (P.mode == MODE_GRID) {
+                // Dense output at every grid point inside this step.
+                while (gi < P.grid_k) {
+                    const R g = P.grid[(size_t)gi * P.B + traj];
+                    const R tau = (g - hi) - lo; // time since the start of the step
+                    if (r_abs(tau) > r_abs(h)) break;
+                    for (uint32_t i = sub; i < n; i += G) {
+                        const R *x = &w[i * P1];
+                        R acc = x[p];
+                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k]);
+                        P.gout[((size_t)gi * n + i) * P.B + traj] = acc;
+                    }
+                    ++gi;
+                }
+            }
+            if (G > 1 && (P.cout_tcs || P.mode == MODE_GRID)) __syncwarp(gmask);
             bool finite = true;
             for (uint32_t i = sub; i < n; i += G) {
                 R *x = &w[i * P1];
@@ -546,6 +593,14 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             time_add(hi, lo, h);
             ++ns;
             if (!finite) so = HY_OUTCOME_ERR_NF_STATE;
+            if (P.cout_tcs && cc < P.cout_cap) {
+                ++cc;
+                if (sub == 0) {
+                    const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
+                    P.cout_thi[(size_t)cc * P.B + traj] = fin_ ? tf_hi : hi;
+                    P.cout_tlo[(size_t)cc * P.B + traj] = fin_ ? tf_lo : lo;
+                }
+            }
 
             if (P.mode == MODE_STEP) {
                 oc = so;
@@ -586,6 +641,67 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             P.n_steps[traj] = ns;
         }
         if (G > 1) __syncwarp(gmask);
+    }
+}
+
+// ---- dense output of the last step (reference update_d_output,
+// expose_batch_integrators.cpp:519-541) ----
+// tc is [n][p+1][B]; one thread per lane, coalesced over lanes.
+template <typename R>
+__global__ void dense_eval_kernel(const R *__restrict__ tc, const R *__restrict__ t_hi, const R *__restrict__ t_lo,
+                                  const R *__restrict__ last_h, const R *__restrict__ t, int rel_time,
+                                  R *__restrict__ out, uint32_t n, uint32_t p, uint32_t B)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= B) return;
+    // tau = time since the START of the last step
+    const R tau = rel_time ? last_h[l] + t[l] : ((t[l] - t_hi[l]) - t_lo[l]) + last_h[l];
+    const uint32_t P1 = p + 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const R *x = tc + (size_t)i * P1 * B + l;
+        R acc = x[(size_t)p * B];
+        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[(size_t)k * B]);
+        out[(size_t)i * B + l] = acc;
+    }
+}
+
+// ---- continuous output evaluation (reference continuous_output_batch::operator(),
+// taylor_expose_c_output.cpp:297-412): per-lane bisection over the recorded step
+// times + Horner.  tcs [S][B][n*(p+1)], times [S+1][B], t [K][B], out [K][n][B].
+template <typename R>
+__global__ void cout_eval_kernel(const R *__restrict__ tcs, const R *__restrict__ thi, const R *__restrict__ tlo,
+                                 const unsigned long long *__restrict__ count, const R *__restrict__ t,
+                                 R *__restrict__ out, uint32_t n, uint32_t p, uint32_t B, uint32_t K)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)K * B) return;
+    const uint32_t l = (uint32_t)(gid % B), q = (uint32_t)(gid / B);
+    const uint32_t S = (uint32_t)count[l], P1 = p + 1;
+    const R tq = t[(size_t)q * B + l];
+    if (S == 0) {
+        for (uint32_t i = 0; i < n; ++i) out[((size_t)q * n + i) * B + l] = tq - tq + (R)NAN;
+        return;
+    }
+    const bool fwd = thi[(size_t)S * B + l] >= thi[l];
+    // first step s whose end time is beyond tq (clamped to the recorded range)
+    uint32_t lo = 0, hi = S - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const R te = thi[(size_t)(mid + 1) * B + l];
+        const bool before = fwd ? (tq < te) : (tq > te);
+        if (before)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    const uint32_t s = lo;
+    const R tau = (tq - thi[(size_t)s * B + l]) - tlo[(size_t)s * B + l];
+    const R *base = tcs + ((size_t)s * B + l) * (size_t)(n * P1);
+    for (uint32_t i = 0; i < n; ++i) {
+        const R *x = base + i * P1;
+        R acc = x[p];
+        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k]);
+        out[((size_t)q * n + i) * B + l] = acc;
     }
 }
 

@@ -272,6 +272,8 @@ class NpTaylorBatch:
             acc = acc * h + X[:, k, :]
         return acc
 
+    step_hook = None  # optional callable(mask, X, t0_hi, t0_lo, h) run after every step
+
     def step(self, max_delta_t=None, backward=False, mask=None):
         """One adaptive step on the lanes selected by ``mask``.
         Returns (outcome[B], h[B])."""
@@ -299,6 +301,8 @@ class NpTaylorBatch:
         self.tc[:, :, upd] = X[:, :, upd]
         if EV.shape[0]:
             self.ev_tc[:, :, upd] = EV[:, :, upd]
+        if self.step_hook is not None:
+            self.step_hook(upd.copy(), X, self.t_hi.copy(), self.t_lo.copy(), h.copy())
         nh, nl = two_float.add(self.t_hi, self.t_lo, h)
         self.t_hi = np.where(upd, nh, self.t_hi).astype(T)
         self.t_lo = np.where(upd, nl, self.t_lo).astype(T)
@@ -370,3 +374,70 @@ class NpTaylorBatch:
         else:
             tau = t - (self.t_hi - self.last_h)
         return self.horner(self.tc, tau.astype(T))
+
+
+    # ---- continuous output / grid built on the step hook ----
+    def propagate_until_recorded(self, t, **kw):
+        """propagate_until while recording, per lane, the start time and the
+        Taylor coefficients of every step.  Returns (result, rec) with
+        rec[lane] = list of (t0_hi, t0_lo, h, tc[n, p+1])."""
+        rec = [[] for _ in range(self.B)]
+
+        def hook(mask, X, t0h, t0l, h):
+            for l in np.nonzero(mask)[0]:
+                rec[l].append((t0h[l], t0l[l], h[l], X[:, :, l].copy()))
+
+        self.step_hook = hook
+        try:
+            res = self.propagate_until(t, **kw)
+        finally:
+            self.step_hook = None
+        return res, rec
+
+    @staticmethod
+    def eval_record(rec_lane, tq):
+        """Continuous-output evaluation for one lane at time tq: the step whose
+        [t_start, t_end) contains tq, clamped to the first/last step."""
+        fwd = rec_lane[-1][2] >= 0
+        s = len(rec_lane) - 1
+        for i, (t0h, t0l, h, X) in enumerate(rec_lane):
+            te = t0h + h
+            if (tq < te) if fwd else (tq > te):
+                s = i
+                break
+        t0h, t0l, h, X = rec_lane[s]
+        tau = (tq - t0h) - t0l
+        p = X.shape[1] - 1
+        acc = X[:, p].copy()
+        for k in range(p - 1, -1, -1):
+            acc = acc * tau + X[:, k]
+        return acc
+
+    def propagate_grid(self, grid, **kw):
+        """grid is [K, B] (monotonic per lane).  Steps are clamped only by the
+        last grid time; interior points come from dense output."""
+        T = self.T
+        grid = np.array(grid, dtype=T).reshape(-1, self.B)
+        K = grid.shape[0]
+        out = np.full((K, self.n, self.B), np.nan, dtype=T)
+        start_state = self.state.copy()
+        start_t = self.t_hi.copy()
+        res, rec = self.propagate_until_recorded(grid[-1], **kw)
+        for l in range(self.B):
+            fwd = grid[-1, l] >= start_t[l]
+            for q in range(K):
+                g = grid[q, l]
+                if (g <= start_t[l]) if fwd else (g >= start_t[l]):
+                    out[q, :, l] = start_state[:, l]
+                    continue
+                # the step during which g is reached (end-inclusive)
+                for (t0h, t0l, h, X) in rec[l]:
+                    tau = (g - t0h) - t0l
+                    if abs(tau) <= abs(h):
+                        p = X.shape[1] - 1
+                        acc = X[:, p].copy()
+                        for k in range(p - 1, -1, -1):
+                            acc = acc * tau + X[:, k]
+                        out[q, :, l] = acc
+                        break
+        return res, out
