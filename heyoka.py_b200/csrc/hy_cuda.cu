@@ -57,6 +57,13 @@ struct hy_ctx {
     unsigned long long *d_nsteps = nullptr;
     unsigned int *d_counter = nullptr;
     void *d_gws = nullptr;
+    // events
+    int32_t *d_ev_dir = nullptr;
+    double *d_ev_cd = nullptr;
+    void *d_cd_elapsed = nullptr, *d_cd_total = nullptr;
+    hy_event_rec *d_log = nullptr;
+    unsigned long long *d_log_count = nullptr;
+    unsigned long long log_cap = 0;
     // continuous output
     void *d_cout_tcs = nullptr, *d_cout_thi = nullptr, *d_cout_tlo = nullptr;
     unsigned long long *d_cout_count = nullptr;
@@ -254,6 +261,14 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.grid = nullptr;
     P.gout = nullptr;
     P.grid_k = 0;
+    P.ev.dir = c->d_ev_dir;
+    P.ev.cooldown = c->d_ev_cd;
+    P.ev.cd_elapsed = (R *)c->d_cd_elapsed;
+    P.ev.cd_total = (R *)c->d_cd_total;
+    P.ev.log = c->d_log;
+    P.ev.log_count = c->d_log_count;
+    P.ev.log_cap = c->log_cap;
+    P.ev.tol = (R)c->tol;
     P.counter = c->d_counter;
     P.gws = (R *)c->d_gws;
     P.B = c->B;
@@ -385,11 +400,13 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
               const uint32_t *level_start, const uint32_t *ev_ref, const int32_t *ev_dir, const double *ev_cooldown,
               double tol, int high_accuracy, uint32_t batch)
 {
-    (void)ev_dir;
-    (void)ev_cooldown;
     if (!out || !dims || !ops || !level_start) return fail("hy_create: null argument");
     if (fp_bits != 32 && fp_bits != 64) return fail("hy_create: fp_bits must be 32 or 64");
     if (dims->order < 2 || dims->order > 62) return fail("hy_create: unsupported Taylor order");
+    if (dims->n_events && dims->order + 1 > (uint32_t)hy::EV_MAXP1)
+        return fail("hy_create: event detection supports Taylor orders up to 31");
+    if (dims->n_tevents > dims->n_events) return fail("hy_create: n_tevents > n_events");
+    if (dims->n_events && (!ev_ref || !ev_dir)) return fail("hy_create: null event arrays");
     int ndev = 0;
     if (hy_device_count(&ndev)) return 1;
     if (ndev == 0) return fail("hy_create: no CUDA device is visible (libhy_cuda has no CPU fallback)");
@@ -432,6 +449,22 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
     CU(cudaMemset(c->d_thi, 0, B * rb));
     CU(cudaMemset(c->d_tlo, 0, B * rb));
     CU(cudaMemset(c->d_lasth, 0, B * rb));
+    if (d.n_events) {
+        const size_t ne = d.n_events, nte = std::max<size_t>(1, d.n_tevents);
+        CU(cudaMalloc(&c->d_ev_dir, ne * 4));
+        CU(cudaMemcpy(c->d_ev_dir, ev_dir, ne * 4, cudaMemcpyHostToDevice));
+        std::vector<double> cd(nte, -1.0);
+        for (size_t i = 0; i < d.n_tevents; ++i) cd[i] = ev_cooldown ? ev_cooldown[i] : -1.0;
+        CU(cudaMalloc(&c->d_ev_cd, nte * 8));
+        CU(cudaMemcpy(c->d_ev_cd, cd.data(), nte * 8, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_cd_elapsed, B * nte * rb));
+        CU(cudaMalloc(&c->d_cd_total, B * nte * rb));
+        c->log_cap = std::min<unsigned long long>(std::max<unsigned long long>(1ULL << 20, 16ULL * B), 1ULL << 26);
+        CU(cudaMalloc(&c->d_log, c->log_cap * sizeof(hy_event_rec)));
+        CU(cudaMalloc(&c->d_log_count, 8));
+        CU(cudaMemset(c->d_log_count, 0, 8));
+        if (hy_reset_cooldowns(c, -1)) return 1;
+    }
     if (choose_geometry(c)) return 1;
     return 0;
 }
@@ -443,7 +476,8 @@ int hy_destroy(hy_ctx *c)
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
                     c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
                     c->d_counter, c->d_gws, c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo, c->d_cout_count,
-                    c->d_tmp_in, c->d_tmp_out};
+                    c->d_tmp_in, c->d_tmp_out, c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log,
+                    c->d_log_count};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -763,18 +797,76 @@ int hy_cout_eval(hy_ctx *c, const void *t, size_t k, void *out)
     return 0;
 }
 
-int hy_events_count(hy_ctx *, uint64_t *n)
+int hy_events_count(hy_ctx *c, uint64_t *n)
 {
-    if (n) *n = 0;
+    if (!c || !n) return fail("null argument");
+    *n = 0;
+    if (!c->d_log_count) return 0;
+    CU(cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, c->d_log_count, 8, cudaMemcpyDeviceToHost));
+    if (v > c->log_cap)
+        return fail("the device event log overflowed (" + std::to_string(v) + " events, capacity " +
+                    std::to_string(c->log_cap) + "): propagate in shorter segments");
+    *n = v;
     return 0;
 }
-int hy_events_drain(hy_ctx *, hy_event_rec *, uint64_t, uint64_t *n)
+
+int hy_events_drain(hy_ctx *c, hy_event_rec *recs, uint64_t cap, uint64_t *n)
 {
-    if (n) *n = 0;
+    if (!c || !n) return fail("null argument");
+    *n = 0;
+    if (!c->d_log_count) return 0;
+    uint64_t have = 0;
+    if (hy_events_count(c, &have)) return 1;
+    const uint64_t m = std::min<uint64_t>(have, cap);
+    if (m && recs) CU(cudaMemcpy(recs, c->d_log, m * sizeof(hy_event_rec), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->d_log_count, 0, 8));
+    *n = m;
     return 0;
 }
-int hy_get_cooldowns(hy_ctx *, void *, void *) { return fail("hy_get_cooldowns: not implemented yet"); }
-int hy_reset_cooldowns(hy_ctx *, int64_t) { return 0; }
+
+int hy_get_cooldowns(hy_ctx *c, void *elapsed, void *total)
+{
+    if (!c) return fail("null ctx");
+    if (!c->d.n_tevents) return 0;
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->B * c->d.n_tevents * c->rb;
+    if (elapsed) CU(cudaMemcpy(elapsed, c->d_cd_elapsed, bytes, cudaMemcpyDeviceToHost));
+    if (total) CU(cudaMemcpy(total, c->d_cd_total, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int hy_set_cooldowns(hy_ctx *c, const void *elapsed, const void *total)
+{
+    if (!c) return fail("null ctx");
+    if (!c->d.n_tevents) return 0;
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->B * c->d.n_tevents * c->rb;
+    if (elapsed) CU(cudaMemcpy(c->d_cd_elapsed, elapsed, bytes, cudaMemcpyHostToDevice));
+    if (total) CU(cudaMemcpy(c->d_cd_total, total, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int hy_reset_cooldowns(hy_ctx *c, int64_t lane)
+{
+    if (!c) return fail("null ctx");
+    if (!c->d.n_tevents || !c->d_cd_total) return 0;
+    CU(cudaSetDevice(c->device));
+    const size_t nte = c->d.n_tevents, B = c->B;
+    if (lane >= (int64_t)B) return fail("hy_reset_cooldowns: lane out of range");
+    const size_t first = lane < 0 ? 0 : (size_t)lane, count = lane < 0 ? B : 1;
+    // total = -1 (not in cooldown), elapsed = 0
+    if (c->fp_bits == 64) {
+        std::vector<double> m1(count * nte, -1.0);
+        CU(cudaMemcpy((double *)c->d_cd_total + first * nte, m1.data(), m1.size() * 8, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> m1(count * nte, -1.0f);
+        CU(cudaMemcpy((float *)c->d_cd_total + first * nte, m1.data(), m1.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemset((char *)c->d_cd_elapsed + first * nte * c->rb, 0, count * nte * c->rb));
+    return 0;
+}
 
 int hy_get_launch_info(hy_ctx *c, hy_launch_info *info)
 {

@@ -20,6 +20,7 @@
 
 #include "../../include/hy_cuda.h"
 #include "hy_schedule.hpp"
+#include "hy_events.cuh"
 
 namespace hy {
 
@@ -85,6 +86,7 @@ template <typename R> struct KParams {
     const R *grid;
     R *gout;
     uint32_t grid_k;
+    EvParams<R> ev; // event detection state (n_events > 0)
     unsigned int *counter;
     R *gws; // global workspace fallback (ws_in_smem == 0)
     uint32_t B, T, TS;
@@ -542,6 +544,24 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                 so = HY_OUTCOME_TIME_LIMIT;
             }
 
+            // ---- event detection: may truncate the step at a terminal event ----
+            int term_ev = -1;
+            if (d.n_events) {
+                R h_eff = h;
+                if (sub == 0)
+                    detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
+                                     term_ev);
+                if (G > 1) {
+                    h_eff = __shfl_sync(gmask, h_eff, 0, G);
+                    term_ev = __shfl_sync(gmask, term_ev, 0, G);
+                }
+                if (term_ev >= 0) {
+                    h = h_eff;
+                    so = -(long long)term_ev - 1;
+                }
+                if (sub == 0 && d.n_tevents) advance_cooldowns<R>(traj, d.n_tevents, h, P.ev);
+            }
+
             // ---- optional tc write, then the state update ----
             if (P.write_tc && P.tc) {
                 for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = w[i];
@@ -607,6 +627,10 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                 break;
             }
             if (so == HY_OUTCOME_ERR_NF_STATE) {
+                oc = so;
+                break;
+            }
+            if (term_ev >= 0) { // terminal event: the lane stops here (the host may resume it)
                 oc = so;
                 break;
             }

@@ -93,6 +93,7 @@ SYMBOLS = [
     "hy_events_count",
     "hy_events_drain",
     "hy_get_cooldowns",
+    "hy_set_cooldowns",
     "hy_reset_cooldowns",
     "hy_get_launch_info",
     "hy_measure_fma_peak",
@@ -281,6 +282,9 @@ class Context:
 
     def get_cooldowns(self, elapsed, total):
         check(lib().hy_get_cooldowns(self._ctx, ptr(elapsed), ptr(total)))
+
+    def set_cooldowns(self, elapsed, total):
+        check(lib().hy_set_cooldowns(self._ctx, ptr(elapsed), ptr(total)))
 
     def reset_cooldowns(self, lane=-1):
         check(lib().hy_reset_cooldowns(self._ctx, C.c_int64(int(lane))))

@@ -483,7 +483,13 @@ class taylor_adaptive_batch_impl:
         self._ctx.step(mdt, backward, write_tc, self._outcome_s, self._h)
         self._pull()
         self._step_res = None
-        self._dispatch_events()
+        term = self._dispatch_events()
+        if term:
+            # A terminal event whose callback returned True is "continuing":
+            # outcome idx instead of -idx-1 (Event detection.ipynb cell 28).
+            for lane, (ev, keep) in term.items():
+                if keep:
+                    self._outcome_s[lane] = ev
 
     # ---- propagate (expose_batch_integrators.cpp:243-314) ----
     def _wrap_callbacks(self, callback):
@@ -567,17 +573,20 @@ class taylor_adaptive_batch_impl:
             self._ctx.propagate(target, 0, 1, mdt, write_tc or c_output, c_output,
                                 oc1, a1, b1, n1)
             self._pull()
-            stop_lanes = self._dispatch_events()
+            term = self._dispatch_events() or {}
             stepped = active & (n1 > 0)
             tot_n[stepped] += n1[stepped]
             succ = stepped & np.isfinite(a1) & (b1 > 0)
             mn = np.where(succ & (a1 < mn), a1, mn).astype(fp)
             mx = np.where(succ & (b1 > mx), b1, mx).astype(fp)
             done = active & (oc1 != int(taylor_outcome.step_limit))
+            for lane, (ev, keep) in term.items():
+                if keep and active[lane]:
+                    # continuing terminal event: the lane goes on (unless it also
+                    # reached its final time, which the next launch reports)
+                    done[lane] = False
             final[done] = oc1[done]
             active &= ~done
-            if stop_lanes is not None:
-                active &= ~stop_lanes
             if max_steps:
                 lim = active & (tot_n >= max_steps)
                 final[lim] = int(taylor_outcome.step_limit)
@@ -760,6 +769,9 @@ class taylor_adaptive_batch_impl:
         """tc / last_h / cooldowns live on the device: push them back."""
         from . import _cabi as cabi
 
+        cds = sd.get("cooldowns")
+        if cds is not None and self._t_events:
+            self._ctx.set_cooldowns(np.ascontiguousarray(cds[0]), np.ascontiguousarray(cds[1]))
         self._saved_tc = sd.get("tc")
         if self._saved_tc is not None:
             if self._p_tc is None:

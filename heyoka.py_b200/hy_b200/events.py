@@ -113,17 +113,22 @@ class t_event_batch_flt(t_event_batch_impl):
 
 
 def dispatch(ta):
-    """Drain the device event log of ``ta`` and run the callbacks.
+    """Drain the device event log of ``ta`` and run the callbacks in
+    chronological order per lane.
 
-    Returns a boolean mask of lanes stopped by a terminal-event callback that
-    returned False (or None when nothing happened)."""
+    Returns ``None`` when nothing was logged, else a dict
+    ``lane -> (event index, keep_going)`` for the terminal events that fired
+    (``keep_going`` is the callback's return value, False without callback)."""
     recs = ta._ctx.events_drain()
     if len(recs) == 0:
         return None
     nte = len(ta._t_events)
-    order = np.lexsort((recs["t"], recs["step"], recs["lane"]))
-    stop = np.zeros(ta._B, dtype=bool)
-    for r in recs[order]:
+    # chronological per lane: increasing t forward in time, decreasing t backward
+    sgn = np.where(np.signbit(ta._p_lasth.array[recs["lane"]]), -1.0, 1.0)
+    order = np.lexsort((recs["ev_idx"], recs["t"] * sgn, recs["step"], recs["lane"]))
+    recs = recs[order]
+    term = {}
+    for r in recs:
         ev = int(r["ev_idx"])
         lane = int(r["lane"])
         if ev >= nte:
@@ -137,15 +142,15 @@ def dispatch(ta):
                 )
         else:
             cb = ta._t_events[ev].callback
+            keep = False
             if cb is not None:
-                ret = cb(ta, int(r["d_sgn"]), lane)
-                if not isinstance(ret, (bool, np.bool_)):
+                keep = cb(ta, int(r["d_sgn"]), lane)
+                if not isinstance(keep, (bool, np.bool_)):
                     raise TypeError(
                         "The call operator of a terminal event callback is expected to return a "
                         "boolean, but a value of type \"{}\" was returned instead".format(
-                            type(ret).__name__
+                            type(keep).__name__
                         )
                     )
-                if not ret:
-                    stop[lane] = True
-    return stop
+            term[lane] = (ev, bool(keep))
+    return term

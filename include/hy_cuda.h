@@ -210,6 +210,7 @@ int hy_cout_eval(hy_ctx *ctx, const void *t, size_t k, void *out);
 int hy_events_count(hy_ctx *ctx, uint64_t *n);
 int hy_events_drain(hy_ctx *ctx, hy_event_rec *recs, uint64_t cap, uint64_t *n);
 int hy_get_cooldowns(hy_ctx *ctx, void *elapsed, void *total); /* [B, n_tevents], total<0: none */
+int hy_set_cooldowns(hy_ctx *ctx, const void *elapsed, const void *total); /* restore (pickle/copy) */
 int hy_reset_cooldowns(hy_ctx *ctx, int64_t lane);             /* -1 = all lanes */
 
 /* Introspection for benches/tests: launch geometry chosen for the tape. */

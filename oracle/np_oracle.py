@@ -103,7 +103,13 @@ class NpTaylorBatch:
     """Lane-independent adaptive Taylor integrator on numpy arrays [B]."""
 
     def __init__(self, sys, state, time=None, pars=None, tol=0.0, fp_type=np.float64,
-                 events=(), high_accuracy=False):
+                 events=(), high_accuracy=False, ev_spec=None):
+        # ev_spec: list (terminal events first) of dicts
+        #   {"dir": -1|0|1, "terminal": bool, "cooldown": float (<0: auto)}
+        # matching `events`; None = the event rows only take part in the norms.
+        self.ev_spec = ev_spec
+        self.ev_log = []   # (lane, ev_idx, t, d_sgn) in detection order
+        self.cd = {}       # (lane, ev_idx) -> [elapsed, total]
         self.T = T = np.dtype(fp_type).type
         self.sys = list(sys)
         self.names = [lhs.name for lhs, _ in self.sys]
@@ -292,8 +298,14 @@ class NpTaylorBatch:
             clamp = np.abs(h) > np.abs(lim)
             # NaN step sizes must not pass silently as "success".
             h = np.where(clamp, lim, h).astype(T)
-            new_state = self.horner(X, h)
         outcome = np.where(clamp, OUT_TIME_LIMIT, OUT_SUCCESS).astype(np.int64)
+        if self.ev_spec:
+            for l in np.nonzero(mask)[0]:
+                h[l], te = self._detect_lane(int(l), EV[:, :, l], h[l])
+                if te >= 0:
+                    outcome[l] = -te - 1
+        with np.errstate(all="ignore"):
+            new_state = self.horner(X, h)
         bad = ~np.all(np.isfinite(new_state), axis=0)
         outcome = np.where(bad, OUT_ERR_NF_STATE, outcome)
         upd = mask
@@ -347,6 +359,9 @@ class NpTaylorBatch:
             bad = active & (oc == OUT_ERR_NF_STATE)
             out[bad] = OUT_ERR_NF_STATE
             active &= ~bad
+            tev = active & (oc > OUT_SUCCESS)  # terminal event codes are small integers
+            out[tev] = oc[tev]
+            active &= ~tev
             fin = active & (oc == OUT_TIME_LIMIT) & (h == rem)
             self.t_hi = np.where(fin, tf, self.t_hi).astype(T)
             self.t_lo = np.where(fin, T(0), self.t_lo).astype(T)
@@ -441,3 +456,111 @@ class NpTaylorBatch:
                         out[q, :, l] = acc
                         break
         return res, out
+
+
+    # ---- events, independent method: the critical points of the
+    # step polynomial split [0, h) into monotonic pieces; a sign change on a
+    # piece brackets exactly one root, refined by bisection in extended precision.
+    @staticmethod
+    def poly_roots_01(q):
+        """Real roots of sum q[k] s^k in [0, 1), ascending."""
+        L = np.longdouble
+        q = np.array(q, dtype=L)
+        p = len(q) - 1
+        roots = []
+        if np.all(q == 0):
+            return roots
+
+        def ev(c, s):
+            acc = L(0)
+            for a in c[::-1]:
+                acc = acc * s + a
+            return acc
+
+        if q[0] == 0:
+            roots.append(0.0)
+        # critical points: real roots of q' in (0, 1), found recursively
+        def real_roots_in_01(c):
+            c = np.array(c, dtype=L)
+            while len(c) > 1 and c[-1] == 0:
+                c = c[:-1]
+            if len(c) <= 1:
+                return []
+            if len(c) == 2:
+                r = -c[0] / c[1]
+                return [r] if 0 < r < 1 else []
+            dc = np.array([k * c[k] for k in range(1, len(c))], dtype=L)
+            brk = [L(0)] + sorted(real_roots_in_01(dc)) + [L(1)]
+            out = []
+            for a, b in zip(brk[:-1], brk[1:]):
+                fa, fb = ev(c, a), ev(c, b)
+                if fa == 0 and a > 0:
+                    out.append(a)
+                if fa * fb < 0:
+                    lo, hi = a, b
+                    for _ in range(200):
+                        m = (lo + hi) / 2
+                        fm = ev(c, m)
+                        if fm == 0 or m == lo or m == hi:
+                            lo = hi = m
+                            break
+                        if (fm > 0) == (fa > 0):
+                            lo = m
+                        else:
+                            hi = m
+                    out.append((lo + hi) / 2)
+            return out
+
+        for r in real_roots_in_01(q):
+            if 0 < r < 1:
+                roots.append(float(r))
+        return sorted(roots)
+
+    def _detect_lane(self, l, ev_tc, h):
+        """Events of lane l in the step [0, h).  Returns (h_eff, terminal idx or -1)."""
+        T = self.T
+        p = self.order
+        if h == 0 or not np.isfinite(h):
+            return h, -1
+        cands = []
+        for e, spec in enumerate(self.ev_spec):
+            g = ev_tc[e].astype(np.longdouble)
+            q = np.array([g[k] * np.longdouble(h) ** k for k in range(p + 1)])
+            for s_ in self.poly_roots_01(q):
+                dq = sum(k * q[k] * np.longdouble(s_) ** (k - 1) for k in range(1, p + 1))
+                sg = int(np.sign(dq)) * (1 if h > 0 else -1)
+                if spec["dir"] != 0 and spec["dir"] != sg:
+                    continue
+                tau = T(s_ * h)
+                if spec["terminal"]:
+                    cd = self.cd.get((l, e))
+                    if cd is not None and abs(tau) < cd[1] - cd[0]:
+                        continue
+                cands.append((abs(tau), e, tau, sg, float(dq / h) if h != 0 else 0.0))
+        cands.sort(key=lambda c: (c[0], c[1]))
+        term = next((c for c in cands if self.ev_spec[c[1]]["terminal"]), None)
+        h_eff, te = h, -1
+        for c in cands:
+            if term is not None and c is not term and not (c[0] < term[0]):
+                continue
+            if self.ev_spec[c[1]]["terminal"] and c is not term:
+                continue
+            self.ev_log.append((l, c[1], float((self.t_hi[l] + c[2]) + self.t_lo[l]), c[3]))
+        if term is not None:
+            h_eff, te = T(term[2]), term[1]
+            spec = self.ev_spec[te]
+            if spec["cooldown"] >= 0:
+                cdv = spec["cooldown"]
+            else:
+                gm = max(1.0, max(abs(float(ev_tc[te][k]) * float(h) ** k) for k in range(p + 1)))
+                cdv = 10 * self.tol * gm / abs(term[4]) if term[4] != 0 else 0.0
+            self.cd[(l, te)] = [-abs(float(h_eff)), cdv]
+        # advance the cooldown clocks
+        for key in [k for k in self.cd if k[0] == l]:
+            el, tot = self.cd[key]
+            el += abs(float(h_eff))
+            if el >= tot:
+                del self.cd[key]
+            else:
+                self.cd[key] = [el, tot]
+        return h_eff, te
