@@ -1,0 +1,279 @@
+"""GPU: behaviour of the drop-in class, mirroring the reference's own tests:
+/root/reference/heyoka/_test_batch_integrator.py (ctor, copy, propagate_for/until,
+time/dtime, pickling, callbacks), _test_ensemble.py (ensemble == serial,
+bit-exact) and _test_var_integrator.py::test_batch."""
+
+import pickle
+from copy import copy, deepcopy
+
+import numpy as np
+import pytest
+
+import hy_b200 as hy
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _ta(fp=np.float64, **kw):
+    return hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC.astype(fp), fp_type=fp, **kw)
+
+
+def test_ctor_and_properties():
+    # _test_batch_integrator.py:13-88
+    ta = _ta()
+    assert ta.batch_size == 4 and ta.dim == 2 and ta.order == 20
+    assert ta.tol == np.finfo(float).eps and not ta.high_accuracy and not ta.compact_mode
+    assert not ta.with_events and not ta.is_variational
+    assert np.all(ta.state == common.PEND_IC) and np.all(ta.time == 0)
+    assert ta.sys[0][1] == hy.make_vars("v")
+    assert len(ta.decomposition) > 0 and "libhy_cuda" in repr(ta)
+    assert ta.llvm_state.opt_level == 3
+    ta2 = hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC, tol=1e-9,
+                                   high_accuracy=True, compact_mode=True, time=[1.0, 2.0, 3.0, 4.0],
+                                   opt_level=2, fast_math=False)
+    assert ta2.order == 12 and ta2.high_accuracy and ta2.compact_mode
+    assert np.all(ta2.time == [1, 2, 3, 4])
+    with pytest.raises(ValueError, match="number of dimensions is 2"):
+        hy.taylor_adaptive_batch(common.pendulum_sys(), [0.0, 1.0])
+    with pytest.raises(ValueError, match="Invalid parameter vector"):
+        hy.taylor_adaptive_batch(common.forced_pendulum_sys(), common.PEND_IC, pars=[[1.0, 2.0]])
+    with pytest.raises(ValueError, match="Invalid time vector"):
+        hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC, time=[0.0])
+    with pytest.raises(TypeError):
+        hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC.astype(np.longdouble))
+    with pytest.raises(TypeError):
+        hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC, fp_type=np.float32, tol=1e-3)
+    with pytest.raises(TypeError):
+        hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC, fp_type=np.longdouble)
+
+
+@pytest.mark.parametrize("fp", [np.float64, np.float32])
+def test_propagate_scalar_vs_vector_identical(fp):
+    # _test_batch_integrator.py:128-170: bit-identical state and propagate_res
+    ic = common.PEND_IC.astype(fp)
+    ta = _ta(fp)
+    ta.propagate_for([fp(10.0)] * 4)
+    st, res = deepcopy(ta.state), deepcopy(ta.propagate_res)
+    ta.set_time(fp(0.0))
+    ta.state[:] = ic
+    ta.propagate_for(fp(10.0))
+    assert np.all(ta.state == st) and res == ta.propagate_res
+    ta.set_time(fp(0.0))
+    ta.state[:] = ic
+    ta.propagate_for([fp(10.0)] * 4, max_delta_t=[fp(1e-2)] * 4)
+    st, res = deepcopy(ta.state), deepcopy(ta.propagate_res)
+    ta.set_time(fp(0.0))
+    ta.state[:] = ic
+    ta.propagate_for(fp(10.0), max_delta_t=fp(1e-2))
+    assert np.all(ta.state == st) and res == ta.propagate_res
+    assert all(r[3] >= 1000 for r in res)
+    ta.set_time(fp(0.0))
+    ta.state[:] = ic
+    ta.propagate_until(fp(10.0), max_steps=5)
+    assert all(r[0] == hy.taylor_outcome.step_limit and r[3] == 5 for r in ta.propagate_res)
+    if fp == np.float32:
+        with pytest.raises(TypeError):
+            ta.propagate_for(10.0)
+
+
+def test_step_callbacks():
+    # _test_batch_integrator.py:170-260, The adaptive integrator.ipynb cells 19-21
+    ta = _ta()
+
+    def cb(ta):
+        ta.counter = getattr(ta, "counter", 0) + 1
+        return True
+
+    ta.propagate_for(10.0, callback=cb)
+    ref = _ta()
+    ref.propagate_for(10.0)
+    assert ta.counter == max(r[3] for r in ref.propagate_res)
+    assert [r[3] for r in ta.propagate_res] == [r[3] for r in ref.propagate_res]
+    assert np.max(np.abs(ta.state - ref.state)) < 1e-14
+
+    class CB:
+        def __init__(self):
+            self.pre = 0
+
+        def __call__(_, ta):
+            assert id(_) == _.orig_id
+            return True
+
+        def pre_hook(self, ta):
+            self.pre += 1
+
+    c = CB()
+    c.orig_id = id(c)
+    ret = ta.propagate_for(1.0, callback=c)
+    assert ret[1] is c and c.pre == 1 and ret[0] is None
+    ret = ta.propagate_for(1.0, callback=[c, cb])
+    assert ret[1][0] is c and ret[1][1] is cb
+    with pytest.raises(TypeError, match="not callable"):
+        ta.propagate_for(10.0, callback="hello world")
+    with pytest.raises(TypeError, match="expected to return a boolean"):
+        ta.propagate_for(10.0, callback=lambda ta: "hello")
+    # stopping callback -> cb_stop
+    ta = _ta()
+    ta.propagate_until(10.0, callback=lambda ta: False)
+    assert all(r[0] == hy.taylor_outcome.cb_stop and r[3] == 1 for r in ta.propagate_res)
+    # max_delta_t with callback: The adaptive integrator.ipynb cell 19
+    ta = hy.taylor_adaptive_batch(common.pendulum_sys(), np.array([[0.05] * 2, [0.025] * 2]))
+    seen = []
+    ta.propagate_until(0.5, max_delta_t=0.1, callback=lambda t: seen.append(float(t.time[0])) or True)
+    assert np.allclose(seen, [0.1, 0.2, 0.30000000000000004, 0.4, 0.5], rtol=0, atol=1e-15)
+    # angle reducer
+    x, v = hy.make_vars("x", "v")
+    ta = hy.taylor_adaptive_batch(common.pendulum_sys(), np.array([[0.05] * 2, [5.0] * 2]))
+    ta.propagate_until(10.0, callback=hy.callback.angle_reducer([x]))
+    assert np.all((ta.state[0] >= 0) & (ta.state[0] < 2 * np.pi))
+
+
+def test_time_and_dtime():
+    # _test_batch_integrator.py:415-488
+    ta = _ta()
+    assert not ta.time.flags.writeable
+    ta.set_time(1.5)
+    assert np.all(ta.time == 1.5)
+    ta.set_time([1.0, 2.0, 3.0, 4.0])
+    assert np.all(ta.time == [1, 2, 3, 4])
+    with pytest.raises(ValueError):
+        ta.set_time([1.0, 2.0])
+    ta.set_time(0.0)
+    ta.propagate_until(1000.1)
+    hi, lo = ta.dtime
+    assert np.all(hi == 1000.1) and not hi.flags.writeable
+    ta.propagate_for(0.1)
+    assert np.any(ta.dtime[1] != 0)
+    ta.set_dtime(1.0, 0.5)
+    assert np.all(ta.dtime[0] == 1.5) and np.all(ta.dtime[1] == 0.0)
+    ta.set_dtime([1.0] * 4, [0.5] * 4)
+    assert np.all(ta.dtime[0] == 1.5)
+    with pytest.raises(TypeError):
+        ta.set_dtime(1.0, [0.5] * 4)
+
+
+def test_copy_deepcopy_pickle():
+    # _test_batch_integrator.py:89-126, :602-690
+    ta = _ta()
+    ta.foo = [1, 2, 3]
+    ta.propagate_until(1.0)
+    c1, c2 = copy(ta), deepcopy(ta)
+    assert c1.foo is ta.foo and c2.foo == ta.foo and c2.foo is not ta.foo
+    assert np.all(c2.state == ta.state) and np.all(c2.time == ta.time)
+    c2.state[:] = 0
+    assert not np.all(ta.state == 0)
+    p = pickle.loads(pickle.dumps(ta))
+    assert p.foo == ta.foo and p.propagate_res == ta.propagate_res
+    ta.step()
+    p.step()
+    assert np.all(p.state == ta.state) and np.all(p.time == ta.time)
+    assert p.step_res == ta.step_res
+
+
+def test_ensemble_equals_serial_bit_exact():
+    # _test_ensemble.py:13-111
+    ta = hy.taylor_adaptive_batch(common.pendulum_sys(), np.zeros((2, 4)))
+    rng = np.random.default_rng(3)
+    ics = rng.uniform(-0.3, 0.3, (10, 2, 4))
+
+    def gen(t, i):
+        t.state[:] = ics[i]
+        return t
+
+    for algo in ("thread", "process"):
+        kw = {"algorithm": algo}
+        if algo == "thread":
+            kw["max_workers"] = 4
+        ret = hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, **kw)
+        assert len(ret) == 10
+        for i in range(10):
+            ser = gen(deepcopy(ta), i)
+            ser.propagate_until(20.0)
+            assert np.all(ret[i][0].state == ser.state)
+            assert np.all(ret[i][0].time == ser.time)
+            assert ret[i][0].propagate_res == ser.propagate_res
+            assert ret[i][1] is None and ret[i][2] is None
+    ret = hy.ensemble_propagate_for_batch(ta, 5.0, 3, gen, c_output=True)
+    for i in range(3):
+        ser = gen(deepcopy(ta), i)
+        co, _ = ser.propagate_for(5.0, c_output=True)
+        assert np.all(ret[i][1](2.5) == co(2.5))
+    grid = np.linspace(0.0, 3.0, 7)
+    ret = hy.ensemble_propagate_grid_batch(ta, grid, 3, gen)
+    for i in range(3):
+        ser = gen(deepcopy(ta), i)
+        _, out = ser.propagate_grid(np.repeat(grid, 4).reshape(-1, 4))
+        assert np.all(ret[i][2] == out)
+    # callbacks are deep-copied per iteration
+    class CB:
+        def __call__(self, ta):
+            return True
+
+    cb = CB()
+    ret = hy.ensemble_propagate_until_batch(ta, 1.0, 3, gen, callback=cb)
+    assert all(r[2] is not cb and isinstance(r[2], CB) for r in ret)
+
+
+def test_lane_results_independent_of_batch_composition():
+    # determinism: a trajectory gives bit-identical results alone or inside a big batch
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(64)
+    big = hy.taylor_adaptive_batch(sys_, ic)
+    big.propagate_until(20.0)
+    small = hy.taylor_adaptive_batch(sys_, ic[:, 5:9].copy())
+    small.propagate_until(20.0)
+    assert np.all(big.state[:, 5:9] == small.state)
+    assert big.propagate_res[5:9] == small.propagate_res
+
+
+def test_variational_batch():
+    # _test_var_integrator.py:144-258 (order 1)
+    x, v = hy.make_vars("x", "v")
+    sys_ = [(x, v), (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x))]
+    vs = hy.var_ode_sys(sys_, hy.var_args.vars)
+    B = 4
+    ic = np.array([[0.2 + 0.01 * i for i in range(B)], [0.3] * B])
+    ta = hy.taylor_adaptive_batch(vs, ic, pars=np.full((1, B), 0.4))
+    assert ta.is_variational and ta.dim == 6 and ta.n_orig_sv == 2 and ta.vorder == 1
+    assert np.all(ta.state[2:, 0] == [1, 0, 0, 1])  # identity ICs auto-filled
+    assert ta.get_vslice(order=1) == slice(2, 6) and ta.get_mindex(3) == [0, 0, 1]
+    ta.propagate_until(3.0)
+    # sensitivities against finite differences of the plain system
+    e = 1e-6
+    for j in range(2):
+        d = np.zeros((2, B))
+        d[j] = e
+        tp = hy.taylor_adaptive_batch(sys_, ic + d, pars=np.full((1, B), 0.4))
+        tm = hy.taylor_adaptive_batch(sys_, ic - d, pars=np.full((1, B), 0.4))
+        tp.propagate_until(3.0)
+        tm.propagate_until(3.0)
+        fd = (tp.state - tm.state) / (2 * e)
+        sens = ta.state[2:].reshape(2, 2, B)[:, j, :]
+        assert np.max(np.abs(fd - sens)) < 1e-8
+    ts = ta.eval_taylor_map(np.zeros((2, B)))
+    assert np.all(ts == ta.state[:2]) and not ts.flags.writeable
+    with pytest.raises(ValueError):
+        ta.eval_taylor_map(np.zeros((3, B)))
+    with pytest.raises(ValueError):
+        _ta().vorder
+
+
+def test_high_accuracy_and_backward():
+    ta = hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC, high_accuracy=True, tol=1e-18)
+    assert ta.order == 22
+    ta.propagate_until(50.0)
+    ta.propagate_until(0.0)
+    assert np.max(np.abs(ta.state - common.PEND_IC)) < 1e-13
+    ta = _ta()
+    ta.step_backward()
+    assert all(r[1] < 0 for r in ta.step_res)
+    ta.step([1e-3] * 4)
+    assert all(r[0] == hy.taylor_outcome.time_limit and r[1] == 1e-3 for r in ta.step_res)
+    # non-finite state -> err_nf_state, not an exception
+    x = hy.make_vars("x")
+    ta = hy.taylor_adaptive_batch([(x, x * x)], np.array([[1.0, 1.0]]))
+    ta.propagate_until(2.0)
+    assert all(r[0] in (hy.taylor_outcome.err_nf_state, hy.taylor_outcome.time_limit)
+               for r in ta.propagate_res)
