@@ -286,13 +286,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     assert np.all(oc == int(hy.taylor_outcome.time_limit)), "some trajectories did not finish"
 
-    t_all = torch.tensor([dev_ms * 1e-3], dtype=torch.float64, device=dev)
-    s_all = torch.tensor([float(tot_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s_all, op=dist.ReduceOp.SUM)
-    t_max, steps_all = float(t_all.item()), float(s_all.item())
-    value = steps_all / t_max
+    from hy_b200.shard import reduce_throughput
+
+    value, t_max, steps_all = reduce_throughput(dev_ms * 1e-3, tot_steps, dist if world > 1 else None, dev)
 
     # ---------------- end-to-end arm through the public API ----------------
     e2e = None
@@ -312,14 +308,10 @@ def main():
             e_steps += int(ta.propagate_res_arrays[3].sum())
         barrier()
         e_wall = time.perf_counter() - t0
-        te = torch.tensor([e_wall], dtype=torch.float64, device=dev)
-        se = torch.tensor([float(e_steps)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        e_val, _, _ = reduce_throughput(e_wall, e_steps, dist if world > 1 else None, dev)
         n, m = dc.n_state, dc.n_par
         e2e = {
-            "value": float(se.item()) / float(te.item()),
+            "value": e_val,
             "unit": UNIT,
             "h2d_bytes_per_step": int(B * 8 * (n + m + 2 + 1)),       # state, pars, t_hi, t_lo, t_final
             "d2h_bytes_per_step": int(B * 8 * (n + 3 + 4)),           # state, t_hi, t_lo, last_h, results
