@@ -97,9 +97,7 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     if (li.ws_in_smem) {
         switch (li.group) {
         case 1: return launch_g<R, 1, true>(P, li, s);
-        case 2: return launch_g<R, 2, true>(P, li, s);
         case 4: return launch_g<R, 4, true>(P, li, s);
-        case 8: return launch_g<R, 8, true>(P, li, s);
         case 16: return launch_g<R, 16, true>(P, li, s);
         case 32: return launch_g<R, 32, true>(P, li, s);
         default: return cudaErrorInvalidValue;
@@ -108,7 +106,6 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     // Global-memory workspace fallback (jets too large for shared memory).
     switch (li.group) {
     case 1: return launch_g<R, 1, false>(P, li, s);
-    case 8: return launch_g<R, 8, false>(P, li, s);
     case 32: return launch_g<R, 32, false>(P, li, s);
     default: return cudaErrorInvalidValue;
     }
@@ -123,12 +120,10 @@ template <typename R, int G, bool SMEM> int regs_of()
 
 template <typename R> int regs_for_group(uint32_t g, bool smem)
 {
-    if (!smem) return g == 1 ? regs_of<R, 1, false>() : (g == 8 ? regs_of<R, 8, false>() : regs_of<R, 32, false>());
+    if (!smem) return g == 1 ? regs_of<R, 1, false>() : regs_of<R, 32, false>();
     switch (g) {
     case 1: return regs_of<R, 1, true>();
-    case 2: return regs_of<R, 2, true>();
     case 4: return regs_of<R, 4, true>();
-    case 8: return regs_of<R, 8, true>();
     case 16: return regs_of<R, 16, true>();
     default: return regs_of<R, 32, true>();
     }
@@ -169,7 +164,7 @@ int choose_geometry(hy_ctx *c)
     uint32_t bestG = 0, bestT = 0;
     bool best_smem = false;
     hy::Program best;
-    for (uint32_t G = 1; G <= 32; G <<= 1) {
+    for (uint32_t G : {1u, 4u, 16u, 32u}) { // group sizes with compiled kernels
         if (Genv && G != Genv) continue;
         hy::Program pr;
         std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), G, pr);
@@ -180,7 +175,7 @@ int choose_geometry(hy_ctx *c)
         const uint32_t budget = (uint32_t)smem_optin - fixed;
         uint32_t Tfit = budget / (RS * (uint32_t)c->rb);
         bool smem = Tfit >= 1 && !force_global;
-        if (!smem && G != 1 && G != 8 && G != 32) continue; // fallback kernels exist for these only
+        if (!smem && G != 1 && G != 32) continue; // fallback kernels exist for these only
         uint32_t T = smem ? std::min(Tfit, max_threads / G) : std::max(1u, 256u / G);
         const double threads = std::min<double>((double)T * G, max_threads);
         const double score = pr.lane_utilisation * threads * (smem ? 1.0 : 0.05);

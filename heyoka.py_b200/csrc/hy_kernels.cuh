@@ -29,14 +29,15 @@ __device__ __forceinline__ double r_fma(double a, double b, double c) { return f
 __device__ __forceinline__ float r_fma(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double r_sqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ float r_sqrt(float a) { return sqrtf(a); }
-__device__ __forceinline__ double r_pow(double a, double b) { return pow(a, b); }
-__device__ __forceinline__ float r_pow(float a, float b) { return powf(a, b); }
-__device__ __forceinline__ double r_exp(double a) { return exp(a); }
-__device__ __forceinline__ float r_exp(float a) { return expf(a); }
-__device__ __forceinline__ double r_log(double a) { return log(a); }
-__device__ __forceinline__ float r_log(float a) { return logf(a); }
-__device__ __forceinline__ void r_sincos(double a, double *s, double *c) { sincos(a, s, c); }
-__device__ __forceinline__ void r_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
+// libm calls are kept out of line: one copy each, so the hot loop stays small.
+__device__ __noinline__ double r_pow(double a, double b) { return pow(a, b); }
+__device__ __noinline__ float r_pow(float a, float b) { return powf(a, b); }
+__device__ __noinline__ double r_exp(double a) { return exp(a); }
+__device__ __noinline__ float r_exp(float a) { return expf(a); }
+__device__ __noinline__ double r_log(double a) { return log(a); }
+__device__ __noinline__ float r_log(float a) { return logf(a); }
+__device__ __noinline__ void r_sincos(double a, double *s, double *c) { sincos(a, s, c); }
+__device__ __noinline__ void r_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
 __device__ __forceinline__ double r_abs(double a) { return fabs(a); }
 __device__ __forceinline__ float r_abs(float a) { return fabsf(a); }
 __device__ __forceinline__ double r_copysign(double a, double b) { return copysign(a, b); }
@@ -109,7 +110,7 @@ template <typename R> struct KParams {
 __device__ __forceinline__ uint32_t roff(uint32_t ref, uint32_t k) { return (ref & 0x7fffffffu) + ((ref >> 31) ? k : 0u); }
 __device__ __forceinline__ uint32_t rbase(uint32_t ref) { return ref & 0x7fffffffu; }
 
-template <typename R> __device__ __forceinline__ R pow0(R x, double alpha)
+template <typename R> __device__ __noinline__ R pow0(R x, double alpha)
 {
     if (alpha == -1.5) return (R)1 / (x * r_sqrt(x));
     if (alpha == -0.5) return (R)1 / r_sqrt(x);
@@ -119,21 +120,130 @@ template <typename R> __device__ __forceinline__ R pow0(R x, double alpha)
     return r_pow(x, (R)alpha);
 }
 
-// sum_{j=0}^{n-1} pa[j] * pb[-j]; two accumulators, unrolled by 4.
+// ---------------------------------------------------------------------------
+// Convolution bodies.  A single warp has to hide its own LDS latency (29 clk)
+// and DFMA latency (8 clk): every body is a loop over BLOCKS of terms; inside a
+// block all loads are predicated (no control flow), issued back-to-back, and
+// feed independent accumulator chains.  No per-term branches, no per-term
+// address arithmetic (immediate offsets from two base registers).
+// ---------------------------------------------------------------------------
+// sum_{j=0}^{n-1} pa[j] * pb[-j]
 template <typename R> __device__ __forceinline__ R conv(const R *__restrict__ pa, const R *__restrict__ pb, int n)
 {
-    R s0 = 0, s1 = 0;
-    int j = 0;
-    for (; j + 4 <= n; j += 4) {
-        const R a0 = pa[j], a1 = pa[j + 1], a2 = pa[j + 2], a3 = pa[j + 3];
-        const R b0 = pb[-j], b1 = pb[-j - 1], b2 = pb[-j - 2], b3 = pb[-j - 3];
-        s0 = r_fma(a0, b0, s0);
-        s1 = r_fma(a1, b1, s1);
-        s0 = r_fma(a2, b2, s0);
-        s1 = r_fma(a3, b3, s1);
+    R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += 8) {
+        R a[8], b[8];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool v = u < m;
+            a[u] = v ? pa[j0 + u] : (R)0;
+            b[u] = v ? pb[-(j0 + u)] : (R)0;
+        }
+        s0 = r_fma(a[0], b[0], s0);
+        s1 = r_fma(a[1], b[1], s1);
+        s2 = r_fma(a[2], b[2], s2);
+        s3 = r_fma(a[3], b[3], s3);
+        s0 = r_fma(a[4], b[4], s0);
+        s1 = r_fma(a[5], b[5], s1);
+        s2 = r_fma(a[6], b[6], s2);
+        s3 = r_fma(a[7], b[7], s3);
     }
-    for (; j < n; ++j) s0 = r_fma(pa[j], pb[-j], s0);
-    return s0 + s1;
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Three products sharing the operand b:  o_i = sum_{j<n} a_i[j] * pb[-j]
+template <typename R>
+__device__ __forceinline__ void conv3(const R *__restrict__ a0, const R *__restrict__ a1, const R *__restrict__ a2,
+                                      const R *__restrict__ pb, int n, R &o0, R &o1, R &o2)
+{
+    R s0a = 0, s1a = 0, s2a = 0, s0b = 0, s1b = 0, s2b = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += 4) {
+        R x[4], y[4], z[4], b[4];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool v = u < m;
+            b[u] = v ? pb[-(j0 + u)] : (R)0;
+            x[u] = v ? a0[j0 + u] : (R)0;
+            y[u] = v ? a1[j0 + u] : (R)0;
+            z[u] = v ? a2[j0 + u] : (R)0;
+        }
+        s0a = r_fma(x[0], b[0], s0a);
+        s1a = r_fma(y[0], b[0], s1a);
+        s2a = r_fma(z[0], b[0], s2a);
+        s0b = r_fma(x[1], b[1], s0b);
+        s1b = r_fma(y[1], b[1], s1b);
+        s2b = r_fma(z[1], b[1], s2b);
+        s0a = r_fma(x[2], b[2], s0a);
+        s1a = r_fma(y[2], b[2], s1a);
+        s2a = r_fma(z[2], b[2], s2a);
+        s0b = r_fma(x[3], b[3], s0b);
+        s1b = r_fma(y[3], b[3], s1b);
+        s2b = r_fma(z[3], b[3], s2b);
+    }
+    o0 = s0a + s0b;
+    o1 = s1a + s1b;
+    o2 = s2a + s2b;
+}
+
+// pow recurrence sum:  sum_{j<n} (kal - j*al1) * ak[-j] * c[j]
+template <typename R>
+__device__ __forceinline__ R conv_pow(const R *__restrict__ ak, const R *__restrict__ c, int n, const R al1, const R kal)
+{
+    R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    R jr = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += 8) {
+        R a[8], b[8];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool v = u < m;
+            a[u] = v ? ak[-(j0 + u)] : (R)0;
+            b[u] = v ? c[j0 + u] : (R)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 4) {
+            s0 = r_fma(r_fma(-(jr + (R)u), al1, kal) * a[u], b[u], s0);
+            s1 = r_fma(r_fma(-(jr + (R)(u + 1)), al1, kal) * a[u + 1], b[u + 1], s1);
+            s2 = r_fma(r_fma(-(jr + (R)(u + 2)), al1, kal) * a[u + 2], b[u + 2], s2);
+            s3 = r_fma(r_fma(-(jr + (R)(u + 3)), al1, kal) * a[u + 3], b[u + 3], s3);
+        }
+        jr += (R)8;
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Same, terms j = 1 .. n-1 only (the caller supplies the j = 0 term from a register).
+template <typename R>
+__device__ __forceinline__ R conv_pow_from1(const R *__restrict__ ak, const R *__restrict__ c, int n, const R al1,
+                                            const R kal)
+{
+    R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    R jr = 1;
+#pragma unroll 1
+    for (int j0 = 1; j0 < n; j0 += 8) {
+        R a[8], b[8];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool v = u < m;
+            a[u] = v ? ak[-(j0 + u)] : (R)0;
+            b[u] = v ? c[j0 + u] : (R)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 4) {
+            s0 = r_fma(r_fma(-(jr + (R)u), al1, kal) * a[u], b[u], s0);
+            s1 = r_fma(r_fma(-(jr + (R)(u + 1)), al1, kal) * a[u + 1], b[u + 1], s1);
+            s2 = r_fma(r_fma(-(jr + (R)(u + 2)), al1, kal) * a[u + 2], b[u + 2], s2);
+            s3 = r_fma(r_fma(-(jr + (R)(u + 3)), al1, kal) * a[u + 3], b[u + 3], s3);
+        }
+        jr += (R)8;
+    }
+    return (s0 + s1) + (s2 + s3);
 }
 
 // One op of the program at order k on the trajectory column `w`.  `lt` is the
@@ -143,35 +253,151 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
                                         const R *__restrict__ rk, const double *__restrict__ s_imm, const uint32_t k,
                                         const R tm)
 {
-    const uint32_t ka = (o.flags & DF_JA) ? k : 0u, kb = (o.flags & DF_JB) ? k : 0u;
-    const uint32_t kd = (o.flags & DF_JDST) ? k : 0u;
     switch (o.opcode) {
+    case DOP_PAIR: {
+        // Fused pair interaction (hy_schedule.hpp): d_i = +-A_i +- B_i, r2 = sum d_i^2,
+        // wj = r2^alpha, t_i = d_i * wj.  Same arithmetic as the separate ops.
+        const DTerm *t = lt + (uint32_t)o.b * G;
+        const uint32_t nd = o.n;
+        // all term records first (independent LDS.128), then all operands
+        DTerm ta[3], tb[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint32_t ii = (uint32_t)i < nd ? (uint32_t)i : 0u;
+            ta[i] = t[(2 * ii) * G];
+            tb[i] = t[(2 * ii + 1) * G];
+        }
+        R av[3], bv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            av[i] = w[roff(ta[i].src, k)];
+            bv[i] = w[roff(ta[i].aux, k)];
+        }
+        R *d0 = w + rbase(tb[0].src), *d1 = w + rbase(tb[1].src), *d2 = w + rbase(tb[2].src);
+        R dk[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int sc = (int)ta[i].coef;
+            const R a = (sc & 1) ? -av[i] : av[i], b = (sc & 2) ? -bv[i] : bv[i];
+            dk[i] = a + b;
+        }
+        d0[k] = dk[0];
+        if (nd > 1) d1[k] = dk[1];
+        if (nd > 2) d2[k] = dk[2];
+        // r2[k] = sum_i ( 2 * sum_{j<half} d_i[j] d_i[k-j]  (+ d_i[k/2]^2 for even k) )
+        // The j = 0 term uses d_i[k], which is still in a register.
+        const int half = (int)((k + 1) >> 1);
+        R q0 = 0, q1 = 0, q2 = 0;
+        if (half > 0) {
+            q0 = d0[0] * dk[0];
+            if (nd > 1) q1 = d1[0] * dk[1];
+            if (nd > 2) q2 = d2[0] * dk[2];
+        }
+#pragma unroll 1
+        for (int j0 = 1; j0 < half; j0 += 4) {
+            R x[4], xr[4], y[4], yr[4], z[4], zr[4];
+            const int m = half - j0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool v = u < m;
+                x[u] = v ? d0[j0 + u] : (R)0;
+                xr[u] = v ? d0[k - (j0 + u)] : (R)0;
+                y[u] = (v && nd > 1) ? d1[j0 + u] : (R)0;
+                yr[u] = (v && nd > 1) ? d1[k - (j0 + u)] : (R)0;
+                z[u] = (v && nd > 2) ? d2[j0 + u] : (R)0;
+                zr[u] = (v && nd > 2) ? d2[k - (j0 + u)] : (R)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                q0 = r_fma(x[u], xr[u], q0);
+                q1 = r_fma(y[u], yr[u], q1);
+                q2 = r_fma(z[u], zr[u], q2);
+            }
+        }
+        R acc = (q0 + q1) + q2;
+        acc = acc + acc;
+        if ((k & 1u) == 0) {
+            const R m0 = k ? d0[k >> 1] : dk[0];
+            R e = m0 * m0;
+            if (nd > 1) {
+                const R m1 = k ? d1[k >> 1] : dk[1];
+                e = r_fma(m1, m1, e);
+            }
+            if (nd > 2) {
+                const R m2 = k ? d2[k >> 1] : dk[2];
+                e = r_fma(m2, m2, e);
+            }
+            acc += e;
+        }
+        R *r2 = w + o.a, *c = w + o.dst;
+        r2[k] = acc;
+        const double alpha = s_imm[o.imm];
+        R ck;
+        if (k == 0) {
+            w[o.dst2] = (R)1 / acc;
+            ck = pow0<R>(acc, alpha);
+        } else {
+            const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;
+            // j = 0 term uses r2[k] = acc from the register
+            R s = (kal * acc) * c[0];
+            if (k > 1) s += conv_pow_from1<R>(r2 + k, c, (int)k, al1, kal);
+            ck = (s * rk[k]) * w[o.dst2];
+        }
+        c[k] = ck;
+        // t_i[k] = sum_{j<=k} d_i[j] c[k-j]; the j = 0 term uses c[k] from the register
+        R s0 = d0[0] * ck, s1 = nd > 1 ? d1[0] * ck : (R)0, s2 = nd > 2 ? d2[0] * ck : (R)0;
+        if (k > 0) {
+            R u0, u1, u2;
+            conv3<R>(d0 + 1, nd > 1 ? d1 + 1 : d0 + 1, nd > 2 ? d2 + 1 : d0 + 1, c + k - 1, (int)k, u0, u1, u2);
+            s0 += u0;
+            s1 += u1;
+            s2 += u2;
+        }
+        w[roff(tb[0].aux, k)] = s0;
+        if (nd > 1) w[roff(tb[1].aux, k)] = s1;
+        if (nd > 2) w[roff(tb[2].aux, k)] = s2;
+    } break;
     case HY_OP_LINCOMB: {
         R acc = 0;
         const DTerm *t = lt + (uint32_t)o.b * G;
         const uint32_t n = o.n;
-        for (uint32_t i = 0; i < n; ++i) {
-            const DTerm tt = t[i * G];
-            const R c = (R)tt.coef * w[tt.aux];
-            acc = r_fma(c, w[roff(tt.src, k)], acc);
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < n; i0 += 4) {
+            // block of 4 terms: records, then multipliers and operands, then the FMAs
+            DTerm tt[4];
+            const uint32_t m = n - i0;
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) tt[u] = t[(i0 + (u < m ? u : 0u)) * G];
+            R mv[4], vv[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                mv[u] = w[tt[u].aux];
+                vv[u] = w[roff(tt[u].src, k)];
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u)
+                if (u < m) acc = r_fma((R)tt[u].coef * mv[u], vv[u], acc);
         }
         if (o.flags & HY_OPF_SVD)
             w[o.dst + k + 1] = acc * rk[k + 1];
         else
-            w[o.dst + kd] = acc;
+            w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc;
     } break;
     case HY_OP_ADDSUB: {
-        R a = w[o.a + ka], b = w[o.b + kb];
+        R a = w[o.a + ((o.flags & DF_JA) ? k : 0u)], b = w[o.b + ((o.flags & DF_JB) ? k : 0u)];
         if (o.flags & HY_OPF_NEGA) a = -a;
         if (o.flags & HY_OPF_NEGB) b = -b;
         const R acc = a + b;
         if (o.flags & HY_OPF_SVD)
             w[o.dst + k + 1] = acc * rk[k + 1];
         else
-            w[o.dst + kd] = acc;
+            w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc;
+    } break;
+    case HY_OP_SVD: {
+        w[o.dst + k + 1] = w[o.a + ((o.flags & DF_JA) ? k : 0u)] * rk[k + 1];
     } break;
     case HY_OP_MUL: {
-        w[o.dst + kd] = conv<R>(w + o.a, w + o.b + k, (int)k + 1);
+        w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = conv<R>(w + o.a, w + o.b + k, (int)k + 1);
     } break;
     case HY_OP_SQUARE: {
         const R *a = w + o.a;
@@ -181,31 +407,23 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             const R m = a[k >> 1];
             acc = r_fma(m, m, acc);
         }
-        w[o.dst + kd] = acc;
+        w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc;
     } break;
     case HY_OP_SUMSQ: {
-        R s0 = 0, s1 = 0;
         const int half = (int)((k + 1) >> 1);
         const DTerm *t = lt + (uint32_t)o.b * G;
         const uint32_t n = o.n;
-        R acc2 = 0;
+        R acc = 0, acc2 = 0;
+#pragma unroll 1
         for (uint32_t i = 0; i < n; ++i) {
             const R *a = w + rbase(t[i * G].src);
-            const R *b = a + k;
-            int j = 0;
-            for (; j + 2 <= half; j += 2) {
-                const R a0 = a[j], a1 = a[j + 1], b0 = b[-j], b1 = b[-j - 1];
-                s0 = r_fma(a0, b0, s0);
-                s1 = r_fma(a1, b1, s1);
-            }
-            if (j < half) s0 = r_fma(a[j], b[-j], s0);
+            acc += conv<R>(a, a + k, half);
             if ((k & 1u) == 0) {
                 const R m = a[k >> 1];
                 acc2 = r_fma(m, m, acc2);
             }
         }
-        R acc = s0 + s1;
-        w[o.dst + kd] = (acc + acc) + acc2;
+        w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = (acc + acc) + acc2;
     } break;
     case HY_OP_MULSH: {
         const R *b = w + o.a + k;
@@ -213,30 +431,13 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
         const int n = (int)k + 1;
         if (o.n == 3) {
             const DTerm t0 = t[0], t1 = t[G], t2 = t[2 * G];
-            const R *a0 = w + rbase(t0.src), *a1 = w + rbase(t1.src), *a2 = w + rbase(t2.src);
-            R s0 = 0, s1 = 0, s2 = 0;
-            int j = 0;
-            for (; j + 2 <= n; j += 2) {
-                const R b0 = b[-j], b1 = b[-j - 1];
-                const R x0 = a0[j], x1 = a1[j], x2 = a2[j];
-                const R y0 = a0[j + 1], y1 = a1[j + 1], y2 = a2[j + 1];
-                s0 = r_fma(x0, b0, s0);
-                s1 = r_fma(x1, b0, s1);
-                s2 = r_fma(x2, b0, s2);
-                s0 = r_fma(y0, b1, s0);
-                s1 = r_fma(y1, b1, s1);
-                s2 = r_fma(y2, b1, s2);
-            }
-            if (j < n) {
-                const R b0 = b[-j];
-                s0 = r_fma(a0[j], b0, s0);
-                s1 = r_fma(a1[j], b0, s1);
-                s2 = r_fma(a2[j], b0, s2);
-            }
+            R s0, s1, s2;
+            conv3<R>(w + rbase(t0.src), w + rbase(t1.src), w + rbase(t2.src), b, n, s0, s1, s2);
             w[roff(t0.aux, k)] = s0;
             w[roff(t1.aux, k)] = s1;
             w[roff(t2.aux, k)] = s2;
         } else {
+#pragma unroll 1
             for (uint32_t i = 0; i < o.n; ++i) {
                 const DTerm ti = t[i * G];
                 w[roff(ti.aux, k)] = conv<R>(w + rbase(ti.src), b, n);
@@ -247,8 +448,8 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
         const R *b = w + o.b;
         R *c = w + o.dst;
         if (k == 0) w[o.dst2] = (R)1 / b[0];
-        R acc = w[o.a + ka];
-        for (uint32_t j = 1; j <= k; ++j) acc = r_fma(-b[j], c[k - j], acc);
+        R acc = w[o.a + ((o.flags & DF_JA) ? k : 0u)];
+        if (k > 0) acc -= conv<R>(b + 1, c + k - 1, (int)k);
         c[k] = acc * w[o.dst2];
     } break;
     case HY_OP_POW:
@@ -261,20 +462,7 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             c[0] = o.opcode == HY_OP_SQRT ? r_sqrt(a[0]) : pow0<R>(a[0], alpha);
         } else {
             const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;
-            R s0 = 0, s1 = 0, jr = 0;
-            const R *ak = a + k;
-            int j = 0;
-            const int n = (int)k;
-            for (; j + 2 <= n; j += 2) {
-                const R a0 = ak[-j], a1 = ak[-j - 1], c0 = c[j], c1 = c[j + 1];
-                const R w0 = r_fma(-jr, al1, kal);
-                const R w1 = r_fma(-(jr + (R)1), al1, kal);
-                jr += (R)2;
-                s0 = r_fma(w0 * a0, c0, s0);
-                s1 = r_fma(w1 * a1, c1, s1);
-            }
-            if (j < n) s0 = r_fma(r_fma(-jr, al1, kal) * ak[-j], c[j], s0);
-            c[k] = ((s0 + s1) * rk[k]) * w[o.dst2];
+            c[k] = (conv_pow<R>(a + k, c, (int)k, al1, kal) * rk[k]) * w[o.dst2];
         }
     } break;
     case HY_OP_EXP: {
@@ -284,6 +472,7 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             c[0] = r_exp(a[0]);
         } else {
             R acc = 0, jr = 1;
+#pragma unroll 1
             for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * a[j], c[k - j], acc);
             c[k] = acc * rk[k];
         }
@@ -296,6 +485,7 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             c[0] = r_log(a[0]);
         } else {
             R acc = 0, jr = 1;
+#pragma unroll 1
             for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * c[j], a[k - j], acc);
             c[k] = r_fma(-acc, rk[k], a[k]) * w[o.dst2];
         }
@@ -309,21 +499,28 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             s[0] = sv;
             c[0] = cv;
         } else {
-            R sa = 0, ca = 0, jr = 1;
-            for (uint32_t j = 1; j <= k; ++j, jr += (R)1) {
-                const R ja = jr * a[j];
-                sa = r_fma(ja, c[k - j], sa);
-                ca = r_fma(ja, s[k - j], ca);
+            R sa0 = 0, ca0 = 0, sa1 = 0, ca1 = 0, jr = 1;
+            uint32_t j = 1;
+#pragma unroll 1
+            for (; j + 1 <= k; j += 2, jr += (R)2) {
+                const R ja0 = jr * a[j], ja1 = (jr + (R)1) * a[j + 1];
+                const R c0 = c[k - j], s0 = s[k - j], c1 = c[k - j - 1], s1 = s[k - j - 1];
+                sa0 = r_fma(ja0, c0, sa0);
+                ca0 = r_fma(ja0, s0, ca0);
+                sa1 = r_fma(ja1, c1, sa1);
+                ca1 = r_fma(ja1, s1, ca1);
             }
-            s[k] = sa * rk[k];
-            c[k] = -(ca * rk[k]);
+            if (j <= k) {
+                const R ja = jr * a[j];
+                sa0 = r_fma(ja, c[k - j], sa0);
+                ca0 = r_fma(ja, s[k - j], ca0);
+            }
+            s[k] = (sa0 + sa1) * rk[k];
+            c[k] = -((ca0 + ca1) * rk[k]);
         }
     } break;
     case HY_OP_TIME: {
         w[o.dst + k] = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);
-    } break;
-    case HY_OP_SVD: {
-        w[o.dst + k + 1] = w[o.a + ka] * rk[k + 1];
     } break;
     default: break; // OP_NOP
     }
@@ -495,21 +692,20 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             const DOp *lops = s_ops + sub;
             const DTerm *lterms = s_terms + sub;
             const uint32_t n_ph = P.pd.n_phases;
-            for (uint32_t k = 0; k < p; ++k) {
+            // (with events, one extra sweep at order p over the event-function ops only)
+            const uint32_t k_end = d.n_events ? p + 1 : p;
+#pragma unroll 1
+            for (uint32_t k = 0; k < k_end; ++k) {
+                const bool ev_sweep = k == p;
+#pragma unroll 1
                 for (uint32_t ph = 0; ph < n_ph; ++ph) {
                     const uint32_t e = s_phase[ph + 1];
-                    for (uint32_t i = s_phase[ph]; i < e; ++i)
-                        exec_op<R, G>(lops[i * G], lterms, w, s_rk, s_imm, k, hi);
-                    if (G > 1) __syncwarp(gmask);
-                }
-            }
-            if (d.n_events) {
-                for (uint32_t ph = 0; ph < n_ph; ++ph) {
-                    const uint32_t e = s_phase[ph + 1];
+#pragma unroll 1
                     for (uint32_t i = s_phase[ph]; i < e; ++i) {
                         const DOp o = lops[i * G];
-                        if ((o.flags & HY_OPF_EVENT) && !(o.flags & HY_OPF_SVD) && o.opcode != HY_OP_SVD)
-                            exec_op<R, G>(o, lterms, w, s_rk, s_imm, p, hi);
+                        if (ev_sweep && (!(o.flags & HY_OPF_EVENT) || (o.flags & HY_OPF_SVD) || o.opcode == HY_OP_SVD))
+                            continue;
+                        exec_op<R, G>(o, lterms, w, s_rk, s_imm, k, hi);
                     }
                     if (G > 1) __syncwarp(gmask);
                 }

@@ -21,6 +21,8 @@
 // from /root/reference/heyoka/expose_batch_integrators.cpp:166-208).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <cstdint>
 #include <map>
 #include <numeric>
@@ -50,7 +52,13 @@ struct DTerm {
 };
 static_assert(sizeof(DTerm) == 16, "DTerm must be 16 bytes");
 
-enum : uint8_t { OP_NOP = 255 };
+enum : uint8_t { OP_NOP = 255, DOP_PAIR = 64 };
+// DOP_PAIR: fused "pair interaction" cluster (superinstruction)
+//   d_i = (+-)A_i (+-)B_i  (i < n <= 3),  r2 = sum_i d_i^2,  w = r2^alpha,  t_i = d_i * w
+// terms (2 per component, in the lane's stream at o.b):
+//   [2i]   src = A_i ref, aux = B_i ref, coef = sign code (0:+a+b 1:-a+b 2:+a-b 3:-a-b)
+//   [2i+1] src = d_i jet ref,  aux = t_i output ref
+// o.a = r2 jet, o.dst = w jet, o.dst2 = scratch row holding 1/r2[0], o.imm = alpha.
 enum : uint8_t { DF_JDST = 0x10, DF_JDST2 = 0x20, DF_JA = 0x40, DF_JB = 0x80 };
 
 struct Program {
@@ -181,6 +189,33 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
     }
     const int NC = (int)clusters.size();
 
+    // ---- 2b. superinstruction fusion: recognise pair-interaction clusters ----
+    //   ADDSUB x n, SUMSQ(n) over their outputs, POW of the sum, MULSH(n) of the
+    //   differences with the power.  Arithmetic (and summation order) is identical
+    //   to the unfused ops; only dispatch and sync overhead is saved.
+    std::vector<char> fused(clusters.size(), 0);
+    const bool allow_fuse = std::getenv("HY_CUDA_NO_PAIR_FUSION") == nullptr;
+    for (size_t c = 0; allow_fuse && c < clusters.size(); ++c) {
+        const auto &m = clusters[c];
+        if (m.size() < 5) continue;
+        const size_t nd = m.size() - 3;
+        if (nd < 1 || nd > 3) continue;
+        bool ok = true;
+        for (size_t i = 0; i < nd && ok; ++i) {
+            const hy_op &o = ops[m[i]];
+            ok = o.opcode == HY_OP_ADDSUB && !(o.flags & (HY_OPF_SVD | HY_OPF_EVENT)) && (o.dst & HY_REF_JET);
+        }
+        if (!ok) continue;
+        const hy_op &sq = ops[m[nd]], &pw = ops[m[nd + 1]], &ms = ops[m[nd + 2]];
+        ok = sq.opcode == HY_OP_SUMSQ && sq.n == nd && pw.opcode == HY_OP_POW && ms.opcode == HY_OP_MULSH &&
+             ms.n == nd && !((sq.flags | pw.flags | ms.flags) & (HY_OPF_SVD | HY_OPF_EVENT)) &&
+             (sq.dst & HY_REF_JET) && pw.a == sq.dst && ms.a == pw.dst;
+        for (size_t i = 0; i < nd && ok; ++i) {
+            ok = terms[sq.b + i].src == ops[m[i]].dst && terms[ms.b + i].src == ops[m[i]].dst;
+        }
+        if (ok) fused[c] = 1;
+    }
+
     // ---- 3. phases = levels of the cluster DAG ----
     std::vector<int> lvl(NC, 0);
     std::vector<char> has_pred(NC, 0), has_succ(NC, 0);
@@ -208,9 +243,15 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
     // ---- 4. rows of equal-signature clusters ----
     auto signature = [&](int c) {
         std::vector<uint32_t> s;
+        if (fused[c]) {
+            s.push_back(((uint32_t)DOP_PAIR << 16) | (uint32_t)(clusters[c].size() - 3));
+            return s;
+        }
         for (int i : clusters[c]) s.push_back(((uint32_t)ops[i].opcode << 16) | (ops[i].n & 0xffffu));
         return s;
     };
+    // program length of a cluster in op slots
+    auto cl_len = [&](int c) { return fused[c] ? (size_t)1 : clusters[c].size(); };
     auto cl_cost = [&](int c) {
         double t = 0;
         for (int i : clusters[c]) t += op_cost(ops[i]);
@@ -247,15 +288,20 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
                          [](const auto &a, const auto &b) { return a.first > b.first; });
         for (auto &row : full_rows) {
             size_t len = 0;
-            for (int c : row.second) len = std::max(len, clusters[c].size());
+            for (int c : row.second) len = std::max(len, cl_len(c));
             double rc = 0;
             for (int c : row.second) rc = std::max(rc, cl_cost(c));
             for (uint32_t s = 0; s < G; ++s) {
                 auto &lp = prog[ph][s];
                 size_t k = 0;
                 if (s < row.second.size()) {
-                    for (int i : clusters[row.second[s]]) lp.push_back(i), ++k;
-                    useful += cl_cost(row.second[s]);
+                    const int c = row.second[s];
+                    if (fused[c]) {
+                        lp.push_back(-2 - c), ++k; // fused cluster marker
+                    } else {
+                        for (int i : clusters[c]) lp.push_back(i), ++k;
+                    }
+                    useful += cl_cost(c);
                 }
                 for (; k < len; ++k) lp.push_back(-1);
             }
@@ -296,7 +342,36 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
         for (uint32_t s = 0; s < G; ++s) {
             const auto &lp = prog[ph][s];
             for (size_t j = 0; j < lp.size(); ++j) {
-                if (lp[j] < 0) continue;
+                if (lp[j] == -1) continue;
+                if (lp[j] <= -2) {
+                    // ---- fused pair-interaction cluster ----
+                    const auto &m = clusters[-2 - lp[j]];
+                    const size_t nd = m.size() - 3;
+                    const hy_op &sq = ops[m[nd]], &pw = ops[m[nd + 1]], &ms = ops[m[nd + 2]];
+                    DOp q{};
+                    q.opcode = DOP_PAIR;
+                    q.n = (uint16_t)nd;
+                    q.a = (uint16_t)(sq.dst & 0x7fffffffu);
+                    q.dst = (uint16_t)(pw.dst & 0x7fffffffu);
+                    q.dst2 = (uint16_t)pw.dst2;
+                    q.imm = imm_of(pw.imm);
+                    q.b = (uint16_t)lane_terms[s].size();
+                    for (size_t i = 0; i < nd; ++i) {
+                        const hy_op &ad = ops[m[i]];
+                        DTerm u{};
+                        u.coef = (double)(((ad.flags & HY_OPF_NEGA) ? 1 : 0) | ((ad.flags & HY_OPF_NEGB) ? 2 : 0));
+                        u.src = fix(ad.a);
+                        u.aux = fix(ad.b);
+                        lane_terms[s].push_back(u);
+                        DTerm v{};
+                        v.coef = 0;
+                        v.src = ad.dst;
+                        v.aux = terms[ms.b + i].dst;
+                        lane_terms[s].push_back(v);
+                    }
+                    out.ops[((size_t)out.phase_slot[ph] + j) * G + s] = q;
+                    continue;
+                }
                 const hy_op &o = ops[lp[j]];
                 DOp q{};
                 q.opcode = (uint8_t)o.opcode;
