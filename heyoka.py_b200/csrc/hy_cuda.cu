@@ -49,7 +49,11 @@ struct hy_ctx {
     hy::Program prog;
     void *d_prog = nullptr; // [ops | terms | imm]
     uint32_t *d_phase = nullptr;
-    uint32_t *d_ev = nullptr;
+    uint32_t *d_ev = nullptr;       // remapped event jet rows (device layout)
+    std::vector<uint32_t> h_ev_ref; // ABI event references
+    uint32_t *d_srow = nullptr;
+    int32_t *d_ssp = nullptr;
+    void *d_gjet = nullptr;
     // lanes (device)
     void *d_state = nullptr, *d_pars = nullptr, *d_thi = nullptr, *d_tlo = nullptr, *d_lasth = nullptr;
     void *d_tf = nullptr, *d_mdt = nullptr, *d_minh = nullptr, *d_maxh = nullptr, *d_tc = nullptr;
@@ -138,7 +142,8 @@ uint32_t env_u32(const char *name, uint32_t dflt)
 
 hy::ProgDims prog_dims(const hy::Program &p)
 {
-    return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases};
+    return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases,
+                        p.ws_len,  p.par_off,  p.one_off,              p.n_spill};
 }
 
 // Choose the launch geometry for a tape: group size G (threads cooperating on
@@ -152,23 +157,23 @@ int choose_geometry(hy_ctx *c)
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const hy_dims &d = c->d;
     const uint32_t max_threads = 512;
-    // Per-trajectory workspace column, padded to an odd element count so that
-    // lanes working on different trajectories hit different banks.
-    const uint32_t RS = hy::ws_rows(d) | 1u;
     hy_launch_info &li = c->li;
     li.n_sm = (uint32_t)prop.multiProcessorCount;
     const bool force_global = env_u32("HY_CUDA_FORCE_GLOBAL_WS", 0) != 0;
     const uint32_t Genv = env_u32("HY_CUDA_GROUP", 0);
 
     double best_score = -1;
-    uint32_t bestG = 0, bestT = 0;
+    uint32_t bestG = 0, bestT = 0, bestRS = 0;
     bool best_smem = false;
     hy::Program best;
     for (uint32_t G : {1u, 4u, 16u, 32u}) { // group sizes with compiled kernels
         if (Genv && G != Genv) continue;
         hy::Program pr;
-        std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), G, pr);
+        std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), G, true, pr);
         if (!err.empty()) return fail("hy_create: " + err);
+        // Per-trajectory workspace column, padded to an odd element count so that
+        // lanes working on different trajectories hit different banks.
+        const uint32_t RS = pr.ws_len | 1u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), G, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
         if (fixed > (uint32_t)smem_optin) continue;
@@ -185,6 +190,7 @@ int choose_geometry(hy_ctx *c)
             bestT = T;
             best_smem = smem;
             best = pr;
+            bestRS = RS;
         }
     }
     if (!bestG) return fail("hy_create: the program does not fit in shared memory for any group size");
@@ -200,6 +206,7 @@ int choose_geometry(hy_ctx *c)
     li.threads = ((T * G + 31) / 32) * 32;
     uint32_t ctas = (c->B + T - 1) / T;
     li.ctas = std::max(1u, std::min(ctas, li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
+    const uint32_t RS = bestRS;
     c->TS = RS;
     c->prog = best;
     hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
@@ -220,6 +227,17 @@ int choose_geometry(hy_ctx *c)
         if (c->d_phase) cudaFree(c->d_phase);
         CU(cudaMalloc(&c->d_phase, c->prog.phase_slot.size() * 4));
         CU(cudaMemcpy(c->d_phase, c->prog.phase_slot.data(), c->prog.phase_slot.size() * 4, cudaMemcpyHostToDevice));
+        for (void *p : {(void *)c->d_srow, (void *)c->d_ssp, (void *)c->d_ev, c->d_gjet})
+            if (p) cudaFree(p);
+        CU(cudaMalloc(&c->d_srow, d.n_state * 4));
+        CU(cudaMemcpy(c->d_srow, c->prog.state_row.data(), d.n_state * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_ssp, d.n_state * 4));
+        CU(cudaMemcpy(c->d_ssp, c->prog.state_spill.data(), d.n_state * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_ev, std::max<size_t>(1, d.n_events) * 4));
+        if (d.n_events) CU(cudaMemcpy(c->d_ev, c->prog.ev_ref.data(), d.n_events * 4, cudaMemcpyHostToDevice));
+        const size_t gj_bytes = (size_t)li.ctas * T * std::max<uint32_t>(1, c->prog.n_spill) * (d.order + 1) * c->rb;
+        CU(cudaMalloc(&c->d_gjet, gj_bytes));
+        CU(cudaMemset(c->d_gjet, 0, gj_bytes));
     }
     if (!li.ws_in_smem) {
         if (c->d_gws) cudaFree(c->d_gws);
@@ -236,6 +254,9 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.prog = c->d_prog;
     P.phase_slot = c->d_phase;
     P.ev_ref = c->d_ev;
+    P.state_row = c->d_srow;
+    P.state_spill = c->d_ssp;
+    P.gjet = (R *)c->d_gjet;
     P.pd = prog_dims(c->prog);
     P.state = (R *)c->d_state;
     P.pars = (const R *)c->d_pars;
@@ -424,8 +445,7 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
     c->h_ops.assign(ops, ops + d.n_ops);
     if (d.n_terms) c->h_terms.assign(terms, terms + d.n_terms);
     c->h_levels.assign(level_start, level_start + d.n_levels + 1);
-    CU(cudaMalloc(&c->d_ev, std::max<size_t>(1, d.n_events) * 4));
-    if (d.n_events) CU(cudaMemcpy(c->d_ev, ev_ref, d.n_events * 4, cudaMemcpyHostToDevice));
+    if (d.n_events) c->h_ev_ref.assign(ev_ref, ev_ref + d.n_events);
     const size_t B = std::max<size_t>(1, batch), rb = c->rb;
     CU(cudaMalloc(&c->d_state, B * d.n_state * rb));
     CU(cudaMalloc(&c->d_pars, B * std::max<size_t>(1, d.n_par) * rb));
@@ -468,7 +488,7 @@ int hy_destroy(hy_ctx *c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
+    void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
                     c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
                     c->d_counter, c->d_gws, c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo, c->d_cout_count,
                     c->d_tmp_in, c->d_tmp_out, c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log,

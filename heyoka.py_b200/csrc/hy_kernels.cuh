@@ -63,13 +63,17 @@ enum { MODE_UNTIL = 0, MODE_FOR = 1, MODE_STEP = 2, MODE_GRID = 3 };
 
 struct ProgDims {
     uint32_t n_slots, n_tslots, n_imm, n_phases;
+    uint32_t ws_len, par_off, one_off, n_spill; // device workspace layout (hy_schedule.hpp)
 };
 
 template <typename R> struct KParams {
     hy_dims d;
     const void *prog;            // [ops | terms | imm] in the smem layout
     const uint32_t *phase_slot;  // [n_phases + 1]
-    const uint32_t *ev_ref;
+    const uint32_t *ev_ref;      // [n_events] device row of each event jet
+    const uint32_t *state_row;   // [n_state] device row of each state variable
+    const int32_t *state_spill;  // [n_state] spill slot or -1
+    R *gjet;                     // spilled state jets: [ctas][T][n_spill][p+1]
     ProgDims pd;
     R *state;      // [n][B]
     const R *pars; // [m][B]
@@ -107,8 +111,18 @@ template <typename R> struct KParams {
 // Orders of a jet are contiguous, so a convolution walks a[+j], b[-j] with
 // immediate offsets.  Trajectory t of the CTA lives at ws + t*RS.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t roff(uint32_t ref, uint32_t k) { return (ref & 0x7fffffffu) + ((ref >> 31) ? k : 0u); }
-__device__ __forceinline__ uint32_t rbase(uint32_t ref) { return ref & 0x7fffffffu; }
+// device reference -> element offset at order k: jets advance by k, spilled
+// (ping-pong) state variables by k & 1, single rows not at all.
+__device__ __forceinline__ uint32_t roff(uint32_t ref, uint32_t k)
+{
+    return (ref & 0x3fffffffu) + ((ref & HY_DREF_JET) ? k : ((ref & HY_DREF_PP) ? (k & 1u) : 0u));
+}
+__device__ __forceinline__ uint32_t rbase(uint32_t ref) { return ref & 0x3fffffffu; }
+// operand offset of a DOp field
+__device__ __forceinline__ uint32_t ooff(uint32_t off, bool jet, bool pp, uint32_t k)
+{
+    return off + (jet ? k : (pp ? (k & 1u) : 0u));
+}
 
 template <typename R> __device__ __noinline__ R pow0(R x, double alpha)
 {
@@ -251,8 +265,20 @@ __device__ __forceinline__ R conv_pow_from1(const R *__restrict__ ak, const R *_
 template <typename R, int G>
 __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ lt, R *__restrict__ w,
                                         const R *__restrict__ rk, const double *__restrict__ s_imm, const uint32_t k,
-                                        const R tm)
+                                        const R tm, R *__restrict__ gj, const uint32_t P1)
 {
+    // State recurrence store: x[k+1] = v.  Resident jets: dst + k + 1.  Spilled state
+    // variables keep orders (k, k+1) on chip and stream the jet to the global scratch.
+#define HY_STORE_SV(v)                                                                                  \
+    do {                                                                                                \
+        const R v_ = (v);                                                                               \
+        if (o.pad & DP_DST) {                                                                           \
+            w[o.dst + ((k + 1u) & 1u)] = v_;                                                            \
+            gj[(uint32_t)(o.dst2 - 1) * P1 + k + 1] = v_;                                               \
+        } else {                                                                                        \
+            w[o.dst + k + 1] = v_;                                                                      \
+        }                                                                                               \
+    } while (0)
     switch (o.opcode) {
     case DOP_PAIR: {
         // Fused pair interaction (hy_schedule.hpp): d_i = +-A_i +- B_i, r2 = sum d_i^2,
@@ -379,22 +405,22 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
                 if (u < m) acc = r_fma((R)tt[u].coef * mv[u], vv[u], acc);
         }
         if (o.flags & HY_OPF_SVD)
-            w[o.dst + k + 1] = acc * rk[k + 1];
+            HY_STORE_SV(acc * rk[k + 1]);
         else
             w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc;
     } break;
     case HY_OP_ADDSUB: {
-        R a = w[o.a + ((o.flags & DF_JA) ? k : 0u)], b = w[o.b + ((o.flags & DF_JB) ? k : 0u)];
+        R a = w[ooff(o.a, o.flags & DF_JA, o.pad & DP_A, k)], b = w[ooff(o.b, o.flags & DF_JB, o.pad & DP_B, k)];
         if (o.flags & HY_OPF_NEGA) a = -a;
         if (o.flags & HY_OPF_NEGB) b = -b;
         const R acc = a + b;
         if (o.flags & HY_OPF_SVD)
-            w[o.dst + k + 1] = acc * rk[k + 1];
+            HY_STORE_SV(acc * rk[k + 1]);
         else
             w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc;
     } break;
     case HY_OP_SVD: {
-        w[o.dst + k + 1] = w[o.a + ((o.flags & DF_JA) ? k : 0u)] * rk[k + 1];
+        HY_STORE_SV(w[ooff(o.a, o.flags & DF_JA, o.pad & DP_A, k)] * rk[k + 1]);
     } break;
     case HY_OP_MUL: {
         w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = conv<R>(w + o.a, w + o.b + k, (int)k + 1);
@@ -448,7 +474,7 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
         const R *b = w + o.b;
         R *c = w + o.dst;
         if (k == 0) w[o.dst2] = (R)1 / b[0];
-        R acc = w[o.a + ((o.flags & DF_JA) ? k : 0u)];
+        R acc = w[ooff(o.a, o.flags & DF_JA, o.pad & DP_A, k)];
         if (k > 0) acc -= conv<R>(b + 1, c + k - 1, (int)k);
         c[k] = acc * w[o.dst2];
     } break;
@@ -524,6 +550,7 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
     } break;
     default: break; // OP_NOP
     }
+#undef HY_STORE_SV
 }
 
 // Error-free time arithmetic.  __dadd_rn & co. forbid
@@ -556,13 +583,12 @@ template <typename R> __device__ __forceinline__ R time_sub(R ahi, R alo, R bhi,
 // Shared-memory carve-up (dynamic smem):
 //   [ops | terms | imm | phase_slot | ev_ref | rk | ws]
 struct SmemLayout {
-    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_rk, off_ws, total;
+    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_srow, off_ssp, off_rk, off_ws, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // Elements of one trajectory's workspace column (before padding to odd).
-__host__ __device__ inline uint32_t ws_rows(const hy_dims &d) { return d.n_rows + d.n_par + d.order + 1; }
 
 __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDims &pd, uint32_t G, uint32_t T,
                                                   uint32_t RS, uint32_t real_bytes, int ws_in_smem)
@@ -579,6 +605,10 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     o += (pd.n_phases + 1) * 4u;
     L.off_ev = o;
     o += d.n_events * 4u;
+    L.off_srow = o;
+    o += d.n_state * 4u;
+    L.off_ssp = o;
+    o += d.n_state * 4u;
     o = align_up(o, 8);
     L.off_rk = o;
     o += (d.order + 2) * real_bytes;
@@ -599,6 +629,8 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
     double *s_imm = reinterpret_cast<double *>(smem_raw + L.off_imm);
     uint32_t *s_phase = reinterpret_cast<uint32_t *>(smem_raw + L.off_phase);
     uint32_t *s_ev = reinterpret_cast<uint32_t *>(smem_raw + L.off_ev);
+    uint32_t *s_srow = reinterpret_cast<uint32_t *>(smem_raw + L.off_srow);
+    int32_t *s_ssp = reinterpret_cast<int32_t *>(smem_raw + L.off_ssp);
     R *s_rk = reinterpret_cast<R *>(smem_raw + L.off_rk);
     const uint32_t RS = P.TS; // workspace stride between trajectories (odd)
 
@@ -610,6 +642,10 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
         for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
         for (uint32_t i = threadIdx.x; i <= P.pd.n_phases; i += blockDim.x) s_phase[i] = P.phase_slot[i];
         for (uint32_t i = threadIdx.x; i < d.n_events; i += blockDim.x) s_ev[i] = P.ev_ref[i];
+        for (uint32_t i = threadIdx.x; i < d.n_state; i += blockDim.x) {
+            s_srow[i] = P.state_row[i];
+            s_ssp[i] = P.state_spill[i];
+        }
         for (uint32_t i = threadIdx.x; i < d.order + 2; i += blockDim.x)
             s_rk[i] = i == 0 ? (R)0 : (R)(1.0 / (double)i);
     }
@@ -620,13 +656,17 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
     const uint32_t sub = threadIdx.x & (G - 1);
     const uint32_t slot = threadIdx.x / G; // trajectory slot in this CTA
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
-    const uint32_t par_off = d.n_rows, one_off = d.n_rows + d.n_par;
+    const uint32_t par_off = P.pd.par_off, one_off = P.pd.one_off;
     if (slot >= P.T) return; // whole groups only: safe w.r.t. group-mask syncs
     R *w;
     if (SMEM)
         w = reinterpret_cast<R *>(smem_raw + L.off_ws) + (size_t)slot * RS;
     else
         w = P.gws + ((size_t)blockIdx.x * P.T + slot) * RS;
+    // global scratch of this trajectory slot's spilled state jets
+    R *gj = P.gjet + ((size_t)blockIdx.x * P.T + slot) * (size_t)P.pd.n_spill * P1;
+    // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
+#define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j)])
     // unit jet [1, 0, ..., 0] (never changes)
     for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
 
@@ -637,7 +677,11 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
         if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
         if (traj >= P.B) break;
 
-        for (uint32_t i = sub; i < n; i += G) w[i * P1] = P.state[(size_t)i * P.B + traj];
+        for (uint32_t i = sub; i < n; i += G) {
+            const R x0 = P.state[(size_t)i * P.B + traj];
+            w[s_srow[i]] = x0;
+            if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = x0;
+        }
         for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i] = P.pars[(size_t)i * P.B + traj];
         R hi = P.t_hi[traj], lo = P.t_lo[traj];
         R mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
@@ -661,7 +705,7 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                 const R dg = (g - hi) - lo;
                 if ((dir >= (R)0 && dg > (R)0) || (dir < (R)0 && dg < (R)0)) break;
                 for (uint32_t i = sub; i < n; i += G)
-                    P.gout[((size_t)gi * n + i) * P.B + traj] = w[i * P1];
+                    P.gout[((size_t)gi * n + i) * P.B + traj] = w[s_srow[i]];
                 ++gi;
             }
         }
@@ -705,7 +749,7 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                         const DOp o = lops[i * G];
                         if (ev_sweep && (!(o.flags & HY_OPF_EVENT) || (o.flags & HY_OPF_SVD) || o.opcode == HY_OP_SVD))
                             continue;
-                        exec_op<R, G>(o, lterms, w, s_rk, s_imm, k, hi);
+                        exec_op<R, G>(o, lterms, w, s_rk, s_imm, k, hi, gj, P1);
                     }
                     if (G > 1) __syncwarp(gmask);
                 }
@@ -714,10 +758,20 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
             for (uint32_t i = sub; i < n + d.n_events; i += G) {
-                const R *x = i < n ? &w[i * P1] : &w[rbase(s_ev[i - n])];
-                n0 = nan_max(n0, r_abs(x[0]));
-                n1 = nan_max(n1, r_abs(x[p - 1]));
-                n2 = nan_max(n2, r_abs(x[p]));
+                R x0, x1, x2;
+                if (i < n) {
+                    x0 = XJ(i, 0);
+                    x1 = XJ(i, p - 1);
+                    x2 = XJ(i, p);
+                } else {
+                    const R *x = &w[s_ev[i - n]];
+                    x0 = x[0];
+                    x1 = x[p - 1];
+                    x2 = x[p];
+                }
+                n0 = nan_max(n0, r_abs(x0));
+                n1 = nan_max(n1, r_abs(x1));
+                n2 = nan_max(n2, r_abs(x2));
             }
 #pragma unroll
             for (int m = G >> 1; m > 0; m >>= 1) {
@@ -760,12 +814,12 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
 
             // ---- optional tc write, then the state update ----
             if (P.write_tc && P.tc) {
-                for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = w[i];
+                for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
                 if (G > 1) __syncwarp(gmask);
             }
             if (P.cout_tcs && cc < P.cout_cap) {
                 R *dstc = P.cout_tcs + ((size_t)cc * P.B + traj) * (size_t)(n * P1);
-                for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = w[i];
+                for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
             }
             if (P.mode == MODE_GRID) {
                 // Dense output at every grid point inside this step.
@@ -774,9 +828,8 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
                     const R tau = (g - hi) - lo; // time since the start of the step
                     if (r_abs(tau) > r_abs(h)) break;
                     for (uint32_t i = sub; i < n; i += G) {
-                        const R *x = &w[i * P1];
-                        R acc = x[p];
-                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k]);
+                        R acc = XJ(i, p);
+                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, XJ(i, k));
                         P.gout[((size_t)gi * n + i) * P.B + traj] = acc;
                     }
                     ++gi;
@@ -785,25 +838,47 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
             if (G > 1 && (P.cout_tcs || P.mode == MODE_GRID)) __syncwarp(gmask);
             bool finite = true;
             for (uint32_t i = sub; i < n; i += G) {
-                R *x = &w[i * P1];
                 R acc;
-                if (!P.high_accuracy) {
-                    acc = x[p];
-                    for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[k]);
-                } else {
-                    R sum = x[0], comp = 0, hk = h;
-                    for (uint32_t k = 1; k <= p; ++k) {
-                        const R term = x[k] * hk;
-                        const R y = ef_sub(term, comp);
-                        const R tt = ef_add(sum, y);
-                        comp = ef_sub(ef_sub(tt, sum), y);
-                        sum = tt;
-                        hk = hk * h;
+                const int sp = s_ssp[i];
+                if (sp >= 0) {
+                    // spilled jet: stream it back from the global scratch (independent loads)
+                    const R *x = gj + (uint32_t)sp * P1;
+                    if (!P.high_accuracy) {
+                        acc = __ldcg(&x[p]);
+                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, __ldcg(&x[k]));
+                    } else {
+                        R sum = __ldcg(&x[0]), comp = 0, hk = h;
+                        for (uint32_t k = 1; k <= p; ++k) {
+                            const R term = __ldcg(&x[k]) * hk;
+                            const R y = ef_sub(term, comp);
+                            const R tt = ef_add(sum, y);
+                            comp = ef_sub(ef_sub(tt, sum), y);
+                            sum = tt;
+                            hk = hk * h;
+                        }
+                        acc = sum;
                     }
-                    acc = sum;
+                    gj[(uint32_t)sp * P1] = acc;
+                } else {
+                    const R *x = &w[s_srow[i]];
+                    if (!P.high_accuracy) {
+                        acc = x[p];
+                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[k]);
+                    } else {
+                        R sum = x[0], comp = 0, hk = h;
+                        for (uint32_t k = 1; k <= p; ++k) {
+                            const R term = x[k] * hk;
+                            const R y = ef_sub(term, comp);
+                            const R tt = ef_add(sum, y);
+                            comp = ef_sub(ef_sub(tt, sum), y);
+                            sum = tt;
+                            hk = hk * h;
+                        }
+                        acc = sum;
+                    }
                 }
                 finite = finite && (r_abs(acc) < r_inf<R>());
-                x[0] = acc;
+                w[s_srow[i]] = acc;
             }
             if (G > 1) finite = !__any_sync(gmask, !finite);
             time_add(hi, lo, h);
@@ -850,7 +925,7 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1
 
         // ---- retire the trajectory ----
         if (G > 1) __syncwarp(gmask);
-        for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[i * P1];
+        for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[s_srow[i]];
         if (sub == 0) {
             P.t_hi[traj] = hi;
             P.t_lo[traj] = lo;

@@ -60,6 +60,11 @@ enum : uint8_t { OP_NOP = 255, DOP_PAIR = 64 };
 //   [2i+1] src = d_i jet ref,  aux = t_i output ref
 // o.a = r2 jet, o.dst = w jet, o.dst2 = scratch row holding 1/r2[0], o.imm = alpha.
 enum : uint8_t { DF_JDST = 0x10, DF_JDST2 = 0x20, DF_JA = 0x40, DF_JB = 0x80 };
+// Ping-pong references (DOp::pad bits / DTerm bit 30): a spilled state variable
+// keeps only orders k and k+1 on chip, at base + (order & 1).
+enum : uint16_t { DP_DST = 0x1, DP_A = 0x4, DP_B = 0x8 };
+#define HY_DREF_JET 0x80000000u
+#define HY_DREF_PP 0x40000000u
 
 struct Program {
     uint32_t G = 1;
@@ -69,6 +74,12 @@ struct Program {
     std::vector<DTerm> terms;         // [n_tslots * G]
     std::vector<double> imm;          // immediates
     uint32_t n_slots = 0, n_tslots = 0;
+    // device workspace layout (per trajectory column)
+    uint32_t ws_len = 0, par_off = 0, one_off = 0;
+    uint32_t n_spill = 0;              // state jets kept in the global scratch
+    std::vector<uint32_t> state_row;   // [n_state] device row: jet base (resident) or ping-pong base (spilled)
+    std::vector<int32_t> state_spill;  // [n_state] spill slot or -1
+    std::vector<uint32_t> ev_ref;      // [n_events] remapped event jet references
     // statistics
     uint32_t n_clusters = 0;
     double lane_utilisation = 0; // useful op slots / (slots * G), cost weighted
@@ -115,13 +126,11 @@ struct UF {
 
 // Build the per-lane program.  Returns an empty string on success, else an
 // error message.
-inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_term *terms, uint32_t G, Program &out)
+inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uint32_t *ev_ref_in,
+                                 uint32_t G, bool spill_ok, Program &out)
 {
     using namespace detail;
     const uint32_t n_ops = d.n_ops;
-    const uint32_t par_off = d.n_rows, one_off = d.n_rows + d.n_par;
-    const uint32_t ws_len = d.n_rows + d.n_par + d.order + 1;
-    if (ws_len > 65535u) return "the system is too large: more than 65535 workspace rows per trajectory";
     const uint32_t P1 = d.order + 1;
 
     // ---- 1. producers of rows written in the same sweep ----
@@ -309,8 +318,101 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
         }
     }
 
+    // ---- 4b. device workspace layout ----
+    // A state variable whose jet is only ever read at the CURRENT order (operands of
+    // LINCOMB / ADDSUB / SVD / DIV numerators / fused pair differences) needs no
+    // on-chip history: its jet goes to a global (L2-resident) scratch, written once
+    // per order and read back once per step by the Horner update; on chip it keeps a
+    // two-entry ping-pong (orders k, k+1).  Everything else is compacted.
+    const uint32_t n_state = d.n_state;
+    std::vector<char> hist(n_state, 0);
+    auto mark_hist = [&](uint32_t ref) {
+        if (ref == HY_REF_ONE) return;
+        const uint32_t b = ref & 0x7fffffffu;
+        if (b % P1 == 0 && b / P1 < n_state) hist[b / P1] = 1;
+    };
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const hy_op &o = ops[i];
+        switch (o.opcode) {
+        case HY_OP_MUL: mark_hist(o.a); mark_hist(o.b); break;
+        case HY_OP_SQUARE: case HY_OP_POW: case HY_OP_SQRT: case HY_OP_EXP: case HY_OP_LOG: case HY_OP_SINCOS:
+            mark_hist(o.a); break;
+        case HY_OP_DIV: mark_hist(o.b); break;
+        case HY_OP_SUMSQ: for (uint32_t j = 0; j < o.n; ++j) mark_hist(terms[o.b + j].src); break;
+        case HY_OP_MULSH: mark_hist(o.a); for (uint32_t j = 0; j < o.n; ++j) mark_hist(terms[o.b + j].src); break;
+        default: break;
+        }
+    }
+    const bool allow_spill = std::getenv("HY_CUDA_NO_SPILL") == nullptr && spill_ok;
+    // (event functions that ARE state variables need the full jet on chip)
+    // collect every row block: base -> size
+    std::map<uint32_t, uint32_t> blocks;
+    auto add_block = [&](uint32_t ref, bool force_jet = false) {
+        if (ref == HY_REF_ONE) return;
+        const uint32_t b = ref & 0x7fffffffu;
+        const uint32_t sz = ((ref & HY_REF_JET) || force_jet) ? P1 : 1u;
+        auto it = blocks.find(b);
+        if (it == blocks.end() || it->second < sz) blocks[b] = sz;
+    };
+    for (uint32_t i = 0; i < n_state; ++i) add_block((i * P1) | HY_REF_JET);
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const hy_op &o = ops[i];
+        if (o.opcode != HY_OP_MULSH) add_block(o.dst);
+        if (o.opcode == HY_OP_SINCOS) add_block(o.dst2);
+        if (o.opcode == HY_OP_DIV || o.opcode == HY_OP_POW || o.opcode == HY_OP_SQRT || o.opcode == HY_OP_LOG)
+            add_block(o.dst2 & 0x7fffffffu);
+        if (is_term_op(o.opcode)) {
+            for (uint32_t j = 0; j < o.n; ++j) {
+                add_block(terms[o.b + j].src);
+                if (o.opcode == HY_OP_MULSH) add_block(terms[o.b + j].dst);
+            }
+            if (o.opcode == HY_OP_MULSH) add_block(o.a);
+        } else if (o.opcode != HY_OP_TIME) {
+            add_block(o.a);
+            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB) add_block(o.b);
+        }
+    }
+    std::vector<char> is_ev_state(n_state, 0);
+    for (uint32_t e = 0; e < d.n_events; ++e) {
+        add_block(ev_ref_in[e], true);
+        const uint32_t b = ev_ref_in[e] & 0x7fffffffu;
+        if (b % P1 == 0 && b / P1 < n_state) is_ev_state[b / P1] = 1;
+    }
+    std::vector<int32_t> spill(n_state, -1);
+    uint32_t n_spill = 0;
+    for (uint32_t i = 0; i < n_state; ++i)
+        if (allow_spill && !hist[i] && !is_ev_state[i]) spill[i] = (int32_t)n_spill++;
+    std::map<uint32_t, uint32_t> new_base;
+    uint32_t row_cnt = 0;
+    for (auto &kv : blocks) {
+        const uint32_t b = kv.first;
+        uint32_t sz = kv.second;
+        if (b % P1 == 0 && b / P1 < n_state && spill[b / P1] >= 0) sz = 2; // ping-pong
+        new_base[b] = row_cnt;
+        row_cnt += sz;
+    }
+    const uint32_t par_off = row_cnt, one_off = row_cnt + d.n_par;
+    const uint32_t ws_len = one_off + P1;
+    if (ws_len > 65535u) return "the system is too large: more than 65535 workspace rows per trajectory";
+    // device reference: new base | JET | PP
+    auto remap = [&](uint32_t ref) -> uint32_t {
+        if (ref == HY_REF_ONE) return one_off | HY_DREF_JET;
+        const uint32_t b = ref & 0x7fffffffu;
+        auto it = new_base.find(b);
+        const uint32_t nb = it == new_base.end() ? 0u : it->second;
+        if (b % P1 == 0 && b / P1 < n_state && spill[b / P1] >= 0) return nb | HY_DREF_PP;
+        return nb | ((ref & HY_REF_JET) ? HY_DREF_JET : 0u);
+    };
+
     // ---- 5. emit ----
     out = Program();
+    out.ws_len = ws_len;
+    out.par_off = par_off;
+    out.one_off = one_off;
+    out.n_spill = n_spill;
+    out.state_spill = spill;
+    for (uint32_t i = 0; i < n_state; ++i) out.state_row.push_back(new_base[i * P1]);
+    for (uint32_t e = 0; e < d.n_events; ++e) out.ev_ref.push_back(remap(ev_ref_in[e] | HY_REF_JET) & 0x3fffffffu);
     out.G = G;
     out.n_phases = (uint32_t)n_ph;
     out.n_clusters = (uint32_t)NC;
@@ -337,7 +439,7 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
         imm_idx[key] = id;
         return id;
     };
-    auto fix = [&](uint32_t ref) { return ref == HY_REF_ONE ? (one_off | HY_REF_JET) : ref; };
+    auto off16 = [&](uint32_t dref) { return (uint16_t)(dref & 0x3fffffffu); };
     for (int ph = 0; ph < n_ph; ++ph)
         for (uint32_t s = 0; s < G; ++s) {
             const auto &lp = prog[ph][s];
@@ -351,22 +453,22 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
                     DOp q{};
                     q.opcode = DOP_PAIR;
                     q.n = (uint16_t)nd;
-                    q.a = (uint16_t)(sq.dst & 0x7fffffffu);
-                    q.dst = (uint16_t)(pw.dst & 0x7fffffffu);
-                    q.dst2 = (uint16_t)pw.dst2;
+                    q.a = off16(remap(sq.dst));
+                    q.dst = off16(remap(pw.dst));
+                    q.dst2 = off16(remap(pw.dst2 & 0x7fffffffu));
                     q.imm = imm_of(pw.imm);
                     q.b = (uint16_t)lane_terms[s].size();
                     for (size_t i = 0; i < nd; ++i) {
                         const hy_op &ad = ops[m[i]];
                         DTerm u{};
                         u.coef = (double)(((ad.flags & HY_OPF_NEGA) ? 1 : 0) | ((ad.flags & HY_OPF_NEGB) ? 2 : 0));
-                        u.src = fix(ad.a);
-                        u.aux = fix(ad.b);
+                        u.src = remap(ad.a);
+                        u.aux = remap(ad.b);
                         lane_terms[s].push_back(u);
                         DTerm v{};
                         v.coef = 0;
-                        v.src = ad.dst;
-                        v.aux = terms[ms.b + i].dst;
+                        v.src = remap(ad.dst);
+                        v.aux = remap(terms[ms.b + i].dst);
                         lane_terms[s].push_back(v);
                     }
                     out.ops[((size_t)out.phase_slot[ph] + j) * G + s] = q;
@@ -377,17 +479,24 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
                 q.opcode = (uint8_t)o.opcode;
                 q.flags = (uint8_t)(o.flags & 0xf);
                 q.n = (uint16_t)o.n;
-                auto setref = [&](uint32_t ref, uint16_t &field, uint8_t jflag) {
-                    ref = fix(ref);
-                    field = (uint16_t)(ref & 0x7fffffffu);
-                    if (ref & HY_REF_JET) q.flags |= jflag;
+                auto setref = [&](uint32_t ref, uint16_t &field, uint8_t jflag, uint16_t pflag) {
+                    const uint32_t r = remap(ref);
+                    field = off16(r);
+                    if (r & HY_DREF_JET) q.flags |= jflag;
+                    if (r & HY_DREF_PP) q.pad |= pflag;
                 };
-                if (o.opcode != HY_OP_MULSH) setref(o.dst, q.dst, DF_JDST);
+                if (o.opcode != HY_OP_MULSH) setref(o.dst, q.dst, DF_JDST, DP_DST);
+                const bool writes_state = o.opcode == HY_OP_SVD || (o.flags & HY_OPF_SVD);
                 if (o.opcode == HY_OP_SINCOS)
-                    setref(o.dst2, q.dst2, DF_JDST2);
-                else
-                    q.dst2 = (uint16_t)o.dst2; // scratch row (DIV/POW/SQRT/LOG)
-                if (o.opcode != HY_OP_TIME) setref(o.a, q.a, DF_JA);
+                    setref(o.dst2, q.dst2, DF_JDST2, 0);
+                else if (o.opcode == HY_OP_DIV || o.opcode == HY_OP_POW || o.opcode == HY_OP_SQRT || o.opcode == HY_OP_LOG)
+                    q.dst2 = off16(remap(o.dst2 & 0x7fffffffu)); // scratch row holding 1/a[0]
+                else if (writes_state) {
+                    // spill slot + 1 of the destination state variable (0: resident)
+                    const uint32_t sv = (o.dst & 0x7fffffffu) / P1;
+                    q.dst2 = (uint16_t)(sv < n_state && spill[sv] >= 0 ? spill[sv] + 1 : 0);
+                }
+                if (o.opcode != HY_OP_TIME) setref(o.a, q.a, DF_JA, DP_A);
                 if (is_term_op(o.opcode)) {
                     if (lane_terms[s].size() + o.n > 65535u) return "too many terms per lane";
                     q.b = (uint16_t)lane_terms[s].size();
@@ -396,15 +505,15 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
                         if (ht.par >= (int32_t)d.n_par) return "parameter index out of bounds";
                         DTerm u{};
                         u.coef = ht.coef;
-                        u.src = fix(ht.src);
+                        u.src = remap(ht.src);
                         if (o.opcode == HY_OP_MULSH)
-                            u.aux = ht.dst;
+                            u.aux = remap(ht.dst);
                         else
                             u.aux = ht.par >= 0 ? par_off + (uint32_t)ht.par : one_off;
                         lane_terms[s].push_back(u);
                     }
                 } else {
-                    setref(o.b, q.b, DF_JB);
+                    setref(o.b, q.b, DF_JB, DP_B);
                 }
                 q.imm = imm_of(o.imm);
                 (void)P1;
