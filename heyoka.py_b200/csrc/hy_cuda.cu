@@ -103,14 +103,12 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
         case 1: return launch_g<R, 1, true>(P, li, s);
         case 4: return launch_g<R, 4, true>(P, li, s);
         case 16: return launch_g<R, 16, true>(P, li, s);
-        case 32: return launch_g<R, 32, true>(P, li, s);
         default: return cudaErrorInvalidValue;
         }
     }
     // Global-memory workspace fallback (jets too large for shared memory).
     switch (li.group) {
     case 1: return launch_g<R, 1, false>(P, li, s);
-    case 32: return launch_g<R, 32, false>(P, li, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -124,12 +122,11 @@ template <typename R, int G, bool SMEM> int regs_of()
 
 template <typename R> int regs_for_group(uint32_t g, bool smem)
 {
-    if (!smem) return g == 1 ? regs_of<R, 1, false>() : regs_of<R, 32, false>();
+    if (!smem) return regs_of<R, 1, false>();
     switch (g) {
     case 1: return regs_of<R, 1, true>();
     case 4: return regs_of<R, 4, true>();
-    case 16: return regs_of<R, 16, true>();
-    default: return regs_of<R, 32, true>();
+    default: return regs_of<R, 16, true>();
     }
 }
 
@@ -156,7 +153,7 @@ int choose_geometry(hy_ctx *c)
     int smem_optin = 0;
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const hy_dims &d = c->d;
-    const uint32_t max_threads = 512;
+    const uint32_t max_threads = 256; // == __launch_bounds__ of propagate_kernel (up to 255 registers per thread)
     hy_launch_info &li = c->li;
     li.n_sm = (uint32_t)prop.multiProcessorCount;
     const bool force_global = env_u32("HY_CUDA_FORCE_GLOBAL_WS", 0) != 0;
@@ -166,7 +163,7 @@ int choose_geometry(hy_ctx *c)
     uint32_t bestG = 0, bestT = 0, bestRS = 0;
     bool best_smem = false;
     hy::Program best;
-    for (uint32_t G : {1u, 4u, 16u, 32u}) { // group sizes with compiled kernels
+    for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
         if (Genv && G != Genv) continue;
         hy::Program pr;
         std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), G, true, pr);
@@ -180,7 +177,7 @@ int choose_geometry(hy_ctx *c)
         const uint32_t budget = (uint32_t)smem_optin - fixed;
         uint32_t Tfit = budget / (RS * (uint32_t)c->rb);
         bool smem = Tfit >= 1 && !force_global;
-        if (!smem && G != 1 && G != 32) continue; // fallback kernels exist for these only
+        if (!smem && G != 1) continue; // the global-workspace fallback kernel exists for G = 1 only
         uint32_t T = smem ? std::min(Tfit, max_threads / G) : std::max(1u, 256u / G);
         const double threads = std::min<double>((double)T * G, max_threads);
         const double score = pr.lane_utilisation * threads * (smem ? 1.0 : 0.05);

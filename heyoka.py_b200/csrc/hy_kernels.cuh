@@ -260,6 +260,80 @@ __device__ __forceinline__ R conv_pow_from1(const R *__restrict__ ak, const R *_
     return (s0 + s1) + (s2 + s3);
 }
 
+// ---------------------------------------------------------------------------
+// Order-specialised body of the fused pair interaction (nd = 3): K is a
+// compile-time constant, every loop is fully unrolled, every operand is an
+// immediate-offset load from four base registers, nothing is predicated.
+// The arithmetic (term order within each chain apart) is the generic path's.
+// ---------------------------------------------------------------------------
+template <typename R, int K>
+__device__ __forceinline__ void pair3_k(R *__restrict__ d0, R *__restrict__ d1, R *__restrict__ d2, R *__restrict__ r2,
+                                        R *__restrict__ c, R *__restrict__ inv, const R dk0, const R dk1, const R dk2,
+                                        const R rkK, const double alpha, R &t0, R &t1, R &t2)
+{
+    d0[K] = dk0;
+    d1[K] = dk1;
+    d2[K] = dk2;
+    constexpr int half = (K + 1) / 2;
+    // r2[K] = 2 * sum_i sum_{j<half} d_i[j] d_i[K-j]  (+ sum_i d_i[K/2]^2 for even K)
+    R q0 = 0, q1 = 0, q2 = 0;
+    if (half > 0) {
+        q0 = d0[0] * dk0;
+        q1 = d1[0] * dk1;
+        q2 = d2[0] * dk2;
+    }
+#pragma unroll
+    for (int j = 1; j < half; ++j) {
+        q0 = r_fma(d0[j], d0[K - j], q0);
+        q1 = r_fma(d1[j], d1[K - j], q1);
+        q2 = r_fma(d2[j], d2[K - j], q2);
+    }
+    R acc = (q0 + q1) + q2;
+    acc = acc + acc;
+    if ((K & 1) == 0) {
+        const R m0 = K ? d0[K / 2] : dk0, m1 = K ? d1[K / 2] : dk1, m2 = K ? d2[K / 2] : dk2;
+        acc += r_fma(m2, m2, r_fma(m1, m1, m0 * m0));
+    }
+    r2[K] = acc;
+    R ck;
+    if (K == 0) {
+        *inv = (R)1 / acc;
+        ck = pow0<R>(acc, alpha);
+    } else {
+        const R al1 = (R)(alpha + 1.0), kal = (R)K * (R)alpha;
+        R s0 = (kal * acc) * c[0], s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            const R wgt = r_fma((R)(-j), al1, kal);
+            const R pr = wgt * r2[K - j];
+            if ((j & 3) == 0) s0 = r_fma(pr, c[j], s0);
+            if ((j & 3) == 1) s1 = r_fma(pr, c[j], s1);
+            if ((j & 3) == 2) s2 = r_fma(pr, c[j], s2);
+            if ((j & 3) == 3) s3 = r_fma(pr, c[j], s3);
+        }
+        ck = (((s0 + s1) + (s2 + s3)) * rkK) * (*inv);
+    }
+    c[K] = ck;
+    // t_i[K] = sum_{j<=K} d_i[j] c[K-j]; j = 0 uses c[K] from the register
+    R a0 = d0[0] * ck, a1 = d1[0] * ck, a2 = d2[0] * ck, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+    for (int j = 1; j <= K; ++j) {
+        const R cj = c[K - j];
+        if (j & 1) {
+            b0 = r_fma(d0[j], cj, b0);
+            b1 = r_fma(d1[j], cj, b1);
+            b2 = r_fma(d2[j], cj, b2);
+        } else {
+            a0 = r_fma(d0[j], cj, a0);
+            a1 = r_fma(d1[j], cj, a1);
+            a2 = r_fma(d2[j], cj, a2);
+        }
+    }
+    t0 = a0 + b0;
+    t1 = a1 + b1;
+    t2 = a2 + b2;
+}
+
 // One op of the program at order k on the trajectory column `w`.  `lt` is the
 // lane's term stream (term c at lt[c * G]).
 template <typename R, int G>
@@ -306,6 +380,24 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
             const int sc = (int)ta[i].coef;
             const R a = (sc & 1) ? -av[i] : av[i], b = (sc & 2) ? -bv[i] : bv[i];
             dk[i] = a + b;
+        }
+        if (nd == 3 && k < 24) {
+            R t0, t1, t2;
+            R *r2 = w + o.a, *c = w + o.dst, *inv = w + o.dst2;
+            const double alpha = s_imm[o.imm];
+            const R rkK = rk[k];
+            switch (k) {
+#define HY_PK(K) case K: pair3_k<R, K>(d0, d1, d2, r2, c, inv, dk[0], dk[1], dk[2], rkK, alpha, t0, t1, t2); break;
+                HY_PK(0) HY_PK(1) HY_PK(2) HY_PK(3) HY_PK(4) HY_PK(5) HY_PK(6) HY_PK(7) HY_PK(8) HY_PK(9) HY_PK(10)
+                HY_PK(11) HY_PK(12) HY_PK(13) HY_PK(14) HY_PK(15) HY_PK(16) HY_PK(17) HY_PK(18) HY_PK(19) HY_PK(20)
+                HY_PK(21) HY_PK(22) HY_PK(23)
+#undef HY_PK
+            default: t0 = t1 = t2 = 0; break;
+            }
+            w[roff(tb[0].aux, k)] = t0;
+            w[roff(tb[1].aux, k)] = t1;
+            w[roff(tb[2].aux, k)] = t2;
+            break;
         }
         d0[k] = dk[0];
         if (nd > 1) d1[k] = dk[1];
@@ -619,7 +711,7 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     return L;
 }
 
-template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(512, 1) propagate_kernel(const KParams<R> P)
+template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
