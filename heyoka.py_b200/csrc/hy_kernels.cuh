@@ -476,26 +476,44 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
         if (nd > 2) w[roff(tb[2].aux, k)] = s2;
     } break;
     case HY_OP_LINCOMB: {
-        R acc = 0;
+        // Specialised on the number of terms (exact, fully unrolled, nothing predicated):
+        // all term records first, then all operands (and multipliers, if any term has a
+        // runtime parameter), then one FMA chain in term order.
         const DTerm *t = lt + (uint32_t)o.b * G;
-        const uint32_t n = o.n;
-#pragma unroll 1
-        for (uint32_t i0 = 0; i0 < n; i0 += 4) {
-            // block of 4 terms: records, then multipliers and operands, then the FMAs
-            DTerm tt[4];
-            const uint32_t m = n - i0;
-#pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) tt[u] = t[(i0 + (u < m ? u : 0u)) * G];
-            R mv[4], vv[4];
-#pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) {
-                mv[u] = w[tt[u].aux];
-                vv[u] = w[roff(tt[u].src, k)];
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < 4; ++u)
-                if (u < m) acc = r_fma((R)tt[u].coef * mv[u], vv[u], acc);
+        const bool nopar = (o.pad & DP_NOPAR) != 0;
+        R acc = 0;
+#define HY_LC(N)                                                                                        \
+    {                                                                                                   \
+        DTerm tt[N];                                                                                    \
+        _Pragma("unroll") for (int u = 0; u < N; ++u) tt[u] = t[u * G];                                 \
+        R vv[N];                                                                                        \
+        _Pragma("unroll") for (int u = 0; u < N; ++u) vv[u] = w[tt[u].src + (k & (tt[u].aux >> 16))];   \
+        if (nopar) {                                                                                    \
+            _Pragma("unroll") for (int u = 0; u < N; ++u) acc = r_fma((R)tt[u].coef, vv[u], acc);       \
+        } else {                                                                                        \
+            R mv[N];                                                                                    \
+            _Pragma("unroll") for (int u = 0; u < N; ++u) mv[u] = w[tt[u].aux & 0xffffu];               \
+            _Pragma("unroll") for (int u = 0; u < N; ++u) acc = r_fma((R)tt[u].coef * mv[u], vv[u], acc); \
+        }                                                                                               \
+    }
+        uint32_t n = o.n;
+        while (n > 8) { // long combinations: peel blocks of 8
+            HY_LC(8)
+            t += 8 * G;
+            n -= 8;
         }
+        switch (n) {
+        case 1: HY_LC(1) break;
+        case 2: HY_LC(2) break;
+        case 3: HY_LC(3) break;
+        case 4: HY_LC(4) break;
+        case 5: HY_LC(5) break;
+        case 6: HY_LC(6) break;
+        case 7: HY_LC(7) break;
+        case 8: HY_LC(8) break;
+        default: break;
+        }
+#undef HY_LC
         if (o.flags & HY_OPF_SVD)
             HY_STORE_SV(acc * rk[k + 1]);
         else

@@ -62,7 +62,10 @@ enum : uint8_t { OP_NOP = 255, DOP_PAIR = 64 };
 enum : uint8_t { DF_JDST = 0x10, DF_JDST2 = 0x20, DF_JA = 0x40, DF_JB = 0x80 };
 // Ping-pong references (DOp::pad bits / DTerm bit 30): a spilled state variable
 // keeps only orders k and k+1 on chip, at base + (order & 1).
-enum : uint16_t { DP_DST = 0x1, DP_A = 0x4, DP_B = 0x8 };
+enum : uint16_t { DP_DST = 0x1, DP_A = 0x4, DP_B = 0x8, DP_NOPAR = 0x10 };
+// LINCOMB terms: aux = multiplier offset (low 16 bits) | order mask (high 16 bits);
+// the operand of the term at order k sits at (src & 0xffffff) + (k & mask):
+// mask = 0xffff for jets, 1 for spilled (ping-pong) state variables, 0 for single rows.
 #define HY_DREF_JET 0x80000000u
 #define HY_DREF_PP 0x40000000u
 
@@ -500,18 +503,27 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
                 if (is_term_op(o.opcode)) {
                     if (lane_terms[s].size() + o.n > 65535u) return "too many terms per lane";
                     q.b = (uint16_t)lane_terms[s].size();
+                    bool has_par = false;
                     for (uint32_t t = 0; t < o.n; ++t) {
                         const hy_term &ht = terms[o.b + t];
                         if (ht.par >= (int32_t)d.n_par) return "parameter index out of bounds";
                         DTerm u{};
                         u.coef = ht.coef;
                         u.src = remap(ht.src);
-                        if (o.opcode == HY_OP_MULSH)
+                        if (o.opcode == HY_OP_MULSH) {
                             u.aux = remap(ht.dst);
-                        else
+                        } else if (o.opcode == HY_OP_LINCOMB) {
+                            const uint32_t r = u.src;
+                            const uint32_t mask = (r & HY_DREF_JET) ? 0xffffu : ((r & HY_DREF_PP) ? 1u : 0u);
+                            u.src = r & 0x3fffffffu;
+                            u.aux = (ht.par >= 0 ? par_off + (uint32_t)ht.par : one_off) | (mask << 16);
+                            if (ht.par >= 0) has_par = true;
+                        } else {
                             u.aux = ht.par >= 0 ? par_off + (uint32_t)ht.par : one_off;
+                        }
                         lane_terms[s].push_back(u);
                     }
+                    if (o.opcode == HY_OP_LINCOMB && !has_par) q.pad |= DP_NOPAR;
                 } else {
                     setref(o.b, q.b, DF_JB, DP_B);
                 }
