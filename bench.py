@@ -125,6 +125,20 @@ class ClockSampler:
         }
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel, per
+    launch, from the committed `ncu --set full` capture of this workload
+    (profiles/r01_ncu_full_bench_kernel.txt); None if the summary is missing."""
+    try:
+        tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_kernel.txt")):
+            if ln.startswith("dram__bytes_read.sum =") or ln.startswith("dram__bytes_write.sum ="):
+                tot += float(ln.split("=")[1]) * 1e6  # the raw page reports Mbyte for this capture
+        return tot or None
+    except Exception:
+        return None
+
+
 def workload(traj, rank):
     from hy_b200 import workloads as W
 
@@ -343,7 +357,7 @@ def main():
             "kernel": "hy::propagate_kernel<double,{}>".format(li["group"]),
             "kernel_ms_per_launch": kern_ms / args.steps,
             "flops_per_trajectory_step": fl,
-            "traffic": None,
+            "traffic": ncu_traffic(),
             "hbm": {
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_gbs": alg_bytes * args.steps / k_s / 1e9,
