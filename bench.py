@@ -153,11 +153,11 @@ def cpu_baseline(sys_, order, horizon, target_s, rank_seed=0):
     from oracle.c_oracle import COracle, lib
 
     dc = D.decompose(sys_, order)
-    lib().ora_num_threads.restype = int
-    cores = int(lib().ora_num_threads())
+    # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly.
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # Calibrate on a tiny run, then size the sample for ~target_s seconds.
     cal_traj, cal_h = 2 * cores, min(horizon, 50.0)
-    o = COracle(dc, W.oss_ensemble(cal_traj, seed=777 + rank_seed))
+    o = COracle(dc, W.oss_ensemble(cal_traj, seed=777 + rank_seed), nthreads=cores)
     t0 = time.perf_counter()
     r = o.propagate_until(cal_h)
     dt = time.perf_counter() - t0
@@ -170,7 +170,7 @@ def cpu_baseline(sys_, order, horizon, target_s, rank_seed=0):
         # Keep at least 4 trajectories per thread: shorten the horizon instead.
         traj = 4 * cores
         h = max(cal_h, horizon * want / (steps_per_traj * traj))
-    o = COracle(dc, W.oss_ensemble(traj, seed=778 + rank_seed))
+    o = COracle(dc, W.oss_ensemble(traj, seed=778 + rank_seed), nthreads=cores)
     t0 = time.perf_counter()
     r = o.propagate_until(h)
     dt = time.perf_counter() - t0
