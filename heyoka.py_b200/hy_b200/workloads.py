@@ -92,3 +92,64 @@ def cr3bp_ensemble(B, seed=20251020, amp=1e-3):
 def forced_pendulum_sys():
     x, v = hy.make_vars("x", "v")
     return [(x, v), (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x))]
+
+
+# Kepler + J2 single satellite (config 4): RHS as in
+# doc/notebooks/Box control for Formation Flying Satellites.ipynb:179-195.
+J2_MU = 398600.4418   # km^3/s^2
+J2_J2 = 1082.645e-6
+J2_RE = 6371.0        # km
+
+
+def kepler_j2_sys():
+    from ._expression import sqrt
+
+    x, y, z, vx, vy, vz = make_vars("x", "y", "z", "vx", "vy", "vz")
+    c = 1.5 * J2_J2 * J2_MU * J2_RE**2
+    r2 = x**2 + y**2 + z**2
+    ax = (-J2_MU * x / r2 - c * x / r2**2 * (1.0 - 5.0 * z**2 / r2)) / sqrt(r2)
+    ay = (-J2_MU * y / r2 - c * y / r2**2 * (1.0 - 5.0 * z**2 / r2)) / sqrt(r2)
+    az = (-J2_MU * z / r2 - c * z / r2**2 * (3.0 - 5.0 * z**2 / r2)) / sqrt(r2)
+    return [(x, vx), (y, vy), (z, vz), (vx, ax), (vy, ay), (vz, az)]
+
+
+def kepler_j2_ensemble(B, seed=20251021):
+    """LEO initial conditions: a in U(6800, 7800) km, e in U(0, 0.02), i in U(0, pi),
+    Omega, omega, M in U(0, 2 pi) -> Cartesian state [6, B]."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(6800.0, 7800.0, B)
+    e = rng.uniform(0.0, 0.02, B)
+    inc = rng.uniform(0.0, np.pi, B)
+    Om, om, M = (rng.uniform(0.0, 2 * np.pi, B) for _ in range(3))
+    E = M.copy()
+    for _ in range(20):
+        E = E - (E - e * np.sin(E) - M) / (1 - e * np.cos(E))
+    xp = a * (np.cos(E) - e)
+    yp = a * np.sqrt(1 - e * e) * np.sin(E)
+    r = a * (1 - e * np.cos(E))
+    vxp = -np.sqrt(J2_MU * a) / r * np.sin(E)
+    vyp = np.sqrt(J2_MU * a) / r * np.sqrt(1 - e * e) * np.cos(E)
+    cO, sO, co, so, ci, si = np.cos(Om), np.sin(Om), np.cos(om), np.sin(om), np.cos(inc), np.sin(inc)
+    R11, R12 = cO * co - sO * so * ci, -cO * so - sO * co * ci
+    R21, R22 = sO * co + cO * so * ci, -sO * so + cO * co * ci
+    R31, R32 = so * si, co * si
+    st = np.stack([R11 * xp + R12 * yp, R21 * xp + R22 * yp, R31 * xp + R32 * yp,
+                   R11 * vxp + R12 * vyp, R21 * vxp + R22 * vyp, R31 * vxp + R32 * vyp])
+    return np.ascontiguousarray(st)
+
+
+def kepler_j2_energy(st):
+    x, y, z, vx, vy, vz = st
+    r2 = x * x + y * y + z * z
+    r = np.sqrt(r2)
+    c = 0.5 * J2_J2 * J2_MU * J2_RE**2
+    return 0.5 * (vx * vx + vy * vy + vz * vz) - J2_MU / r + c / (r2 * r) * (3.0 * z * z / r2 - 1.0)
+
+
+def cr3bp_jacobi(st, mu=0.01):
+    """Jacobi constant of the CR3BP in the (x, y, z, px, py, pz) variables."""
+    x, y, z, px, py, pz = st
+    r1 = np.sqrt((x - mu) ** 2 + y * y + z * z)
+    r2 = np.sqrt((x - mu + 1) ** 2 + y * y + z * z)
+    vx, vy = px + y, py - x
+    return (x * x + y * y) + 2 * (1 - mu) / r1 + 2 * mu / r2 - (vx * vx + vy * vy + pz * pz)
