@@ -16,13 +16,13 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libhy_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("hy_oracle.c", "hy_oracle_impl.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("hy_oracle.c", "hy_oracle_impl.h", "hy_baseline_simd.c")]
     srcs.append(os.path.join(_HERE, "..", "include", "hy_cuda.h"))
     stale = not os.path.exists(so) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)
     )
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return so
 
 
@@ -132,3 +132,29 @@ class COracle:
 
     def propagate_for(self, dt, max_steps=0, max_delta_t=None, h_log_cap=0):
         return self._call(dt, 1, max_steps, max_delta_t, 0, 0, h_log_cap)
+
+
+_SIMD = None
+
+
+def simd_propagate_until(dc, state, t, pars=None, nthreads=0):
+    """SIMD-batched multithreaded CPU baseline (oracle/hy_baseline_simd.c): FP64
+    propagate_until from time 0.  Returns (final state, n_steps)."""
+    global _SIMD
+    if _SIMD is None:
+        build()
+        _SIMD = C.CDLL(os.path.join(_HERE, "libhy_baseline_simd.so"))
+        _SIMD.ora_simd_propagate_until.restype = C.c_int
+    st = np.ascontiguousarray(np.array(state, dtype=np.float64).reshape(dc.n_state, -1))
+    B = st.shape[1]
+    pr = (np.zeros((max(dc.n_par, 1), B)) if pars is None
+          else np.ascontiguousarray(np.array(pars, dtype=np.float64).reshape(dc.n_par, B)))
+    t0 = np.zeros(B)
+    tf = np.ascontiguousarray(np.broadcast_to(np.array(t, dtype=np.float64), (B,)))
+    ns = np.zeros(B, dtype=np.uint64)
+    dims = make_dims(dc)
+    rc = _SIMD.ora_simd_propagate_until(C.byref(dims), _p(dc.ops), _p(dc.terms), C.c_uint32(B), _p(st), _p(pr),
+                                        _p(t0), _p(tf), _p(ns), C.c_int(nthreads))
+    if rc != 0:
+        raise RuntimeError("simd baseline failure {}".format(rc))
+    return st, ns

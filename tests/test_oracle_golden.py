@@ -162,3 +162,24 @@ def test_c_oracle_vs_np_oracle_nbody():
     rc = c.propagate_until(20.0)
     assert list(rc[3]) == list(ra[3])
     assert np.max(np.abs(a.state - c.state) / np.maximum(1, np.abs(c.state))) < 1e-13
+
+
+def test_simd_baseline_matches_scalar_oracle():
+    # oracle/hy_baseline_simd.c (bench.py's cpu_baseline) against the pinned scalar oracle
+    from oracle.c_oracle import simd_propagate_until
+
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(19, amp=1e-3)   # not a multiple of the SIMD width
+    dc = D.decompose(sys_, 20)
+    o = COracle(dc, ic)
+    r = o.propagate_until(30.0)
+    st, ns = simd_propagate_until(dc, ic, 30.0, nthreads=2)
+    assert np.array_equal(ns, r[3])
+    assert np.max(np.abs(st - o.state) / np.maximum(1, np.abs(o.state))) < 1e-12
+    # a system with sin/cos, parameters and time
+    g = G["batch_forced_pendulum"]
+    dc = D.decompose(common.forced_pendulum_sys(), 20)
+    st, ns = simd_propagate_until(dc, g["ic"], [10.0, 11.0, 12.0, 13.0], pars=g["pars"])
+    o = COracle(dc, g["ic"], pars=g["pars"])
+    r = o.propagate_until([10.0, 11.0, 12.0, 13.0])
+    assert np.array_equal(ns, r[3]) and np.max(np.abs(st - o.state)) < 1e-12
