@@ -176,7 +176,7 @@ template <typename R> __device__ inline int ev_find_roots(const R *c_in, int p, 
 template <typename R>
 __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, uint32_t n_events, uint32_t n_tevents,
                                      int p, R h, R t_hi, R t_lo, uint32_t traj, unsigned long long step_idx,
-                                     const EvParams<R> &E, R &h_out, int &term_out)
+                                     const EvParams<R> E, R &h_out, int &term_out)
 {
     h_out = h;
     term_out = -1;
@@ -290,7 +290,7 @@ __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, u
 
 // Advance the cooldown clocks of a trajectory by |h| (run by one lane).
 template <typename R>
-__device__ inline void advance_cooldowns(uint32_t traj, uint32_t n_tevents, R h, const EvParams<R> &E)
+__device__ inline void advance_cooldowns(uint32_t traj, uint32_t n_tevents, R h, const EvParams<R> E)
 {
     const R ah = h < 0 ? -h : h;
     for (uint32_t e = 0; e < n_tevents; ++e) {
