@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "hy_kernels.cuh"
+#include "hy_nbody_match.hpp"
 
 namespace {
 
@@ -86,10 +87,10 @@ struct hy_ctx {
 
 namespace {
 
-template <typename R, int G, bool SMEM>
+template <typename R, int G, bool SMEM, int NB = 0>
 cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
 {
-    auto kern = hy::propagate_kernel<R, G, SMEM>;
+    auto kern = hy::propagate_kernel<R, G, SMEM, NB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
@@ -98,6 +99,9 @@ cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStre
 
 template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
 {
+    // register-resident N-body kernels (hy_nbody_reg.cuh)
+    if (li.kernel_variant == 6) return launch_g<R, 16, true, 6>(P, li, s);
+    if (li.kernel_variant) return cudaErrorInvalidValue;
     if (li.ws_in_smem) {
         switch (li.group) {
         case 1: return launch_g<R, 1, true>(P, li, s);
@@ -113,15 +117,16 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     }
 }
 
-template <typename R, int G, bool SMEM> int regs_of()
+template <typename R, int G, bool SMEM, int NB = 0> int regs_of()
 {
     cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, hy::propagate_kernel<R, G, SMEM>) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&a, hy::propagate_kernel<R, G, SMEM, NB>) != cudaSuccess) return 0;
     return a.numRegs;
 }
 
-template <typename R> int regs_for_group(uint32_t g, bool smem)
+template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant)
 {
+    if (variant == 6) return regs_of<R, 16, true, 6>();
     if (!smem) return regs_of<R, 1, false>();
     switch (g) {
     case 1: return regs_of<R, 1, true>();
@@ -163,7 +168,40 @@ int choose_geometry(hy_ctx *c)
     uint32_t bestG = 0, bestT = 0, bestRS = 0;
     bool best_smem = false;
     hy::Program best;
+    li.kernel_variant = 0;
+    // Register-resident kernel for N-body tapes (hy_nbody_reg.cuh): the jets of the pair
+    // interactions live in registers, the state jets + a small exchange buffer in shared memory.
+    hy::NbMatch nbm;
+    if (!force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
+        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) && nbm.nb == 6) {
+        hy::Program pr;
+        pr.G = 16;
+        pr.n_phases = 0;
+        pr.phase_slot = {0};
+        pr.imm = nbm.imm;
+        const uint32_t SP = (uint32_t)hy::NBR_SP;
+        pr.ws_len = d.n_state * SP + 2u * hy::NBR_MAXB * hy::NBR_QS;
+        pr.par_off = pr.one_off = pr.ws_len;
+        pr.n_spill = 0;
+        for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back(i * SP);
+        pr.state_spill.assign(d.n_state, -1);
+        pr.n_clusters = nbm.n_pairs;
+        pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
+        // column stride: 16-byte aligned rows, the two trajectories of a warp in different bank halves
+        const uint32_t RS = (pr.ws_len + 15u) / 16u * 16u + 8u;
+        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
+        const uint32_t fixed = L0.total + 64;
+        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 1) {
+            bestG = 16;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 16u);
+            bestRS = RS;
+            best_smem = true;
+            best = pr;
+            li.kernel_variant = nbm.nb;
+        }
+    }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
+        if (li.kernel_variant) break;
         if (Genv && G != Genv) continue;
         hy::Program pr;
         std::string err = hy::build_program(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), G, true, pr);
@@ -209,8 +247,8 @@ int choose_geometry(hy_ctx *c)
     hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
     li.smem_bytes = L.total;
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
-    li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G, li.ws_in_smem)
-                                                     : regs_for_group<float>(G, li.ws_in_smem));
+    li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G, li.ws_in_smem, li.kernel_variant)
+                                                     : regs_for_group<float>(G, li.ws_in_smem, li.kernel_variant));
     // Upload the program blob [ops | terms | imm] (same layout as in shared memory).
     {
         std::vector<unsigned char> blob(L.off_phase, 0);
@@ -287,6 +325,7 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.B = c->B;
     P.T = c->li.traj_per_cta;
     P.TS = c->TS;
+    P.nb_tb_off = c->d.n_state * (uint32_t)hy::NBR_SP;
     P.max_steps = max_steps;
     P.mode = mode;
     P.backward = backward;

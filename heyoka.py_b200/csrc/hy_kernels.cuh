@@ -21,6 +21,7 @@
 #include "../../include/hy_cuda.h"
 #include "hy_schedule.hpp"
 #include "hy_events.cuh"
+#include "hy_nbody_reg.cuh"
 
 namespace hy {
 
@@ -95,6 +96,7 @@ template <typename R> struct KParams {
     unsigned int *counter;
     R *gws; // global workspace fallback (ws_in_smem == 0)
     uint32_t B, T, TS;
+    uint32_t nb_tb_off; // register-resident N-body path: offset of the exchange buffer in the column
     unsigned long long max_steps;
     int mode, backward, write_tc, high_accuracy, ws_in_smem;
     R rhofac, inv_p, inv_pm1;
@@ -275,25 +277,35 @@ __device__ __forceinline__ void pair3_k(R *__restrict__ d0, R *__restrict__ d1, 
     d1[K] = dk1;
     d2[K] = dk2;
     constexpr int half = (K + 1) / 2;
+    // Term order: every chain adds the term that involves the newest value (d[K], r2[K],
+    // c[K]) LAST.  hy_nbody_reg.cuh uses the same order: the two paths agree bit for bit.
     // r2[K] = 2 * sum_i sum_{j<half} d_i[j] d_i[K-j]  (+ sum_i d_i[K/2]^2 for even K)
     R q0 = 0, q1 = 0, q2 = 0;
-    if (half > 0) {
-        q0 = d0[0] * dk0;
-        q1 = d1[0] * dk1;
-        q2 = d2[0] * dk2;
+    if (half > 1) {
+        q0 = d0[1] * d0[K - 1];
+        q1 = d1[1] * d1[K - 1];
+        q2 = d2[1] * d2[K - 1];
     }
 #pragma unroll
-    for (int j = 1; j < half; ++j) {
+    for (int j = 2; j < half; ++j) {
         q0 = r_fma(d0[j], d0[K - j], q0);
         q1 = r_fma(d1[j], d1[K - j], q1);
         q2 = r_fma(d2[j], d2[K - j], q2);
     }
+    R e = 0;
+    if ((K & 1) == 0 && K > 0) {
+        const R m0 = d0[K / 2], m1 = d1[K / 2], m2 = d2[K / 2];
+        e = r_fma(m2, m2, r_fma(m1, m1, m0 * m0));
+    }
+    if (half > 0) {
+        q0 = r_fma(d0[0], dk0, q0);
+        q1 = r_fma(d1[0], dk1, q1);
+        q2 = r_fma(d2[0], dk2, q2);
+    }
     R acc = (q0 + q1) + q2;
     acc = acc + acc;
-    if ((K & 1) == 0) {
-        const R m0 = K ? d0[K / 2] : dk0, m1 = K ? d1[K / 2] : dk1, m2 = K ? d2[K / 2] : dk2;
-        acc += r_fma(m2, m2, r_fma(m1, m1, m0 * m0));
-    }
+    if (K == 0) e = r_fma(dk2, dk2, r_fma(dk1, dk1, dk0 * dk0));
+    if ((K & 1) == 0) acc += e;
     r2[K] = acc;
     R ck;
     if (K == 0) {
@@ -301,7 +313,7 @@ __device__ __forceinline__ void pair3_k(R *__restrict__ d0, R *__restrict__ d1, 
         ck = pow0<R>(acc, alpha);
     } else {
         const R al1 = (R)(alpha + 1.0), kal = (R)K * (R)alpha;
-        R s0 = (kal * acc) * c[0], s1 = 0, s2 = 0, s3 = 0;
+        R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
         for (int j = 1; j < K; ++j) {
             const R wgt = r_fma((R)(-j), al1, kal);
@@ -311,13 +323,25 @@ __device__ __forceinline__ void pair3_k(R *__restrict__ d0, R *__restrict__ d1, 
             if ((j & 3) == 2) s2 = r_fma(pr, c[j], s2);
             if ((j & 3) == 3) s3 = r_fma(pr, c[j], s3);
         }
-        ck = (((s0 + s1) + (s2 + s3)) * rkK) * (*inv);
+        const R tot = r_fma(kal * acc, c[0], (s0 + s1) + (s2 + s3));
+        ck = (tot * rkK) * (*inv);
     }
     c[K] = ck;
-    // t_i[K] = sum_{j<=K} d_i[j] c[K-j]; j = 0 uses c[K] from the register
-    R a0 = d0[0] * ck, a1 = d1[0] * ck, a2 = d2[0] * ck, b0 = 0, b1 = 0, b2 = 0;
+    // t_i[K] = sum_{j<=K} d_i[j] c[K-j]; j = K uses d[K] from the register, j = 0 (newest c) goes last
+    R a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    if (K >= 1) {
+        if (K & 1) {
+            b0 = dk0 * c[0];
+            b1 = dk1 * c[0];
+            b2 = dk2 * c[0];
+        } else {
+            a0 = dk0 * c[0];
+            a1 = dk1 * c[0];
+            a2 = dk2 * c[0];
+        }
+    }
 #pragma unroll
-    for (int j = 1; j <= K; ++j) {
+    for (int j = K - 1; j >= 1; --j) {
         const R cj = c[K - j];
         if (j & 1) {
             b0 = r_fma(d0[j], cj, b0);
@@ -329,9 +353,15 @@ __device__ __forceinline__ void pair3_k(R *__restrict__ d0, R *__restrict__ d1, 
             a2 = r_fma(d2[j], cj, a2);
         }
     }
-    t0 = a0 + b0;
-    t1 = a1 + b1;
-    t2 = a2 + b2;
+    if (K == 0) {
+        t0 = dk0 * ck;
+        t1 = dk1 * ck;
+        t2 = dk2 * ck;
+    } else {
+        t0 = r_fma(d0[0], ck, a0 + b0);
+        t1 = r_fma(d1[0], ck, a1 + b1);
+        t2 = r_fma(d2[0], ck, a2 + b2);
+    }
 }
 
 // One op of the program at order k on the trajectory column `w`.  `lt` is the
@@ -729,7 +759,10 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     return L;
 }
 
-template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
+// NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); the tape
+// interpreter is not instantiated.  NB = 0: tape interpreter.
+template <typename R, int G, bool SMEM, int NB = 0>
+__global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
@@ -778,7 +811,21 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(256, 1
     // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
 #define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j)])
     // unit jet [1, 0, ..., 0] (never changes)
-    for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
+    if constexpr (NB == 0)
+        for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
+    // register-resident N-body path: per-lane constants (pair, exchange slots, body)
+    NbrLane nl{};
+    if constexpr (NB > 0) {
+        const uint8_t *lb = reinterpret_cast<const uint8_t *>(s_imm + NBR_LANE0 + sub);
+        nl.xa = 6u * NBR_SP * lb[0];
+        nl.xb = 6u * NBR_SP * lb[1];
+        nl.ta = P.nb_tb_off + NBR_QS * lb[0] + 3u * lb[2];
+        nl.tb = P.nb_tb_off + NBR_QS * lb[1] + 3u * lb[3];
+        nl.body = sub < (uint32_t)NB;
+        const uint32_t bd = nl.body ? sub : 0u;
+        nl.xbody = 6u * NBR_SP * bd;
+        nl.tin = P.nb_tb_off + NBR_QS * bd;
+    }
 
     for (;;) {
         // ---- fetch the next trajectory for this group ----
@@ -843,25 +890,30 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(256, 1
             }
 
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
-            const DOp *lops = s_ops + sub;
-            const DTerm *lterms = s_terms + sub;
-            const uint32_t n_ph = P.pd.n_phases;
-            // (with events, one extra sweep at order p over the event-function ops only)
-            const uint32_t k_end = d.n_events ? p + 1 : p;
+            if constexpr (NB > 0) {
+                nbr_jets<R, NB, NBR_PMAX>(w, s_imm + NBR_CS * (nl.body ? sub : 0u), nl, gmask, p);
+            } else {
+                const DOp *lops = s_ops + sub;
+                const DTerm *lterms = s_terms + sub;
+                const uint32_t n_ph = P.pd.n_phases;
+                // (with events, one extra sweep at order p over the event-function ops only)
+                const uint32_t k_end = d.n_events ? p + 1 : p;
 #pragma unroll 1
-            for (uint32_t k = 0; k < k_end; ++k) {
-                const bool ev_sweep = k == p;
+                for (uint32_t k = 0; k < k_end; ++k) {
+                    const bool ev_sweep = k == p;
 #pragma unroll 1
-                for (uint32_t ph = 0; ph < n_ph; ++ph) {
-                    const uint32_t e = s_phase[ph + 1];
+                    for (uint32_t ph = 0; ph < n_ph; ++ph) {
+                        const uint32_t e = s_phase[ph + 1];
 #pragma unroll 1
-                    for (uint32_t i = s_phase[ph]; i < e; ++i) {
-                        const DOp o = lops[i * G];
-                        if (ev_sweep && (!(o.flags & HY_OPF_EVENT) || (o.flags & HY_OPF_SVD) || o.opcode == HY_OP_SVD))
-                            continue;
-                        exec_op<R, G>(o, lterms, w, s_rk, s_imm, k, hi, gj, P1);
+                        for (uint32_t i = s_phase[ph]; i < e; ++i) {
+                            const DOp o = lops[i * G];
+                            if (ev_sweep &&
+                                (!(o.flags & HY_OPF_EVENT) || (o.flags & HY_OPF_SVD) || o.opcode == HY_OP_SVD))
+                                continue;
+                            exec_op<R, G>(o, lterms, w, s_rk, s_imm, k, hi, gj, P1);
+                        }
+                        if (G > 1) __syncwarp(gmask);
                     }
-                    if (G > 1) __syncwarp(gmask);
                 }
             }
 
@@ -893,8 +945,18 @@ template <typename R, int G, bool SMEM> __global__ void __launch_bounds__(256, 1
                 h = n0 + n1 + n2; // NaN
             } else {
                 const R num = n0 < (R)1 ? (R)1 : n0;
-                const R rho_p = r_pow(num / n2, P.inv_p);
-                const R rho_pm1 = r_pow(num / n1, P.inv_pm1);
+                R rho_p, rho_pm1;
+                if (G > 1) {
+                    // one pow call for both radii: even lanes take order p, odd lanes order p-1
+                    const bool odd = sub & 1u;
+                    const R r = r_pow(num / (odd ? n1 : n2), odd ? P.inv_pm1 : P.inv_p);
+                    const R o = shfl_xor<R>(gmask, r, 1);
+                    rho_p = odd ? o : r;
+                    rho_pm1 = odd ? r : o;
+                } else {
+                    rho_p = r_pow(num / n2, P.inv_p);
+                    rho_pm1 = r_pow(num / n1, P.inv_pm1);
+                }
                 h = (rho_p < rho_pm1 ? rho_p : rho_pm1) * P.rhofac;
             }
             if (signbit(lim)) h = -h;

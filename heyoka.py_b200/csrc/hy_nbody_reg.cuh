@@ -1,0 +1,228 @@
+// hy_nbody_reg.cuh - REGISTER-RESIDENT jets for pairwise central-force tapes
+// (the Newtonian N-body problem, BASELINE config 2).
+//
+// The tape interpreter in hy_kernels.cuh reads every convolution operand from
+// shared memory (1.3 loads per DFMA), which caps it at ~1/8 of the FP64 pipe.
+// When hy_create recognises the tape of an N-body system (hy_nbody_match.hpp)
+// the same persistent kernel computes the jets with this file instead:
+//
+//  * lane s of the G-lane group owns body pair s = (A, B):  d = x_A - x_B,
+//    r2 = d.d, w = r2^(-3/2), t = d*w.  The jets of d (3 components), r2 and w
+//    live in REGISTERS for the whole step: the order loop is fully unrolled
+//    (compile-time K), so every operand is a register and every weight of the
+//    power recurrence an immediate.  5(p-1) values per lane = 190 registers in
+//    FP64 at order 20.
+//  * the first NB lanes of the group double as BODY lanes: after each order
+//    they gather the 3(NB-1) pair products of their body from a small
+//    shared-memory exchange buffer, form the acceleration (the tape's LINCOMB,
+//    same term order), and write v[k+1] and x[k+2] into the state jets, which
+//    live in shared memory (only the Horner update reads their history).
+//  * ONE __syncwarp per order: t[k] feeds d[k+2], not d[k+1], so the gather of
+//    order k overlaps the convolutions of order k+1 (double-buffered exchange).
+//
+// Arithmetic: the same recurrences, term order and roundings as the tape
+// interpreter's fused pair op (pair3_k) + LINCOMB + SVD - the two paths agree
+// bit for bit (tests/test_gpu_nbody_reg.py).
+//
+// Reference path replaced: the JIT-compiled taylor_step of
+// hey::taylor_adaptive_batch<T> ([UPSTREAM], called from
+// /root/reference/heyoka/expose_batch_integrators.cpp:233-314).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hy {
+
+constexpr int NBR_PMAX = 20;   // highest Taylor order of the register-resident path
+constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
+constexpr int NBR_QS = 16;     // exchange row stride per body: 3*(NB-1) <= 15, padded to 16
+constexpr int NBR_SP = NBR_PMAX + 1; // state jet stride in the trajectory column
+
+// Host-built description of a matched N-body tape (hy_nbody_match.hpp).  It travels in
+// the program's immediate table (shared memory):
+//   imm[body * NBR_CS + q]   coefficient of term q of the body's acceleration sums
+//   imm[NBR_LANE0 + s]       8 bytes: pa, pb, qa, qb of lane s (pair: d = x[pa] - x[pb];
+//                            qa/qb: term slot of the pair in body pa's / pb's sums)
+constexpr int NBR_CS = 8;
+constexpr int NBR_LANE0 = NBR_MAXB * NBR_CS;
+constexpr int NBR_NIMM = NBR_LANE0 + 16;
+
+// ---- one order of one pair, everything in registers ----
+// d*, r2, c: jets (orders 0..PMAX-2 are re-read later); dk*: d[K] (just formed).
+// Term order (shared with pair3_k in hy_kernels.cuh): every chain adds the term
+// that involves the newest value LAST, so the chains start before it arrives.
+template <typename R, int K, int PMAX>
+__device__ __forceinline__ void nbr_pair_order(R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX], R (&r2)[PMAX],
+                                               R (&c)[PMAX], R &inv, const R dk0, const R dk1, const R dk2, R &t0,
+                                               R &t1, R &t2)
+{
+    constexpr int half = (K + 1) / 2;
+    // r2[K] = 2 * sum_i sum_{j<half} d_i[j] d_i[K-j]  (+ sum_i d_i[K/2]^2 for even K)
+    R q0 = 0, q1 = 0, q2 = 0;
+    if constexpr (half > 1) {
+        q0 = d0[1] * d0[K - 1];
+        q1 = d1[1] * d1[K - 1];
+        q2 = d2[1] * d2[K - 1];
+#pragma unroll
+        for (int j = 2; j < half; ++j) {
+            q0 = fma(d0[j], d0[K - j], q0);
+            q1 = fma(d1[j], d1[K - j], q1);
+            q2 = fma(d2[j], d2[K - j], q2);
+        }
+    }
+    R e = 0;
+    if constexpr ((K & 1) == 0 && K > 0) e = fma(d2[K / 2], d2[K / 2], fma(d1[K / 2], d1[K / 2], d0[K / 2] * d0[K / 2]));
+    if constexpr (half > 0) {
+        q0 = fma(d0[0], dk0, q0);
+        q1 = fma(d1[0], dk1, q1);
+        q2 = fma(d2[0], dk2, q2);
+    }
+    R acc = (q0 + q1) + q2;
+    acc = acc + acc;
+    if constexpr (K == 0) e = fma(dk2, dk2, fma(dk1, dk1, dk0 * dk0));
+    if constexpr ((K & 1) == 0) acc += e;
+    // w[K] by the power recurrence, alpha = -3/2: weights K*alpha - j*(alpha+1) are immediates
+    R ck;
+    if constexpr (K == 0) {
+        inv = (R)1 / acc;
+        ck = (R)1 / (acc * sqrt(acc));
+    } else {
+        constexpr double alpha = -1.5, al1 = alpha + 1.0, kal = (double)K * alpha;
+        R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            const R pr = (R)(kal - (double)j * al1) * r2[K - j];
+            if ((j & 3) == 0) s0 = fma(pr, c[j], s0);
+            if ((j & 3) == 1) s1 = fma(pr, c[j], s1);
+            if ((j & 3) == 2) s2 = fma(pr, c[j], s2);
+            if ((j & 3) == 3) s3 = fma(pr, c[j], s3);
+        }
+        const R tot = fma((R)kal * acc, c[0], (s0 + s1) + (s2 + s3));
+        ck = (tot * (R)(1.0 / (double)K)) * inv;
+    }
+    // t_i[K] = sum_{j<=K} d_i[j] w[K-j]; the j = 0 term (newest w) goes last
+    R a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    if constexpr (K >= 1) {
+        // j = K uses d[K] from the register
+        if constexpr (K & 1) {
+            b0 = dk0 * c[0];
+            b1 = dk1 * c[0];
+            b2 = dk2 * c[0];
+        } else {
+            a0 = dk0 * c[0];
+            a1 = dk1 * c[0];
+            a2 = dk2 * c[0];
+        }
+#pragma unroll
+        for (int j = K - 1; j >= 1; --j) {
+            const R cj = c[K - j];
+            if (j & 1) {
+                b0 = fma(d0[j], cj, b0);
+                b1 = fma(d1[j], cj, b1);
+                b2 = fma(d2[j], cj, b2);
+            } else {
+                a0 = fma(d0[j], cj, a0);
+                a1 = fma(d1[j], cj, a1);
+                a2 = fma(d2[j], cj, a2);
+            }
+        }
+    }
+    if constexpr (K == 0) {
+        t0 = dk0 * ck;
+        t1 = dk1 * ck;
+        t2 = dk2 * ck;
+    } else {
+        t0 = fma(d0[0], ck, a0 + b0);
+        t1 = fma(d1[0], ck, a1 + b1);
+        t2 = fma(d2[0], ck, a2 + b2);
+    }
+    if constexpr (K < PMAX - 1) {
+        d0[K] = dk0;
+        d1[K] = dk1;
+        d2[K] = dk2;
+        r2[K] = acc;
+        c[K] = ck;
+    }
+}
+
+// Per-lane constants of the register-resident path.
+// Element offsets into the trajectory column `w` (shared memory), so that every access
+// is `LDS/STS [base + immediate]`.
+struct NbrLane {
+    uint32_t xa, xb;   // state jets of the pair's bodies (x component, order 0)
+    uint32_t ta, tb;   // exchange slots the pair writes (buffer 0, component 0)
+    uint32_t xbody;    // state jets of this lane's body (lanes < NB)
+    uint32_t tin;      // exchange row of this lane's body (buffer 0)
+    bool body;
+};
+
+template <typename R, int NB, int PMAX, int K> struct NbrOrders {
+    static __device__ __forceinline__ void run(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const unsigned gmask, const uint32_t p,
+                                               R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX], R (&r2)[PMAX],
+                                               R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
+    {
+        if (K >= p) return;
+        constexpr int SP = NBR_SP, QS = NBR_QS, NQ = NB - 1;
+        constexpr int buf = (K & 1) * (NBR_MAXB * QS);
+        R t0, t1, t2;
+        nbr_pair_order<R, K, PMAX>(d0, d1, d2, r2, c, inv, dk0, dk1, dk2, t0, t1, t2);
+        w[L.ta + buf + 0] = t0;
+        w[L.ta + buf + 1] = t1;
+        w[L.ta + buf + 2] = t2;
+        w[L.tb + buf + 0] = t0;
+        w[L.tb + buf + 1] = t1;
+        w[L.tb + buf + 2] = t2;
+        __syncwarp(gmask);
+        // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago)
+        if (K + 1 < p) {
+            dk0 = w[L.xa + 0 * SP + K + 1] - w[L.xb + 0 * SP + K + 1];
+            dk1 = w[L.xa + 1 * SP + K + 1] - w[L.xb + 1 * SP + K + 1];
+            dk2 = w[L.xa + 2 * SP + K + 1] - w[L.xb + 2 * SP + K + 1];
+        }
+        if (L.body) {
+            // acceleration of this body at order K: the tape's LINCOMB (term order kept),
+            // then v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
+            R a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const R cf = (R)coef[q];
+                a0 = fma(cf, w[L.tin + buf + 3 * q + 0], a0);
+                a1 = fma(cf, w[L.tin + buf + 3 * q + 1], a1);
+                a2 = fma(cf, w[L.tin + buf + 3 * q + 2], a2);
+            }
+            constexpr R rk1 = (R)(1.0 / (double)(K + 1)), rk2 = (R)(1.0 / (double)(K + 2));
+            const R v0 = a0 * rk1, v1 = a1 * rk1, v2 = a2 * rk1;
+            w[L.xbody + 3 * SP + K + 1] = v0;
+            w[L.xbody + 4 * SP + K + 1] = v1;
+            w[L.xbody + 5 * SP + K + 1] = v2;
+            if (K + 2 <= p) {
+                w[L.xbody + 0 * SP + K + 2] = v0 * rk2;
+                w[L.xbody + 1 * SP + K + 2] = v1 * rk2;
+                w[L.xbody + 2 * SP + K + 2] = v2 * rk2;
+            }
+        }
+        if constexpr (K + 1 < PMAX) NbrOrders<R, NB, PMAX, K + 1>::run(w, coef, L, gmask, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+    }
+};
+
+// All orders 0..p-1 of one step.  On entry the order-0 rows of the state jets
+// hold the state (visible to the whole group); on exit rows 0..p are complete.
+template <typename R, int NB, int PMAX>
+__device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const unsigned gmask, const uint32_t p)
+{
+    constexpr int SP = NBR_SP;
+    R d0[PMAX], d1[PMAX], d2[PMAX], r2[PMAX], c[PMAX], inv = 0;
+    // x[1] = v[0]
+    if (L.body) {
+        w[L.xbody + 0 * SP + 1] = w[L.xbody + 3 * SP];
+        w[L.xbody + 1 * SP + 1] = w[L.xbody + 4 * SP];
+        w[L.xbody + 2 * SP + 1] = w[L.xbody + 5 * SP];
+    }
+    const R dk0 = w[L.xa + 0 * SP] - w[L.xb + 0 * SP];
+    const R dk1 = w[L.xa + 1 * SP] - w[L.xb + 1 * SP];
+    const R dk2 = w[L.xa + 2 * SP] - w[L.xb + 2 * SP];
+    NbrOrders<R, NB, PMAX, 0>::run(w, coef, L, gmask, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+    __syncwarp(gmask);
+}
+
+} // namespace hy

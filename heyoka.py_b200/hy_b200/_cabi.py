@@ -50,6 +50,7 @@ class launch_info_t(C.Structure):
             "ws_in_smem",
             "n_sm",
             "regs_per_thread",
+            "kernel_variant",
         )
     ]
 

@@ -223,6 +223,8 @@ typedef struct hy_launch_info {
     uint32_t ws_in_smem;     /* 1: jets in shared memory, 0: global fallback */
     uint32_t n_sm;
     uint32_t regs_per_thread;
+    uint32_t kernel_variant; /* 0: tape interpreter; N > 0: register-resident
+                                N-body kernel for N bodies (hy_nbody_reg.cuh)    */
 } hy_launch_info;
 int hy_get_launch_info(hy_ctx *ctx, hy_launch_info *info);
 
