@@ -816,11 +816,12 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
     // register-resident N-body path: per-lane constants (pair, exchange slots, body)
     NbrLane nl{};
     if constexpr (NB > 0) {
-        const uint8_t *lb = reinterpret_cast<const uint8_t *>(s_imm + NBR_LANE0 + sub);
-        nl.xa = 6u * NBR_SP * lb[0];
-        nl.xb = 6u * NBR_SP * lb[1];
-        nl.ta = P.nb_tb_off + NBR_QS * lb[0] + 3u * lb[2];
-        nl.tb = P.nb_tb_off + NBR_QS * lb[1] + 3u * lb[3];
+        // lane record (hy_nbody_match.hpp): 4 x uint16 = body a, body b, exchange slot a, exchange slot b
+        const uint2 lr = *reinterpret_cast<const uint2 *>(s_imm + NBR_LANE0 + sub);
+        nl.xa = 6u * NBR_SP * (lr.x & 0xffffu);
+        nl.xb = 6u * NBR_SP * (lr.x >> 16);
+        nl.ta = P.nb_tb_off + (lr.y & 0xffffu);
+        nl.tb = P.nb_tb_off + (lr.y >> 16);
         nl.body = sub < (uint32_t)NB;
         const uint32_t bd = nl.body ? sub : 0u;
         nl.xbody = 6u * NBR_SP * bd;

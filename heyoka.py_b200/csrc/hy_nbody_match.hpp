@@ -158,8 +158,11 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
     for (uint32_t s = 0; s < 16; ++s) {
         const uint32_t pr = s < NP ? s : 0; // idle lanes mirror pair 0 (they store identical values)
         if (qa[pr] < 0 || qb[pr] < 0) return false;
-        uint8_t bytes[8] = {(uint8_t)pairs[pr].a, (uint8_t)pairs[pr].b, (uint8_t)qa[pr], (uint8_t)qb[pr], 0, 0, 0, 0};
-        std::memcpy(&out.imm[NBR_LANE0 + s], bytes, 8);
+        // lane record: body a, body b, exchange slots (element offsets inside the exchange buffer)
+        const uint16_t rec[4] = {(uint16_t)pairs[pr].a, (uint16_t)pairs[pr].b,
+                                 (uint16_t)(NBR_QS * pairs[pr].a + 3 * qa[pr]),
+                                 (uint16_t)(NBR_QS * pairs[pr].b + 3 * qb[pr])};
+        std::memcpy(&out.imm[NBR_LANE0 + s], rec, 8);
     }
     return true;
 }

@@ -35,15 +35,15 @@ namespace hy {
 
 constexpr int NBR_PMAX = 20;   // highest Taylor order of the register-resident path
 constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
-constexpr int NBR_QS = 16;     // exchange row stride per body: 3*(NB-1) <= 15, padded to 16
+constexpr int NBR_QS = 17;     // exchange row stride per body (3*(NB-1) <= 15 used): odd => the body lanes read conflict-free
 constexpr int NBR_SP = NBR_PMAX + 1; // state jet stride in the trajectory column
 
 // Host-built description of a matched N-body tape (hy_nbody_match.hpp).  It travels in
 // the program's immediate table (shared memory):
 //   imm[body * NBR_CS + q]   coefficient of term q of the body's acceleration sums
-//   imm[NBR_LANE0 + s]       8 bytes: pa, pb, qa, qb of lane s (pair: d = x[pa] - x[pb];
-//                            qa/qb: term slot of the pair in body pa's / pb's sums)
-constexpr int NBR_CS = 8;
+//   imm[NBR_LANE0 + s]       4 x uint16 of lane s: bodies a, b of its pair (d = x[a] - x[b]) and the
+//                            offsets of the two exchange slots the pair writes (NBR_QS * body + 3 * term)
+constexpr int NBR_CS = 9; // odd stride: the body lanes read their coefficient rows conflict-free
 constexpr int NBR_LANE0 = NBR_MAXB * NBR_CS;
 constexpr int NBR_NIMM = NBR_LANE0 + 16;
 
@@ -174,7 +174,8 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
         w[L.tb + buf + 2] = t2;
         __syncwarp(gmask);
         // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago)
-        if (K + 1 < p) {
+        // (rows up to NBR_PMAX exist whatever p is: no run-time guard on K + 1 < p)
+        if constexpr (K + 1 < PMAX) {
             dk0 = w[L.xa + 0 * SP + K + 1] - w[L.xb + 0 * SP + K + 1];
             dk1 = w[L.xa + 1 * SP + K + 1] - w[L.xb + 1 * SP + K + 1];
             dk2 = w[L.xa + 2 * SP + K + 1] - w[L.xb + 2 * SP + K + 1];
@@ -195,7 +196,7 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
             w[L.xbody + 3 * SP + K + 1] = v0;
             w[L.xbody + 4 * SP + K + 1] = v1;
             w[L.xbody + 5 * SP + K + 1] = v2;
-            if (K + 2 <= p) {
+            if constexpr (K + 2 <= PMAX) {
                 w[L.xbody + 0 * SP + K + 2] = v0 * rk2;
                 w[L.xbody + 1 * SP + K + 2] = v1 * rk2;
                 w[L.xbody + 2 * SP + K + 2] = v2 * rk2;

@@ -24,7 +24,7 @@ for ln in dis:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur_line = int(m.group(2)) if m.group(1).endswith("hy_kernels.cuh") else -1
+        cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);", ln)
     if m:
@@ -35,6 +35,7 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
 agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
+opagg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
 base = None
 tot = [0, 0, 0, 0, 0]
 for r in rows[hi + 1:]:
@@ -44,7 +45,9 @@ for r in rows[hi + 1:]:
     if base is None:
         base = a
     off = a - base
-    line = addr2line.get(off, (None, ""))[0]
+    line, sass = addr2line.get(off, ((None, 0), ""))
+    opc = sass.split()[0] if sass and not sass.startswith("@") else (sass.split()[1] if len(sass.split()) > 1 else "?")
+    opc = opc.split(".")[0]
     def f(name):
         try:
             return float(r[col[name]] or 0)
@@ -53,10 +56,26 @@ for r in rows[hi + 1:]:
     v = [f("Instructions Executed"), f("# Samples"), f("L1 Wavefronts Shared"), f("L1 Wavefronts Shared Excessive"), f("Thread Instructions Executed")]
     for i in range(5):
         agg[line][i] += v[i]
+        opagg[opc][i] += v[i]
         tot[i] += v[i]
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "heyoka.py_b200", "csrc", "hy_kernels.cuh")).read().splitlines()
+srcdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "heyoka.py_b200", "csrc")
+srcs = {}
+def src_line(fl):
+    f, l = fl
+    if f is None:
+        return "?"
+    if f not in srcs:
+        try:
+            srcs[f] = open(os.path.join(srcdir, f)).read().splitlines()
+        except Exception:
+            srcs[f] = []
+    t = srcs[f]
+    return "%s:%d  %s" % (f, l, t[l - 1].strip()[:80] if 0 < l <= len(t) else "")
 print("total inst %.3g samples %d smem wavefronts %.3g excessive %.3g" % (tot[0], tot[1], tot[2], tot[3]))
 print("%6s %7s %7s %7s %7s  %s" % ("line", "inst%", "samp%", "wf%", "exc%", "source"))
 for line, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    s = src[line - 1].strip()[:90] if line and 0 < line <= len(src) else str(line)
-    print("%6s %7.2f %7.2f %7.2f %7.2f  %s" % (line, 100 * v[0] / tot[0], 100 * v[1] / max(tot[1], 1), 100 * v[2] / max(tot[2], 1), 100 * v[3] / max(tot[3], 1), s))
+    s = src_line(line)
+    print("%6s %7.2f %7.2f %7.2f %7.2f  %s" % ("", 100 * v[0] / tot[0], 100 * v[1] / max(tot[1], 1), 100 * v[2] / max(tot[2], 1), 100 * v[3] / max(tot[3], 1), s))
+print("per opcode: inst% samp% active-threads/inst")
+for opc, v in sorted(opagg.items(), key=lambda kv: -kv[1][0])[:25]:
+    print("%12s %7.2f %7.2f %6.1f" % (opc, 100 * v[0] / tot[0], 100 * v[1] / max(tot[1], 1), v[4] / max(v[0], 1)))
