@@ -187,13 +187,14 @@ int choose_geometry(hy_ctx *c)
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = nbm.n_pairs;
         pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
-        // column stride: 16-byte aligned rows, the two trajectories of a warp in different bank halves
-        const uint32_t RS = (pr.ws_len + 15u) / 16u * 16u + 8u;
+        // column stride
+        // (= 9 mod 16: the 2 x NB body lanes of a warp, which sit in one half-warp, hit distinct banks)
+        const uint32_t RS = (pr.ws_len + 15u) / 16u * 16u + 9u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
-        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 1) {
+        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 2) {
             bestG = 16;
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 16u);
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 16u) & ~1u;
             bestRS = RS;
             best_smem = true;
             best = pr;
@@ -236,6 +237,7 @@ int choose_geometry(hy_ctx *c)
     // Do not keep more trajectories resident than the batch can feed.
     uint32_t per_cta_needed = std::max(1u, (c->B + li.n_sm - 1) / li.n_sm);
     T = std::max(1u, std::min(T, per_cta_needed));
+    if (li.kernel_variant) T = (T + 1u) & ~1u; // whole warps: the two trajectories of a warp step in lockstep
     li.group = G;
     li.traj_per_cta = T;
     li.threads = ((T * G + 31) / 32) * 32;

@@ -800,7 +800,8 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
     const uint32_t slot = threadIdx.x / G; // trajectory slot in this CTA
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
     const uint32_t par_off = P.pd.par_off, one_off = P.pd.one_off;
-    if (slot >= P.T) return; // whole groups only: safe w.r.t. group-mask syncs
+    // whole groups only: safe w.r.t. group-mask syncs (NB > 0: T is even, whole warps run)
+    if (slot >= P.T) return;
     R *w;
     if (SMEM)
         w = reinterpret_cast<R *>(smem_raw + L.off_ws) + (size_t)slot * RS;
@@ -818,81 +819,109 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
     if constexpr (NB > 0) {
         // lane record (hy_nbody_match.hpp): 4 x uint16 = body a, body b, exchange slot a, exchange slot b
         const uint2 lr = *reinterpret_cast<const uint2 *>(s_imm + NBR_LANE0 + sub);
-        nl.xa = 6u * NBR_SP * (lr.x & 0xffffu);
-        nl.xb = 6u * NBR_SP * (lr.x >> 16);
-        nl.ta = P.nb_tb_off + (lr.y & 0xffffu);
-        nl.tb = P.nb_tb_off + (lr.y >> 16);
-        nl.body = sub < (uint32_t)NB;
-        const uint32_t bd = nl.body ? sub : 0u;
-        nl.xbody = 6u * NBR_SP * bd;
-        nl.tin = P.nb_tb_off + NBR_QS * bd;
+        nl.xa = (int32_t)(6u * NBR_SP * (lr.x & 0xffffu));
+        nl.xb = (int32_t)(6u * NBR_SP * (lr.x >> 16));
+        nl.ta = (int32_t)(P.nb_tb_off + (lr.y & 0xffffu));
+        nl.tb = (int32_t)(P.nb_tb_off + (lr.y >> 16));
+        // Body lanes: lanes 0..2NB-1 of the WARP serve the NB bodies of its two trajectories
+        // (all in one half-warp: a 64-bit shared access costs one wavefront per active half-warp).
+        nl.body = lane < 2u * NB;
+        const uint32_t bt = nl.body ? lane / NB : 0u, bd = nl.body ? lane % NB : 0u;
+        const int32_t col = (bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
+        nl.xbody = col + (int32_t)(6u * NBR_SP * bd);
+        nl.tin = col + (int32_t)(P.nb_tb_off + NBR_QS * bd);
+        nl.coef = (int32_t)(NBR_CS * bd);
     }
 
+    // Persistent loop: every iteration is ONE step of the group's current trajectory (or the
+    // fetch of a new one).  NB > 0: the two trajectories of a warp step in lockstep (the jets are a
+    // warp-wide phase); a half-warp without a live trajectory idles through it on stale data.
+    bool have = false;
+    unsigned int traj = 0;
+    R hi = 0, lo = 0, mdt = 0, tf_hi = 0, tf_lo = 0;
+    uint32_t gi = 0; // next grid point to emit (MODE_GRID)
+    uint32_t cc = 0; // recorded continuous-output steps
+    long long oc = HY_OUTCOME_TIME_LIMIT;
+    R mn = r_inf<R>(), mx = 0, h = 0;
+    unsigned long long ns = 0;
     for (;;) {
-        // ---- fetch the next trajectory for this group ----
-        unsigned int traj = 0;
-        if (sub == 0) traj = atomicAdd(P.counter, 1u);
-        if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
-        if (traj >= P.B) break;
-
-        for (uint32_t i = sub; i < n; i += G) {
-            const R x0 = P.state[(size_t)i * P.B + traj];
-            w[s_srow[i]] = x0;
-            if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = x0;
-        }
-        for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i] = P.pars[(size_t)i * P.B + traj];
-        R hi = P.t_hi[traj], lo = P.t_lo[traj];
-        R mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
-        R tf_hi = 0, tf_lo = 0;
-        if (P.mode == MODE_FOR) {
-            tf_hi = hi;
-            tf_lo = lo;
-            time_add(tf_hi, tf_lo, P.tf[traj]);
-        } else if (P.mode == MODE_UNTIL) {
-            tf_hi = P.tf[traj];
-        } else if (P.mode == MODE_GRID) {
-            tf_hi = P.grid[(size_t)(P.grid_k - 1) * P.B + traj];
-        }
-        uint32_t gi = 0;   // next grid point to emit (MODE_GRID)
-        uint32_t cc = 0;   // recorded continuous-output steps
-        if (P.mode == MODE_GRID) {
-            // Grid points at (or before) the starting time take the current state.
-            const R dir = tf_hi - hi;
-            while (gi < P.grid_k) {
-                const R g = P.grid[(size_t)gi * P.B + traj];
-                const R dg = (g - hi) - lo;
-                if ((dir >= (R)0 && dg > (R)0) || (dir < (R)0 && dg < (R)0)) break;
-                for (uint32_t i = sub; i < n; i += G)
-                    P.gout[((size_t)gi * n + i) * P.B + traj] = w[s_srow[i]];
-                ++gi;
-            }
-        }
-        if (P.cout_tcs && sub == 0) {
-            P.cout_thi[traj] = hi;
-            P.cout_tlo[traj] = lo;
-        }
-        if (P.mode != MODE_STEP) mdt = r_abs(mdt);
-        long long oc = HY_OUTCOME_TIME_LIMIT;
-        R mn = r_inf<R>(), mx = 0, h = 0;
-        unsigned long long ns = 0;
-        if (G > 1) __syncwarp(gmask);
-
-        for (;;) {
-            R rem = 0, lim;
-            if (P.mode == MODE_STEP) {
-                lim = P.mdt ? mdt : (P.backward ? -r_inf<R>() : r_inf<R>());
-            } else {
-                rem = time_sub(tf_hi, tf_lo, hi, lo);
-                if (rem == (R)0) {
-                    oc = HY_OUTCOME_TIME_LIMIT;
-                    break;
+        if (!have) {
+            // ---- fetch the next trajectory for this group ----
+            if (sub == 0) traj = atomicAdd(P.counter, 1u);
+            if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
+            if (traj < P.B) {
+                have = true;
+                for (uint32_t i = sub; i < n; i += G) {
+                    const R x0 = P.state[(size_t)i * P.B + traj];
+                    w[s_srow[i]] = x0;
+                    if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = x0;
                 }
-                lim = r_abs(rem) < mdt ? rem : r_copysign(mdt, rem);
+                for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i] = P.pars[(size_t)i * P.B + traj];
+                hi = P.t_hi[traj];
+                lo = P.t_lo[traj];
+                mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
+                tf_hi = 0;
+                tf_lo = 0;
+                if (P.mode == MODE_FOR) {
+                    tf_hi = hi;
+                    tf_lo = lo;
+                    time_add(tf_hi, tf_lo, P.tf[traj]);
+                } else if (P.mode == MODE_UNTIL) {
+                    tf_hi = P.tf[traj];
+                } else if (P.mode == MODE_GRID) {
+                    tf_hi = P.grid[(size_t)(P.grid_k - 1) * P.B + traj];
+                }
+                gi = 0;
+                cc = 0;
+                if (P.mode == MODE_GRID) {
+                    // Grid points at (or before) the starting time take the current state.
+                    const R dir = tf_hi - hi;
+                    while (gi < P.grid_k) {
+                        const R g = P.grid[(size_t)gi * P.B + traj];
+                        const R dg = (g - hi) - lo;
+                        if ((dir >= (R)0 && dg > (R)0) || (dir < (R)0 && dg < (R)0)) break;
+                        for (uint32_t i = sub; i < n; i += G)
+                            P.gout[((size_t)gi * n + i) * P.B + traj] = w[s_srow[i]];
+                        ++gi;
+                    }
+                }
+                if (P.cout_tcs && sub == 0) {
+                    P.cout_thi[traj] = hi;
+                    P.cout_tlo[traj] = lo;
+                }
+                if (P.mode != MODE_STEP) mdt = r_abs(mdt);
+                oc = HY_OUTCOME_TIME_LIMIT;
+                mn = r_inf<R>();
+                mx = 0;
+                h = 0;
+                ns = 0;
+                if (G > 1) __syncwarp(gmask);
             }
+        }
+        if constexpr (NB > 0) {
+            if (!__any_sync(0xffffffffu, have)) break;
+        } else {
+            if (!have) break;
+        }
 
+        bool fin = false; // the trajectory ends with this iteration
+        R rem = 0, lim = 0;
+        if (P.mode == MODE_STEP) {
+            lim = P.mdt ? mdt : (P.backward ? -r_inf<R>() : r_inf<R>());
+        } else {
+            rem = time_sub(tf_hi, tf_lo, hi, lo);
+            if (rem == (R)0) {
+                oc = HY_OUTCOME_TIME_LIMIT;
+                fin = true; // already there: nothing to integrate
+            }
+            lim = r_abs(rem) < mdt ? rem : r_copysign(mdt, rem);
+        }
+        const bool stepping = have && !fin;
+
+        if (NB > 0 || stepping) {
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
             if constexpr (NB > 0) {
-                nbr_jets<R, NB, NBR_PMAX>(w, s_imm + NBR_CS * (nl.body ? sub : 0u), nl, gmask, p);
+                nbr_jets<R, NB, NBR_PMAX>(w, s_imm + nl.coef, nl, p);
             } else {
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;
@@ -918,6 +947,9 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
                 }
             }
 
+        }
+
+        if (stepping) {
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
             for (uint32_t i = sub; i < n + d.n_events; i += G) {
@@ -1066,49 +1098,45 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
                 }
             }
 
-            if (P.mode == MODE_STEP) {
+            // ---- does the trajectory end here? ----
+            if (P.mode == MODE_STEP || so == HY_OUTCOME_ERR_NF_STATE || term_ev >= 0) {
+                // single step / non-finite state / terminal event (the host may resume the lane)
                 oc = so;
-                break;
-            }
-            if (so == HY_OUTCOME_ERR_NF_STATE) {
-                oc = so;
-                break;
-            }
-            if (term_ev >= 0) { // terminal event: the lane stops here (the host may resume it)
-                oc = so;
-                break;
-            }
-            if (so == HY_OUTCOME_SUCCESS) {
-                const R ah = r_abs(h);
-                if (ah < mn) mn = ah;
-                if (ah > mx) mx = ah;
-            }
-            if (so == HY_OUTCOME_TIME_LIMIT && h == rem) {
-                hi = tf_hi;
-                lo = tf_lo;
-                oc = HY_OUTCOME_TIME_LIMIT;
-                break;
-            }
-            if (P.max_steps && ns >= P.max_steps) {
-                oc = HY_OUTCOME_STEP_LIMIT;
-                break;
+                fin = true;
+            } else {
+                if (so == HY_OUTCOME_SUCCESS) {
+                    const R ah = r_abs(h);
+                    if (ah < mn) mn = ah;
+                    if (ah > mx) mx = ah;
+                }
+                if (so == HY_OUTCOME_TIME_LIMIT && h == rem) {
+                    hi = tf_hi;
+                    lo = tf_lo;
+                    oc = HY_OUTCOME_TIME_LIMIT;
+                    fin = true;
+                } else if (P.max_steps && ns >= P.max_steps) {
+                    oc = HY_OUTCOME_STEP_LIMIT;
+                    fin = true;
+                }
             }
             if (G > 1) __syncwarp(gmask);
         }
 
         // ---- retire the trajectory ----
-        if (G > 1) __syncwarp(gmask);
-        for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[s_srow[i]];
-        if (sub == 0) {
-            P.t_hi[traj] = hi;
-            P.t_lo[traj] = lo;
-            P.last_h[traj] = h;
-            P.outcome[traj] = oc;
-            P.min_h[traj] = mn;
-            P.max_h[traj] = mx;
-            P.n_steps[traj] = ns;
+        if (have && fin) {
+            for (uint32_t i = sub; i < n; i += G) P.state[(size_t)i * P.B + traj] = w[s_srow[i]];
+            if (sub == 0) {
+                P.t_hi[traj] = hi;
+                P.t_lo[traj] = lo;
+                P.last_h[traj] = h;
+                P.outcome[traj] = oc;
+                P.min_h[traj] = mn;
+                P.max_h[traj] = mx;
+                P.n_steps[traj] = ns;
+            }
+            have = false;
+            if (G > 1) __syncwarp(gmask);
         }
-        if (G > 1) __syncwarp(gmask);
     }
 }
 

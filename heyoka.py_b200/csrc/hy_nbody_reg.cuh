@@ -149,15 +149,16 @@ __device__ __forceinline__ void nbr_pair_order(R (&d0)[PMAX], R (&d1)[PMAX], R (
 // Element offsets into the trajectory column `w` (shared memory), so that every access
 // is `LDS/STS [base + immediate]`.
 struct NbrLane {
-    uint32_t xa, xb;   // state jets of the pair's bodies (x component, order 0)
-    uint32_t ta, tb;   // exchange slots the pair writes (buffer 0, component 0)
-    uint32_t xbody;    // state jets of this lane's body (lanes < NB)
-    uint32_t tin;      // exchange row of this lane's body (buffer 0)
+    int32_t xa, xb;   // state jets of the pair's bodies (x component, order 0)
+    int32_t ta, tb;   // exchange slots the pair writes (buffer 0, component 0)
+    int32_t xbody;    // state jets of this lane's body (body lanes; may point into the
+    int32_t tin;      // exchange row of this lane's body   neighbouring trajectory's column)
+    int32_t coef;     // offset of the body's coefficient row in the immediate table
     bool body;
 };
 
 template <typename R, int NB, int PMAX, int K> struct NbrOrders {
-    static __device__ __forceinline__ void run(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const unsigned gmask, const uint32_t p,
+    static __device__ __forceinline__ void run(R *__restrict__ w, const R (&cf)[NB - 1], const NbrLane &L, const uint32_t p,
                                                R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX], R (&r2)[PMAX],
                                                R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
     {
@@ -172,7 +173,7 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
         w[L.tb + buf + 0] = t0;
         w[L.tb + buf + 1] = t1;
         w[L.tb + buf + 2] = t2;
-        __syncwarp(gmask);
+        __syncwarp();
         // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago)
         // (rows up to NBR_PMAX exist whatever p is: no run-time guard on K + 1 < p)
         if constexpr (K + 1 < PMAX) {
@@ -186,10 +187,9 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
             R a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const R cf = (R)coef[q];
-                a0 = fma(cf, w[L.tin + buf + 3 * q + 0], a0);
-                a1 = fma(cf, w[L.tin + buf + 3 * q + 1], a1);
-                a2 = fma(cf, w[L.tin + buf + 3 * q + 2], a2);
+                a0 = fma(cf[q], w[L.tin + buf + 3 * q + 0], a0);
+                a1 = fma(cf[q], w[L.tin + buf + 3 * q + 1], a1);
+                a2 = fma(cf[q], w[L.tin + buf + 3 * q + 2], a2);
             }
             constexpr R rk1 = (R)(1.0 / (double)(K + 1)), rk2 = (R)(1.0 / (double)(K + 2));
             const R v0 = a0 * rk1, v1 = a1 * rk1, v2 = a2 * rk1;
@@ -202,17 +202,23 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
                 w[L.xbody + 2 * SP + K + 2] = v2 * rk2;
             }
         }
-        if constexpr (K + 1 < PMAX) NbrOrders<R, NB, PMAX, K + 1>::run(w, coef, L, gmask, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+        if constexpr (K + 1 < PMAX) NbrOrders<R, NB, PMAX, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
     }
 };
 
 // All orders 0..p-1 of one step.  On entry the order-0 rows of the state jets
 // hold the state (visible to the whole group); on exit rows 0..p are complete.
 template <typename R, int NB, int PMAX>
-__device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const unsigned gmask, const uint32_t p)
+__device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const uint32_t p)
 {
     constexpr int SP = NBR_SP;
     R d0[PMAX], d1[PMAX], d2[PMAX], r2[PMAX], c[PMAX], inv = 0;
+    // coefficients of this lane's body (registers for the whole step)
+    R cf[NB - 1];
+#pragma unroll
+    for (int q = 0; q < NB - 1; ++q) cf[q] = (R)coef[q];
+    // the body lanes read the other trajectory's state: make the whole warp's updates visible
+    __syncwarp();
     // x[1] = v[0]
     if (L.body) {
         w[L.xbody + 0 * SP + 1] = w[L.xbody + 3 * SP];
@@ -222,8 +228,8 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     const R dk0 = w[L.xa + 0 * SP] - w[L.xb + 0 * SP];
     const R dk1 = w[L.xa + 1 * SP] - w[L.xb + 1 * SP];
     const R dk2 = w[L.xa + 2 * SP] - w[L.xb + 2 * SP];
-    NbrOrders<R, NB, PMAX, 0>::run(w, coef, L, gmask, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
-    __syncwarp(gmask);
+    NbrOrders<R, NB, PMAX, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+    __syncwarp();
 }
 
 } // namespace hy
