@@ -921,7 +921,10 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
         if (NB > 0 || stepping) {
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
             if constexpr (NB > 0) {
-                nbr_jets<R, NB, NBR_PMAX>(w, s_imm + nl.coef, nl, p);
+                if (p == (uint32_t)NBR_PMAX)
+                    nbr_jets<R, NB, NBR_PMAX, true>(w, s_imm + nl.coef, nl, p);
+                else
+                    nbr_jets<R, NB, NBR_PMAX, false>(w, s_imm + nl.coef, nl, p);
             } else {
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;

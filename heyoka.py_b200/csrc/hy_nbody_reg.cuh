@@ -157,12 +157,51 @@ struct NbrLane {
     bool body;
 };
 
-template <typename R, int NB, int PMAX, int K> struct NbrOrders {
+// Predicated shared-memory accesses (no branch: the body lanes' work stays in the same
+// basic block as the pair convolutions of the next order, so ptxas interleaves the two
+// and the exchange latency hides behind the DFMA stream).
+__device__ __forceinline__ double lds_if(const double *p, bool on)
+{
+    double v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.shared.f64 %0, [%1];\n\t}"
+                 : "=d"(v)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)on)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_if(const float *p, bool on)
+{
+    float v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.shared.f32 %0, [%1];\n\t}"
+                 : "=f"(v)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)on)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_if(double *p, double v, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}"
+                 :
+                 : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(v), "r"((int)on)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_if(float *p, float v, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}"
+                 :
+                 : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(v), "r"((int)on)
+                 : "memory");
+}
+
+// FULL: the Taylor order equals PMAX (no run-time order checks, one basic block per order).
+template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
     static __device__ __forceinline__ void run(R *__restrict__ w, const R (&cf)[NB - 1], const NbrLane &L, const uint32_t p,
                                                R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX], R (&r2)[PMAX],
                                                R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
     {
-        if (K >= p) return;
+        if constexpr (!FULL) {
+            if (K >= p) return;
+        }
         constexpr int SP = NBR_SP, QS = NBR_QS, NQ = NB - 1;
         constexpr int buf = (K & 1) * (NBR_MAXB * QS);
         R t0, t1, t2;
@@ -181,34 +220,37 @@ template <typename R, int NB, int PMAX, int K> struct NbrOrders {
             dk1 = w[L.xa + 1 * SP + K + 1] - w[L.xb + 1 * SP + K + 1];
             dk2 = w[L.xa + 2 * SP + K + 1] - w[L.xb + 2 * SP + K + 1];
         }
-        if (L.body) {
-            // acceleration of this body at order K: the tape's LINCOMB (term order kept),
-            // then v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
+        {
+            // BODY LANES (predicated, the other lanes compute on zeros): acceleration of the
+            // body at order K - the tape's LINCOMB, term order kept - then
+            // v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
+            const bool on = L.body;
             R a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                a0 = fma(cf[q], w[L.tin + buf + 3 * q + 0], a0);
-                a1 = fma(cf[q], w[L.tin + buf + 3 * q + 1], a1);
-                a2 = fma(cf[q], w[L.tin + buf + 3 * q + 2], a2);
+                a0 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 0], on), a0);
+                a1 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 1], on), a1);
+                a2 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 2], on), a2);
             }
             constexpr R rk1 = (R)(1.0 / (double)(K + 1)), rk2 = (R)(1.0 / (double)(K + 2));
             const R v0 = a0 * rk1, v1 = a1 * rk1, v2 = a2 * rk1;
-            w[L.xbody + 3 * SP + K + 1] = v0;
-            w[L.xbody + 4 * SP + K + 1] = v1;
-            w[L.xbody + 5 * SP + K + 1] = v2;
+            sts_if(&w[L.xbody + 3 * SP + K + 1], v0, on);
+            sts_if(&w[L.xbody + 4 * SP + K + 1], v1, on);
+            sts_if(&w[L.xbody + 5 * SP + K + 1], v2, on);
             if constexpr (K + 2 <= PMAX) {
-                w[L.xbody + 0 * SP + K + 2] = v0 * rk2;
-                w[L.xbody + 1 * SP + K + 2] = v1 * rk2;
-                w[L.xbody + 2 * SP + K + 2] = v2 * rk2;
+                sts_if(&w[L.xbody + 0 * SP + K + 2], v0 * rk2, on);
+                sts_if(&w[L.xbody + 1 * SP + K + 2], v1 * rk2, on);
+                sts_if(&w[L.xbody + 2 * SP + K + 2], v2 * rk2, on);
             }
         }
-        if constexpr (K + 1 < PMAX) NbrOrders<R, NB, PMAX, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+        if constexpr (K + 1 < PMAX)
+            NbrOrders<R, NB, PMAX, FULL, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
     }
 };
 
 // All orders 0..p-1 of one step.  On entry the order-0 rows of the state jets
 // hold the state (visible to the whole group); on exit rows 0..p are complete.
-template <typename R, int NB, int PMAX>
+template <typename R, int NB, int PMAX, bool FULL>
 __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const uint32_t p)
 {
     constexpr int SP = NBR_SP;
@@ -228,7 +270,7 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     const R dk0 = w[L.xa + 0 * SP] - w[L.xb + 0 * SP];
     const R dk1 = w[L.xa + 1 * SP] - w[L.xb + 1 * SP];
     const R dk2 = w[L.xa + 2 * SP] - w[L.xb + 2 * SP];
-    NbrOrders<R, NB, PMAX, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+    NbrOrders<R, NB, PMAX, FULL, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
     __syncwarp();
 }
 
