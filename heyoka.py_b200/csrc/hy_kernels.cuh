@@ -43,6 +43,19 @@ __device__ __forceinline__ double r_abs(double a) { return fabs(a); }
 __device__ __forceinline__ float r_abs(float a) { return fabsf(a); }
 __device__ __forceinline__ double r_copysign(double a, double b) { return copysign(a, b); }
 __device__ __forceinline__ float r_copysign(float a, float b) { return copysignf(a, b); }
+// x^e for the step-size radii (x > 0, e = 1/p): exp(log(x) * e).  The error of log() is
+// scaled by e <= 1/2, so the result is good to ~1 ulp - at a third of the cost of pow().
+#ifndef HY_T_NORM
+#define HY_T_NORM 1
+#endif
+#ifndef HY_T_HORNER
+#define HY_T_HORNER 1
+#endif
+#ifndef HY_T_ROOT
+#define HY_T_ROOT 1
+#endif
+__device__ __noinline__ double r_root(double x, double e) { return HY_T_ROOT ? exp(log(x) * e) : pow(x, e); }
+__device__ __noinline__ float r_root(float x, float e) { return expf(logf(x) * e); }
 template <typename R> __device__ __forceinline__ R r_inf();
 template <> __device__ __forceinline__ double r_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
@@ -955,21 +968,35 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
         if (stepping) {
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
-            for (uint32_t i = sub; i < n + d.n_events; i += G) {
-                R x0, x1, x2;
-                if (i < n) {
-                    x0 = XJ(i, 0);
-                    x1 = XJ(i, p - 1);
-                    x2 = XJ(i, p);
-                } else {
-                    const R *x = &w[s_ev[i - n]];
-                    x0 = x[0];
-                    x1 = x[p - 1];
-                    x2 = x[p];
+            if constexpr (NB > 0 && HY_T_NORM) {
+                // state jets at w[i * NBR_SP + order], three variables per lane at most
+#pragma unroll
+                for (int u = 0; u < (6 * NB + G - 1) / G; ++u) {
+                    const uint32_t i = sub + u * G;
+                    if (i < 6u * NB) {
+                        const R *x = w + i * NBR_SP;
+                        n0 = nan_max(n0, r_abs(x[0]));
+                        n1 = nan_max(n1, r_abs(x[p - 1]));
+                        n2 = nan_max(n2, r_abs(x[p]));
+                    }
                 }
-                n0 = nan_max(n0, r_abs(x0));
-                n1 = nan_max(n1, r_abs(x1));
-                n2 = nan_max(n2, r_abs(x2));
+            } else {
+                for (uint32_t i = sub; i < n + d.n_events; i += G) {
+                    R x0, x1, x2;
+                    if (i < n) {
+                        x0 = XJ(i, 0);
+                        x1 = XJ(i, p - 1);
+                        x2 = XJ(i, p);
+                    } else {
+                        const R *x = &w[s_ev[i - n]];
+                        x0 = x[0];
+                        x1 = x[p - 1];
+                        x2 = x[p];
+                    }
+                    n0 = nan_max(n0, r_abs(x0));
+                    n1 = nan_max(n1, r_abs(x1));
+                    n2 = nan_max(n2, r_abs(x2));
+                }
             }
 #pragma unroll
             for (int m = G >> 1; m > 0; m >>= 1) {
@@ -985,13 +1012,13 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
                 if (G > 1) {
                     // one pow call for both radii: even lanes take order p, odd lanes order p-1
                     const bool odd = sub & 1u;
-                    const R r = r_pow(num / (odd ? n1 : n2), odd ? P.inv_pm1 : P.inv_p);
+                    const R r = r_root(num / (odd ? n1 : n2), odd ? P.inv_pm1 : P.inv_p);
                     const R o = shfl_xor<R>(gmask, r, 1);
                     rho_p = odd ? o : r;
                     rho_pm1 = odd ? r : o;
                 } else {
-                    rho_p = r_pow(num / n2, P.inv_p);
-                    rho_pm1 = r_pow(num / n1, P.inv_pm1);
+                    rho_p = r_root(num / n2, P.inv_p);
+                    rho_pm1 = r_root(num / n1, P.inv_pm1);
                 }
                 h = (rho_p < rho_pm1 ? rho_p : rho_pm1) * P.rhofac;
             }
@@ -1045,6 +1072,36 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             }
             if (G > 1 && (P.cout_tcs || P.mode == MODE_GRID)) __syncwarp(gmask);
             bool finite = true;
+            if (NB > 0 && HY_T_HORNER && !P.high_accuracy) {
+                // Horner with direct addressing, the lane's variables interleaved (independent chains)
+                constexpr int NV = NB > 0 ? (6 * NB + G - 1) / G : 1;
+                const R *x[NV];
+                R acc[NV];
+#pragma unroll
+                for (int u = 0; u < NV; ++u) {
+                    const uint32_t i = sub + u * G;
+                    x[u] = w + (i < n ? i : sub) * NBR_SP;
+                    acc[u] = x[u][p];
+                }
+                if (p == (uint32_t)NBR_PMAX) {
+#pragma unroll
+                    for (int k = NBR_PMAX - 1; k >= 0; --k)
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], h, x[u][k]);
+                } else {
+                    for (uint32_t k = p; k-- > 0;)
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], h, x[u][k]);
+                }
+#pragma unroll
+                for (int u = 0; u < NV; ++u) {
+                    const uint32_t i = sub + u * G;
+                    if (i < n) {
+                        finite = finite && (r_abs(acc[u]) < r_inf<R>());
+                        w[i * NBR_SP] = acc[u];
+                    }
+                }
+            } else {
             for (uint32_t i = sub; i < n; i += G) {
                 R acc;
                 const int sp = s_ssp[i];
@@ -1087,6 +1144,7 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
                 }
                 finite = finite && (r_abs(acc) < r_inf<R>());
                 w[s_srow[i]] = acc;
+            }
             }
             if (G > 1) finite = !__any_sync(gmask, !finite);
             time_add(hi, lo, h);

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "csrc", "libhy_cuda.so")
+LIB_PATH = os.environ.get("HY_CUDA_LIB") or os.path.join(_HERE, "..", "csrc", "libhy_cuda.so")
 
 _lib = None
 
