@@ -157,22 +157,29 @@ def cpu_baseline(sys_, order, horizon, target_s, rank_seed=0):
     dc = D.decompose(sys_, order)
     # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly.
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # Calibrate on a tiny run, then size the sample for ~target_s seconds.
+    # Calibrate on tiny runs (the first one also pays thread start-up), then size the
+    # sample for ~target_s seconds; grow it once more if it still came out short.
     cal_traj, cal_h = 8 * cores, min(horizon, 400.0)
-    t0 = time.perf_counter()
-    _, ns = simd_propagate_until(dc, W.oss_ensemble(cal_traj, seed=777 + rank_seed), cal_h, nthreads=cores)
-    dt = time.perf_counter() - t0
-    rate = float(ns.sum()) / max(dt, 1e-9)
-    steps_per_traj = float(ns.mean()) * horizon / cal_h
-    want = rate * target_s
-    traj = max(8 * cores, int(want / steps_per_traj) // 8 * 8)
-    h = horizon
-    if traj * steps_per_traj > 1.5 * want:
-        # Keep at least one full SIMD batch per thread: shorten the horizon instead.
-        h = max(cal_h, horizon * want / (steps_per_traj * traj))
-    t0 = time.perf_counter()
-    _, ns = simd_propagate_until(dc, W.oss_ensemble(traj, seed=778 + rank_seed), h, nthreads=cores)
-    dt = time.perf_counter() - t0
+    rate, steps_per_traj = 0.0, 1.0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        _, ns = simd_propagate_until(dc, W.oss_ensemble(cal_traj, seed=777 + rank_seed), cal_h, nthreads=cores)
+        dt = time.perf_counter() - t0
+        rate = float(ns.sum()) / max(dt, 1e-9)
+        steps_per_traj = float(ns.mean()) * horizon / cal_h
+    for _ in range(3):
+        want = rate * target_s
+        traj = max(8 * cores, int(want / steps_per_traj) // 8 * 8)
+        h = horizon
+        if traj * steps_per_traj > 1.5 * want:
+            # Keep at least one full SIMD batch per thread: shorten the horizon instead.
+            h = max(cal_h, horizon * want / (steps_per_traj * traj))
+        t0 = time.perf_counter()
+        _, ns = simd_propagate_until(dc, W.oss_ensemble(traj, seed=778 + rank_seed), h, nthreads=cores)
+        dt = time.perf_counter() - t0
+        rate = float(ns.sum()) / max(dt, 1e-9)
+        if dt >= 0.5 * target_s:
+            break
     val = float(ns.sum()) / dt
     return {
         "value": val,
@@ -353,7 +360,10 @@ def main():
             "frac": achieved_tf / fma_peak if fma_peak else None,
             "peak_source": "measured DFMA microbenchmark (hy_measure_fma_peak) on this GPU; "
                            "MEASURED_PEAKS.json holds no FP64 figure",
-            "kernel": "hy::propagate_kernel<double,{}>".format(li["group"]),
+            "kernel": "hy::propagate_kernel<double,{},true,{}>{}".format(
+                li["group"], li.get("kernel_variant", 0),
+                " (register-resident N-body jets, hy_nbody_reg.cuh)" if li.get("kernel_variant") else
+                " (tape interpreter)"),
             "kernel_ms_per_launch": kern_ms / args.steps,
             "flops_per_trajectory_step": fl,
             "traffic": ncu_traffic(),
@@ -367,7 +377,9 @@ def main():
                 "operand_loads_per_trajectory_step": lo,
                 "achieved_gbs": steps_rank * lo * 8 / k_s / 1e9,
                 "peak_gbs": 128.0 * li["n_sm"] * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                "note": "shared-memory crossbar (128 B/clk/SM) is the practical bound of the tape interpreter",
+                "note": "operand loads of the tape (what the tape INTERPRETER would read from shared memory; "
+                        "with kernel_variant > 0 the convolution operands are registers and shared memory "
+                        "carries only the per-order exchange)",
             },
         }
         cpu = None

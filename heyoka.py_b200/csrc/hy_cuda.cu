@@ -179,17 +179,15 @@ int choose_geometry(hy_ctx *c)
         pr.n_phases = 0;
         pr.phase_slot = {0};
         pr.imm = nbm.imm;
-        const uint32_t SP = (uint32_t)hy::NBR_SP;
-        pr.ws_len = d.n_state * SP + 2u * hy::NBR_MAXB * hy::NBR_QS;
+        pr.ws_len = (uint32_t)hy::NBR_WS;
         pr.par_off = pr.one_off = pr.ws_len;
         pr.n_spill = 0;
-        for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back(i * SP);
+        for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back((uint32_t)hy::nbr_state_off((int)i));
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = nbm.n_pairs;
         pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
-        // column stride
-        // (= 9 mod 16: the 2 x NB body lanes of a warp, which sit in one half-warp, hit distinct banks)
-        const uint32_t RS = (pr.ws_len + 15u) / 16u * 16u + 9u;
+        // column stride: even (16-byte aligned vectors); + 2 spreads the two trajectories of a warp over the banks
+        const uint32_t RS = (pr.ws_len + 1u) / 2u * 2u + 2u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
         if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 2) {
@@ -327,7 +325,7 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.B = c->B;
     P.T = c->li.traj_per_cta;
     P.TS = c->TS;
-    P.nb_tb_off = c->d.n_state * (uint32_t)hy::NBR_SP;
+    P.nb_tb_off = (uint32_t)hy::NBR_TB0;
     P.max_steps = max_steps;
     P.mode = mode;
     P.backward = backward;

@@ -823,27 +823,31 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
     // global scratch of this trajectory slot's spilled state jets
     R *gj = P.gjet + ((size_t)blockIdx.x * P.T + slot) * (size_t)P.pd.n_spill * P1;
     // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
-#define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j)])
+// (NB > 0: the orders of a state variable are NBR_JS elements apart, see hy_nbody_reg.cuh)
+    constexpr uint32_t XS = NB > 0 ? (uint32_t)NBR_JS : 1u;
+#define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j) * XS])
     // unit jet [1, 0, ..., 0] (never changes)
     if constexpr (NB == 0)
         for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
     // register-resident N-body path: per-lane constants (pair, exchange slots, body)
-    NbrLane nl{};
+    NbrLane<(NB > 0 ? NB : 2)> nl{};
     if constexpr (NB > 0) {
-        // lane record (hy_nbody_match.hpp): 4 x uint16 = body a, body b, exchange slot a, exchange slot b
+        // lane record (hy_nbody_match.hpp): bodies a, b of the lane's pair
         const uint2 lr = *reinterpret_cast<const uint2 *>(s_imm + NBR_LANE0 + sub);
-        nl.xa = (int32_t)(6u * NBR_SP * (lr.x & 0xffffu));
-        nl.xb = (int32_t)(6u * NBR_SP * (lr.x >> 16));
-        nl.ta = (int32_t)(P.nb_tb_off + (lr.y & 0xffffu));
-        nl.tb = (int32_t)(P.nb_tb_off + (lr.y >> 16));
+        nl.xa = (int32_t)(NBR_BS * lr.x);
+        nl.xb = (int32_t)(NBR_BS * lr.y);
+        nl.ta = (int32_t)(NBR_TB0 + NBR_TS * sub);
         // Body lanes: lanes 0..2NB-1 of the WARP serve the NB bodies of its two trajectories
         // (all in one half-warp: a 64-bit shared access costs one wavefront per active half-warp).
         nl.body = lane < 2u * NB;
         const uint32_t bt = nl.body ? lane / NB : 0u, bd = nl.body ? lane % NB : 0u;
         const int32_t col = (bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
-        nl.xbody = col + (int32_t)(6u * NBR_SP * bd);
-        nl.tin = col + (int32_t)(P.nb_tb_off + NBR_QS * bd);
+        nl.xbody = col + (int32_t)(NBR_BS * bd);
         nl.coef = (int32_t)(NBR_CS * bd);
+#pragma unroll
+        for (int q = 0; q < NB - 1; ++q)
+            nl.tin[q] = col + NBR_TB0 +
+                        NBR_TS * (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
     }
 
     // Persistent loop: every iteration is ONE step of the group's current trajectory (or the
@@ -965,19 +969,25 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
 
         }
 
-        if (stepping) {
+        // ---- the rest of the step ----
+        // NB > 0: BOTH half-warps run it, converged, so that every warp-level primitive uses the
+        // full mask (a partial mask costs a ~90-clock MATCH/VOTE check per use); a half-warp that is
+        // not stepping computes on stale data and commits nothing (`stepping` guards every side effect).
+        if (NB > 0 || stepping) {
+            constexpr unsigned TM_FULL = 0xffffffffu;
+            const unsigned tmask = NB > 0 ? TM_FULL : gmask;
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
-            if constexpr (NB > 0 && HY_T_NORM) {
-                // state jets at w[i * NBR_SP + order], three variables per lane at most
+            if constexpr (NB > 0) {
+                // state jets at w[nbr_state_off(i) + order * NBR_JS], three variables per lane at most
 #pragma unroll
                 for (int u = 0; u < (6 * NB + G - 1) / G; ++u) {
                     const uint32_t i = sub + u * G;
                     if (i < 6u * NB) {
-                        const R *x = w + i * NBR_SP;
+                        const R *x = w + nbr_state_off((int)i);
                         n0 = nan_max(n0, r_abs(x[0]));
-                        n1 = nan_max(n1, r_abs(x[p - 1]));
-                        n2 = nan_max(n2, r_abs(x[p]));
+                        n1 = nan_max(n1, r_abs(x[(p - 1) * NBR_JS]));
+                        n2 = nan_max(n2, r_abs(x[p * NBR_JS]));
                     }
                 }
             } else {
@@ -1000,38 +1010,40 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             }
 #pragma unroll
             for (int m = G >> 1; m > 0; m >>= 1) {
-                n0 = nan_max(n0, shfl_xor<R>(gmask, n0, m));
-                n1 = nan_max(n1, shfl_xor<R>(gmask, n1, m));
-                n2 = nan_max(n2, shfl_xor<R>(gmask, n2, m));
+                n0 = nan_max(n0, shfl_xor<R>(tmask, n0, m));
+                n1 = nan_max(n1, shfl_xor<R>(tmask, n1, m));
+                n2 = nan_max(n2, shfl_xor<R>(tmask, n2, m));
             }
-            if (n0 != n0 || n1 != n1 || n2 != n2) {
-                h = n0 + n1 + n2; // NaN
-            } else {
+            R hn; // the new step size
+            {
+                const bool isnan_ = n0 != n0 || n1 != n1 || n2 != n2;
                 const R num = n0 < (R)1 ? (R)1 : n0;
                 R rho_p, rho_pm1;
                 if (G > 1) {
-                    // one pow call for both radii: even lanes take order p, odd lanes order p-1
+                    // one root call for both radii: even lanes take order p, odd lanes order p-1
                     const bool odd = sub & 1u;
                     const R r = r_root(num / (odd ? n1 : n2), odd ? P.inv_pm1 : P.inv_p);
-                    const R o = shfl_xor<R>(gmask, r, 1);
+                    const R o = shfl_xor<R>(tmask, r, 1);
                     rho_p = odd ? o : r;
                     rho_pm1 = odd ? r : o;
                 } else {
                     rho_p = r_root(num / n2, P.inv_p);
                     rho_pm1 = r_root(num / n1, P.inv_pm1);
                 }
-                h = (rho_p < rho_pm1 ? rho_p : rho_pm1) * P.rhofac;
+                hn = (rho_p < rho_pm1 ? rho_p : rho_pm1) * P.rhofac;
+                if (isnan_) hn = n0 + n1 + n2; // NaN
             }
-            if (signbit(lim)) h = -h;
+            if (signbit(lim)) hn = -hn;
             long long so = HY_OUTCOME_SUCCESS;
-            if (r_abs(h) > r_abs(lim)) {
-                h = lim;
+            if (r_abs(hn) > r_abs(lim)) {
+                hn = lim;
                 so = HY_OUTCOME_TIME_LIMIT;
             }
+            if (stepping) h = hn;
 
             // ---- event detection: may truncate the step at a terminal event ----
             int term_ev = -1;
-            if (d.n_events) {
+            if (NB == 0 && d.n_events) {
                 R h_eff = h;
                 if (sub == 0)
                     detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
@@ -1048,139 +1060,154 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             }
 
             // ---- optional tc write, then the state update ----
-            if (P.write_tc && P.tc) {
-                for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
+            if (stepping && (P.write_tc || P.cout_tcs || P.mode == MODE_GRID)) {
+                if (P.write_tc && P.tc) {
+                    for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
+                    if (G > 1) __syncwarp(gmask);
+                }
+                if (P.cout_tcs && cc < P.cout_cap) {
+                    R *dstc = P.cout_tcs + ((size_t)cc * P.B + traj) * (size_t)(n * P1);
+                    for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
+                }
+                if (P.mode == MODE_GRID) {
+                    // Dense output at every grid point inside this step.
+                    while (gi < P.grid_k) {
+                        const R g = P.grid[(size_t)gi * P.B + traj];
+                        const R tau = (g - hi) - lo; // time since the start of the step
+                        if (r_abs(tau) > r_abs(h)) break;
+                        for (uint32_t i = sub; i < n; i += G) {
+                            R acc = XJ(i, p);
+                            for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, XJ(i, k));
+                            P.gout[((size_t)gi * n + i) * P.B + traj] = acc;
+                        }
+                        ++gi;
+                    }
+                }
                 if (G > 1) __syncwarp(gmask);
             }
-            if (P.cout_tcs && cc < P.cout_cap) {
-                R *dstc = P.cout_tcs + ((size_t)cc * P.B + traj) * (size_t)(n * P1);
-                for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
-            }
-            if (P.mode == MODE_GRID) {
-                // Dense output at every grid point inside this step.
-                while (gi < P.grid_k) {
-                    const R g = P.grid[(size_t)gi * P.B + traj];
-                    const R tau = (g - hi) - lo; // time since the start of the step
-                    if (r_abs(tau) > r_abs(h)) break;
-                    for (uint32_t i = sub; i < n; i += G) {
-                        R acc = XJ(i, p);
-                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, XJ(i, k));
-                        P.gout[((size_t)gi * n + i) * P.B + traj] = acc;
-                    }
-                    ++gi;
-                }
-            }
-            if (G > 1 && (P.cout_tcs || P.mode == MODE_GRID)) __syncwarp(gmask);
+            if constexpr (NB > 0) __syncwarp(); // reconverge the two half-warps
             bool finite = true;
-            if (NB > 0 && HY_T_HORNER && !P.high_accuracy) {
+            if (NB > 0 && !P.high_accuracy) {
                 // Horner with direct addressing, the lane's variables interleaved (independent chains)
                 constexpr int NV = NB > 0 ? (6 * NB + G - 1) / G : 1;
-                const R *x[NV];
+                R *x[NV];
                 R acc[NV];
 #pragma unroll
                 for (int u = 0; u < NV; ++u) {
                     const uint32_t i = sub + u * G;
-                    x[u] = w + (i < n ? i : sub) * NBR_SP;
-                    acc[u] = x[u][p];
+                    x[u] = w + nbr_state_off((int)(i < n ? i : sub));
+                    acc[u] = x[u][p * NBR_JS];
                 }
                 if (p == (uint32_t)NBR_PMAX) {
 #pragma unroll
                     for (int k = NBR_PMAX - 1; k >= 0; --k)
 #pragma unroll
-                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], h, x[u][k]);
+                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], hn, x[u][k * NBR_JS]);
                 } else {
                     for (uint32_t k = p; k-- > 0;)
 #pragma unroll
-                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], h, x[u][k]);
+                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], hn, x[u][k * NBR_JS]);
                 }
 #pragma unroll
                 for (int u = 0; u < NV; ++u) {
                     const uint32_t i = sub + u * G;
                     if (i < n) {
                         finite = finite && (r_abs(acc[u]) < r_inf<R>());
-                        w[i * NBR_SP] = acc[u];
+                        if (stepping) x[u][0] = acc[u];
                     }
                 }
+            } else if (stepping) {
+                for (uint32_t i = sub; i < n; i += G) {
+                    R acc;
+                    const int sp = s_ssp[i];
+                    if (sp >= 0) {
+                        // spilled jet: stream it back from the global scratch (independent loads)
+                        const R *x = gj + (uint32_t)sp * P1;
+                        if (!P.high_accuracy) {
+                            acc = __ldcg(&x[p]);
+                            for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, __ldcg(&x[k]));
+                        } else {
+                            R sum = __ldcg(&x[0]), comp = 0, hk = h;
+                            for (uint32_t k = 1; k <= p; ++k) {
+                                const R term = __ldcg(&x[k]) * hk;
+                                const R y = ef_sub(term, comp);
+                                const R tt = ef_add(sum, y);
+                                comp = ef_sub(ef_sub(tt, sum), y);
+                                sum = tt;
+                                hk = hk * h;
+                            }
+                            acc = sum;
+                        }
+                        gj[(uint32_t)sp * P1] = acc;
+                    } else {
+                        const R *x = &w[s_srow[i]];
+                        if (!P.high_accuracy) {
+                            acc = x[p * XS];
+                            for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[k * XS]);
+                        } else {
+                            R sum = x[0], comp = 0, hk = h;
+                            for (uint32_t k = 1; k <= p; ++k) {
+                                const R term = x[k * XS] * hk;
+                                const R y = ef_sub(term, comp);
+                                const R tt = ef_add(sum, y);
+                                comp = ef_sub(ef_sub(tt, sum), y);
+                                sum = tt;
+                                hk = hk * h;
+                            }
+                            acc = sum;
+                        }
+                    }
+                    finite = finite && (r_abs(acc) < r_inf<R>());
+                    w[s_srow[i]] = acc;
+                }
+            }
+            if constexpr (NB > 0) {
+                // one full-mask ballot, each half-warp looks at its own 16 bits
+                const unsigned bad = __ballot_sync(TM_FULL, !finite);
+                finite = ((bad >> (lane & 16u)) & 0xffffu) == 0u;
             } else {
-            for (uint32_t i = sub; i < n; i += G) {
-                R acc;
-                const int sp = s_ssp[i];
-                if (sp >= 0) {
-                    // spilled jet: stream it back from the global scratch (independent loads)
-                    const R *x = gj + (uint32_t)sp * P1;
-                    if (!P.high_accuracy) {
-                        acc = __ldcg(&x[p]);
-                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, __ldcg(&x[k]));
-                    } else {
-                        R sum = __ldcg(&x[0]), comp = 0, hk = h;
-                        for (uint32_t k = 1; k <= p; ++k) {
-                            const R term = __ldcg(&x[k]) * hk;
-                            const R y = ef_sub(term, comp);
-                            const R tt = ef_add(sum, y);
-                            comp = ef_sub(ef_sub(tt, sum), y);
-                            sum = tt;
-                            hk = hk * h;
-                        }
-                        acc = sum;
-                    }
-                    gj[(uint32_t)sp * P1] = acc;
-                } else {
-                    const R *x = &w[s_srow[i]];
-                    if (!P.high_accuracy) {
-                        acc = x[p];
-                        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, h, x[k]);
-                    } else {
-                        R sum = x[0], comp = 0, hk = h;
-                        for (uint32_t k = 1; k <= p; ++k) {
-                            const R term = x[k] * hk;
-                            const R y = ef_sub(term, comp);
-                            const R tt = ef_add(sum, y);
-                            comp = ef_sub(ef_sub(tt, sum), y);
-                            sum = tt;
-                            hk = hk * h;
-                        }
-                        acc = sum;
+                if (G > 1) finite = !__any_sync(gmask, !finite);
+            }
+            if (stepping) {
+                time_add(hi, lo, h);
+                ++ns;
+                if (!finite) so = HY_OUTCOME_ERR_NF_STATE;
+                if (P.cout_tcs && cc < P.cout_cap) {
+                    ++cc;
+                    if (sub == 0) {
+                        const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
+                        P.cout_thi[(size_t)cc * P.B + traj] = fin_ ? tf_hi : hi;
+                        P.cout_tlo[(size_t)cc * P.B + traj] = fin_ ? tf_lo : lo;
                     }
                 }
-                finite = finite && (r_abs(acc) < r_inf<R>());
-                w[s_srow[i]] = acc;
-            }
-            }
-            if (G > 1) finite = !__any_sync(gmask, !finite);
-            time_add(hi, lo, h);
-            ++ns;
-            if (!finite) so = HY_OUTCOME_ERR_NF_STATE;
-            if (P.cout_tcs && cc < P.cout_cap) {
-                ++cc;
-                if (sub == 0) {
-                    const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
-                    P.cout_thi[(size_t)cc * P.B + traj] = fin_ ? tf_hi : hi;
-                    P.cout_tlo[(size_t)cc * P.B + traj] = fin_ ? tf_lo : lo;
-                }
-            }
 
-            // ---- does the trajectory end here? ----
-            if (P.mode == MODE_STEP || so == HY_OUTCOME_ERR_NF_STATE || term_ev >= 0) {
-                // single step / non-finite state / terminal event (the host may resume the lane)
-                oc = so;
-                fin = true;
-            } else {
-                if (so == HY_OUTCOME_SUCCESS) {
-                    const R ah = r_abs(h);
-                    if (ah < mn) mn = ah;
-                    if (ah > mx) mx = ah;
-                }
-                if (so == HY_OUTCOME_TIME_LIMIT && h == rem) {
-                    hi = tf_hi;
-                    lo = tf_lo;
-                    oc = HY_OUTCOME_TIME_LIMIT;
+                // ---- does the trajectory end here? ----
+                if (P.mode == MODE_STEP || so == HY_OUTCOME_ERR_NF_STATE || term_ev >= 0) {
+                    // single step / non-finite state / terminal event (the host may resume the lane)
+                    oc = so;
                     fin = true;
-                } else if (P.max_steps && ns >= P.max_steps) {
-                    oc = HY_OUTCOME_STEP_LIMIT;
-                    fin = true;
+                } else {
+                    if (so == HY_OUTCOME_SUCCESS) {
+                        const R ah = r_abs(h);
+                        if (ah < mn) mn = ah;
+                        if (ah > mx) mx = ah;
+                    }
+                    if (so == HY_OUTCOME_TIME_LIMIT && h == rem) {
+                        hi = tf_hi;
+                        lo = tf_lo;
+                        oc = HY_OUTCOME_TIME_LIMIT;
+                        fin = true;
+                    } else if (P.max_steps && ns >= P.max_steps) {
+                        oc = HY_OUTCOME_STEP_LIMIT;
+                        fin = true;
+                    }
                 }
             }
-            if (G > 1) __syncwarp(gmask);
+            if constexpr (NB > 0) {
+                __syncwarp();
+            } else {
+                if (G > 1) __syncwarp(gmask);
+            }
         }
 
         // ---- retire the trajectory ----

@@ -153,15 +153,15 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
             if (slot >= 0) return false; // the same pair twice in one sum
             slot = (int)q;
             out.imm[b * NBR_CS + q] = r0[q].second;
+            // pair slot (= lane) whose products feed this term
+            const uint32_t src[2] = {(uint32_t)pr, 0u};
+            std::memcpy(&out.imm[NBR_OFF0 + b * NBR_CS + q], src, 8);
         }
     }
     for (uint32_t s = 0; s < 16; ++s) {
-        const uint32_t pr = s < NP ? s : 0; // idle lanes mirror pair 0 (they store identical values)
+        const uint32_t pr = s < NP ? s : 0; // idle lanes mirror pair 0
         if (qa[pr] < 0 || qb[pr] < 0) return false;
-        // lane record: body a, body b, exchange slots (element offsets inside the exchange buffer)
-        const uint16_t rec[4] = {(uint16_t)pairs[pr].a, (uint16_t)pairs[pr].b,
-                                 (uint16_t)(NBR_QS * pairs[pr].a + 3 * qa[pr]),
-                                 (uint16_t)(NBR_QS * pairs[pr].b + 3 * qb[pr])};
+        const uint32_t rec[2] = {(uint32_t)pairs[pr].a, (uint32_t)pairs[pr].b}; // lane record
         std::memcpy(&out.imm[NBR_LANE0 + s], rec, 8);
     }
     return true;

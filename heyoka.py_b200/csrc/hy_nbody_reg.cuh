@@ -12,13 +12,17 @@
 //    (compile-time K), so every operand is a register and every weight of the
 //    power recurrence an immediate.  5(p-1) values per lane = 190 registers in
 //    FP64 at order 20.
-//  * the first NB lanes of the group double as BODY lanes: after each order
-//    they gather the 3(NB-1) pair products of their body from a small
-//    shared-memory exchange buffer, form the acceleration (the tape's LINCOMB,
-//    same term order), and write v[k+1] and x[k+2] into the state jets, which
-//    live in shared memory (only the Horner update reads their history).
+//  * the two trajectories of a warp step in lockstep.  Lanes 0..2NB-1 of the warp
+//    double as BODY lanes (all in one half-warp: a 64-bit shared access costs one
+//    wavefront per active half-warp): after each order they gather the NB-1 pair
+//    products of their body from a small shared-memory exchange buffer, form the
+//    acceleration (the tape's LINCOMB, same term order), and write v[k+1] and
+//    x[k+2] into the state jets, which live in shared memory (only the Horner
+//    update reads their history).  Vectors move as one 128-bit + one 64-bit access.
 //  * ONE __syncwarp per order: t[k] feeds d[k+2], not d[k+1], so the gather of
-//    order k overlaps the convolutions of order k+1 (double-buffered exchange).
+//    order k overlaps the convolutions of order k+1 (double-buffered exchange);
+//    the body lanes' work is predicated, not branched, so it shares a basic block
+//    with the next order's convolutions and ptxas interleaves the two.
 //
 // Arithmetic: the same recurrences, term order and roundings as the tape
 // interpreter's fused pair op (pair3_k) + LINCOMB + SVD - the two paths agree
@@ -35,17 +39,30 @@ namespace hy {
 
 constexpr int NBR_PMAX = 20;   // highest Taylor order of the register-resident path
 constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
-constexpr int NBR_QS = 17;     // exchange row stride per body (3*(NB-1) <= 15 used): odd => the body lanes read conflict-free
-constexpr int NBR_SP = NBR_PMAX + 1; // state jet stride in the trajectory column
+
+// Trajectory column (shared memory, elements):
+//   body b, order k:  [x, y, z, -, vx, vy, vz, -]  at  b * NBR_BS + k * NBR_JS   (16-byte aligned
+//                     triples: one 128-bit + one 64-bit access moves a vector)
+//   exchange buffer:  2 x 16 pair slots of NBR_TS elements (t0, t1, t2 used) at NBR_TB0
+// NBR_BS = 8 * 21 + 2 and NBR_TS = 6 keep the 128-bit accesses of a quarter-warp conflict-free.
+constexpr int NBR_JS = 8;                            // stride between orders of a state variable
+constexpr int NBR_BS = NBR_JS * (NBR_PMAX + 1) + 2;  // stride between bodies
+constexpr int NBR_TS = 6;                            // stride between pair slots of the exchange buffer
+constexpr int NBR_TB0 = NBR_MAXB * NBR_BS;           // offset of the exchange buffer
+constexpr int NBR_TBUF = 16 * NBR_TS;                // one exchange buffer
+constexpr int NBR_WS = NBR_TB0 + 2 * NBR_TBUF;       // column length
+// element offset of state variable i (order 0) in the column
+__host__ __device__ constexpr int nbr_state_off(int i) { return (i / 6) * NBR_BS + (i % 6) + ((i % 6) >= 3 ? 1 : 0); }
 
 // Host-built description of a matched N-body tape (hy_nbody_match.hpp).  It travels in
 // the program's immediate table (shared memory):
-//   imm[body * NBR_CS + q]   coefficient of term q of the body's acceleration sums
-//   imm[NBR_LANE0 + s]       4 x uint16 of lane s: bodies a, b of its pair (d = x[a] - x[b]) and the
-//                            offsets of the two exchange slots the pair writes (NBR_QS * body + 3 * term)
-constexpr int NBR_CS = 9; // odd stride: the body lanes read their coefficient rows conflict-free
+//   imm[body * NBR_CS + q]             coefficient of term q of the body's acceleration sums
+//   imm[NBR_LANE0 + s]                 2 x uint32 of lane s: bodies a, b of its pair (d = x[a] - x[b])
+//   imm[NBR_OFF0 + body * NBR_CS + q]  uint32: pair slot index feeding term q of the body's sums
+constexpr int NBR_CS = 9; // odd stride: the body lanes read their rows conflict-free
 constexpr int NBR_LANE0 = NBR_MAXB * NBR_CS;
-constexpr int NBR_NIMM = NBR_LANE0 + 16;
+constexpr int NBR_OFF0 = NBR_LANE0 + 16;
+constexpr int NBR_NIMM = NBR_OFF0 + NBR_MAXB * NBR_CS;
 
 // ---- one order of one pair, everything in registers ----
 // d*, r2, c: jets (orders 0..PMAX-2 are re-read later); dk*: d[K] (just formed).
@@ -145,103 +162,131 @@ __device__ __forceinline__ void nbr_pair_order(R (&d0)[PMAX], R (&d1)[PMAX], R (
     }
 }
 
-// Per-lane constants of the register-resident path.
-// Element offsets into the trajectory column `w` (shared memory), so that every access
-// is `LDS/STS [base + immediate]`.
-struct NbrLane {
-    int32_t xa, xb;   // state jets of the pair's bodies (x component, order 0)
-    int32_t ta, tb;   // exchange slots the pair writes (buffer 0, component 0)
-    int32_t xbody;    // state jets of this lane's body (body lanes; may point into the
-    int32_t tin;      // exchange row of this lane's body   neighbouring trajectory's column)
-    int32_t coef;     // offset of the body's coefficient row in the immediate table
+// Per-lane constants of the register-resident path: element offsets into the trajectory
+// column `w` (shared memory), so that every access is `LDS/STS [base + immediate]`.
+template <int NB> struct NbrLane {
+    int32_t xa, xb;      // blocks of the pair's bodies
+    int32_t ta;          // exchange slot the pair writes (buffer 0)
+    int32_t xbody;       // block of this lane's body (body lanes; may point into the
+    int32_t tin[NB - 1]; // exchange slots of the body's terms   neighbouring column)
+    int32_t coef;        // offset of the body's coefficient row in the immediate table
     bool body;
 };
 
-// Predicated shared-memory accesses (no branch: the body lanes' work stays in the same
-// basic block as the pair convolutions of the next order, so ptxas interleaves the two
-// and the exchange latency hides behind the DFMA stream).
-__device__ __forceinline__ double lds_if(const double *p, bool on)
+// 128-bit + 64-bit shared-memory moves of a 3-vector (16-byte aligned), optionally predicated.
+// The predicated forms keep the body lanes' work in the same basic block as the pair
+// convolutions of the next order, so ptxas interleaves the two.
+template <typename R> struct Vec3 {
+    R x, y, z;
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lds3(const double *p, Vec3<double> &v)
 {
-    double v;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.shared.f64 %0, [%1];\n\t}"
-                 : "=d"(v)
-                 : "r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)on)
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%3];\n\tld.shared.f64 %2, [%3+16];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z)
+                 : "r"(smem_u32(p))
                  : "memory");
-    return v;
 }
-__device__ __forceinline__ float lds_if(const float *p, bool on)
+__device__ __forceinline__ void lds3(const float *p, Vec3<float> &v)
 {
-    float v;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.shared.f32 %0, [%1];\n\t}"
-                 : "=f"(v)
-                 : "r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)on)
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%3];\n\tld.shared.f32 %2, [%3+8];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z)
+                 : "r"(smem_u32(p))
                  : "memory");
-    return v;
 }
-__device__ __forceinline__ void sts_if(double *p, double v, bool on)
+__device__ __forceinline__ void sts3(double *p, double x, double y, double z)
 {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}"
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n\tst.shared.f64 [%0+16], %3;"
                  :
-                 : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(v), "r"((int)on)
+                 : "r"(smem_u32(p)), "d"(x), "d"(y), "d"(z)
                  : "memory");
 }
-__device__ __forceinline__ void sts_if(float *p, float v, bool on)
+__device__ __forceinline__ void sts3(float *p, float x, float y, float z)
 {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}"
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n\tst.shared.f32 [%0+8], %3;"
                  :
-                 : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(v), "r"((int)on)
+                 : "r"(smem_u32(p)), "f"(x), "f"(y), "f"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void lds3_if(const double *p, Vec3<double> &v, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
+                 "mov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+                 "mov.f64 %2, 0d0000000000000000;\n\t"
+                 "@q ld.shared.v2.f64 {%0, %1}, [%3];\n\t@q ld.shared.f64 %2, [%3+16];\n\t}"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z)
+                 : "r"(smem_u32(p)), "r"((int)on)
+                 : "memory");
+}
+__device__ __forceinline__ void lds3_if(const float *p, Vec3<float> &v, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
+                 "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
+                 "@q ld.shared.v2.f32 {%0, %1}, [%3];\n\t@q ld.shared.f32 %2, [%3+8];\n\t}"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z)
+                 : "r"(smem_u32(p)), "r"((int)on)
+                 : "memory");
+}
+__device__ __forceinline__ void sts3_if(double *p, double x, double y, double z, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
+                 "@q st.shared.v2.f64 [%0], {%1, %2};\n\t@q st.shared.f64 [%0+16], %3;\n\t}"
+                 :
+                 : "r"(smem_u32(p)), "d"(x), "d"(y), "d"(z), "r"((int)on)
+                 : "memory");
+}
+__device__ __forceinline__ void sts3_if(float *p, float x, float y, float z, bool on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
+                 "@q st.shared.v2.f32 [%0], {%1, %2};\n\t@q st.shared.f32 [%0+8], %3;\n\t}"
+                 :
+                 : "r"(smem_u32(p)), "f"(x), "f"(y), "f"(z), "r"((int)on)
                  : "memory");
 }
 
 // FULL: the Taylor order equals PMAX (no run-time order checks, one basic block per order).
 template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
-    static __device__ __forceinline__ void run(R *__restrict__ w, const R (&cf)[NB - 1], const NbrLane &L, const uint32_t p,
-                                               R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX], R (&r2)[PMAX],
-                                               R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
+    static __device__ __forceinline__ void run(R *__restrict__ w, const R (&cf)[NB - 1], const NbrLane<NB> &L,
+                                               const uint32_t p, R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX],
+                                               R (&r2)[PMAX], R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
     {
         if constexpr (!FULL) {
             if (K >= p) return;
         }
-        constexpr int SP = NBR_SP, QS = NBR_QS, NQ = NB - 1;
-        constexpr int buf = (K & 1) * (NBR_MAXB * QS);
+        constexpr int JS = NBR_JS, NQ = NB - 1;
+        constexpr int buf = (K & 1) * NBR_TBUF;
         R t0, t1, t2;
         nbr_pair_order<R, K, PMAX>(d0, d1, d2, r2, c, inv, dk0, dk1, dk2, t0, t1, t2);
-        w[L.ta + buf + 0] = t0;
-        w[L.ta + buf + 1] = t1;
-        w[L.ta + buf + 2] = t2;
-        w[L.tb + buf + 0] = t0;
-        w[L.tb + buf + 1] = t1;
-        w[L.tb + buf + 2] = t2;
+        sts3(&w[L.ta + buf], t0, t1, t2);
         __syncwarp();
-        // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago)
-        // (rows up to NBR_PMAX exist whatever p is: no run-time guard on K + 1 < p)
+        // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago; rows up to
+        // NBR_PMAX exist whatever p is: no run-time guard on K + 1 < p)
         if constexpr (K + 1 < PMAX) {
-            dk0 = w[L.xa + 0 * SP + K + 1] - w[L.xb + 0 * SP + K + 1];
-            dk1 = w[L.xa + 1 * SP + K + 1] - w[L.xb + 1 * SP + K + 1];
-            dk2 = w[L.xa + 2 * SP + K + 1] - w[L.xb + 2 * SP + K + 1];
+            Vec3<R> xa, xb;
+            lds3(&w[L.xa + (K + 1) * JS], xa);
+            lds3(&w[L.xb + (K + 1) * JS], xb);
+            dk0 = xa.x - xb.x;
+            dk1 = xa.y - xb.y;
+            dk2 = xa.z - xb.z;
         }
         {
-            // BODY LANES (predicated, the other lanes compute on zeros): acceleration of the
-            // body at order K - the tape's LINCOMB, term order kept - then
-            // v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
+            // BODY LANES (predicated; the other lanes compute on zeros and store nothing):
+            // acceleration of the body at order K - the tape's LINCOMB, term order kept -
+            // then v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
             const bool on = L.body;
             R a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                a0 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 0], on), a0);
-                a1 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 1], on), a1);
-                a2 = fma(cf[q], lds_if(&w[L.tin + buf + 3 * q + 2], on), a2);
+                Vec3<R> t;
+                lds3_if(&w[L.tin[q] + buf], t, on);
+                a0 = fma(cf[q], t.x, a0);
+                a1 = fma(cf[q], t.y, a1);
+                a2 = fma(cf[q], t.z, a2);
             }
             constexpr R rk1 = (R)(1.0 / (double)(K + 1)), rk2 = (R)(1.0 / (double)(K + 2));
             const R v0 = a0 * rk1, v1 = a1 * rk1, v2 = a2 * rk1;
-            sts_if(&w[L.xbody + 3 * SP + K + 1], v0, on);
-            sts_if(&w[L.xbody + 4 * SP + K + 1], v1, on);
-            sts_if(&w[L.xbody + 5 * SP + K + 1], v2, on);
-            if constexpr (K + 2 <= PMAX) {
-                sts_if(&w[L.xbody + 0 * SP + K + 2], v0 * rk2, on);
-                sts_if(&w[L.xbody + 1 * SP + K + 2], v1 * rk2, on);
-                sts_if(&w[L.xbody + 2 * SP + K + 2], v2 * rk2, on);
-            }
+            sts3_if(&w[L.xbody + (K + 1) * JS + 4], v0, v1, v2, on);
+            if constexpr (K + 2 <= PMAX) sts3_if(&w[L.xbody + (K + 2) * JS], v0 * rk2, v1 * rk2, v2 * rk2, on);
         }
         if constexpr (K + 1 < PMAX)
             NbrOrders<R, NB, PMAX, FULL, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
@@ -251,9 +296,10 @@ template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
 // All orders 0..p-1 of one step.  On entry the order-0 rows of the state jets
 // hold the state (visible to the whole group); on exit rows 0..p are complete.
 template <typename R, int NB, int PMAX, bool FULL>
-__device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane &L, const uint32_t p)
+__device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane<NB> &L,
+                                         const uint32_t p)
 {
-    constexpr int SP = NBR_SP;
+    constexpr int JS = NBR_JS;
     R d0[PMAX], d1[PMAX], d2[PMAX], r2[PMAX], c[PMAX], inv = 0;
     // coefficients of this lane's body (registers for the whole step)
     R cf[NB - 1];
@@ -262,15 +308,15 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     // the body lanes read the other trajectory's state: make the whole warp's updates visible
     __syncwarp();
     // x[1] = v[0]
-    if (L.body) {
-        w[L.xbody + 0 * SP + 1] = w[L.xbody + 3 * SP];
-        w[L.xbody + 1 * SP + 1] = w[L.xbody + 4 * SP];
-        w[L.xbody + 2 * SP + 1] = w[L.xbody + 5 * SP];
+    {
+        Vec3<R> v;
+        lds3_if(&w[L.xbody + 4], v, L.body);
+        sts3_if(&w[L.xbody + JS], v.x, v.y, v.z, L.body);
     }
-    const R dk0 = w[L.xa + 0 * SP] - w[L.xb + 0 * SP];
-    const R dk1 = w[L.xa + 1 * SP] - w[L.xb + 1 * SP];
-    const R dk2 = w[L.xa + 2 * SP] - w[L.xb + 2 * SP];
-    NbrOrders<R, NB, PMAX, FULL, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+    Vec3<R> xa, xb;
+    lds3(&w[L.xa], xa);
+    lds3(&w[L.xb], xb);
+    NbrOrders<R, NB, PMAX, FULL, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, xa.x - xb.x, xa.y - xb.y, xa.z - xb.z);
     __syncwarp();
 }
 
