@@ -128,12 +128,14 @@ class ClockSampler:
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel, per
     launch, from the committed `ncu --set full` capture of this workload
-    (profiles/r01_ncu_full_bench_kernel.txt); None if the summary is missing."""
+    (profiles/r01_ncu_full_bench_kernel.txt, lines `name [unit] = value`); None if
+    the summary is missing."""
     try:
         tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_kernel.txt")):
-            if ln.startswith("dram__bytes_read.sum =") or ln.startswith("dram__bytes_write.sum ="):
-                tot += float(ln.split("=")[1]) * 1e6  # the raw page reports Mbyte for this capture
+            if ln.startswith("dram__bytes_read.sum [") or ln.startswith("dram__bytes_write.sum ["):
+                unit = ln.split("[")[1].split("]")[0]
+                tot += float(ln.split("=")[1]) * mult[unit]
         return tot or None
     except Exception:
         return None

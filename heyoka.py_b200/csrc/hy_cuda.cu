@@ -173,7 +173,7 @@ int choose_geometry(hy_ctx *c)
     // interactions live in registers, the state jets + a small exchange buffer in shared memory.
     hy::NbMatch nbm;
     if (!force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
-        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) && nbm.nb == 6) {
+        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) && hy::nbody_kernel_compiled(nbm.nb)) {
         hy::Program pr;
         pr.G = 16;
         pr.n_phases = 0;
@@ -923,6 +923,15 @@ int hy_get_launch_info(hy_ctx *c, hy_launch_info *info)
 {
     if (!c || !info) return fail("null argument");
     *info = c->li;
+    return 0;
+}
+
+int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term *terms, uint32_t *variant)
+{
+    if (!dims || !ops || !variant) return fail("hy_tape_kernel_variant: null argument");
+    hy::NbMatch m;
+    *variant = 0;
+    if (hy::match_nbody(*dims, ops, terms, m) && hy::nbody_kernel_compiled(m.nb)) *variant = m.nb;
     return 0;
 }
 

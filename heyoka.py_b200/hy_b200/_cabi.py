@@ -97,6 +97,7 @@ SYMBOLS = [
     "hy_set_cooldowns",
     "hy_reset_cooldowns",
     "hy_get_launch_info",
+    "hy_tape_kernel_variant",
     "hy_measure_fma_peak",
 ]
 
@@ -294,6 +295,16 @@ class Context:
         li = launch_info_t()
         check(lib().hy_get_launch_info(self._ctx, C.byref(li)))
         return {k: getattr(li, k) for k, _ in launch_info_t._fields_}
+
+
+def tape_kernel_variant(dc):
+    """Kernel hy_create would pick for the decomposition `dc` (no device needed):
+    0 = tape interpreter, N = register-resident N-body kernel for N bodies."""
+    dims = dims_t(dc.n_state, dc.n_par, dc.order, dc.n_rows, len(dc.ops), len(dc.terms),
+                  len(dc.level_start) - 1, dc.n_events, 0)
+    v = C.c_uint32(0)
+    check(lib().hy_tape_kernel_variant(C.byref(dims), ptr(dc.ops), ptr(dc.terms), C.byref(v)))
+    return v.value
 
 
 def measure_fma_peak(device=0, fp_bits=64):

@@ -228,6 +228,14 @@ typedef struct hy_launch_info {
 } hy_launch_info;
 int hy_get_launch_info(hy_ctx *ctx, hy_launch_info *info);
 
+/* Which kernel hy_create would pick for a tape (no device needed): 0 = the tape
+ * interpreter, N > 0 = the register-resident N-body kernel for N bodies.  The
+ * latter needs the tape of a Newtonian N-body system in Cartesian coordinates
+ * (what the reference's model.nbody builds, expose_models.cpp:237-272), no
+ * events or parameters, every pair present, order <= 20 (hy_nbody_match.hpp). */
+int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term *terms,
+                           uint32_t *variant);
+
 /* DFMA/FFMA peak microbenchmark used as the compute roof (no peak for
  * FP64/FP32 FMA is in MEASURED_PEAKS.json): returns TFLOP/s. */
 int hy_measure_fma_peak(int device, int fp_bits, double *tflops);

@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     assert D.op_dtype.itemsize == 32 and D.term_dtype.itemsize == 24
     assert ctypes.sizeof(_cabi.dims_t) == 36
     assert ctypes.sizeof(_cabi.event_rec_t) == 24 and _cabi.event_rec_dtype.itemsize == 24
-    assert ctypes.sizeof(_cabi.launch_info_t) == 32
+    assert ctypes.sizeof(_cabi.launch_info_t) == 36  # 9 x uint32 (incl. kernel_variant)
 
 
 def test_no_cpu_fallback():

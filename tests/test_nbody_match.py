@@ -1,0 +1,63 @@
+"""CPU tests of the tape matcher that selects the register-resident N-body
+kernel (csrc/hy_nbody_match.hpp, through the C ABI hy_tape_kernel_variant; no
+device needed).  Anything that is not exactly the tape of the reference's
+model.nbody (expose_models.cpp:237-272) must stay on the tape interpreter."""
+
+import numpy as np
+
+import hy_b200 as hy
+from hy_b200 import _cabi, decompose as D
+
+import common
+
+
+def _variant(sys_, order=20, **kw):
+    return _cabi.tape_kernel_variant(D.decompose(sys_, order, **kw))
+
+
+def test_outer_solar_system_matches():
+    assert _variant(common.oss_sys()) == 6
+    # any masses / G, and any order up to 20
+    sys_ = hy.model.nbody(6, masses=[3.0, 1e-3, 2e-4, 5e-5, 1e-5, 7e-9], Gconst=0.5)
+    assert _variant(sys_) == 6
+    assert _variant(sys_, order=12) == 6
+    assert _variant(sys_, order=9) == 6
+
+
+def test_non_matching_tapes_keep_the_interpreter():
+    # order above the unrolled maximum
+    assert _variant(common.oss_sys(), order=22) == 0
+    # other systems
+    assert _variant(common.pendulum_sys()) == 0
+    assert _variant(common.cr3bp_sys()) == 0
+    # body counts without a compiled kernel
+    assert _variant(hy.model.nbody(3)) == 0
+    assert _variant(hy.model.nbody(7)) == 0
+    # a massless body drops terms from the sums: not the full pattern
+    assert _variant(hy.model.nbody(6, masses=[1.0, 1e-3, 1e-3, 1e-3, 1e-3, 0.0])) == 0
+
+
+def test_perturbed_nbody_is_rejected():
+    # an extra force term / a different exponent must not be swallowed by the matcher
+    sys_ = common.oss_sys()
+    x0 = sys_[0][0]
+    pert = list(sys_)
+    pert[3] = (pert[3][0], pert[3][1] + 1e-9 * x0)
+    assert _variant(pert) == 0
+    xs = hy.make_vars(*["q{}".format(i) for i in range(36)])
+    # same structure with r^-2 forces (exponent -1.0 instead of -1.5)
+    eqs = []
+    acc = {i: [0, 0, 0] for i in range(6)}
+    for i in range(6):
+        for j in range(i + 1, 6):
+            dd = [xs[6 * j + c] - xs[6 * i + c] for c in range(3)]
+            w = hy.pow(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2], -1.0)
+            for c in range(3):
+                acc[i][c] = acc[i][c] + 0.3 * (dd[c] * w)
+                acc[j][c] = acc[j][c] + (-0.2) * (dd[c] * w)
+    for i in range(6):
+        for c in range(3):
+            eqs.append((xs[6 * i + c], xs[6 * i + 3 + c]))
+        for c in range(3):
+            eqs.append((xs[6 * i + 3 + c], acc[i][c]))
+    assert _variant(eqs) == 0
