@@ -837,10 +837,12 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
         nl.xa = (int32_t)(NBR_BS * lr.x);
         nl.xb = (int32_t)(NBR_BS * lr.y);
         nl.ta = (int32_t)(NBR_TB0 + NBR_TS * sub);
-        // Body lanes: lanes 0..2NB-1 of the WARP serve the NB bodies of its two trajectories
-        // (all in one half-warp: a 64-bit shared access costs one wavefront per active half-warp).
-        nl.body = lane < 2u * NB;
-        const uint32_t bt = nl.body ? lane / NB : 0u, bd = nl.body ? lane % NB : 0u;
+        // Body lanes: lanes of the FIRST half-warp serve the NB bodies of the warp's two trajectories
+        // (a 64-bit shared access costs one wavefront per active half-warp).
+        // (trajectory 0: lanes 0..NB-1, trajectory 1: lanes 8..8+NB-1 - one quarter-warp each, so the
+        // 128-bit accesses of the two trajectories never meet in one wavefront)
+        nl.body = lane < 16u && (lane & 7u) < (uint32_t)NB;
+        const uint32_t bt = nl.body ? lane >> 3 : 0u, bd = nl.body ? lane & 7u : 0u;
         const int32_t col = (bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
         nl.xbody = col + (int32_t)(NBR_BS * bd);
         nl.coef = (int32_t)(NBR_CS * bd);
@@ -978,17 +980,21 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             const unsigned tmask = NB > 0 ? TM_FULL : gmask;
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
+            // NB > 0: lane `sub` < 2 NB owns one 3-vector of the state (position or velocity of a body;
+            // the assignment keeps the 128-bit accesses of a quarter-warp conflict-free)
+            const uint32_t vb = sub < (uint32_t)NB ? sub : (sub < 8u ? sub - 2u : sub - 8u);  // body
+            const uint32_t voff = vb * (uint32_t)NBR_BS + (sub < (uint32_t)NB ? 0u : 4u);       // block offset
+            const bool vown = NB > 0 && sub < 2u * NB && vb < (uint32_t)NB;
             if constexpr (NB > 0) {
-                // state jets at w[nbr_state_off(i) + order * NBR_JS], three variables per lane at most
-#pragma unroll
-                for (int u = 0; u < (6 * NB + G - 1) / G; ++u) {
-                    const uint32_t i = sub + u * G;
-                    if (i < 6u * NB) {
-                        const R *x = w + nbr_state_off((int)i);
-                        n0 = nan_max(n0, r_abs(x[0]));
-                        n1 = nan_max(n1, r_abs(x[(p - 1) * NBR_JS]));
-                        n2 = nan_max(n2, r_abs(x[p * NBR_JS]));
-                    }
+                static_assert(NB == 6 || NB == 0, "vector assignment of the tail is laid out for 6 bodies");
+                if (vown) {
+                    Vec3<R> a, b, c;
+                    lds3(w + voff, a);
+                    lds3(w + voff + (p - 1) * NBR_JS, b);
+                    lds3(w + voff + p * NBR_JS, c);
+                    n0 = nan_max(nan_max(nan_max(n0, r_abs(a.x)), r_abs(a.y)), r_abs(a.z));
+                    n1 = nan_max(nan_max(nan_max(n1, r_abs(b.x)), r_abs(b.y)), r_abs(b.z));
+                    n2 = nan_max(nan_max(nan_max(n2, r_abs(c.x)), r_abs(c.y)), r_abs(c.z));
                 }
             } else {
                 for (uint32_t i = sub; i < n + d.n_events; i += G) {
@@ -1088,33 +1094,29 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             if constexpr (NB > 0) __syncwarp(); // reconverge the two half-warps
             bool finite = true;
             if (NB > 0 && !P.high_accuracy) {
-                // Horner with direct addressing, the lane's variables interleaved (independent chains)
-                constexpr int NV = NB > 0 ? (6 * NB + G - 1) / G : 1;
-                R *x[NV];
-                R acc[NV];
+                // Horner on the lane's 3-vector: three independent chains, 128-bit + 64-bit loads
+                if (vown) {
+                    R *x = w + voff;
+                    Vec3<R> acc, t;
+                    lds3(x + p * NBR_JS, acc);
+                    if (p == (uint32_t)NBR_PMAX) {
 #pragma unroll
-                for (int u = 0; u < NV; ++u) {
-                    const uint32_t i = sub + u * G;
-                    x[u] = w + nbr_state_off((int)(i < n ? i : sub));
-                    acc[u] = x[u][p * NBR_JS];
-                }
-                if (p == (uint32_t)NBR_PMAX) {
-#pragma unroll
-                    for (int k = NBR_PMAX - 1; k >= 0; --k)
-#pragma unroll
-                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], hn, x[u][k * NBR_JS]);
-                } else {
-                    for (uint32_t k = p; k-- > 0;)
-#pragma unroll
-                        for (int u = 0; u < NV; ++u) acc[u] = r_fma(acc[u], hn, x[u][k * NBR_JS]);
-                }
-#pragma unroll
-                for (int u = 0; u < NV; ++u) {
-                    const uint32_t i = sub + u * G;
-                    if (i < n) {
-                        finite = finite && (r_abs(acc[u]) < r_inf<R>());
-                        if (stepping) x[u][0] = acc[u];
+                        for (int k = NBR_PMAX - 1; k >= 0; --k) {
+                            lds3(x + k * NBR_JS, t);
+                            acc.x = r_fma(acc.x, hn, t.x);
+                            acc.y = r_fma(acc.y, hn, t.y);
+                            acc.z = r_fma(acc.z, hn, t.z);
+                        }
+                    } else {
+                        for (uint32_t k = p; k-- > 0;) {
+                            lds3(x + k * NBR_JS, t);
+                            acc.x = r_fma(acc.x, hn, t.x);
+                            acc.y = r_fma(acc.y, hn, t.y);
+                            acc.z = r_fma(acc.z, hn, t.z);
+                        }
                     }
+                    finite = r_abs(acc.x) < r_inf<R>() && r_abs(acc.y) < r_inf<R>() && r_abs(acc.z) < r_inf<R>();
+                    if (stepping) sts3(x, acc.x, acc.y, acc.z);
                 }
             } else if (stepping) {
                 for (uint32_t i = sub; i < n; i += G) {
