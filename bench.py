@@ -227,11 +227,30 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything libraries print on stdout (e.g. NCCL's version banner) to
+    stderr: stdout carries exactly ONE line, the bench JSON."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -411,7 +430,7 @@ def main():
             "clocks": clocks,
             "trajectory_steps_per_step": steps_all / args.steps,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
