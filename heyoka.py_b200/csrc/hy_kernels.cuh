@@ -842,7 +842,9 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
         // (trajectory 0: lanes 0..NB-1, trajectory 1: lanes 8..8+NB-1 - one quarter-warp each, so the
         // 128-bit accesses of the two trajectories never meet in one wavefront)
         nl.body = lane < 16u && (lane & 7u) < (uint32_t)NB;
-        const uint32_t bt = nl.body ? lane >> 3 : 0u, bd = nl.body ? lane & 7u : 0u;
+        // (every lane gets valid body addresses - the loads of the body phase are not predicated:
+        // lanes 16..31 mirror lanes 0..15, the spare lanes of a quarter-warp mirror its first bodies)
+        const uint32_t bt = (lane >> 3) & 1u, bd = (lane & 7u) % (uint32_t)NB;
         const int32_t col = (bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
         nl.xbody = col + (int32_t)(NBR_BS * bd);
         nl.coef = (int32_t)(NBR_CS * bd);
@@ -1100,12 +1102,15 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
                     Vec3<R> acc, t;
                     lds3(x + p * NBR_JS, acc);
                     if (p == (uint32_t)NBR_PMAX) {
+                        // all loads first (independent), then the three FMA chains
+                        Vec3<R> c[NBR_PMAX];
+#pragma unroll
+                        for (int k = 0; k < NBR_PMAX; ++k) lds3(x + k * NBR_JS, c[k]);
 #pragma unroll
                         for (int k = NBR_PMAX - 1; k >= 0; --k) {
-                            lds3(x + k * NBR_JS, t);
-                            acc.x = r_fma(acc.x, hn, t.x);
-                            acc.y = r_fma(acc.y, hn, t.y);
-                            acc.z = r_fma(acc.z, hn, t.z);
+                            acc.x = r_fma(acc.x, hn, c[k].x);
+                            acc.y = r_fma(acc.y, hn, c[k].y);
+                            acc.z = r_fma(acc.z, hn, c[k].z);
                         }
                     } else {
                         for (uint32_t k = p; k-- > 0;) {

@@ -180,33 +180,31 @@ template <typename R> struct Vec3 {
     R x, y, z;
 };
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// (plain typed accesses: the compiler knows the alignment from the vector type and is free to
+// schedule them; __syncwarp orders them like any other memory access)
 __device__ __forceinline__ void lds3(const double *p, Vec3<double> &v)
 {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%3];\n\tld.shared.f64 %2, [%3+16];"
-                 : "=d"(v.x), "=d"(v.y), "=d"(v.z)
-                 : "r"(smem_u32(p))
-                 : "memory");
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    v.x = a.x;
+    v.y = a.y;
+    v.z = p[2];
 }
 __device__ __forceinline__ void lds3(const float *p, Vec3<float> &v)
 {
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%3];\n\tld.shared.f32 %2, [%3+8];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z)
-                 : "r"(smem_u32(p))
-                 : "memory");
+    const float2 a = *reinterpret_cast<const float2 *>(p);
+    v.x = a.x;
+    v.y = a.y;
+    v.z = p[2];
 }
 __device__ __forceinline__ void sts3(double *p, double x, double y, double z)
 {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n\tst.shared.f64 [%0+16], %3;"
-                 :
-                 : "r"(smem_u32(p)), "d"(x), "d"(y), "d"(z)
-                 : "memory");
+    *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+    p[2] = z;
 }
 __device__ __forceinline__ void sts3(float *p, float x, float y, float z)
 {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n\tst.shared.f32 [%0+8], %3;"
-                 :
-                 : "r"(smem_u32(p)), "f"(x), "f"(y), "f"(z)
-                 : "memory");
+    *reinterpret_cast<float2 *>(p) = make_float2(x, y);
+    p[2] = z;
 }
 __device__ __forceinline__ void lds3_if(const double *p, Vec3<double> &v, bool on)
 {
@@ -270,15 +268,17 @@ template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
             dk2 = xa.z - xb.z;
         }
         {
-            // BODY LANES (predicated; the other lanes compute on zeros and store nothing):
-            // acceleration of the body at order K - the tape's LINCOMB, term order kept -
-            // then v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2)
+            // BODY LANES: acceleration of the body at order K - the tape's LINCOMB, term order
+            // kept - then v[K+1] = a[K]/(K+1) and x[K+2] = v[K+1]/(K+2).  No branch: every lane runs
+            // the loads and the arithmetic (the other lanes mirror a body lane: a zeroing move and a
+            // predicate per load would cost more issue slots than the duplicate wavefronts), only
+            // the stores are predicated.
             const bool on = L.body;
             R a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 Vec3<R> t;
-                lds3_if(&w[L.tin[q] + buf], t, on);
+                lds3(&w[L.tin[q] + buf], t); // (unpredicated: the other lanes mirror a body lane's address)
                 a0 = fma(cf[q], t.x, a0);
                 a1 = fma(cf[q], t.y, a1);
                 a2 = fma(cf[q], t.z, a2);
@@ -310,7 +310,7 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     // x[1] = v[0]
     {
         Vec3<R> v;
-        lds3_if(&w[L.xbody + 4], v, L.body);
+        lds3(&w[L.xbody + 4], v);
         sts3_if(&w[L.xbody + JS], v.x, v.y, v.z, L.body);
     }
     Vec3<R> xa, xb;
