@@ -12,6 +12,7 @@
 
 #include "hy_kernels.cuh"
 #include "hy_nbody_match.hpp"
+#include "hy_nb_launch.hpp"
 
 namespace {
 
@@ -100,8 +101,14 @@ cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStre
 template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
 {
     // register-resident N-body kernels (hy_nbody_reg.cuh)
-    if (li.kernel_variant == 6) return launch_g<R, 16, true, 6>(P, li, s);
-    if (li.kernel_variant) return cudaErrorInvalidValue;
+    switch (li.kernel_variant) { // instantiated in hy_nb3.cu ... hy_nb6.cu
+    case 0: break;
+    case 3: return hy::launch_nbody_kernel<R, 3>(P, li, s);
+    case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s);
+    case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s);
+    case 6: return hy::launch_nbody_kernel<R, 6>(P, li, s);
+    default: return cudaErrorInvalidValue;
+    }
     if (li.ws_in_smem) {
         switch (li.group) {
         case 1: return launch_g<R, 1, true>(P, li, s);
@@ -126,7 +133,13 @@ template <typename R, int G, bool SMEM, int NB = 0> int regs_of()
 
 template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant)
 {
-    if (variant == 6) return regs_of<R, 16, true, 6>();
+    switch (variant) {
+    case 3: return hy::regs_nbody_kernel<R, 3>();
+    case 4: return hy::regs_nbody_kernel<R, 4>();
+    case 5: return hy::regs_nbody_kernel<R, 5>();
+    case 6: return hy::regs_nbody_kernel<R, 6>();
+    default: break;
+    }
     if (!smem) return regs_of<R, 1, false>();
     switch (g) {
     case 1: return regs_of<R, 1, true>();

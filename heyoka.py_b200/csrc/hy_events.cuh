@@ -174,7 +174,7 @@ template <typename R> __device__ inline int ev_find_roots(const R *c_in, int p, 
 // event that truncated it (-1: none).  Non-terminal events before the
 // truncation point and the terminal event itself are appended to the log.
 template <typename R>
-__device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, uint32_t n_events, uint32_t n_tevents,
+static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, uint32_t n_events, uint32_t n_tevents,
                                      int p, R h, R t_hi, R t_lo, uint32_t traj, unsigned long long step_idx,
                                      const EvParams<R> E, R &h_out, int &term_out)
 {

@@ -31,31 +31,22 @@ __device__ __forceinline__ float r_fma(float a, float b, float c) { return fmaf(
 __device__ __forceinline__ double r_sqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ float r_sqrt(float a) { return sqrtf(a); }
 // libm calls are kept out of line: one copy each, so the hot loop stays small.
-__device__ __noinline__ double r_pow(double a, double b) { return pow(a, b); }
-__device__ __noinline__ float r_pow(float a, float b) { return powf(a, b); }
-__device__ __noinline__ double r_exp(double a) { return exp(a); }
-__device__ __noinline__ float r_exp(float a) { return expf(a); }
-__device__ __noinline__ double r_log(double a) { return log(a); }
-__device__ __noinline__ float r_log(float a) { return logf(a); }
-__device__ __noinline__ void r_sincos(double a, double *s, double *c) { sincos(a, s, c); }
-__device__ __noinline__ void r_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
+static __device__ __noinline__ double r_pow(double a, double b) { return pow(a, b); }
+static __device__ __noinline__ float r_pow(float a, float b) { return powf(a, b); }
+static __device__ __noinline__ double r_exp(double a) { return exp(a); }
+static __device__ __noinline__ float r_exp(float a) { return expf(a); }
+static __device__ __noinline__ double r_log(double a) { return log(a); }
+static __device__ __noinline__ float r_log(float a) { return logf(a); }
+static __device__ __noinline__ void r_sincos(double a, double *s, double *c) { sincos(a, s, c); }
+static __device__ __noinline__ void r_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
 __device__ __forceinline__ double r_abs(double a) { return fabs(a); }
 __device__ __forceinline__ float r_abs(float a) { return fabsf(a); }
 __device__ __forceinline__ double r_copysign(double a, double b) { return copysign(a, b); }
 __device__ __forceinline__ float r_copysign(float a, float b) { return copysignf(a, b); }
 // x^e for the step-size radii (x > 0, e = 1/p): exp(log(x) * e).  The error of log() is
 // scaled by e <= 1/2, so the result is good to ~1 ulp - at a third of the cost of pow().
-#ifndef HY_T_NORM
-#define HY_T_NORM 1
-#endif
-#ifndef HY_T_HORNER
-#define HY_T_HORNER 1
-#endif
-#ifndef HY_T_ROOT
-#define HY_T_ROOT 1
-#endif
-__device__ __noinline__ double r_root(double x, double e) { return HY_T_ROOT ? exp(log(x) * e) : pow(x, e); }
-__device__ __noinline__ float r_root(float x, float e) { return expf(logf(x) * e); }
+static __device__ __noinline__ double r_root(double x, double e) { return exp(log(x) * e); }
+static __device__ __noinline__ float r_root(float x, float e) { return expf(logf(x) * e); }
 template <typename R> __device__ __forceinline__ R r_inf();
 template <> __device__ __forceinline__ double r_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
@@ -984,11 +975,13 @@ __global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
             R n0 = 0, n1 = 0, n2 = 0;
             // NB > 0: lane `sub` < 2 NB owns one 3-vector of the state (position or velocity of a body;
             // the assignment keeps the 128-bit accesses of a quarter-warp conflict-free)
-            const uint32_t vb = sub < (uint32_t)NB ? sub : (sub < 8u ? sub - 2u : sub - 8u);  // body
+            // (NB = 6: positions of bodies 0-5 on lanes 0-5, velocities of bodies 4, 5 on lanes 6, 7 and of
+            // bodies 0-3 on lanes 8-11 - conflict-free quarter-warps; otherwise positions first, then velocities)
+            const uint32_t vb = NB == 6 ? (sub < 6u ? sub : (sub < 8u ? sub - 2u : sub - 8u))
+                                        : (sub < (uint32_t)NB ? sub : sub - (uint32_t)NB);     // body
             const uint32_t voff = vb * (uint32_t)NBR_BS + (sub < (uint32_t)NB ? 0u : 4u);       // block offset
             const bool vown = NB > 0 && sub < 2u * NB && vb < (uint32_t)NB;
             if constexpr (NB > 0) {
-                static_assert(NB == 6 || NB == 0, "vector assignment of the tail is laid out for 6 bodies");
                 if (vown) {
                     Vec3<R> a, b, c;
                     lds3(w + voff, a);

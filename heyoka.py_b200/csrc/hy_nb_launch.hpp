@@ -1,0 +1,35 @@
+// hy_nb_launch.hpp - launch entry points of the register-resident N-body kernels.
+// Every body count is instantiated in its own translation unit (hy_nb3.cu ... hy_nb6.cu:
+// the fully unrolled order loops are long, nvcc compiles the units in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hy_kernels.cuh"
+
+namespace hy {
+
+template <typename R, int NB> cudaError_t launch_nbody_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s);
+template <typename R, int NB> int regs_nbody_kernel();
+
+#define HY_NB_INSTANTIATE(NB)                                                                            \
+    template <typename R, int N> cudaError_t launch_nbody_kernel(const KParams<R> &P, const hy_launch_info &li, \
+                                                                 cudaStream_t s)                        \
+    {                                                                                                    \
+        auto kern = propagate_kernel<R, 16, true, N>;                                                    \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes); \
+        if (e != cudaSuccess) return e;                                                                  \
+        kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);                                              \
+        return cudaGetLastError();                                                                       \
+    }                                                                                                    \
+    template <typename R, int N> int regs_nbody_kernel()                                                 \
+    {                                                                                                    \
+        cudaFuncAttributes a{};                                                                          \
+        if (cudaFuncGetAttributes(&a, propagate_kernel<R, 16, true, N>) != cudaSuccess) return 0;        \
+        return a.numRegs;                                                                                \
+    }                                                                                                    \
+    template cudaError_t launch_nbody_kernel<double, NB>(const KParams<double> &, const hy_launch_info &, cudaStream_t); \
+    template cudaError_t launch_nbody_kernel<float, NB>(const KParams<float> &, const hy_launch_info &, cudaStream_t);  \
+    template int regs_nbody_kernel<double, NB>();                                                        \
+    template int regs_nbody_kernel<float, NB>();
+
+} // namespace hy

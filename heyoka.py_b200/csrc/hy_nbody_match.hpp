@@ -31,8 +31,8 @@ struct NbMatch {
     std::vector<double> imm; // NBR_NIMM entries (layout in hy_nbody_reg.cuh)
 };
 
-// body counts with a compiled register-resident kernel (hy_cuda.cu: launch<>)
-inline bool nbody_kernel_compiled(uint32_t nb) { return nb == 6; }
+// body counts with a compiled register-resident kernel (hy_nb3.cu ... hy_nb6.cu)
+inline bool nbody_kernel_compiled(uint32_t nb) { return nb >= 3 && nb <= 6; }
 
 inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms, NbMatch &out)
 {

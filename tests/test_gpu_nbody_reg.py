@@ -78,6 +78,31 @@ def test_bitwise_vs_interpreter(fp):
     assert a.propagate_res == b.propagate_res
 
 
+@pytest.mark.parametrize("nb", [3, 4, 5])
+def test_smaller_systems_bitwise_and_oracle(nb):
+    # the first nb bodies of the outer Solar System (Sun + giant planets)
+    B = 37
+    sys_ = hy.model.nbody(nb, masses=list(common.OSS_MASSES[:nb]), Gconst=common.OSS_G)
+    ic = common.oss_ensemble(B, amp=1e-4)[: 6 * nb].copy()
+    a = _make(sys_, ic)
+    b = _make(sys_, ic, interp=True)
+    assert a._ctx.launch_info()["kernel_variant"] == nb
+    assert b._ctx.launch_info()["kernel_variant"] == 0
+    a.step(write_tc=True)
+    b.step(write_tc=True)
+    assert np.array_equal(a.tc, b.tc)
+    assert np.array_equal(a.state, b.state)
+    a.propagate_until(80.0)
+    b.propagate_until(80.0)
+    assert np.array_equal(a.state, b.state)
+    assert a.propagate_res == b.propagate_res
+    orc = COracle(D.decompose(sys_, a.order), ic)
+    orc.step()
+    oc, mn, mx, ns, _ = orc.propagate_until(80.0)
+    assert [r[3] for r in a.propagate_res] == list(ns)
+    assert _rel(a.state, orc.state) < 1e-11
+
+
 def test_oracle_parity_fp64():
     B = 48
     sys_ = common.oss_sys()

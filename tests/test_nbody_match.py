@@ -24,14 +24,19 @@ def test_outer_solar_system_matches():
     assert _variant(sys_, order=9) == 6
 
 
+def test_smaller_body_counts_match():
+    for nb in (3, 4, 5):
+        assert _variant(hy.model.nbody(nb, masses=[1.0] + [1e-3] * (nb - 1), Gconst=0.7)) == nb
+
+
 def test_non_matching_tapes_keep_the_interpreter():
     # order above the unrolled maximum
     assert _variant(common.oss_sys(), order=22) == 0
     # other systems
     assert _variant(common.pendulum_sys()) == 0
     assert _variant(common.cr3bp_sys()) == 0
-    # body counts without a compiled kernel
-    assert _variant(hy.model.nbody(3)) == 0
+    # body counts without a compiled kernel (3..6 have one)
+    assert _variant(hy.model.nbody(2)) == 0
     assert _variant(hy.model.nbody(7)) == 0
     # a massless body drops terms from the sums: not the full pattern
     assert _variant(hy.model.nbody(6, masses=[1.0, 1e-3, 1e-3, 1e-3, 1e-3, 0.0])) == 0
