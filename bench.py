@@ -326,6 +326,15 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     assert np.all(oc == int(hy.taylor_outcome.time_limit)), "some trajectories did not finish"
+    # Sanity of what was timed (outside the timed region): the final state of the device arm
+    # conserves the energy of every trajectory.
+    from hy_b200 import workloads as W
+
+    st_end = np.empty_like(ic)
+    ctx.download(state=st_end)
+    e0_, e1_ = W.oss_energy(ic), W.oss_energy(st_end)
+    energy_drift = float(np.max(np.abs((e1_ - e0_) / e0_)))
+    assert energy_drift < 1e-10, energy_drift
 
     from hy_b200.shard import reduce_throughput
 
@@ -422,6 +431,8 @@ def main():
                 "l2": "flushed between iterations (256 MiB memset)",
                 "launch": li,
                 "wall_s_timed_region": wall,
+                "check": {"max_rel_energy_drift_after_timed_steps": energy_drift,
+                          "all_outcomes_time_limit": True},
             },
             "roofline": roof,
             "cpu_baseline": cpu,
