@@ -103,6 +103,21 @@ def test_smaller_systems_bitwise_and_oracle(nb):
     assert _rel(a.state, orc.state) < 1e-11
 
 
+@pytest.mark.parametrize("B", [1, 2, 3, 17])
+def test_tiny_batches(B):
+    # fewer trajectories than one warp / one CTA holds: the spare half-warps idle through the steps
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(B, amp=1e-5)
+    a = _make(sys_, ic)
+    b = _make(sys_, ic, interp=True)
+    assert a._ctx.launch_info()["kernel_variant"] == 6
+    a.propagate_until(30.0)
+    b.propagate_until(30.0)
+    assert np.array_equal(a.state, b.state)
+    assert a.propagate_res == b.propagate_res
+    assert np.all(a.time == 30.0)
+
+
 def test_oracle_parity_fp64():
     B = 48
     sys_ = common.oss_sys()
