@@ -173,8 +173,8 @@ template <int NB> struct NbrLane {
     bool body;
 };
 
-// 128-bit + 64-bit shared-memory moves of a 3-vector (16-byte aligned), optionally predicated.
-// The predicated forms keep the body lanes' work in the same basic block as the pair
+// 128-bit + 64-bit shared-memory moves of a 3-vector (16-byte aligned).  The body lanes' stores
+// are predicated inline PTX, not a branch: their work stays in the same basic block as the pair
 // convolutions of the next order, so ptxas interleaves the two.
 template <typename R> struct Vec3 {
     R x, y, z;
@@ -206,25 +206,7 @@ __device__ __forceinline__ void sts3(float *p, float x, float y, float z)
     *reinterpret_cast<float2 *>(p) = make_float2(x, y);
     p[2] = z;
 }
-__device__ __forceinline__ void lds3_if(const double *p, Vec3<double> &v, bool on)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
-                 "mov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
-                 "mov.f64 %2, 0d0000000000000000;\n\t"
-                 "@q ld.shared.v2.f64 {%0, %1}, [%3];\n\t@q ld.shared.f64 %2, [%3+16];\n\t}"
-                 : "=d"(v.x), "=d"(v.y), "=d"(v.z)
-                 : "r"(smem_u32(p)), "r"((int)on)
-                 : "memory");
-}
-__device__ __forceinline__ void lds3_if(const float *p, Vec3<float> &v, bool on)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
-                 "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
-                 "@q ld.shared.v2.f32 {%0, %1}, [%3];\n\t@q ld.shared.f32 %2, [%3+8];\n\t}"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z)
-                 : "r"(smem_u32(p)), "r"((int)on)
-                 : "memory");
-}
+// Predicated vector store (no branch: the code stays in one basic block).
 __device__ __forceinline__ void sts3_if(double *p, double x, double y, double z, bool on)
 {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
