@@ -171,7 +171,7 @@ int choose_geometry(hy_ctx *c)
     int smem_optin = 0;
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const hy_dims &d = c->d;
-    const uint32_t max_threads = 256; // == __launch_bounds__ of propagate_kernel (up to 255 registers per thread)
+    const uint32_t max_threads = 256; // == __launch_bounds__ of the 255-register kernels (hy_max_threads)
     hy_launch_info &li = c->li;
     li.n_sm = (uint32_t)prop.multiProcessorCount;
     const bool force_global = env_u32("HY_CUDA_FORCE_GLOBAL_WS", 0) != 0;
@@ -228,8 +228,9 @@ int choose_geometry(hy_ctx *c)
         uint32_t Tfit = budget / (RS * (uint32_t)c->rb);
         bool smem = Tfit >= 1 && !force_global;
         if (!smem && G != 1) continue; // the global-workspace fallback kernel exists for G = 1 only
-        uint32_t T = smem ? std::min(Tfit, max_threads / G) : std::max(1u, 256u / G);
-        const double threads = std::min<double>((double)T * G, max_threads);
+        const uint32_t mt = (uint32_t)hy::hy_max_threads((int)G, smem, 0); // 512 for the small-group interpreter variants
+        uint32_t T = smem ? std::min(Tfit, mt / G) : std::max(1u, 256u / G);
+        const double threads = std::min<double>((double)T * G, mt);
         const double score = pr.lane_utilisation * threads * (smem ? 1.0 : 0.05);
         if (score > best_score * 1.02) {
             best_score = score;

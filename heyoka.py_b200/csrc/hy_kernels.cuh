@@ -763,10 +763,18 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     return L;
 }
 
+// Threads per CTA (= the register budget: 65536 / threads).  The interpreter's small-group
+// variants (G < 16: small systems, short jets) trade registers for resident trajectories;
+// G = 16 and the register-resident N-body kernels need all 255 registers.
+__host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB)
+{
+    return (NB == 0 && smem && G < 16) ? 512 : 256;
+}
+
 // NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); the tape
 // interpreter is not instantiated.  NB = 0: tape interpreter.
 template <typename R, int G, bool SMEM, int NB = 0>
-__global__ void __launch_bounds__(256, 1) propagate_kernel(const KParams<R> P)
+__global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
