@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -107,6 +108,9 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s);
     case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s);
     case 6: return hy::launch_nbody_kernel<R, 6>(P, li, s);
+    case 106: // warpgroup rotation (experimental)
+        if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_wgx(P, li, s);
+        return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
     if (li.ws_in_smem) {
@@ -134,6 +138,7 @@ template <typename R, int G, bool SMEM, int NB = 0> int regs_of()
 template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant)
 {
     switch (variant) {
+    case 106: return 168;
     case 3: return hy::regs_nbody_kernel<R, 3>();
     case 4: return hy::regs_nbody_kernel<R, 4>();
     case 5: return hy::regs_nbody_kernel<R, 5>();
@@ -192,7 +197,10 @@ int choose_geometry(hy_ctx *c)
         pr.n_phases = 0;
         pr.phase_slot = {0};
         pr.imm = nbm.imm;
-        pr.ws_len = (uint32_t)hy::NBR_WS;
+        // experimental: warpgroup rotation (24 trajectories per SM, registers traded between warpgroups)
+        const bool wgx = env_u32("HY_CUDA_WGX", 0) != 0 && nbm.nb == 6 && c->fp_bits == 64 &&
+                         d.order == (uint32_t)hy::NBR_PMAX && c->B >= 24u * li.n_sm;
+        pr.ws_len = (uint32_t)hy::nbr_ws(wgx);
         pr.par_off = pr.one_off = pr.ws_len;
         pr.n_spill = 0;
         for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back((uint32_t)hy::nbr_state_off((int)i));
@@ -205,11 +213,15 @@ int choose_geometry(hy_ctx *c)
         const uint32_t fixed = L0.total + 64;
         if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 2) {
             bestG = 16;
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 16u) & ~1u;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), (wgx ? 384u : max_threads) / 16u) & ~1u;
             bestRS = RS;
             best_smem = true;
             best = pr;
             li.kernel_variant = nbm.nb;
+            if (wgx) {
+                if (bestT != 24u) return fail("hy_create: HY_CUDA_WGX needs 24 trajectories per CTA in shared memory");
+                li.kernel_variant = 106;
+            }
         }
     }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
@@ -250,6 +262,7 @@ int choose_geometry(hy_ctx *c)
     uint32_t per_cta_needed = std::max(1u, (c->B + li.n_sm - 1) / li.n_sm);
     T = std::max(1u, std::min(T, per_cta_needed));
     if (li.kernel_variant) T = (T + 1u) & ~1u; // whole warps: the two trajectories of a warp step in lockstep
+    if (li.kernel_variant == 106) T = 24;      // whole warpgroups
     li.group = G;
     li.traj_per_cta = T;
     li.threads = ((T * G + 31) / 32) * 32;
@@ -340,6 +353,7 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.T = c->li.traj_per_cta;
     P.TS = c->TS;
     P.nb_tb_off = (uint32_t)hy::NBR_TB0;
+    P.wgx_wgs = env_u32("HY_CUDA_WGX_WGS", 3);
     P.max_steps = max_steps;
     P.mode = mode;
     P.backward = backward;

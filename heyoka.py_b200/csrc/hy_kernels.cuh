@@ -101,6 +101,7 @@ template <typename R> struct KParams {
     R *gws; // global workspace fallback (ws_in_smem == 0)
     uint32_t B, T, TS;
     uint32_t nb_tb_off; // register-resident N-body path: offset of the exchange buffer in the column
+    uint32_t wgx_wgs;   // WGX: warpgroups that take work (3; fewer for experiments)
     unsigned long long max_steps;
     int mode, backward, write_tc, high_accuracy, ws_in_smem;
     R rhofac, inv_p, inv_pm1;
@@ -773,8 +774,10 @@ __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB)
 
 // NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); the tape
 // interpreter is not instantiated.  NB = 0: tape interpreter.
-template <typename R, int G, bool SMEM, int NB = 0>
-__global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kernel(const KParams<R> P)
+// WGX: warpgroup rotation (hy_nbody_reg.cuh): 384 threads, 24 trajectories, registers traded
+// between the warpgroups at the phase boundaries of the step.
+template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false>
+__global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
@@ -835,7 +838,7 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
         const uint2 lr = *reinterpret_cast<const uint2 *>(s_imm + NBR_LANE0 + sub);
         nl.xa = (int32_t)(NBR_BS * lr.x);
         nl.xb = (int32_t)(NBR_BS * lr.y);
-        nl.ta = (int32_t)(NBR_TB0 + NBR_TS * sub);
+        nl.ta = (int32_t)(NBR_TB0 + nbr_ts(WGX) * sub);
         // Body lanes: lanes of the FIRST half-warp serve the NB bodies of the warp's two trajectories
         // (a 64-bit shared access costs one wavefront per active half-warp).
         // (trajectory 0: lanes 0..NB-1, trajectory 1: lanes 8..8+NB-1 - one quarter-warp each, so the
@@ -850,9 +853,15 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
 #pragma unroll
         for (int q = 0; q < NB - 1; ++q)
             nl.tin[q] = col + NBR_TB0 +
-                        NBR_TS * (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
+                        nbr_ts(WGX) * (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
     }
 
+    const uint32_t wg = threadIdx.x >> 7; // warpgroup (WGX)
+    if constexpr (WGX) {
+        // every warpgroup starts in the tail state; the first two to reach their jets get the registers
+        wg_bar(wg);
+        wg_reg_dec<NBR_WGX_TREG>();
+    }
     // Persistent loop: every iteration is ONE step of the group's current trajectory (or the
     // fetch of a new one).  NB > 0: the two trajectories of a warp step in lockstep (the jets are a
     // warp-wide phase); a half-warp without a live trajectory idles through it on stale data.
@@ -867,7 +876,7 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
     for (;;) {
         if (!have) {
             // ---- fetch the next trajectory for this group ----
-            if (sub == 0) traj = atomicAdd(P.counter, 1u);
+            if (sub == 0) traj = (WGX && wg >= P.wgx_wgs) ? P.B : atomicAdd(P.counter, 1u);
             if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
             if (traj < P.B) {
                 have = true;
@@ -918,7 +927,9 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
                 if (G > 1) __syncwarp(gmask);
             }
         }
-        if constexpr (NB > 0) {
+        if constexpr (WGX) {
+            if (!wg_any(wg, have)) break; // (warpgroup-wide vote: the four warps trade registers together)
+        } else if constexpr (NB > 0) {
             if (!__any_sync(0xffffffffu, have)) break;
         } else {
             if (!have) break;
@@ -941,7 +952,14 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
         if (NB > 0 || stepping) {
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
             if constexpr (NB > 0) {
-                if (p == (uint32_t)NBR_PMAX)
+                if constexpr (WGX) {
+                    // acquire the jet registers (blocks until another warpgroup has left its jets)
+                    wg_bar(wg);
+                    wg_reg_inc<NBR_WGX_JREG>();
+                    nbr_jets<R, NB, NBR_PMAX, true, true>(w, s_imm + nl.coef, nl, p);
+                    wg_bar(wg);
+                    wg_reg_dec<NBR_WGX_TREG>();
+                } else if (p == (uint32_t)NBR_PMAX)
                     nbr_jets<R, NB, NBR_PMAX, true>(w, s_imm + nl.coef, nl, p);
                 else
                     nbr_jets<R, NB, NBR_PMAX, false>(w, s_imm + nl.coef, nl, p);
@@ -1102,7 +1120,7 @@ __global__ void __launch_bounds__(hy_max_threads(G, SMEM, NB), 1) propagate_kern
                     R *x = w + voff;
                     Vec3<R> acc, t;
                     lds3(x + p * NBR_JS, acc);
-                    if (p == (uint32_t)NBR_PMAX) {
+                    if (!WGX && p == (uint32_t)NBR_PMAX) {
                         // all loads first (independent), then the three FMA chains
                         Vec3<R> c[NBR_PMAX];
 #pragma unroll

@@ -47,10 +47,14 @@ constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
 // NBR_BS = 8 * 21 + 2 and NBR_TS = 6 keep the 128-bit accesses of a quarter-warp conflict-free.
 constexpr int NBR_JS = 8;                            // stride between orders of a state variable
 constexpr int NBR_BS = NBR_JS * (NBR_PMAX + 1) + 2;  // stride between bodies
-constexpr int NBR_TS = 6;                            // stride between pair slots of the exchange buffer
 constexpr int NBR_TB0 = NBR_MAXB * NBR_BS;           // offset of the exchange buffer
-constexpr int NBR_TBUF = 16 * NBR_TS;                // one exchange buffer
-constexpr int NBR_WS = NBR_TB0 + 2 * NBR_TBUF;       // column length
+// stride between pair slots of the exchange buffer: 6 (conflict-free 128-bit stores); the
+// warpgroup-rotation variant (WGX, 24 trajectories per SM) packs them at 4 to fit shared memory
+__host__ __device__ constexpr int nbr_ts(bool wgx) { return wgx ? 4 : 6; }
+__host__ __device__ constexpr int nbr_tbuf(bool wgx) { return 16 * nbr_ts(wgx); }            // one exchange buffer
+__host__ __device__ constexpr int nbr_ws(bool wgx) { return NBR_TB0 + 2 * nbr_tbuf(wgx); }    // column length
+// register budgets of the warpgroup-rotation variant (3 warpgroups x 168 = 2 x JREG + TREG)
+constexpr int NBR_WGX_JREG = 224, NBR_WGX_TREG = 56;
 // element offset of state variable i (order 0) in the column
 __host__ __device__ constexpr int nbr_state_off(int i) { return (i / 6) * NBR_BS + (i % 6) + ((i % 6) >= 3 ? 1 : 0); }
 
@@ -225,7 +229,7 @@ __device__ __forceinline__ void sts3_if(float *p, float x, float y, float z, boo
 }
 
 // FULL: the Taylor order equals PMAX (no run-time order checks, one basic block per order).
-template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
+template <typename R, int NB, int PMAX, bool FULL, bool WGX, int K> struct NbrOrders {
     static __device__ __forceinline__ void run(R *__restrict__ w, const R (&cf)[NB - 1], const NbrLane<NB> &L,
                                                const uint32_t p, R (&d0)[PMAX], R (&d1)[PMAX], R (&d2)[PMAX],
                                                R (&r2)[PMAX], R (&c)[PMAX], R &inv, R dk0, R dk1, R dk2)
@@ -234,7 +238,7 @@ template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
             if (K >= p) return;
         }
         constexpr int JS = NBR_JS, NQ = NB - 1;
-        constexpr int buf = (K & 1) * NBR_TBUF;
+        constexpr int buf = (K & 1) * nbr_tbuf(WGX);
         R t0, t1, t2;
         nbr_pair_order<R, K, PMAX>(d0, d1, d2, r2, c, inv, dk0, dk1, dk2, t0, t1, t2);
         sts3(&w[L.ta + buf], t0, t1, t2);
@@ -271,13 +275,13 @@ template <typename R, int NB, int PMAX, bool FULL, int K> struct NbrOrders {
             if constexpr (K + 2 <= PMAX) sts3_if(&w[L.xbody + (K + 2) * JS], v0 * rk2, v1 * rk2, v2 * rk2, on);
         }
         if constexpr (K + 1 < PMAX)
-            NbrOrders<R, NB, PMAX, FULL, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
+            NbrOrders<R, NB, PMAX, FULL, WGX, K + 1>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, dk0, dk1, dk2);
     }
 };
 
 // All orders 0..p-1 of one step.  On entry the order-0 rows of the state jets
 // hold the state (visible to the whole group); on exit rows 0..p are complete.
-template <typename R, int NB, int PMAX, bool FULL>
+template <typename R, int NB, int PMAX, bool FULL, bool WGX = false>
 __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane<NB> &L,
                                          const uint32_t p)
 {
@@ -298,8 +302,26 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     Vec3<R> xa, xb;
     lds3(&w[L.xa], xa);
     lds3(&w[L.xb], xb);
-    NbrOrders<R, NB, PMAX, FULL, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, xa.x - xb.x, xa.y - xb.y, xa.z - xb.z);
+    NbrOrders<R, NB, PMAX, FULL, WGX, 0>::run(w, cf, L, p, d0, d1, d2, r2, c, inv, xa.x - xb.x, xa.y - xb.y, xa.z - xb.z);
     __syncwarp();
+}
+
+// ---- warpgroup rotation (WGX): register hand-over between the warpgroups of a CTA ----
+// The 190 jet registers are live only during the jets.  Three warpgroups share the register file:
+// two hold NBR_WGX_JREG registers (jets), one NBR_WGX_TREG (tail of the step / waiting); a warpgroup
+// releases its registers when it leaves the jets and re-acquires them (blocking) before the next ones.
+template <int N> __device__ __forceinline__ void wg_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void wg_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// named barrier of one warpgroup (ids 1..3; 0 is __syncthreads)
+__device__ __forceinline__ void wg_bar(uint32_t wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1u) : "memory"); }
+__device__ __forceinline__ bool wg_any(uint32_t wg, bool v)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r)
+                 : "r"((uint32_t)v), "r"(wg + 1u)
+                 : "memory");
+    return r != 0;
 }
 
 } // namespace hy
