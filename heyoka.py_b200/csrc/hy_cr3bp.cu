@@ -1,0 +1,25 @@
+// Register-resident CR3BP kernel (see hy_cr3bp_reg.cuh, hy_nb_launch.hpp): two lanes per trajectory.
+#include "hy_nb_launch.hpp"
+
+namespace hy {
+
+template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+{
+    auto kern = propagate_kernel<R, 2, true, -1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
+    return cudaGetLastError();
+}
+template <typename R> int regs_cr3bp_kernel()
+{
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, propagate_kernel<R, 2, true, -1>) != cudaSuccess) return 0;
+    return a.numRegs;
+}
+template cudaError_t launch_cr3bp_kernel<double>(const KParams<double> &, const hy_launch_info &, cudaStream_t);
+template cudaError_t launch_cr3bp_kernel<float>(const KParams<float> &, const hy_launch_info &, cudaStream_t);
+template int regs_cr3bp_kernel<double>();
+template int regs_cr3bp_kernel<float>();
+
+} // namespace hy

@@ -13,6 +13,7 @@
 
 #include "hy_kernels.cuh"
 #include "hy_nbody_match.hpp"
+#include "hy_cr3bp_match.hpp"
 #include "hy_nb_launch.hpp"
 
 namespace {
@@ -111,6 +112,7 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     case 106: // warpgroup rotation (experimental)
         if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_wgx(P, li, s);
         return cudaErrorInvalidValue;
+    case hy::CRB_VARIANT: return hy::launch_cr3bp_kernel<R>(P, li, s); // hy_cr3bp.cu
     default: return cudaErrorInvalidValue;
     }
     if (li.ws_in_smem) {
@@ -139,6 +141,7 @@ template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant
 {
     switch (variant) {
     case 106: return 168;
+    case hy::CRB_VARIANT: return hy::regs_cr3bp_kernel<R>();
     case 3: return hy::regs_nbody_kernel<R, 3>();
     case 4: return hy::regs_nbody_kernel<R, 4>();
     case 5: return hy::regs_nbody_kernel<R, 5>();
@@ -224,6 +227,38 @@ int choose_geometry(hy_ctx *c)
             }
         }
     }
+    // Register-resident CR3BP kernel (hy_cr3bp_reg.cuh): two lanes per trajectory, state jets
+    // [order][variable] in shared memory.
+    hy::CrbMatch crm;
+    if (!li.kernel_variant && !force_global && !Genv && env_u32("HY_CUDA_NO_CR3BP_REG", 0) == 0 &&
+        hy::match_cr3bp(d, c->h_ops.data(), c->h_terms.data(), c->fp_bits, crm)) {
+        hy::Program pr;
+        pr.G = 2;
+        pr.n_phases = 0;
+        pr.phase_slot = {0};
+        pr.imm = crm.imm;
+        pr.ws_len = (uint32_t)hy::CRB_XS * (d.order + 1);
+        pr.par_off = pr.one_off = pr.ws_len;
+        pr.n_spill = 0;
+        for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back(i);
+        pr.state_spill.assign(d.n_state, -1);
+        pr.n_clusters = 2;
+        pr.lane_utilisation = 1.0;
+        // column stride = 2 * odd: the 16 lanes of a half-warp (8 trajectories x 2 lanes, three
+        // elements apart) hit 16 different 64-bit banks
+        uint32_t RS = pr.ws_len;
+        while (RS % 4u != 2u) ++RS;
+        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 2, 0, RS, (uint32_t)c->rb, 0);
+        const uint32_t fixed = L0.total + 64;
+        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 16) {
+            bestG = 2;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 2u) & ~15u;
+            bestRS = RS;
+            best_smem = true;
+            best = pr;
+            li.kernel_variant = (uint32_t)hy::CRB_VARIANT;
+        }
+    }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
         if (li.kernel_variant) break;
         if (Genv && G != Genv) continue;
@@ -263,6 +298,7 @@ int choose_geometry(hy_ctx *c)
     T = std::max(1u, std::min(T, per_cta_needed));
     if (li.kernel_variant) T = (T + 1u) & ~1u; // whole warps: the two trajectories of a warp step in lockstep
     if (li.kernel_variant == 106) T = 24;      // whole warpgroups
+    if (li.kernel_variant == (uint32_t)hy::CRB_VARIANT) T = (T + 15u) & ~15u; // whole warps (16 trajectories)
     li.group = G;
     li.traj_per_cta = T;
     li.threads = ((T * G + 31) / 32) * 32;
@@ -960,6 +996,9 @@ int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term 
     hy::NbMatch m;
     *variant = 0;
     if (hy::match_nbody(*dims, ops, terms, m) && hy::nbody_kernel_compiled(m.nb)) *variant = m.nb;
+    hy::CrbMatch cm; // (FP64 order, then FP32 order: the introspection call does not know the precision)
+    if (!*variant && (hy::match_cr3bp(*dims, ops, terms, 64, cm) || hy::match_cr3bp(*dims, ops, terms, 32, cm)))
+        *variant = (uint32_t)hy::CRB_VARIANT;
     return 0;
 }
 

@@ -22,6 +22,7 @@
 #include "hy_schedule.hpp"
 #include "hy_events.cuh"
 #include "hy_nbody_reg.cuh"
+#include "hy_cr3bp_reg.cuh"
 
 namespace hy {
 
@@ -772,8 +773,9 @@ __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB)
     return (NB == 0 && smem && G < 16) ? 512 : 256;
 }
 
-// NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); the tape
-// interpreter is not instantiated.  NB = 0: tape interpreter.
+// NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); NB < 0: for the
+// CR3BP tape (hy_cr3bp_reg.cuh, G = 2); the tape interpreter is not instantiated.  NB = 0: tape
+// interpreter.  NB != 0: the trajectories of a warp step in lockstep.
 // WGX: warpgroup rotation (hy_nbody_reg.cuh): 384 threads, 24 trajectories, registers traded
 // between the warpgroups at the phase boundaries of the step.
 template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false>
@@ -826,7 +828,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
     R *gj = P.gjet + ((size_t)blockIdx.x * P.T + slot) * (size_t)P.pd.n_spill * P1;
     // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
 // (NB > 0: the orders of a state variable are NBR_JS elements apart, see hy_nbody_reg.cuh)
-    constexpr uint32_t XS = NB > 0 ? (uint32_t)NBR_JS : 1u;
+    constexpr uint32_t XS = NB > 0 ? (uint32_t)NBR_JS : (NB < 0 ? (uint32_t)CRB_XS : 1u);
 #define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j) * XS])
     // unit jet [1, 0, ..., 0] (never changes)
     if constexpr (NB == 0)
@@ -856,6 +858,16 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
                         nbr_ts(WGX) * (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
     }
 
+    // register-resident CR3BP path: per-lane constants
+    CrbLane<R> cl{};
+    if constexpr (NB < 0) {
+        cl.sub = sub != 0u;
+        cl.soff = 3 * (int32_t)sub;
+        cl.c = (R)s_imm[sub];
+        cl.m = (R)s_imm[2u + sub];
+        cl.ga = (R)s_imm[4u + 2u * sub];
+        cl.gb = (R)s_imm[5u + 2u * sub];
+    }
     const uint32_t wg = threadIdx.x >> 7; // warpgroup (WGX)
     if constexpr (WGX) {
         // every warpgroup starts in the tail state; the first two to reach their jets get the registers
@@ -865,6 +877,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
     // Persistent loop: every iteration is ONE step of the group's current trajectory (or the
     // fetch of a new one).  NB > 0: the two trajectories of a warp step in lockstep (the jets are a
     // warp-wide phase); a half-warp without a live trajectory idles through it on stale data.
+#ifdef HY_WGX_PROF
+    long long prof_wait = 0, prof_jets = 0, prof_rel = 0, prof_n = 0;
+    const long long prof_t0 = clock64();
+#endif
     bool have = false;
     unsigned int traj = 0;
     R hi = 0, lo = 0, mdt = 0, tf_hi = 0, tf_lo = 0;
@@ -929,7 +945,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
         }
         if constexpr (WGX) {
             if (!wg_any(wg, have)) break; // (warpgroup-wide vote: the four warps trade registers together)
-        } else if constexpr (NB > 0) {
+        } else if constexpr (NB != 0) {
             if (!__any_sync(0xffffffffu, have)) break;
         } else {
             if (!have) break;
@@ -949,20 +965,44 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
         }
         const bool stepping = have && !fin;
 
-        if (NB > 0 || stepping) {
+        if (NB != 0 || stepping) {
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
             if constexpr (NB > 0) {
                 if constexpr (WGX) {
                     // acquire the jet registers (blocks until another warpgroup has left its jets)
+#ifdef HY_WGX_PROF
+                    const long long c0 = clock64();
+#endif
                     wg_bar(wg);
                     wg_reg_inc<NBR_WGX_JREG>();
+#ifdef HY_WGX_PROF
+                    const long long c1 = clock64();
+#endif
                     nbr_jets<R, NB, NBR_PMAX, true, true>(w, s_imm + nl.coef, nl, p);
+#ifdef HY_WGX_PROF
+                    const long long c2 = clock64();
+#endif
                     wg_bar(wg);
                     wg_reg_dec<NBR_WGX_TREG>();
-                } else if (p == (uint32_t)NBR_PMAX)
+#ifdef HY_WGX_PROF
+                    prof_wait += c1 - c0;
+                    prof_jets += c2 - c1;
+                    prof_rel += clock64() - c2;
+                    ++prof_n;
+#endif
+                } else if (p == (uint32_t)NBR_PMAX) {
+#ifdef HY_WGX_PROF
+                    const long long c1 = clock64();
+#endif
                     nbr_jets<R, NB, NBR_PMAX, true>(w, s_imm + nl.coef, nl, p);
-                else
+#ifdef HY_WGX_PROF
+                    prof_jets += clock64() - c1;
+                    ++prof_n;
+#endif
+                } else
                     nbr_jets<R, NB, NBR_PMAX, false>(w, s_imm + nl.coef, nl, p);
+            } else if constexpr (NB < 0) {
+                crb_jets<R, CrbPmax<R>::value>(w, cl);
             } else {
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;
@@ -994,9 +1034,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
         // NB > 0: BOTH half-warps run it, converged, so that every warp-level primitive uses the
         // full mask (a partial mask costs a ~90-clock MATCH/VOTE check per use); a half-warp that is
         // not stepping computes on stale data and commits nothing (`stepping` guards every side effect).
-        if (NB > 0 || stepping) {
+        if (NB != 0 || stepping) {
             constexpr unsigned TM_FULL = 0xffffffffu;
-            const unsigned tmask = NB > 0 ? TM_FULL : gmask;
+            const unsigned tmask = NB != 0 ? TM_FULL : gmask;
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
             // NB > 0: lane `sub` < 2 NB owns one 3-vector of the state (position or velocity of a body;
@@ -1112,7 +1152,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
                 }
                 if (G > 1) __syncwarp(gmask);
             }
-            if constexpr (NB > 0) __syncwarp(); // reconverge the two half-warps
+            if constexpr (NB != 0) __syncwarp(); // reconverge the trajectories of the warp
             bool finite = true;
             if (NB > 0 && !P.high_accuracy) {
                 // Horner on the lane's 3-vector: three independent chains, 128-bit + 64-bit loads
@@ -1191,6 +1231,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
                 // one full-mask ballot, each half-warp looks at its own 16 bits
                 const unsigned bad = __ballot_sync(TM_FULL, !finite);
                 finite = ((bad >> (lane & 16u)) & 0xffffu) == 0u;
+            } else if constexpr (NB < 0) {
+                __syncwarp();
+                const unsigned bad = __ballot_sync(TM_FULL, !finite);
+                finite = ((bad >> (lane & ~1u)) & 3u) == 0u;
             } else {
                 if (G > 1) finite = !__any_sync(gmask, !finite);
             }
@@ -1229,7 +1273,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
                     }
                 }
             }
-            if constexpr (NB > 0) {
+            if constexpr (NB != 0) {
                 __syncwarp();
             } else {
                 if (G > 1) __syncwarp(gmask);
@@ -1252,6 +1296,14 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) pr
             if (G > 1) __syncwarp(gmask);
         }
     }
+#ifdef HY_WGX_PROF
+    if constexpr (NB > 0) {
+        if (blockIdx.x == 0 && lane == 0 && prof_n)
+            printf("warp %u: iters %lld  per iter: wait %lld jets %lld release %lld tail %lld\n", threadIdx.x >> 5, prof_n,
+                   prof_wait / prof_n, prof_jets / prof_n, prof_rel / prof_n,
+                   (clock64() - prof_t0 - prof_wait - prof_jets - prof_rel) / prof_n);
+    }
+#endif
 }
 
 // ---- dense output of the last step (reference update_d_output,

@@ -13,6 +13,10 @@ template <typename R, int NB> int regs_nbody_kernel();
 // warpgroup-rotation variant (experimental, HY_CUDA_WGX=1): FP64, 6 bodies, order 20 only
 cudaError_t launch_nbody_kernel_wgx(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s);
 
+// register-resident CR3BP kernel (hy_cr3bp_reg.cuh, instantiated in hy_cr3bp.cu)
+template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s);
+template <typename R> int regs_cr3bp_kernel();
+
 #define HY_NB_INSTANTIATE(NB)                                                                            \
     template <typename R, int N> cudaError_t launch_nbody_kernel(const KParams<R> &P, const hy_launch_info &li, \
                                                                  cudaStream_t s)                        \

@@ -34,7 +34,6 @@ def test_non_matching_tapes_keep_the_interpreter():
     assert _variant(common.oss_sys(), order=22) == 0
     # other systems
     assert _variant(common.pendulum_sys()) == 0
-    assert _variant(common.cr3bp_sys()) == 0
     # body counts without a compiled kernel (3..6 have one)
     assert _variant(hy.model.nbody(2)) == 0
     assert _variant(hy.model.nbody(7)) == 0
@@ -66,3 +65,29 @@ def test_perturbed_nbody_is_rejected():
         for c in range(3):
             eqs.append((xs[6 * i + 3 + c], acc[i][c]))
     assert _variant(eqs) == 0
+
+
+# ---- the CR3BP matcher (csrc/hy_cr3bp_match.hpp): exactly the tape of model.cr3bp
+# (expose_models.cpp:395-400) at the compiled orders (20 in FP64, 9 in FP32) ----
+CRB = 203
+
+
+def test_cr3bp_matches():
+    for mu in (0.01, 1e-3, 0.3):
+        assert _variant(hy.model.cr3bp(mu=mu)) == CRB
+        assert _variant(hy.model.cr3bp(mu=mu), order=9) == CRB
+    assert _variant(common.cr3bp_sys()) == CRB
+
+
+def test_cr3bp_lookalikes_keep_the_interpreter():
+    # other orders
+    assert _variant(common.cr3bp_sys(), order=12) == 0
+    assert _variant(common.cr3bp_sys(), order=22) == 0
+    # same structure with one altered equation
+    sys_ = hy.model.cr3bp(mu=0.01)
+    (x, fx), (y, fy), (z, fz), (px, fpx), (py, fpy), (pz, fpz) = sys_
+    assert _variant([(x, fx), (y, fy), (z, fz), (px, fpx), (py, fpy), (pz, fpz + 1e-3 * z)]) == 0
+    assert _variant([(x, fx), (y, fy), (z, 2.0 * fz), (px, fpx), (py, fpy), (pz, fpz)]) == 0
+    assert _variant([(x, fx), (y, fy + x), (z, fz), (px, fpx), (py, fpy), (pz, fpz)]) == 0
+    # variables in another order
+    assert _variant([(y, fy), (x, fx), (z, fz), (px, fpx), (py, fpy), (pz, fpz)]) == 0
