@@ -252,7 +252,8 @@ int choose_geometry(hy_ctx *c)
         const uint32_t fixed = L0.total + 64;
         if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 16) {
             bestG = 2;
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), max_threads / 2u) & ~15u;
+            const uint32_t mt = (uint32_t)hy::hy_max_threads(2, true, -1, (int)c->rb);
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), mt / 2u) & ~15u;
             bestRS = RS;
             best_smem = true;
             best = pr;

@@ -768,9 +768,13 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
 // Threads per CTA (= the register budget: 65536 / threads).  The interpreter's small-group
 // variants (G < 16: small systems, short jets) trade registers for resident trajectories;
 // G = 16 and the register-resident N-body kernels need all 255 registers.
-__host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB)
+#ifndef HY_CRB_F32_THREADS
+#define HY_CRB_F32_THREADS 768
+#endif
+// (rb: bytes per real.  The FP32 CR3BP kernel holds 5 x 9 jet registers: more warps instead.)
+__host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB, int rb = 8)
 {
-    return (NB == 0 && smem && G < 16) ? 512 : 256;
+    return (NB < 0 && rb == 4) ? HY_CRB_F32_THREADS : ((NB == 0 && smem && G < 16) ? 512 : 256);
 }
 
 // NB > 0: register-resident jets for a matched N-body tape (hy_nbody_reg.cuh); NB < 0: for the
@@ -779,7 +783,7 @@ __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB)
 // WGX: warpgroup rotation (hy_nbody_reg.cuh): 384 threads, 24 trajectories, registers traded
 // between the warpgroups at the phase boundaries of the step.
 template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false>
-__global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB), 1) propagate_kernel(const KParams<R> P)
+__global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)sizeof(R)), 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const hy_dims &d = P.d;
