@@ -858,8 +858,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         nl.coef = (int32_t)(NBR_CS * bd);
 #pragma unroll
         for (int q = 0; q < NB - 1; ++q)
+#ifndef HY_NBR_SMEM_EXCHANGE
+            // source lane of term q: the pair lanes of trajectory bt are lanes 16 bt .. 16 bt + 14
+            nl.tin[q] = (int32_t)(16u * bt) + (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
+#else
             nl.tin[q] = col + NBR_TB0 +
                         nbr_ts(WGX) * (int32_t) * reinterpret_cast<const uint32_t *>(s_imm + NBR_OFF0 + NBR_CS * bd + q);
+#endif
     }
 
     // register-resident CR3BP path: per-lane constants

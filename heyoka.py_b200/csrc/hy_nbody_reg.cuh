@@ -172,7 +172,8 @@ template <int NB> struct NbrLane {
     int32_t xa, xb;      // blocks of the pair's bodies
     int32_t ta;          // exchange slot the pair writes (buffer 0)
     int32_t xbody;       // block of this lane's body (body lanes; may point into the
-    int32_t tin[NB - 1]; // exchange slots of the body's terms   neighbouring column)
+    int32_t tin[NB - 1]; // pair lanes feeding the body's terms  neighbouring column)
+                         // (HY_NBR_SMEM_EXCHANGE: their exchange slots)
     int32_t coef;        // offset of the body's coefficient row in the immediate table
     bool body;
 };
@@ -241,7 +242,9 @@ template <typename R, int NB, int PMAX, bool FULL, bool WGX, int K> struct NbrOr
         constexpr int buf = (K & 1) * nbr_tbuf(WGX);
         R t0, t1, t2;
         nbr_pair_order<R, K, PMAX>(d0, d1, d2, r2, c, inv, dk0, dk1, dk2, t0, t1, t2);
+#ifdef HY_NBR_SMEM_EXCHANGE
         sts3(&w[L.ta + buf], t0, t1, t2);
+#endif
         __syncwarp();
         // d[K+1] = x_a[K+1] - x_b[K+1]  (x[K+1] was written one order ago; rows up to
         // NBR_PMAX exist whatever p is: no run-time guard on K + 1 < p)
@@ -264,7 +267,15 @@ template <typename R, int NB, int PMAX, bool FULL, bool WGX, int K> struct NbrOr
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 Vec3<R> t;
+#ifndef HY_NBR_SMEM_EXCHANGE
+                // the pair products come straight from the pair lanes' registers (tin = source lane):
+                // no exchange buffer, no store -> load round trip (+5 % over the shared-memory exchange)
+                t.x = __shfl_sync(0xffffffffu, t0, L.tin[q]);
+                t.y = __shfl_sync(0xffffffffu, t1, L.tin[q]);
+                t.z = __shfl_sync(0xffffffffu, t2, L.tin[q]);
+#else
                 lds3(&w[L.tin[q] + buf], t); // (unpredicated: the other lanes mirror a body lane's address)
+#endif
                 a0 = fma(cf[q], t.x, a0);
                 a1 = fma(cf[q], t.y, a1);
                 a2 = fma(cf[q], t.z, a2);

@@ -10,8 +10,14 @@ rep, so, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
+# (one cubin per translation unit: take the one that holds the kernel)
+dis = []
+for f in sorted(os.listdir(tmp)):
+    if f.endswith(".cubin"):
+        out = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if any(ln.startswith("//--------------------- .text.") and kname in ln for ln in out.splitlines()):
+            dis = out.splitlines()
+            break
 # locate function text section
 addr2line = {}
 cur_line = None
