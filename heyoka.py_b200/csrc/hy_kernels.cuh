@@ -889,6 +889,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #ifdef HY_WGX_PROF
     long long prof_wait = 0, prof_jets = 0, prof_rel = 0, prof_n = 0;
     const long long prof_t0 = clock64();
+    long long prof_c = 0; // HY_TAIL_PROF: "wait" = norms + step size, "release" = state update
 #endif
     bool have = false;
     unsigned int traj = 0;
@@ -1005,7 +1006,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #endif
                     nbr_jets<R, NB, NBR_PMAX, true>(w, s_imm + nl.coef, nl, p);
 #ifdef HY_WGX_PROF
-                    prof_jets += clock64() - c1;
+                    prof_c = clock64();
+                    prof_jets += prof_c - c1;
                     ++prof_n;
 #endif
                 } else
@@ -1116,6 +1118,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 so = HY_OUTCOME_TIME_LIMIT;
             }
             if (stepping) h = hn;
+#if defined(HY_WGX_PROF) && defined(HY_TAIL_PROF)
+            {
+                const long long t_ = clock64();
+                prof_wait += t_ - prof_c;
+                prof_c = t_;
+            }
+#endif
 
             // ---- event detection: may truncate the step at a terminal event ----
             int term_ev = -1;
@@ -1247,6 +1256,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             } else {
                 if (G > 1) finite = !__any_sync(gmask, !finite);
             }
+#if defined(HY_WGX_PROF) && defined(HY_TAIL_PROF)
+            prof_rel += clock64() - prof_c;
+#endif
             if (stepping) {
                 time_add(hi, lo, h);
                 ++ns;
