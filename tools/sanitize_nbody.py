@@ -11,3 +11,13 @@ print(ta._ctx.launch_info())
 ta.step(write_tc=True)
 ta.propagate_until(3.0)
 print("ok", ta.propagate_res[0])
+# the register-resident CR3BP kernel (FP64 and FP32), with continuous output and a grid
+from hy_b200 import workloads as W
+for fp in (np.float64, np.float32):
+    ic3 = W.cr3bp_ensemble(37).astype(fp)
+    tb = hy.taylor_adaptive_batch(W.cr3bp_sys(0.01), ic3, fp_type=fp)
+    print(tb._ctx.launch_info())
+    tb.step(write_tc=True)
+    tb.propagate_until(fp(1.5), c_output=True)
+    tb.propagate_grid(np.repeat(np.linspace(1.5, 2.0, 5), 37).reshape(5, 37).astype(fp))
+    print("ok", tb.propagate_res[0])
