@@ -223,16 +223,22 @@ typedef struct hy_launch_info {
     uint32_t ws_in_smem;     /* 1: jets in shared memory, 0: global fallback */
     uint32_t n_sm;
     uint32_t regs_per_thread;
-    uint32_t kernel_variant; /* 0: tape interpreter; N > 0: register-resident
-                                N-body kernel for N bodies (hy_nbody_reg.cuh)    */
+    uint32_t kernel_variant; /* 0: tape interpreter; 3..6: register-resident
+                                N-body kernel for N bodies (hy_nbody_reg.cuh);
+                                203: register-resident CR3BP kernel
+                                (hy_cr3bp_reg.cuh); 106: experimental
+                                warpgroup-rotation N-body kernel (HY_CUDA_WGX=1) */
 } hy_launch_info;
 int hy_get_launch_info(hy_ctx *ctx, hy_launch_info *info);
 
 /* Which kernel hy_create would pick for a tape (no device needed): 0 = the tape
- * interpreter, N > 0 = the register-resident N-body kernel for N bodies.  The
- * latter needs the tape of a Newtonian N-body system in Cartesian coordinates
- * (what the reference's model.nbody builds, expose_models.cpp:237-272), no
- * events or parameters, every pair present, order <= 20 (hy_nbody_match.hpp). */
+ * interpreter, 3..6 = the register-resident N-body kernel for that many bodies,
+ * 203 = the register-resident CR3BP kernel.  The N-body kernel needs the tape of
+ * a Newtonian N-body system in Cartesian coordinates (what the reference's
+ * model.nbody builds, expose_models.cpp:237-272), no events or parameters, every
+ * pair present, order <= 20 (hy_nbody_match.hpp); the CR3BP kernel exactly the
+ * tape of model.cr3bp (expose_models.cpp:395-400) at order 20 (FP64) or 9 (FP32),
+ * no events or parameters (hy_cr3bp_match.hpp). */
 int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term *terms,
                            uint32_t *variant);
 
