@@ -182,3 +182,24 @@ def test_energy_conservation_1000_steps():
     assert min(r[3] for r in ta.propagate_res) >= 900
     e1 = common.oss_energy(ta.state)
     assert np.max(np.abs((e1 - e0) / e0)) < 5e-14
+
+
+def test_warpgroup_rotation_variant_bitwise():
+    # experimental HY_CUDA_WGX=1 kernel (setmaxnreg register hand-over between warpgroups):
+    # slower than the default, kept for measurement - it must still agree bit for bit
+    B = 24 * 148 + 77
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(B, amp=1e-6)
+    a = _make(sys_, ic)
+    os.environ["HY_CUDA_WGX"] = "1"
+    try:
+        b = _make(sys_, ic)
+    finally:
+        os.environ.pop("HY_CUDA_WGX", None)
+    assert a._ctx.launch_info()["kernel_variant"] == 6
+    if b._ctx.launch_info()["kernel_variant"] != 106:
+        pytest.skip("warpgroup-rotation geometry not available on this device")
+    a.propagate_until(20.0)
+    b.propagate_until(20.0)
+    assert np.array_equal(a.state, b.state)
+    assert a.propagate_res == b.propagate_res
