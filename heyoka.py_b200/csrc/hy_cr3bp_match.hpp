@@ -18,7 +18,7 @@
 //   22,23  z' = pz, pz' = z NG                       SVD
 //
 // The eight coefficients are free (they carry mu); everything else must match exactly, otherwise
-// the tape stays on the interpreter.  No events, no runtime parameters, Taylor order = the
+// the tape stays on the interpreter.  No events, no runtime parameters, Taylor order up to the
 // compiled one (20 in FP64, 9 in FP32: tol = eps).
 #pragma once
 #include <cstdint>
@@ -36,7 +36,7 @@ struct CrbMatch {
 inline bool match_cr3bp(const hy_dims &d, const hy_op *ops, const hy_term *terms, int fp_bits, CrbMatch &out)
 {
     const uint32_t pmax = fp_bits == 64 ? (uint32_t)CrbPmax<double>::value : (uint32_t)CrbPmax<float>::value;
-    if (d.n_events || d.n_par || d.n_state != 6 || d.n_ops != 24 || d.order != pmax) return false;
+    if (d.n_events || d.n_par || d.n_state != 6 || d.n_ops != 24 || d.order > pmax || d.order < 2) return false;
     const uint32_t P1 = d.order + 1;
     auto sv = [&](int i) { return HY_REF_JET | ((uint32_t)i * P1); };
     const uint32_t X = sv(0), Y = sv(1), Z = sv(2), PX = sv(3), PY = sv(4), PZ = sv(5);

@@ -30,10 +30,10 @@ constexpr int CRB_NIMM = 8;     // immediates: cA cB | mA mB | gA gB | nA nB
 constexpr int CRB_VARIANT = 203; // hy_launch_info.kernel_variant of this kernel
 template <typename R> struct CrbPmax;
 template <> struct CrbPmax<double> {
-    static constexpr int value = 20; // tol = eps64
+    static constexpr int value = 20; // tol = eps64 (lower orders take the order-checked path)
 };
 template <> struct CrbPmax<float> {
-    static constexpr int value = 9; // tol = eps32
+    static constexpr int value = 9; // tol = eps32 (lower orders take the order-checked path)
 };
 
 template <typename R> struct CrbLane {
@@ -84,11 +84,16 @@ template <typename R, int PMAX, int K> __device__ __forceinline__ R crb_square(c
     return acc;
 }
 
-template <typename R, int PMAX, int K> struct CrbOrders {
-    static __device__ __forceinline__ void run(R *__restrict__ w, const CrbLane<R> &L, R (&X)[PMAX], R (&J)[PMAX],
-                                               R (&Q)[PMAX], R (&C)[PMAX], R (&GG)[PMAX], R &inv, const R xk,
-                                               const R yk, const R zk, const R pxk, const R pyk, const R pzk)
+// FULL: the Taylor order equals PMAX (no run-time order checks).
+template <typename R, int PMAX, bool FULL, int K> struct CrbOrders {
+    static __device__ __forceinline__ void run(R *__restrict__ w, const CrbLane<R> &L, const uint32_t p, R (&X)[PMAX],
+                                               R (&J)[PMAX], R (&Q)[PMAX], R (&C)[PMAX], R (&GG)[PMAX], R &inv,
+                                               const R xk, const R yk, const R zk, const R pxk, const R pyk,
+                                               const R pzk)
     {
+        if constexpr (!FULL) {
+            if (K >= p) return; // (warp-uniform)
+        }
         const bool sub = L.sub;
         // ---- this order of the lane's coordinates (LINCOMB x + c: the constant enters at order 0 only) ----
         if constexpr (K == 0)
@@ -143,18 +148,20 @@ template <typename R, int PMAX, int K> struct CrbOrders {
         o[0] = sub ? pxn : xn;
         o[1] = sub ? pyn : yn;
         o[2] = sub ? pzn : zn;
-        if constexpr (K + 1 < PMAX) CrbOrders<R, PMAX, K + 1>::run(w, L, X, J, Q, C, GG, inv, xn, yn, zn, pxn, pyn, pzn);
+        if constexpr (K + 1 < PMAX)
+            CrbOrders<R, PMAX, FULL, K + 1>::run(w, L, p, X, J, Q, C, GG, inv, xn, yn, zn, pxn, pyn, pzn);
     }
 };
 
-// All orders 0..PMAX-1 of one step.  On entry row 0 of the column holds the state; on exit rows
-// 0..PMAX are complete (visible to both lanes after the closing __syncwarp).
-template <typename R, int PMAX> __device__ __forceinline__ void crb_jets(R *__restrict__ w, const CrbLane<R> &L)
+// All orders 0..p-1 of one step (p <= PMAX).  On entry row 0 of the column holds the state; on exit
+// rows 0..p are complete (visible to both lanes after the closing __syncwarp).
+template <typename R, int PMAX, bool FULL>
+__device__ __forceinline__ void crb_jets(R *__restrict__ w, const CrbLane<R> &L, const uint32_t p)
 {
     R X[PMAX], J[PMAX], Q[PMAX], C[PMAX], GG[PMAX], inv = 0;
     __syncwarp();
     const R x0 = w[0], y0 = w[1], z0 = w[2], px0 = w[3], py0 = w[4], pz0 = w[5];
-    CrbOrders<R, PMAX, 0>::run(w, L, X, J, Q, C, GG, inv, x0, y0, z0, px0, py0, pz0);
+    CrbOrders<R, PMAX, FULL, 0>::run(w, L, p, X, J, Q, C, GG, inv, x0, y0, z0, px0, py0, pz0);
     __syncwarp();
 }
 

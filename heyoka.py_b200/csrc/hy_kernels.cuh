@@ -1013,7 +1013,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 } else
                     nbr_jets<R, NB, NBR_PMAX, false>(w, s_imm + nl.coef, nl, p);
             } else if constexpr (NB < 0) {
-                crb_jets<R, CrbPmax<R>::value>(w, cl);
+                if (p == (uint32_t)CrbPmax<R>::value)
+                    crb_jets<R, CrbPmax<R>::value, true>(w, cl, p);
+                else
+                    crb_jets<R, CrbPmax<R>::value, false>(w, cl, p);
             } else {
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;

@@ -48,8 +48,10 @@ def test_variant_selected():
     assert _make(sys_, ic)._ctx.launch_info()["kernel_variant"] == CRB
     assert _make(sys_, ic.astype(np.float32), fp_type=np.float32)._ctx.launch_info()["kernel_variant"] == CRB
     assert _make(sys_, ic, interp=True)._ctx.launch_info()["kernel_variant"] == 0
-    # other orders and event-carrying systems keep the interpreter
-    assert _make(sys_, ic, tol=1e-9)._ctx.launch_info()["kernel_variant"] == 0
+    # lower orders take the order-checked path of the same kernel
+    assert _make(sys_, ic, tol=1e-9)._ctx.launch_info()["kernel_variant"] == CRB
+    # orders above the unrolled maximum and event-carrying systems keep the interpreter
+    assert _make(sys_, ic, tol=1e-18)._ctx.launch_info()["kernel_variant"] == 0
     x = hy.make_vars("x")
     ev = hy.t_event_batch(x - 5.0)
     assert hy.taylor_adaptive_batch(sys_, ic, t_events=[ev])._ctx.launch_info()["kernel_variant"] == 0
@@ -79,6 +81,25 @@ def test_bitwise_vs_interpreter(fp, mu):
     assert np.array_equal(a.time, tf)
     a.propagate_for(fp(-2.5))
     b.propagate_for(fp(-2.5))
+    assert np.array_equal(a.state, b.state)
+    assert a.propagate_res == b.propagate_res
+
+
+@pytest.mark.parametrize("fp,tol,order", [(np.float64, 1e-9, 12), (np.float64, 1e-4, 6), (np.float32, 1e-4, 6)])
+def test_lower_orders_bitwise(fp, tol, order):
+    # orders below the unrolled maximum: run-time order checks in the register kernel
+    B = 75
+    sys_ = W.cr3bp_sys(0.01)
+    ic = W.cr3bp_ensemble(B).astype(fp)
+    a = _make(sys_, ic, fp_type=fp, tol=fp(tol))
+    b = _make(sys_, ic, interp=True, fp_type=fp, tol=fp(tol))
+    assert a.order == order and b.order == order
+    assert a._ctx.launch_info()["kernel_variant"] == CRB and b._ctx.launch_info()["kernel_variant"] == 0
+    a.step(write_tc=True)
+    b.step(write_tc=True)
+    assert np.array_equal(a.tc, b.tc)
+    a.propagate_until(fp(6.0))
+    b.propagate_until(fp(6.0))
     assert np.array_equal(a.state, b.state)
     assert a.propagate_res == b.propagate_res
 
