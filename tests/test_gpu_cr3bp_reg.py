@@ -190,3 +190,30 @@ def test_jacobi_constant_large_batch():
     assert np.all(ta.time == 20.0)
     j0, j1 = W.cr3bp_jacobi(ic), W.cr3bp_jacobi(ta.state)
     assert np.max(np.abs((j1 - j0) / j0)) < 1e-13
+
+
+def test_ensemble_copy_and_batch_composition():
+    # the ensemble driver deep-copies the integrator per iteration (hy_clone keeps the kernel choice);
+    # a trajectory gives bit-identical results alone, inside a big batch, and through the ensemble
+    from copy import deepcopy
+
+    sys_ = W.cr3bp_sys(0.01)
+    ics = W.cr3bp_ensemble(40).reshape(6, 10, 4).transpose(1, 0, 2).copy()  # 10 iterations x [6, 4]
+    ta = hy.taylor_adaptive_batch(sys_, np.ascontiguousarray(ics[0]))
+    assert ta._ctx.launch_info()["kernel_variant"] == CRB
+
+    def gen(t, i):
+        t.state[:] = ics[i]
+        return t
+
+    ret = hy.ensemble_propagate_until_batch(ta, 6.0, 10, gen, algorithm="thread", max_workers=4)
+    assert len(ret) == 10
+    big = hy.taylor_adaptive_batch(sys_, np.ascontiguousarray(np.concatenate(list(ics), axis=1)))
+    big.propagate_until(6.0)
+    for i in range(10):
+        assert ret[i][0]._ctx.launch_info()["kernel_variant"] == CRB
+        ser = gen(deepcopy(ta), i)
+        ser.propagate_until(6.0)
+        assert np.array_equal(ret[i][0].state, ser.state)
+        assert ret[i][0].propagate_res == ser.propagate_res
+        assert np.array_equal(big.state[:, 4 * i:4 * i + 4], ser.state)
