@@ -193,15 +193,26 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
     R best_tau = 0;
     for (uint32_t e = 0; e < n_events; ++e) {
         const R *g = w + (ev_ref[e] & 0x7fffffffu);
+        // Fast exclusion, straight from the jet in shared memory (no per-thread array: with the
+        // shared-memory carve-out at its maximum, local memory lives in L2): interval Horner of
+        // g over tau in [0, h] (or [h, 0]).
+        {
+            R lo = g[p], hi = g[p];
+            for (int k = p - 1; k >= 0; --k) {
+                const R a = lo * h, b = hi * h; // (h < 0 swaps the ends)
+                const R mn = a < b ? a : b, mx = a < b ? b : a;
+                lo = (mn < 0 ? mn : (R)0) + g[k];
+                hi = (mx > 0 ? mx : (R)0) + g[k];
+            }
+            if (lo > (R)0 || hi < (R)0) continue;
+        }
         // q(s) = g(h s)
-        R hk = 1, gmax = 0;
+        R hk = 1;
         for (int k = 0; k <= p; ++k) {
             q[k] = g[k] * hk;
             hk *= h;
-            const R a = q[k] < 0 ? -q[k] : q[k];
-            gmax = a > gmax ? a : gmax;
         }
-        // fast exclusion: enclosure of q over [0, 1]
+        // second exclusion on the scaled polynomial: enclosure of q over [0, 1]
         R lo = q[p], hi = q[p];
         for (int k = p - 1; k >= 0; --k) {
             lo = (lo < 0 ? lo : (R)0) + q[k];
@@ -229,8 +240,6 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
                     best_tau = tau;
                     best_ev = (int)e;
                     best_sg = sg;
-                    // automatic cooldown needs |dg/dtau| and the error scale of g
-                    (void)gmax;
                 }
             } else if (nc < 2 * EV_MAXROOTS) {
                 cand_ev[nc] = (int)e;

@@ -821,7 +821,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     const uint32_t slot = threadIdx.x / G; // trajectory slot in this CTA
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
     const uint32_t par_off = P.pd.par_off, one_off = P.pd.one_off;
-    // whole groups only: safe w.r.t. group-mask syncs (NB > 0: T is even, whole warps run)
+    // whole groups only: safe w.r.t. group-mask syncs (NB != 0: T is such that whole warps run)
+    // (wmask: the lanes of this warp that own a trajectory slot - the interpreter's warp-level syncs)
+    const unsigned wmask = __ballot_sync(0xffffffffu, slot < P.T);
     if (slot >= P.T) return;
     R *w;
     if (SMEM)
@@ -900,6 +902,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     R mn = r_inf<R>(), mx = 0, h = 0;
     unsigned long long ns = 0;
     for (;;) {
+#ifndef HY_INTERP_NO_LOCKSTEP
+        // Interpreter: every group of the warp runs the SAME program, so the groups stay converged as
+        // long as they start their steps together.  Ragged step counts would let a group that fetched
+        // a new trajectory drift out of phase (each group then issues its own copy of the op stream:
+        // 3x slower on config 5) - re-align the warp at the top of every iteration.
+        if constexpr (NB == 0 && G < 32) __syncwarp(wmask);
+#endif
         if (!have) {
             // ---- fetch the next trajectory for this group ----
             if (sub == 0) traj = (WGX && wg >= P.wgx_wgs) ? P.B : atomicAdd(P.counter, 1u);
@@ -958,7 +967,11 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         } else if constexpr (NB != 0) {
             if (!__any_sync(0xffffffffu, have)) break;
         } else {
+#ifndef HY_INTERP_NO_LOCKSTEP
+            if (!__any_sync(wmask, have)) break; // (groups without work idle until the whole warp is done)
+#else
             if (!have) break;
+#endif
         }
 
         bool fin = false; // the trajectory ends with this iteration

@@ -27,5 +27,5 @@ for with_ev in (0, 1):
         ta.propagate_until(T_END)
         ms, _ = ta._ctx.last_timing()
         ns = int(ta.propagate_res_arrays[3].sum())
-        print("  rep", rep, "steps", ns, "ms %.2f" % ms, "steps/s %.4g" % (ns / (ms * 1e-3)),
+        print("  rep", rep, "steps", ns, "max/lane", int(ta.propagate_res_arrays[3].max()), "ms %.2f" % ms, "steps/s %.4g" % (ns / (ms * 1e-3)),
               "stopped by an event:", int((ta.propagate_res_arrays[0] > -10).sum()), flush=True)
