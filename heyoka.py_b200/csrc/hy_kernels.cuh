@@ -10,7 +10,11 @@
 //    SHARED MEMORY: nothing but the initial/final state crosses HBM.
 //  * the tape (ops, terms, level boundaries) is staged once per CTA in shared
 //    memory; the ops of one dependency level are spread over the G lanes of the
-//    group and levels are separated by __syncwarp(group mask).
+//    group and levels are separated by __syncwarp(group mask).  The groups of a
+//    warp run the same program in lockstep (re-aligned at every iteration).
+//  * matched tapes skip the interpreter: register-resident jets for N-body systems
+//    (hy_nbody_reg.cuh, NB > 0) and for the CR3BP (hy_cr3bp_reg.cuh, NB < 0); the
+//    persistent loop, the tail of the step and every API feature are shared code.
 //
 // This replaces the reference's JIT-compiled taylor_step + C++ propagate loop
 // (/root/reference/heyoka/expose_batch_integrators.cpp:233-314 -> [UPSTREAM]).

@@ -15,14 +15,17 @@
 //  * the two trajectories of a warp step in lockstep.  Lanes 0..2NB-1 of the warp
 //    double as BODY lanes (all in one half-warp: a 64-bit shared access costs one
 //    wavefront per active half-warp): after each order they gather the NB-1 pair
-//    products of their body from a small shared-memory exchange buffer, form the
-//    acceleration (the tape's LINCOMB, same term order), and write v[k+1] and
-//    x[k+2] into the state jets, which live in shared memory (only the Horner
-//    update reads their history).  Vectors move as one 128-bit + one 64-bit access.
-//  * ONE __syncwarp per order: t[k] feeds d[k+2], not d[k+1], so the gather of
-//    order k overlaps the convolutions of order k+1 (double-buffered exchange);
-//    the body lanes' work is predicated, not branched, so it shares a basic block
-//    with the next order's convolutions and ptxas interleaves the two.
+//    products of their body from the pair lanes' registers by warp shuffle (the
+//    shared-memory exchange buffer it replaced is kept under
+//    -DHY_NBR_SMEM_EXCHANGE for A/B measurements), form the acceleration (the
+//    tape's LINCOMB, same term order), and write v[k+1] and x[k+2] into the state
+//    jets, which live in shared memory (the pair lanes read x[k+1] from there, the
+//    Horner update the whole history).  Vectors move as one 128-bit + one 64-bit
+//    access.
+//  * ONE __syncwarp per order (for the positions): t[k] feeds d[k+2], not d[k+1],
+//    so the gather of order k overlaps the convolutions of order k+1; the body
+//    lanes' work is predicated, not branched, so it shares a basic block with the
+//    next order's convolutions and ptxas interleaves the two.
 //
 // Arithmetic: the same recurrences, term order and roundings as the tape
 // interpreter's fused pair op (pair3_k) + LINCOMB + SVD - the two paths agree
@@ -44,6 +47,8 @@ constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
 //   body b, order k:  [x, y, z, -, vx, vy, vz, -]  at  b * NBR_BS + k * NBR_JS   (16-byte aligned
 //                     triples: one 128-bit + one 64-bit access moves a vector)
 //   exchange buffer:  2 x 16 pair slots of NBR_TS elements (t0, t1, t2 used) at NBR_TB0
+//                     (used only with -DHY_NBR_SMEM_EXCHANGE; the default moves the pair
+//                     products by shuffle and leaves it idle)
 // NBR_BS = 8 * 21 + 2 and NBR_TS = 6 keep the 128-bit accesses of a quarter-warp conflict-free.
 constexpr int NBR_JS = 8;                            // stride between orders of a state variable
 constexpr int NBR_BS = NBR_JS * (NBR_PMAX + 1) + 2;  // stride between bodies
