@@ -109,6 +109,9 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
     case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s);
     case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s);
     case 6: return hy::launch_nbody_kernel<R, 6>(P, li, s);
+    case hy::NBR_VARIANT_P22: // 6 bodies, unrolled to order 22 (hy_nb6.cu)
+        if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_p22(P, li, s);
+        return cudaErrorInvalidValue;
     case 106: // warpgroup rotation (experimental)
         if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_wgx(P, li, s);
         return cudaErrorInvalidValue;
@@ -146,6 +149,7 @@ template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant
     case 4: return hy::regs_nbody_kernel<R, 4>();
     case 5: return hy::regs_nbody_kernel<R, 5>();
     case 6: return hy::regs_nbody_kernel<R, 6>();
+    case hy::NBR_VARIANT_P22: return hy::regs_nbody_kernel_p22();
     default: break;
     }
     if (!smem) return regs_of<R, 1, false>();
@@ -194,7 +198,8 @@ int choose_geometry(hy_ctx *c)
     // interactions live in registers, the state jets + a small exchange buffer in shared memory.
     hy::NbMatch nbm;
     if (!force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
-        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) && hy::nbody_kernel_compiled(nbm.nb)) {
+        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) &&
+        hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits)) {
         hy::Program pr;
         pr.G = 16;
         pr.n_phases = 0;
@@ -220,7 +225,7 @@ int choose_geometry(hy_ctx *c)
             bestRS = RS;
             best_smem = true;
             best = pr;
-            li.kernel_variant = nbm.nb;
+            li.kernel_variant = hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits);
             if (wgx) {
                 if (bestT != 24u) return fail("hy_create: HY_CUDA_WGX needs 24 trajectories per CTA in shared memory");
                 li.kernel_variant = 106;
@@ -996,7 +1001,8 @@ int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term 
     if (!dims || !ops || !variant) return fail("hy_tape_kernel_variant: null argument");
     hy::NbMatch m;
     *variant = 0;
-    if (hy::match_nbody(*dims, ops, terms, m) && hy::nbody_kernel_compiled(m.nb)) *variant = m.nb;
+    // (the introspection call does not know the precision: FP64 assumed for orders above 20)
+    if (hy::match_nbody(*dims, ops, terms, m)) *variant = hy::nbody_kernel_variant(m.nb, dims->order, 64);
     hy::CrbMatch cm; // (FP64 order, then FP32 order: the introspection call does not know the precision)
     if (!*variant && (hy::match_cr3bp(*dims, ops, terms, 64, cm) || hy::match_cr3bp(*dims, ops, terms, 32, cm)))
         *variant = (uint32_t)hy::CRB_VARIANT;

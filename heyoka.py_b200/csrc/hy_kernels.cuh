@@ -786,7 +786,9 @@ __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB, int r
 // interpreter.  NB != 0: the trajectories of a warp step in lockstep.
 // WGX: warpgroup rotation (hy_nbody_reg.cuh): 384 threads, 24 trajectories, registers traded
 // between the warpgroups at the phase boundaries of the step.
-template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false>
+// PM: the order the register-resident N-body jets are unrolled to (NBR_PMAX, or NBR_LMAX for the
+// high-accuracy 6-body build).
+template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false, int PM = NBR_PMAX>
 __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)sizeof(R)), 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1005,7 +1007,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #ifdef HY_WGX_PROF
                     const long long c1 = clock64();
 #endif
-                    nbr_jets<R, NB, NBR_PMAX, true, true>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, true, true>(w, s_imm + nl.coef, nl, p);
 #ifdef HY_WGX_PROF
                     const long long c2 = clock64();
 #endif
@@ -1017,18 +1019,18 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     prof_rel += clock64() - c2;
                     ++prof_n;
 #endif
-                } else if (p == (uint32_t)NBR_PMAX) {
+                } else if (p == (uint32_t)PM) {
 #ifdef HY_WGX_PROF
                     const long long c1 = clock64();
 #endif
-                    nbr_jets<R, NB, NBR_PMAX, true>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, true>(w, s_imm + nl.coef, nl, p);
 #ifdef HY_WGX_PROF
                     prof_c = clock64();
                     prof_jets += prof_c - c1;
                     ++prof_n;
 #endif
                 } else
-                    nbr_jets<R, NB, NBR_PMAX, false>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, false>(w, s_imm + nl.coef, nl, p);
             } else if constexpr (NB < 0) {
                 if (p == (uint32_t)CrbPmax<R>::value)
                     crb_jets<R, CrbPmax<R>::value, true>(w, cl, p);
@@ -1198,13 +1200,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     R *x = w + voff;
                     Vec3<R> acc, t;
                     lds3(x + p * NBR_JS, acc);
-                    if (!WGX && p == (uint32_t)NBR_PMAX) {
+                    if (!WGX && p == (uint32_t)PM) {
                         // all loads first (independent), then the three FMA chains
-                        Vec3<R> c[NBR_PMAX];
+                        Vec3<R> c[PM];
 #pragma unroll
-                        for (int k = 0; k < NBR_PMAX; ++k) lds3(x + k * NBR_JS, c[k]);
+                        for (int k = 0; k < PM; ++k) lds3(x + k * NBR_JS, c[k]);
 #pragma unroll
-                        for (int k = NBR_PMAX - 1; k >= 0; --k) {
+                        for (int k = PM - 1; k >= 0; --k) {
                             acc.x = r_fma(acc.x, hn, c[k].x);
                             acc.y = r_fma(acc.y, hn, c[k].y);
                             acc.z = r_fma(acc.z, hn, c[k].z);

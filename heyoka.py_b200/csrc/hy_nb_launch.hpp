@@ -13,6 +13,9 @@ template <typename R, int NB> int regs_nbody_kernel();
 // warpgroup-rotation variant (experimental, HY_CUDA_WGX=1): FP64, 6 bodies, order 20 only
 cudaError_t launch_nbody_kernel_wgx(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s);
 
+// 6 bodies, FP64, unrolled to order NBR_LMAX = 22 (tol = 1e-18, the reference's benchmark configuration)
+cudaError_t launch_nbody_kernel_p22(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s);
+int regs_nbody_kernel_p22();
 // register-resident CR3BP kernel (hy_cr3bp_reg.cuh, instantiated in hy_cr3bp.cu)
 template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s);
 template <typename R> int regs_cr3bp_kernel();

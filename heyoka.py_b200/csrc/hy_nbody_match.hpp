@@ -14,7 +14,7 @@
 // with state variables ordered (x, y, z, vx, vy, vz) per body - it fills the
 // descriptor consumed by the register-resident kernel (hy_nbody_reg.cuh).
 // Anything else (events, parameters, missing pairs, other exponents, more than
-// NBR_MAXB bodies, orders above NBR_PMAX) is left to the tape interpreter.
+// NBR_MAXB bodies, orders above NBR_PMAX - NBR_LMAX for 6 bodies in FP64) is left to the tape interpreter.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -33,11 +33,19 @@ struct NbMatch {
 
 // body counts with a compiled register-resident kernel (hy_nb3.cu ... hy_nb6.cu)
 inline bool nbody_kernel_compiled(uint32_t nb) { return nb >= 3 && nb <= 6; }
+// kernel variant for a matched tape of nb bodies at Taylor order p (0: none compiled)
+inline uint32_t nbody_kernel_variant(uint32_t nb, uint32_t order, int fp_bits)
+{
+    if (!nbody_kernel_compiled(nb)) return 0;
+    if (order <= (uint32_t)NBR_PMAX) return nb;
+    return (nb == 6 && fp_bits == 64 && order <= (uint32_t)NBR_LMAX) ? (uint32_t)NBR_VARIANT_P22 : 0u;
+}
 
 inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms, NbMatch &out)
 {
     const uint32_t P1 = d.order + 1, n = d.n_state;
-    if (d.n_events || d.n_par || n % 6 || d.order > (uint32_t)NBR_PMAX || d.order < 2) return false;
+    // (orders NBR_PMAX + 1 .. NBR_LMAX: only the 6-body FP64 build has a kernel - the caller checks)
+    if (d.n_events || d.n_par || n % 6 || d.order > (uint32_t)NBR_LMAX || d.order < 2) return false;
     const uint32_t NB = n / 6;
     if (NB < 2 || NB > (uint32_t)NBR_MAXB) return false;
     const uint32_t NP = NB * (NB - 1) / 2;

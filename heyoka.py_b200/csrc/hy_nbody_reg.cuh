@@ -40,7 +40,10 @@
 
 namespace hy {
 
-constexpr int NBR_PMAX = 20;   // highest Taylor order of the register-resident path
+constexpr int NBR_PMAX = 20;   // Taylor order of the fully unrolled register-resident kernels (tol = eps64)
+constexpr int NBR_LMAX = 22;   // rows of the column layout; also the order of the 6-body FP64 high-accuracy
+                               // build (tol = 1e-18: the reference's own benchmark, ensemble_batch_perf.ipynb)
+constexpr int NBR_VARIANT_P22 = 226; // hy_launch_info.kernel_variant of that build
 constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
 
 // Trajectory column (shared memory, elements):
@@ -49,14 +52,18 @@ constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
 //   exchange buffer:  2 x 16 pair slots of NBR_TS elements (t0, t1, t2 used) at NBR_TB0
 //                     (used only with -DHY_NBR_SMEM_EXCHANGE; the default moves the pair
 //                     products by shuffle and leaves it idle)
-// NBR_BS = 8 * 21 + 2 and NBR_TS = 6 keep the 128-bit accesses of a quarter-warp conflict-free.
+// NBR_BS = 8 * 23 + 2 and NBR_TS = 6 keep the 128-bit accesses of a quarter-warp conflict-free.
 constexpr int NBR_JS = 8;                            // stride between orders of a state variable
-constexpr int NBR_BS = NBR_JS * (NBR_PMAX + 1) + 2;  // stride between bodies
+constexpr int NBR_BS = NBR_JS * (NBR_LMAX + 1) + 2;  // stride between bodies
 constexpr int NBR_TB0 = NBR_MAXB * NBR_BS;           // offset of the exchange buffer
 // stride between pair slots of the exchange buffer: 6 (conflict-free 128-bit stores); the
 // warpgroup-rotation variant (WGX, 24 trajectories per SM) packs them at 4 to fit shared memory
 __host__ __device__ constexpr int nbr_ts(bool wgx) { return wgx ? 4 : 6; }
+#ifdef HY_NBR_SMEM_EXCHANGE
 __host__ __device__ constexpr int nbr_tbuf(bool wgx) { return 16 * nbr_ts(wgx); }            // one exchange buffer
+#else
+__host__ __device__ constexpr int nbr_tbuf(bool) { return 0; } // (pair products travel by shuffle: no buffer)
+#endif
 __host__ __device__ constexpr int nbr_ws(bool wgx) { return NBR_TB0 + 2 * nbr_tbuf(wgx); }    // column length
 // register budgets of the warpgroup-rotation variant (3 warpgroups x 168 = 2 x JREG + TREG)
 constexpr int NBR_WGX_JREG = 224, NBR_WGX_TREG = 56;

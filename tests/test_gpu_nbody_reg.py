@@ -48,8 +48,12 @@ def test_variant_selected():
     # other systems / events / orders above 20 keep the interpreter
     tc = hy.taylor_adaptive_batch(common.pendulum_sys(), common.PEND_IC)
     assert tc._ctx.launch_info()["kernel_variant"] == 0
+    # tol = 1e-18 (order 22, the reference's benchmark configuration): the 6-body FP64 order-22 build
     td = _make(common.oss_sys(), common.oss_ensemble(8), tol=1e-18)
-    assert td.order == 22 and td._ctx.launch_info()["kernel_variant"] == 0
+    assert td.order == 22 and td._ctx.launch_info()["kernel_variant"] == 226
+    te = _make(hy.model.nbody(5, masses=list(common.OSS_MASSES[:5]), Gconst=common.OSS_G),
+               common.oss_ensemble(8)[:30].copy(), tol=1e-18)
+    assert te.order == 22 and te._ctx.launch_info()["kernel_variant"] == 0
 
 
 @pytest.mark.parametrize("fp", [np.float64, np.float32])
@@ -203,3 +207,34 @@ def test_warpgroup_rotation_variant_bitwise():
     b.propagate_until(20.0)
     assert np.array_equal(a.state, b.state)
     assert a.propagate_res == b.propagate_res
+
+
+@pytest.mark.parametrize("high_accuracy", [False, True])
+def test_order22_build_bitwise_and_oracle(high_accuracy):
+    # tol = 1e-18 -> order 22 (ensemble_batch_perf.ipynb:233 runs the outer Solar System with
+    # high_accuracy=True, tol=1e-18): propagate_kernel<double,16,true,6,false,22>
+    B = 77
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(B, amp=1e-4)
+    a = _make(sys_, ic, tol=1e-18, high_accuracy=high_accuracy)
+    b = _make(sys_, ic, interp=True, tol=1e-18, high_accuracy=high_accuracy)
+    assert a.order == 22 and a._ctx.launch_info()["kernel_variant"] == 226
+    assert b._ctx.launch_info()["kernel_variant"] == 0
+    a.step(write_tc=True)
+    b.step(write_tc=True)
+    assert np.array_equal(a.tc, b.tc)
+    assert np.array_equal(a.state, b.state)
+    tf = np.linspace(40.0, 60.0, B)
+    a.propagate_until(tf)
+    b.propagate_until(tf)
+    assert np.array_equal(a.state, b.state)
+    assert a.propagate_res == b.propagate_res
+    a.propagate_for(-7.5)
+    b.propagate_for(-7.5)
+    assert np.array_equal(a.state, b.state)
+    if not high_accuracy:
+        orc = COracle(D.decompose(sys_, 22), ic, tol=1e-18)
+        orc.step()
+        orc.propagate_until(tf)
+        orc.propagate_for(-7.5)
+        assert _rel(a.state, orc.state) < 1e-11

@@ -30,8 +30,11 @@ def test_smaller_body_counts_match():
 
 
 def test_non_matching_tapes_keep_the_interpreter():
-    # order above the unrolled maximum
-    assert _variant(common.oss_sys(), order=22) == 0
+    # orders above the unrolled maximum (20; 22 for the 6-body high-accuracy build, variant 226)
+    assert _variant(common.oss_sys(), order=22) == 226
+    assert _variant(common.oss_sys(), order=21) == 226
+    assert _variant(common.oss_sys(), order=23) == 0
+    assert _variant(hy.model.nbody(5, masses=[1.0, 1e-3, 1e-3, 1e-3, 1e-3]), order=22) == 0
     # other systems
     assert _variant(common.pendulum_sys()) == 0
     # body counts without a compiled kernel (3..6 have one)
