@@ -156,3 +156,45 @@ def test_propagate_grid_errors():
         ta.propagate_grid(np.zeros((3, 5)))
     with pytest.raises(ValueError):
         ta.propagate_grid(np.zeros((0, 4)))
+
+
+@pytest.mark.parametrize("env", [{"HY_CUDA_GROUP": "1"}, {"HY_CUDA_GROUP": "4"}, {"HY_CUDA_GROUP": "16"},
+                                 {"HY_CUDA_FORCE_GLOBAL_WS": "1"}])
+def test_launch_geometries_agree_bitwise(env):
+    # The scheduler spreads the tape over G lanes per trajectory (1, 4 or 16) and keeps the jets in shared
+    # memory, or - for systems too large for it - in global memory: the arithmetic does not depend on
+    # the geometry, so every choice must reproduce the default one bit for bit.
+    import os
+    from hy_b200 import workloads as W
+
+    def make(sys_, ic, extra):
+        old = {k: os.environ.get(k) for k in list(extra) + ["HY_CUDA_NO_CR3BP_REG"]}
+        os.environ.update(extra)
+        os.environ["HY_CUDA_NO_CR3BP_REG"] = "1"  # the tape interpreter is what this test is about
+        try:
+            return hy.taylor_adaptive_batch(sys_, ic)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    B = 150
+    for sys_, ic, t_end in ((W.cr3bp_sys(0.01), W.cr3bp_ensemble(B), 6.0),
+                            (W.pendulum_sys(), np.linspace(-1.0, 1.0, 2 * B).reshape(2, B), 15.0)):
+        a = make(sys_, ic, {})
+        b = make(sys_, ic, env)
+        lb = b._ctx.launch_info()
+        if "HY_CUDA_GROUP" in env:
+            assert lb["group"] == int(env["HY_CUDA_GROUP"]) and lb["kernel_variant"] == 0
+        else:
+            assert lb["ws_in_smem"] == 0 and lb["kernel_variant"] == 0
+        a.step(write_tc=True)
+        b.step(write_tc=True)
+        assert np.array_equal(a.tc, b.tc)
+        tf = np.linspace(0.5 * t_end, t_end, B)
+        a.propagate_until(tf)
+        b.propagate_until(tf)
+        assert np.array_equal(a.state, b.state)
+        assert a.propagate_res == b.propagate_res
