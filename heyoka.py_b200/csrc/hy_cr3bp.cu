@@ -17,6 +17,20 @@ template <typename R> int regs_cr3bp_kernel()
     if (cudaFuncGetAttributes(&a, propagate_kernel<R, 2, true, -1>) != cudaSuccess) return 0;
     return a.numRegs;
 }
+cudaError_t launch_cr3bp_kernel_p22(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s)
+{
+    auto kern = propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
+    return cudaGetLastError();
+}
+int regs_cr3bp_kernel_p22()
+{
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI>) != cudaSuccess) return 0;
+    return a.numRegs;
+}
 template cudaError_t launch_cr3bp_kernel<double>(const KParams<double> &, const hy_launch_info &, cudaStream_t);
 template cudaError_t launch_cr3bp_kernel<float>(const KParams<float> &, const hy_launch_info &, cudaStream_t);
 template int regs_cr3bp_kernel<double>();

@@ -19,7 +19,7 @@
 //
 // The eight coefficients are free (they carry mu); everything else must match exactly, otherwise
 // the tape stays on the interpreter.  No events, no runtime parameters, Taylor order up to the
-// compiled one (20 in FP64, 9 in FP32: tol = eps).
+// compiled ones (FP64: 20 - tol = eps - and 22 - tol = 1e-18; FP32: 9).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -35,7 +35,8 @@ struct CrbMatch {
 
 inline bool match_cr3bp(const hy_dims &d, const hy_op *ops, const hy_term *terms, int fp_bits, CrbMatch &out)
 {
-    const uint32_t pmax = fp_bits == 64 ? (uint32_t)CrbPmax<double>::value : (uint32_t)CrbPmax<float>::value;
+    // (FP64: orders above CrbPmax<double> take the order-22 build, see cr3bp_kernel_variant)
+    const uint32_t pmax = fp_bits == 64 ? (uint32_t)CRB_PMAX_HI : (uint32_t)CrbPmax<float>::value;
     if (d.n_events || d.n_par || d.n_state != 6 || d.n_ops != 24 || d.order > pmax || d.order < 2) return false;
     const uint32_t P1 = d.order + 1;
     auto sv = [&](int i) { return HY_REF_JET | ((uint32_t)i * P1); };
@@ -111,6 +112,12 @@ inline bool match_cr3bp(const hy_dims &d, const hy_op *ops, const hy_term *terms
     // 22,23: z' = pz, pz' = T3
     if (!un(22, HY_OP_SVD, PZ) || ops[22].dst != Z || !un(23, HY_OP_SVD, T[3]) || ops[23].dst != PZ) return false;
     return true;
+}
+
+// kernel variant serving a matched tape at Taylor order p
+inline uint32_t cr3bp_kernel_variant(uint32_t order, int fp_bits)
+{
+    return (fp_bits == 64 && order > (uint32_t)CrbPmax<double>::value) ? (uint32_t)CRB_VARIANT_P22 : (uint32_t)CRB_VARIANT;
 }
 
 } // namespace hy

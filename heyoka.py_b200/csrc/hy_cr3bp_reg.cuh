@@ -28,6 +28,9 @@ namespace hy {
 constexpr int CRB_XS = 6;       // stride between orders of a state variable in the column
 constexpr int CRB_NIMM = 8;     // immediates: cA cB | mA mB | gA gB | nA nB
 constexpr int CRB_VARIANT = 203; // hy_launch_info.kernel_variant of this kernel
+constexpr int CRB_VARIANT_P22 = 222; // FP64 build unrolled to order 22 (tol = 1e-18, the setting of the
+                                     // reference's "restricted three-body problem" notebook): orders 21..22
+constexpr int CRB_PMAX_HI = 22;
 template <typename R> struct CrbPmax;
 template <> struct CrbPmax<double> {
     static constexpr int value = 20; // tol = eps64 (lower orders take the order-checked path)

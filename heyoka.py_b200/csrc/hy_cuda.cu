@@ -116,6 +116,9 @@ template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launc
         if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_wgx(P, li, s);
         return cudaErrorInvalidValue;
     case hy::CRB_VARIANT: return hy::launch_cr3bp_kernel<R>(P, li, s); // hy_cr3bp.cu
+    case hy::CRB_VARIANT_P22:
+        if constexpr (std::is_same<R, double>::value) return hy::launch_cr3bp_kernel_p22(P, li, s);
+        return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
     if (li.ws_in_smem) {
@@ -145,6 +148,7 @@ template <typename R> int regs_for_group(uint32_t g, bool smem, uint32_t variant
     switch (variant) {
     case 106: return 168;
     case hy::CRB_VARIANT: return hy::regs_cr3bp_kernel<R>();
+    case hy::CRB_VARIANT_P22: return hy::regs_cr3bp_kernel_p22();
     case 3: return hy::regs_nbody_kernel<R, 3>();
     case 4: return hy::regs_nbody_kernel<R, 4>();
     case 5: return hy::regs_nbody_kernel<R, 5>();
@@ -262,7 +266,7 @@ int choose_geometry(hy_ctx *c)
             bestRS = RS;
             best_smem = true;
             best = pr;
-            li.kernel_variant = (uint32_t)hy::CRB_VARIANT;
+            li.kernel_variant = hy::cr3bp_kernel_variant(d.order, c->fp_bits);
         }
     }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
@@ -304,7 +308,8 @@ int choose_geometry(hy_ctx *c)
     T = std::max(1u, std::min(T, per_cta_needed));
     if (li.kernel_variant) T = (T + 1u) & ~1u; // whole warps: the two trajectories of a warp step in lockstep
     if (li.kernel_variant == 106) T = 24;      // whole warpgroups
-    if (li.kernel_variant == (uint32_t)hy::CRB_VARIANT) T = (T + 15u) & ~15u; // whole warps (16 trajectories)
+    if (li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22)
+        T = (T + 15u) & ~15u; // whole warps (16 trajectories)
     li.group = G;
     li.traj_per_cta = T;
     li.threads = ((T * G + 31) / 32) * 32;
@@ -1005,7 +1010,7 @@ int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term 
     if (hy::match_nbody(*dims, ops, terms, m)) *variant = hy::nbody_kernel_variant(m.nb, dims->order, 64);
     hy::CrbMatch cm; // (FP64 order, then FP32 order: the introspection call does not know the precision)
     if (!*variant && (hy::match_cr3bp(*dims, ops, terms, 64, cm) || hy::match_cr3bp(*dims, ops, terms, 32, cm)))
-        *variant = (uint32_t)hy::CRB_VARIANT;
+        *variant = hy::cr3bp_kernel_variant(dims->order, 64);
     return 0;
 }
 

@@ -1032,10 +1032,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 } else
                     nbr_jets<R, NB, PM, false>(w, s_imm + nl.coef, nl, p);
             } else if constexpr (NB < 0) {
-                if (p == (uint32_t)CrbPmax<R>::value)
-                    crb_jets<R, CrbPmax<R>::value, true>(w, cl, p);
+                // (PM = NBR_PMAX: the standard builds; PM = CRB_PMAX_HI: the FP64 order-22 build)
+                constexpr int CPM = PM == NBR_PMAX ? CrbPmax<R>::value : PM;
+                if (p == (uint32_t)CPM)
+                    crb_jets<R, CPM, true>(w, cl, p);
                 else
-                    crb_jets<R, CrbPmax<R>::value, false>(w, cl, p);
+                    crb_jets<R, CPM, false>(w, cl, p);
             } else {
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;

@@ -19,6 +19,9 @@ int regs_nbody_kernel_p22();
 // register-resident CR3BP kernel (hy_cr3bp_reg.cuh, instantiated in hy_cr3bp.cu)
 template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s);
 template <typename R> int regs_cr3bp_kernel();
+// FP64 build unrolled to order 22 (kernel variant CRB_VARIANT_P22)
+cudaError_t launch_cr3bp_kernel_p22(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s);
+int regs_cr3bp_kernel_p22();
 
 #define HY_NB_INSTANTIATE(NB)                                                                            \
     template <typename R, int N> cudaError_t launch_nbody_kernel(const KParams<R> &P, const hy_launch_info &li, \

@@ -227,6 +227,7 @@ typedef struct hy_launch_info {
                                 N-body kernel for N bodies (hy_nbody_reg.cuh);
                                 226: the 6-body FP64 build unrolled to order 22
                                 (tol = 1e-18, orders 21..22);
+                                222: the FP64 CR3BP build unrolled to order 22;
                                 203: register-resident CR3BP kernel
                                 (hy_cr3bp_reg.cuh); 106: experimental
                                 warpgroup-rotation N-body kernel (HY_CUDA_WGX=1) */
@@ -240,8 +241,8 @@ int hy_get_launch_info(hy_ctx *ctx, hy_launch_info *info);
  * model.nbody builds, expose_models.cpp:237-272), no events or parameters, every
  * pair present, order <= 20 (226: 6 bodies, FP64 assumed, orders 21..22)
  * (hy_nbody_match.hpp); the CR3BP kernel exactly the
- * tape of model.cr3bp (expose_models.cpp:395-400) at order 20 (FP64) or 9 (FP32),
- * no events or parameters (hy_cr3bp_match.hpp). */
+ * tape of model.cr3bp (expose_models.cpp:395-400) at orders up to 20 (FP64; 222:
+ * orders 21..22) or 9 (FP32), no events or parameters (hy_cr3bp_match.hpp). */
 int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term *terms,
                            uint32_t *variant);
 

@@ -50,8 +50,11 @@ def test_variant_selected():
     assert _make(sys_, ic, interp=True)._ctx.launch_info()["kernel_variant"] == 0
     # lower orders take the order-checked path of the same kernel
     assert _make(sys_, ic, tol=1e-9)._ctx.launch_info()["kernel_variant"] == CRB
-    # orders above the unrolled maximum and event-carrying systems keep the interpreter
-    assert _make(sys_, ic, tol=1e-18)._ctx.launch_info()["kernel_variant"] == 0
+    # tol = 1e-18 (order 22, the setting of the reference's CR3BP notebook): the FP64 order-22 build
+    t22 = _make(sys_, ic, tol=1e-18)
+    assert t22.order == 22 and t22._ctx.launch_info()["kernel_variant"] == 222
+    # orders above that and event-carrying systems keep the interpreter
+    assert _make(sys_, ic, tol=1e-21)._ctx.launch_info()["kernel_variant"] == 0
     x = hy.make_vars("x")
     ev = hy.t_event_batch(x - 5.0)
     assert hy.taylor_adaptive_batch(sys_, ic, t_events=[ev])._ctx.launch_info()["kernel_variant"] == 0
@@ -85,7 +88,8 @@ def test_bitwise_vs_interpreter(fp, mu):
     assert a.propagate_res == b.propagate_res
 
 
-@pytest.mark.parametrize("fp,tol,order", [(np.float64, 1e-9, 12), (np.float64, 1e-4, 6), (np.float32, 1e-4, 6)])
+@pytest.mark.parametrize("fp,tol,order", [(np.float64, 1e-9, 12), (np.float64, 1e-4, 6), (np.float32, 1e-4, 6),
+                                          (np.float64, 1e-18, 22), (np.float64, 1e-17, 21)])
 def test_lower_orders_bitwise(fp, tol, order):
     # orders below the unrolled maximum: run-time order checks in the register kernel
     B = 75
@@ -94,7 +98,8 @@ def test_lower_orders_bitwise(fp, tol, order):
     a = _make(sys_, ic, fp_type=fp, tol=fp(tol))
     b = _make(sys_, ic, interp=True, fp_type=fp, tol=fp(tol))
     assert a.order == order and b.order == order
-    assert a._ctx.launch_info()["kernel_variant"] == CRB and b._ctx.launch_info()["kernel_variant"] == 0
+    assert a._ctx.launch_info()["kernel_variant"] == (222 if order > 20 else CRB)
+    assert b._ctx.launch_info()["kernel_variant"] == 0
     a.step(write_tc=True)
     b.step(write_tc=True)
     assert np.array_equal(a.tc, b.tc)
