@@ -222,3 +222,27 @@ def test_ensemble_copy_and_batch_composition():
         assert np.array_equal(ret[i][0].state, ser.state)
         assert ret[i][0].propagate_res == ser.propagate_res
         assert np.array_equal(big.state[:, 4 * i:4 * i + 4], ser.state)
+
+
+@pytest.mark.parametrize("fp", [np.float64, np.float32])
+def test_non_finite_lanes_stop_alone(fp):
+    # a NaN initial condition and a start exactly on a primary (r = 0): those lanes end with
+    # err_nf_state, their neighbours in the warp are unaffected (outcomes and states as on the interpreter)
+    B = 40
+    sys_ = W.cr3bp_sys(0.01)
+    ic = W.cr3bp_ensemble(B).astype(fp)
+    ic[1, 3] = np.nan
+    ic[:, 18] = [0.01, 0.0, 0.0, 0.1, 0.2, 0.0]  # x = mu, y = z = 0: on the first primary
+    a = _make(sys_, ic, fp_type=fp)
+    b = _make(sys_, ic, interp=True, fp_type=fp)
+    assert a._ctx.launch_info()["kernel_variant"] == CRB
+    a.propagate_until(fp(3.0))
+    b.propagate_until(fp(3.0))
+    oa = [int(r[0]) for r in a.propagate_res]
+    assert oa == [int(r[0]) for r in b.propagate_res]
+    nf = int(hy.taylor_outcome.err_nf_state)
+    assert oa[3] == nf and oa[18] == nf
+    ok = [i for i in range(B) if i not in (3, 18)]
+    assert all(oa[i] == int(hy.taylor_outcome.time_limit) for i in ok)
+    assert np.array_equal(a.state[:, ok], b.state[:, ok])
+    assert np.all(a.time[ok] == fp(3.0))
