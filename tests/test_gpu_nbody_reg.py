@@ -238,3 +238,26 @@ def test_order22_build_bitwise_and_oracle(high_accuracy):
         orc.propagate_until(tf)
         orc.propagate_for(-7.5)
         assert _rel(a.state, orc.state) < 1e-11
+
+
+def test_non_finite_lanes_stop_alone():
+    # a NaN coordinate and two bodies on top of each other (r = 0): those trajectories end with
+    # err_nf_state; the other trajectory of the same warp is unaffected (the finiteness ballot is per half-warp)
+    B = 9
+    sys_ = common.oss_sys()
+    ic = common.oss_ensemble(B, amp=1e-6)
+    ic[7, 2] = np.nan
+    ic[6:9, 5] = ic[0:3, 5]  # body 1 placed on body 0
+    a = _make(sys_, ic)
+    b = _make(sys_, ic, interp=True)
+    assert a._ctx.launch_info()["kernel_variant"] == 6
+    a.propagate_until(30.0)
+    b.propagate_until(30.0)
+    oa = [int(r[0]) for r in a.propagate_res]
+    assert oa == [int(r[0]) for r in b.propagate_res]
+    nf = int(hy.taylor_outcome.err_nf_state)
+    assert oa[2] == nf and oa[5] == nf
+    ok = [i for i in range(B) if i not in (2, 5)]
+    assert all(oa[i] == int(hy.taylor_outcome.time_limit) for i in ok)
+    assert np.array_equal(a.state[:, ok], b.state[:, ok])
+    assert np.all(a.time[ok] == 30.0)
