@@ -409,7 +409,7 @@ def main():
                 "peak_gbs": 128.0 * li["n_sm"] * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                 "note": "operand loads of the tape (what the tape INTERPRETER would read from shared memory; "
                         "with kernel_variant > 0 the convolution operands are registers and shared memory "
-                        "carries only the per-order exchange)",
+                        "carries only the state jets; the pair products travel by warp shuffle)",
             },
         }
         cpu = None
