@@ -246,3 +246,23 @@ def test_non_finite_lanes_stop_alone(fp):
     assert all(oa[i] == int(hy.taylor_outcome.time_limit) for i in ok)
     assert np.array_equal(a.state[:, ok], b.state[:, ok])
     assert np.all(a.time[ok] == fp(3.0))
+
+
+@pytest.mark.parametrize("interp", [False, True])
+def test_notebook_golden_A13(interp):
+    # The reference's own numbers (The restricted three-body problem.ipynb:110-112, SURVEY.md App. B A13;
+    # tests/golden/notebook_golden.json): tol = 1e-18 -> order 22, 753 steps to t = 200, min / max step size
+    # and final state as printed - reproduced by the order-22 register build (and by the interpreter).
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_golden.json")) as f:
+        g = json.load(f)["cr3bp"]
+    ic = np.repeat(np.array(g["ic"], dtype=float)[:, None], 4, axis=1)
+    ta = _make(W.cr3bp_sys(g["mu"]), ic, interp=interp, tol=g["tol"])
+    assert ta.order == 22 and ta._ctx.launch_info()["kernel_variant"] == (0 if interp else 222)
+    ta.propagate_until(g["t_end"])
+    for oc, mn, mx, ns in ta.propagate_res:
+        assert int(ns) == g["steps"]
+        assert abs(mn - g["min_h"]) / g["min_h"] < 1e-12
+        assert abs(mx - g["max_h"]) / g["max_h"] < 1e-12
+    assert np.max(np.abs(ta.state - np.array(g["final_state"])[:, None])) < 1e-8
