@@ -141,31 +141,99 @@ def ncu_traffic():
         return None
 
 
-def workload(traj, rank):
+# --------------------------------------------------------------------------------------
+# The configurations of BASELINE.json: system, seeded ICs, horizon,
+# what one bench "step" is.  --config 2 (default) is the headline.
+# --------------------------------------------------------------------------------------
+def make_config(cfg, traj, rank, horizon, segment):
+    import hy_b200 as hy
     from hy_b200 import workloads as W
 
-    sys_ = W.oss_sys()
-    ic = W.oss_ensemble(traj, seed=20251019 + 7919 * rank)
-    return sys_, ic
+    c = {"cfg": cfg, "fp": np.float64, "events": None, "pars": None, "c_output": False,
+         "grid_eval": 0, "reset_each_step": False}
+    seed = 20251017 + cfg + 7919 * rank
+    if cfg == 2:
+        c.update(name="outer Solar System 6-body (model.nbody(6)) ensemble, FP64, tol=eps (order 20), "
+                      "ICs x(1+U(-1e-12,1e-12)) recentred",
+                 sys=W.oss_sys(), ic=W.oss_ensemble(traj, seed=seed), horizon=horizon or 1e4,
+                 unit_t="yr")
+        c["segment"] = segment or c["horizon"] / 10.0
+        c["step_desc"] = "propagate_for({:g} yr) over the whole shard, continuing from the previous step".format(c["segment"])
+        c["check"] = lambda ic, st: float(np.max(np.abs((W.oss_energy(st) - W.oss_energy(ic)) / W.oss_energy(ic))))
+        c["check_name"], c["check_tol"] = "max_rel_energy_drift", 1e-10
+    elif cfg == 3:
+        c.update(name="CR3BP (model.cr3bp, mu=0.01) ensemble, FP64, tol=eps (order 20), ICs base + U(-1e-3,1e-3), "
+                      "propagate_until(20) with c_output=True, then c_out on a [16, B] time grid",
+                 sys=W.cr3bp_sys(0.01), ic=W.cr3bp_ensemble(traj, seed=seed), horizon=horizon or 20.0,
+                 unit_t="", c_output=True, grid_eval=16, reset_each_step=True)
+        c["segment"] = c["horizon"]
+        c["step_desc"] = "ICs reset on the device, propagate_until(20, c_output=True), 16 x B dense evaluations"
+        c["check"] = lambda ic, st: float(np.max(np.abs((W.cr3bp_jacobi(st) - W.cr3bp_jacobi(ic)) / W.cr3bp_jacobi(ic))))
+        c["check_name"], c["check_tol"] = "max_rel_jacobi_drift", 1e-10
+    elif cfg == 4:
+        vs = hy.var_ode_sys(W.kepler_j2_sys(), hy.var_args.vars)
+        ic6 = W.kepler_j2_ensemble(traj, seed=seed)
+        ic = np.zeros((42, traj))
+        ic[:6] = ic6
+        ic[6:] = vs._initial_var_state(np.float64)[:, None]
+        c.update(name="Kepler+J2 orbit ensemble with first-order variational equations (var_ode_sys, 42 state "
+                      "variables), FP64, tol=eps (order 20), LEO ICs",
+                 sys=vs.sys, ic=ic, horizon=horizon or 6e4, unit_t="s")
+        c["segment"] = segment or c["horizon"] / 10.0
+        c["step_desc"] = "propagate_for({:g} s) over the whole shard, continuing from the previous step".format(c["segment"])
+        c["check"] = lambda ic, st: float(np.max(np.abs(
+            (W.kepler_j2_energy(st[:6]) - W.kepler_j2_energy(ic[:6])) / W.kepler_j2_energy(ic[:6]))))
+        c["check_name"], c["check_tol"] = "max_rel_energy_drift", 1e-10
+    elif cfg == 5:
+        mu = 0.01
+        x, y, z = hy.make_vars("x", "y", "z")
+        evs = [(x - mu) ** 2 + y * y + z * z - 0.012 ** 2,
+               (x - mu + 1.0) ** 2 + y * y + z * z - 0.012 ** 2,
+               x * x + y * y + z * z - 5.0 ** 2]
+        rng = np.random.default_rng(seed)
+        ic = np.array([-0.80, 0.0, 0.0, 0.0, -0.6276410653920693, 0.0])[:, None] * np.ones((1, traj))
+        ic[0] += rng.uniform(-1e-2, 1e-2, traj)
+        ic[4] += rng.uniform(-1e-2, 1e-2, traj)
+        c.update(name="CR3BP (mu=0.01) ensemble with three stopping terminal events (collision spheres R=0.012 "
+                      "around both primaries, escape sphere R=5), FP64, tol=eps (order 20), planar chaotic family",
+                 sys=W.cr3bp_sys(mu), ic=ic, horizon=horizon or 2000.0, unit_t="", events=evs,
+                 reset_each_step=True)
+        c["segment"] = segment or c["horizon"] / 10.0
+        c["horizon_step"] = c["segment"]
+        c["step_desc"] = ("ICs reset on the device, propagate_until({:g}) with event detection "
+                          "(1/10 of the configuration's t = {:g})".format(c["segment"], c["horizon"]))
+        c["check"] = lambda ic, st: float(np.nanmax(np.abs((W.cr3bp_jacobi(st) - W.cr3bp_jacobi(ic)) / W.cr3bp_jacobi(ic))))
+        c["check_name"], c["check_tol"] = "max_rel_jacobi_drift", 1e-6
+    else:
+        raise SystemExit("unknown --config {}".format(cfg))
+    return c
 
 
-def cpu_baseline(sys_, order, horizon, target_s, rank_seed=0):
+def cpu_baseline(cfgd, order, target_s, rank_seed=0):
     """Time the CPU port on all host cores on a bounded sample: the SIMD-batched,
     multithreaded restatement (oracle/hy_baseline_simd.c: 8 lanes in lock-step per
     thread, OpenMP over batches) - the shape of the reference's own CPU ensemble."""
-    from hy_b200 import decompose as D, workloads as W
+    from hy_b200 import decompose as D
     from oracle.c_oracle import simd_propagate_until
 
-    dc = D.decompose(sys_, order)
+    sys_, horizon = cfgd["sys"], cfgd["segment"] if cfgd["reset_each_step"] else cfgd["horizon"]
+    dc = D.decompose(sys_, order, events=cfgd["events"] or ())
     # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly.
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    full = cfgd["ic"]
+    ntot = full.shape[1]
+
+    def sample(k, off):
+        idx = (np.arange(k) + off) % ntot
+        return np.ascontiguousarray(full[:, idx])
+
     # Calibrate on tiny runs (the first one also pays thread start-up), then size the
     # sample for ~target_s seconds; grow it once more if it still came out short.
-    cal_traj, cal_h = 8 * cores, min(horizon, 400.0)
+    cal_traj, cal_h = 8 * cores, min(horizon, horizon / 25.0 if cfgd["cfg"] == 2 else horizon)
     rate, steps_per_traj = 0.0, 1.0
     for _ in range(2):
         t0 = time.perf_counter()
-        _, ns = simd_propagate_until(dc, W.oss_ensemble(cal_traj, seed=777 + rank_seed), cal_h, nthreads=cores)
+        _, ns = simd_propagate_until(dc, sample(cal_traj, 11 * rank_seed), cal_h, nthreads=cores)
         dt = time.perf_counter() - t0
         rate = float(ns.sum()) / max(dt, 1e-9)
         steps_per_traj = float(ns.mean()) * horizon / cal_h
@@ -177,19 +245,25 @@ def cpu_baseline(sys_, order, horizon, target_s, rank_seed=0):
             # Keep at least one full SIMD batch per thread: shorten the horizon instead.
             h = max(cal_h, horizon * want / (steps_per_traj * traj))
         t0 = time.perf_counter()
-        _, ns = simd_propagate_until(dc, W.oss_ensemble(traj, seed=778 + rank_seed), h, nthreads=cores)
+        _, ns = simd_propagate_until(dc, sample(traj, 13 * rank_seed + 5), h, nthreads=cores)
         dt = time.perf_counter() - t0
         rate = float(ns.sum()) / max(dt, 1e-9)
         if dt >= 0.5 * target_s:
             break
     val = float(ns.sum()) / dt
+    extra = ""
+    if cfgd["events"]:
+        extra = "; the event functions are integrated (they enter the step-size norms) but the CPU port runs no root finding"
+    if cfgd["c_output"]:
+        extra = "; the CPU port does not record the continuous output"
     return {
         "value": val,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": "{} trajectories x {:.0f} yr = {} steps in {:.1f} s (SIMD-batched C port of the reference "
-                  "algorithm: 8 lanes/thread in lock-step, OpenMP over batches)".format(traj, h, int(ns.sum()), dt),
+        "sample": "{} trajectories x t = {:g} = {} steps in {:.1f} s (SIMD-batched C port of the reference "
+                  "algorithm: 8 lanes/thread in lock-step, OpenMP over batches{})".format(
+                      traj, h, int(ns.sum()), dt, extra),
     }, dt, int(ns.sum())
 
 
@@ -197,15 +271,15 @@ def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
         return
-    from hy_b200 import decompose as D, workloads as W
+    from hy_b200 import decompose as D
 
-    sys_ = W.oss_sys()
+    cfgd = make_config(args.config, 4096, 0, args.horizon, args.segment)
     order = D.taylor_order(float(np.finfo(np.float64).eps))
     tot_steps, tot_t = 0, 0.0
     per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     info = None
     for i in range(args.warmup + args.steps):
-        info, dt, ns = cpu_baseline(sys_, order, args.horizon, per, rank_seed=i)
+        info, dt, ns = cpu_baseline(cfgd, order, per, rank_seed=i)
         if i >= args.warmup:
             tot_steps += ns
             tot_t += dt
@@ -213,13 +287,13 @@ def run_reference(args):
     info["value"] = val
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric_name(args.config), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": "outer Solar System 6-body ensemble, FP64, tol=eps (order 20), "
-                        "propagate_until {:g} yr; bounded CPU sample".format(args.horizon),
+            "workload": cfgd["name"] + "; bounded CPU sample",
+            "config_id": args.config,
             "note": "reference arithmetic (heyoka C++ 7.11) not installable here: C oracle port "
                     "of the same algorithm on all host threads",
         },
@@ -228,6 +302,12 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+def metric_name(cfg):
+    return {2: METRIC, 3: "ensemble trajectory-steps/s (FP64 CR3BP, c_output)",
+            4: "ensemble trajectory-steps/s (FP64 Kepler+J2 variational)",
+            5: "ensemble trajectory-steps/s (FP64 CR3BP, terminal events)"}[cfg]
 
 
 _REAL_STDOUT = None

@@ -36,6 +36,29 @@ int fail(const std::string &msg)
 
 } // namespace
 
+// Continuous-output record: owns the chunk pool written by the propagate kernel
+// (hy_kernels.cuh, RecDev) and everything needed to evaluate it.  Created by
+// hy_propagate(c_output) inside a context, handed to the caller by hy_cout_detach.
+struct hy_cout {
+    int device = 0;
+    size_t rb = 8;
+    uint32_t B = 0, n = 0, P1 = 0;
+    std::vector<void *> segs; // pool segments (device)
+    void **d_seg = nullptr;   // device copy of the segment table (HY_REC_MAXSEG entries)
+    uint32_t seg_chunks = 0, rec_len = 0, chunk_len = 0;
+    void *d_lane = nullptr; // one allocation: next | dir_next | head | tail | count | nchunks | dir_off | t0_hi | t0_lo
+    unsigned int *d_next = nullptr, *d_dir_next = nullptr;
+    uint32_t *d_head = nullptr, *d_tail = nullptr, *d_count = nullptr, *d_nch = nullptr, *d_dir_off = nullptr;
+    void *d_t0hi = nullptr, *d_t0lo = nullptr;
+    uint32_t *d_dir = nullptr;
+    size_t dir_cap = 0;
+    bool indexed = false;
+    cudaStream_t stream = nullptr;
+    void *d_tmp_in = nullptr, *d_tmp_out = nullptr;
+    size_t tmp_in_bytes = 0, tmp_out_bytes = 0;
+};
+constexpr int HY_REC_MAXSEG = 64;
+
 struct hy_ctx {
     int device = 0;
     int fp_bits = 64;
@@ -46,8 +69,8 @@ struct hy_ctx {
     int high_accuracy = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // tape (device)
-    std::vector<hy_op> h_ops; // the ABI tape (kept for re-scheduling)
+    // tape (host copies: kept for re-scheduling and for hy_clone)
+    std::vector<hy_op> h_ops;
     std::vector<hy_term> h_terms;
     std::vector<uint32_t> h_levels;
     hy::Program prog;
@@ -55,15 +78,20 @@ struct hy_ctx {
     uint32_t *d_phase = nullptr;
     uint32_t *d_ev = nullptr;       // remapped event jet rows (device layout)
     std::vector<uint32_t> h_ev_ref; // ABI event references
+    std::vector<int32_t> h_ev_dir;
+    std::vector<double> h_ev_cd;
     uint32_t *d_srow = nullptr;
     int32_t *d_ssp = nullptr;
     void *d_gjet = nullptr;
     // lanes (device)
     void *d_state = nullptr, *d_pars = nullptr, *d_thi = nullptr, *d_tlo = nullptr, *d_lasth = nullptr;
-    void *d_tf = nullptr, *d_mdt = nullptr, *d_minh = nullptr, *d_maxh = nullptr, *d_tc = nullptr;
+    void *d_tf = nullptr, *d_tfhi = nullptr, *d_tflo = nullptr, *d_mdt = nullptr, *d_minh = nullptr, *d_maxh = nullptr,
+         *d_tc = nullptr;
     long long *d_outcome = nullptr;
     unsigned long long *d_nsteps = nullptr;
     unsigned int *d_counter = nullptr;
+    unsigned char *d_active = nullptr;
+    uint32_t *d_gidx = nullptr;
     void *d_gws = nullptr;
     // events
     int32_t *d_ev_dir = nullptr;
@@ -72,11 +100,12 @@ struct hy_ctx {
     hy_event_rec *d_log = nullptr;
     unsigned long long *d_log_count = nullptr;
     unsigned long long log_cap = 0;
-    // continuous output
-    void *d_cout_tcs = nullptr, *d_cout_thi = nullptr, *d_cout_tlo = nullptr;
-    unsigned long long *d_cout_count = nullptr;
-    uint64_t cout_S = 0; // recorded capacity == max steps over lanes
-    // scratch for grid / dense / cout evaluation
+    // angle reduction (device-side post-step op)
+    uint32_t *d_red = nullptr;
+    uint32_t n_red = 0;
+    // continuous output: the record being written / a recycled one
+    hy_cout *rec = nullptr, *rec_spare = nullptr;
+    // scratch for grid / dense evaluation
     void *d_tmp_in = nullptr, *d_tmp_out = nullptr;
     size_t tmp_in_bytes = 0, tmp_out_bytes = 0;
     // launch geometry
@@ -176,6 +205,8 @@ hy::ProgDims prog_dims(const hy::Program &p)
     return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases,
                         p.ws_len,  p.par_off,  p.one_off,              p.n_spill};
 }
+
+int upload_program(hy_ctx *c);
 
 // Choose the launch geometry for a tape: group size G (threads cooperating on
 // one trajectory), trajectories per CTA T; schedule the tape for that G and
@@ -323,7 +354,17 @@ int choose_geometry(hy_ctx *c)
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
     li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G, li.ws_in_smem, li.kernel_variant)
                                                      : regs_for_group<float>(G, li.ws_in_smem, li.kernel_variant));
-    // Upload the program blob [ops | terms | imm] (same layout as in shared memory).
+    return upload_program(c);
+}
+
+// Upload the scheduled program of `c` (c->prog, c->li, c->TS) to its device.
+int upload_program(hy_ctx *c)
+{
+    const hy_dims &d = c->d;
+    hy_launch_info &li = c->li;
+    const uint32_t G = li.group, T = li.traj_per_cta, RS = c->TS;
+    hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
+    // The program blob [ops | terms | imm] (same layout as in shared memory).
     {
         std::vector<unsigned char> blob(L.off_phase, 0);
         std::memcpy(blob.data() + L.off_ops, c->prog.ops.data(), c->prog.ops.size() * sizeof(hy::DOp));
@@ -355,8 +396,180 @@ int choose_geometry(hy_ctx *c)
     return 0;
 }
 
-template <typename R>
-hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc)
+// ---------------------------------------------------------------------------
+// Continuous-output record (hy_cout): chunk pool + per-lane lists.
+// ---------------------------------------------------------------------------
+void rec_free(hy_cout *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    for (void *p : r->segs)
+        if (p) cudaFree(p);
+    for (void *p : {(void *)r->d_seg, r->d_lane, (void *)r->d_dir, r->d_tmp_in, r->d_tmp_out})
+        if (p) cudaFree(p);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+int rec_add_segment(hy_cout *r)
+{
+    if ((int)r->segs.size() >= HY_REC_MAXSEG) return fail("continuous output: too many pool segments");
+    const size_t bytes = (size_t)r->seg_chunks * r->chunk_len * r->rb;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + (64u << 20) > free_b)
+        return fail("hy_propagate: continuous output needs another " + std::to_string(bytes >> 20) +
+                    " MiB of device memory but only " + std::to_string(free_b >> 20) + " MiB are free");
+    void *p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    r->segs.push_back(p);
+    CU(cudaMemcpy(r->d_seg + (r->segs.size() - 1), &p, sizeof(void *), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int rec_create(hy_ctx *c, hy_cout **out)
+{
+    hy_cout *r = new hy_cout();
+    *out = r;
+    r->device = c->device;
+    r->rb = c->rb;
+    r->B = c->B;
+    r->n = c->d.n_state;
+    r->P1 = c->d.order + 1;
+    r->rec_len = r->n * r->P1 + 2u;
+    r->chunk_len = 2u + hy::HY_REC_CH * r->rec_len;
+    const size_t chunk_bytes = (size_t)r->chunk_len * r->rb;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    // first segment: room for 4 chunks (32 steps) per lane, within 40 % of the free memory; at least 256 chunks
+    size_t want = std::max<size_t>(256, (size_t)4 * r->B);
+    want = std::min<size_t>(want, (size_t)(0.4 * (double)free_b / (double)chunk_bytes));
+    r->seg_chunks = (uint32_t)std::max<size_t>(16, std::min<size_t>(want, 0x7fffffffu / HY_REC_MAXSEG));
+    CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&r->d_seg, HY_REC_MAXSEG * sizeof(void *)));
+    CU(cudaMemset(r->d_seg, 0, HY_REC_MAXSEG * sizeof(void *)));
+    const size_t B = r->B;
+    const size_t lane_bytes = 16 + 5 * B * 4 + 2 * B * 8;
+    CU(cudaMalloc(&r->d_lane, lane_bytes));
+    char *q = (char *)r->d_lane;
+    r->d_next = (unsigned int *)q;
+    r->d_dir_next = (unsigned int *)(q + 8);
+    q += 16;
+    r->d_t0hi = q, q += B * 8;
+    r->d_t0lo = q, q += B * 8;
+    r->d_head = (uint32_t *)q, q += B * 4;
+    r->d_tail = (uint32_t *)q, q += B * 4;
+    r->d_count = (uint32_t *)q, q += B * 4;
+    r->d_nch = (uint32_t *)q, q += B * 4;
+    r->d_dir_off = (uint32_t *)q;
+    return rec_add_segment(r);
+}
+
+// Empty the record (stream-ordered on `s`).
+int rec_reset(hy_cout *r, cudaStream_t s)
+{
+    const size_t B = r->B;
+    CU(cudaMemsetAsync(r->d_lane, 0, 16 + 2 * B * 8, s));                  // next, dir_next, t0
+    CU(cudaMemsetAsync(r->d_head, 0xff, 2 * B * 4, s));                    // head, tail = NONE
+    CU(cudaMemsetAsync(r->d_count, 0, 3 * B * 4, s));                      // count, nchunks, dir_off
+    r->indexed = false;
+    return 0;
+}
+
+template <typename R> hy::RecDev<R> rec_dev(const hy_cout *r, int on, int append)
+{
+    hy::RecDev<R> d{};
+    if (!r) return d;
+    d.seg = (R *const *)r->d_seg;
+    d.seg_chunks = r->seg_chunks;
+    d.cap_chunks = (uint32_t)(r->seg_chunks * r->segs.size());
+    d.next = r->d_next;
+    d.head = r->d_head;
+    d.tail = r->d_tail;
+    d.count = r->d_count;
+    d.nchunks = r->d_nch;
+    d.t0_hi = (R *)r->d_t0hi;
+    d.t0_lo = (R *)r->d_t0lo;
+    d.rec_len = r->rec_len;
+    d.chunk_len = r->chunk_len;
+    d.on = on;
+    d.append = append;
+    return d;
+}
+
+int rec_ensure_tmp(hy_cout *r, size_t in_bytes, size_t out_bytes)
+{
+    if (in_bytes > r->tmp_in_bytes) {
+        if (r->d_tmp_in) cudaFree(r->d_tmp_in);
+        r->d_tmp_in = nullptr;
+        r->tmp_in_bytes = 0;
+        CU(cudaMalloc(&r->d_tmp_in, in_bytes));
+        r->tmp_in_bytes = in_bytes;
+    }
+    if (out_bytes > r->tmp_out_bytes) {
+        if (r->d_tmp_out) cudaFree(r->d_tmp_out);
+        r->d_tmp_out = nullptr;
+        r->tmp_out_bytes = 0;
+        CU(cudaMalloc(&r->d_tmp_out, out_bytes));
+        r->tmp_out_bytes = out_bytes;
+    }
+    return 0;
+}
+
+// Build the chunk directory (once per recording).
+int rec_index(hy_cout *r)
+{
+    if (r->indexed) return 0;
+    CU(cudaSetDevice(r->device));
+    unsigned int used = 0;
+    CU(cudaMemcpyAsync(&used, r->d_next, 4, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    const size_t cap = (size_t)r->seg_chunks * r->segs.size();
+    const size_t need = std::max<size_t>(1, std::min<size_t>(used, cap));
+    if (need > r->dir_cap) {
+        if (r->d_dir) cudaFree(r->d_dir);
+        r->d_dir = nullptr;
+        r->dir_cap = 0;
+        CU(cudaMalloc((void **)&r->d_dir, need * 4));
+        r->dir_cap = need;
+    }
+    CU(cudaMemsetAsync(r->d_dir_next, 0, 4, r->stream));
+    const unsigned th = 128, bl = (unsigned)((r->B + th - 1) / th);
+    if (r->rb == 8)
+        hy::rec_index_kernel<double><<<bl, th, 0, r->stream>>>(rec_dev<double>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                               r->d_dir_next, r->B);
+    else
+        hy::rec_index_kernel<float><<<bl, th, 0, r->stream>>>(rec_dev<float>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                              r->d_dir_next, r->B);
+    CU(cudaGetLastError());
+    r->indexed = true;
+    return 0;
+}
+
+__global__ void mask_outcome_kernel(const long long *__restrict__ outcome, long long code,
+                                    unsigned char *__restrict__ active, uint32_t B)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < B) active[l] = outcome[l] == code ? 1 : 0;
+}
+
+struct RunArgs {
+    int mode = hy::MODE_UNTIL;
+    int backward = 0;
+    uint64_t max_steps = 0;
+    bool have_mdt = false;
+    int write_tc = 0;
+    int rec_on = 0, rec_append = 0;
+    const void *grid = nullptr;
+    void *gout = nullptr;
+    uint32_t grid_k = 0;
+    bool use_active = false;
+    int resume = 0;
+    int pause_on_nt = 0;
+    uint64_t launch_steps = 0;
+};
+
+template <typename R> hy::KParams<R> make_params(hy_ctx *c, const RunArgs &a)
 {
     hy::KParams<R> P{};
     P.d = c->d;
@@ -372,20 +585,25 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.t_hi = (R *)c->d_thi;
     P.t_lo = (R *)c->d_tlo;
     P.last_h = (R *)c->d_lasth;
-    P.tf = (const R *)c->d_tf;
-    P.mdt = have_mdt ? (const R *)c->d_mdt : nullptr;
+    P.tf_hi = (const R *)c->d_tfhi;
+    P.tf_lo = (const R *)c->d_tflo;
+    P.mdt = a.have_mdt ? (const R *)c->d_mdt : nullptr;
+    P.active = a.use_active ? c->d_active : nullptr;
+    P.gidx = c->d_gidx;
+    P.resume = a.resume;
+    P.pause_on_nt = a.pause_on_nt;
+    P.launch_steps = a.launch_steps;
+    P.red_idx = c->d_red;
+    P.n_red = c->n_red;
+    P.rec = rec_dev<R>(c->rec, a.rec_on, a.rec_append);
     P.outcome = c->d_outcome;
     P.min_h = (R *)c->d_minh;
     P.max_h = (R *)c->d_maxh;
     P.n_steps = c->d_nsteps;
     P.tc = (R *)c->d_tc;
-    P.cout_tcs = nullptr;
-    P.cout_thi = nullptr;
-    P.cout_tlo = nullptr;
-    P.cout_cap = 0;
-    P.grid = nullptr;
-    P.gout = nullptr;
-    P.grid_k = 0;
+    P.grid = (const R *)a.grid;
+    P.gout = (R *)a.gout;
+    P.grid_k = a.grid_k;
     P.ev.dir = c->d_ev_dir;
     P.ev.cooldown = c->d_ev_cd;
     P.ev.cd_elapsed = (R *)c->d_cd_elapsed;
@@ -401,10 +619,10 @@ hy::KParams<R> make_params(hy_ctx *c, int mode, int backward, uint64_t max_steps
     P.TS = c->TS;
     P.nb_tb_off = (uint32_t)hy::NBR_TB0;
     P.wgx_wgs = env_u32("HY_CUDA_WGX_WGS", 3);
-    P.max_steps = max_steps;
-    P.mode = mode;
-    P.backward = backward;
-    P.write_tc = write_tc;
+    P.max_steps = a.max_steps;
+    P.mode = a.mode;
+    P.backward = a.backward;
+    P.write_tc = a.write_tc;
     P.high_accuracy = c->high_accuracy;
     P.ws_in_smem = (int)c->li.ws_in_smem;
     const double p = (double)c->d.order;
@@ -424,88 +642,138 @@ int ensure_tc(hy_ctx *c)
     return 0;
 }
 
-struct RunExtras {
-    bool record_cout = false;
-    const void *grid = nullptr;
-    void *gout = nullptr;
-    uint32_t grid_k = 0;
-};
-
 int ensure_tmp(hy_ctx *c, size_t in_bytes, size_t out_bytes)
 {
     if (in_bytes > c->tmp_in_bytes) {
         if (c->d_tmp_in) cudaFree(c->d_tmp_in);
         c->d_tmp_in = nullptr;
+        c->tmp_in_bytes = 0;
         CU(cudaMalloc(&c->d_tmp_in, in_bytes));
         c->tmp_in_bytes = in_bytes;
     }
     if (out_bytes > c->tmp_out_bytes) {
         if (c->d_tmp_out) cudaFree(c->d_tmp_out);
         c->d_tmp_out = nullptr;
+        c->tmp_out_bytes = 0;
         CU(cudaMalloc(&c->d_tmp_out, out_bytes));
         c->tmp_out_bytes = out_bytes;
     }
     return 0;
 }
 
-template <typename R> void apply_extras(hy_ctx *c, hy::KParams<R> &P, const RunExtras &x)
+// One launch of the persistent kernel, stream-ordered, NO host synchronisation
+// (the caller synchronises once, after queueing the result copies).
+int launch_once(hy_ctx *c, const RunArgs &a)
 {
-    if (x.record_cout) {
-        P.cout_tcs = (R *)c->d_cout_tcs;
-        P.cout_thi = (R *)c->d_cout_thi;
-        P.cout_tlo = (R *)c->d_cout_tlo;
-        P.cout_cap = (uint32_t)c->cout_S;
-    }
-    P.grid = (const R *)x.grid;
-    P.gout = (R *)x.gout;
-    P.grid_k = x.grid_k;
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+    cudaError_t e;
+    if (c->fp_bits == 64)
+        e = launch<double>(make_params<double>(c, a), c->li, c->stream);
+    else
+        e = launch<float>(make_params<float>(c, a), c->li, c->stream);
+    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+    ++c->last_launches;
+    return 0;
 }
 
-int run_kernel(hy_ctx *c, int mode, int backward, uint64_t max_steps, bool have_mdt, int write_tc,
-               const RunExtras &x = RunExtras())
+// Launch (and, while recording, re-launch the lanes that ran out of recorder
+// pool after growing it).  Timing brackets all launches of the call.
+int run_kernel(hy_ctx *c, RunArgs a)
 {
-    if (c->B == 0) {
-        c->last_ms = 0;
-        c->last_launches = 0;
-        return 0;
-    }
-    if (write_tc && ensure_tc(c)) return 1;
-    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+    c->last_ms = 0;
+    c->last_launches = 0;
+    if (c->B == 0) return 0;
+    if (a.write_tc && ensure_tc(c)) return 1;
     CU(cudaEventRecord(c->ev0, c->stream));
-    cudaError_t e;
-    if (c->fp_bits == 64) {
-        auto P = make_params<double>(c, mode, backward, max_steps, have_mdt, write_tc);
-        apply_extras(c, P, x);
-        e = launch<double>(P, c->li, c->stream);
-    } else {
-        auto P = make_params<float>(c, mode, backward, max_steps, have_mdt, write_tc);
-        apply_extras(c, P, x);
-        e = launch<float>(P, c->li, c->stream);
+    if (launch_once(c, a)) return 1;
+    while (a.rec_on) {
+        // pool exhausted?  (4-byte read-back per recording launch)
+        unsigned int used = 0;
+        CU(cudaMemcpyAsync(&used, c->rec->d_next, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const size_t cap = (size_t)c->rec->seg_chunks * c->rec->segs.size();
+        if (used <= cap) break;
+        // every id below cap was handed out; the failed requests pushed the counter past it
+        const unsigned int capu = (unsigned int)cap;
+        CU(cudaMemcpyAsync(c->rec->d_next, &capu, 4, cudaMemcpyHostToDevice, c->stream));
+        if (rec_add_segment(c->rec)) return 1;
+        const unsigned th = 256, bl = (unsigned)((c->B + th - 1) / th);
+        mask_outcome_kernel<<<bl, th, 0, c->stream>>>(c->d_outcome, HY_OUTCOME_PAUSED_POOL, c->d_active, c->B);
+        CU(cudaGetLastError());
+        a.use_active = true;
+        a.resume = 1;
+        a.rec_append = 1;
+        if (launch_once(c, a)) return 1;
     }
-    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// After the stream has been synchronised: kernel time of the call.
+void finish_timing(hy_ctx *c)
+{
+    if (!c->last_launches) return;
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->last_ms = ms;
-    c->last_launches = 1;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+}
+
+int alloc_lanes(hy_ctx *c)
+{
+    const hy_dims &d = c->d;
+    const size_t B = std::max<size_t>(1, c->B), rb = c->rb;
+    CU(cudaMalloc(&c->d_state, B * d.n_state * rb));
+    CU(cudaMalloc(&c->d_pars, B * std::max<size_t>(1, d.n_par) * rb));
+    // one allocation for the per-lane vectors
+    //   thi tlo lasth tf tfhi tflo mdt minh maxh (9 x rb) | outcome nsteps (2 x 8) | gidx (4) | active (1) | counter
+    const size_t vec = B * rb;
+    void *blk = nullptr;
+    const size_t bytes = 9 * ((vec + 15) / 16 * 16) + 2 * B * 8 + (B * 4 + 15) / 16 * 16 + (B + 15) / 16 * 16 + 16;
+    CU(cudaMalloc(&blk, bytes));
+    CU(cudaMemset(blk, 0, bytes));
+    char *q = (char *)blk;
+    const size_t vs = (vec + 15) / 16 * 16;
+    c->d_thi = q, q += vs;
+    c->d_tlo = q, q += vs;
+    c->d_lasth = q, q += vs;
+    c->d_tf = q, q += vs;
+    c->d_tfhi = q, q += vs;
+    c->d_tflo = q, q += vs;
+    c->d_mdt = q, q += vs;
+    c->d_minh = q, q += vs;
+    c->d_maxh = q, q += vs;
+    c->d_outcome = (long long *)q, q += B * 8;
+    c->d_nsteps = (unsigned long long *)q, q += B * 8;
+    c->d_gidx = (uint32_t *)q, q += (B * 4 + 15) / 16 * 16;
+    c->d_active = (unsigned char *)q, q += (B + 15) / 16 * 16;
+    c->d_counter = (unsigned int *)q;
+    CU(cudaMemset(c->d_state, 0, B * d.n_state * rb));
+    CU(cudaMemset(c->d_pars, 0, B * std::max<size_t>(1, d.n_par) * rb));
+    if (d.n_events) {
+        const size_t ne = d.n_events, nte = std::max<size_t>(1, d.n_tevents);
+        CU(cudaMalloc(&c->d_ev_dir, ne * 4));
+        CU(cudaMemcpy(c->d_ev_dir, c->h_ev_dir.data(), ne * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_ev_cd, nte * 8));
+        CU(cudaMemcpy(c->d_ev_cd, c->h_ev_cd.data(), nte * 8, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_cd_elapsed, B * nte * rb));
+        CU(cudaMalloc(&c->d_cd_total, B * nte * rb));
+        c->log_cap = std::min<unsigned long long>(std::max<unsigned long long>(1ULL << 20, 16ULL * B), 1ULL << 26);
+        CU(cudaMalloc(&c->d_log, c->log_cap * sizeof(hy_event_rec)));
+        CU(cudaMalloc(&c->d_log_count, 8));
+        CU(cudaMemset(c->d_log_count, 0, 8));
+    }
+    return 0;
+}
+
+int common_init(hy_ctx *c)
+{
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
     return 0;
 }
 
 } // namespace
-
-template <typename R> static void cout_transpose(const hy_ctx *c, const std::vector<R> &src,
-                                                 const std::vector<unsigned long long> &cnt, R *dst, uint64_t S)
-{
-    // device layout [S][B][n*P1] -> reference layout [S][n][P1][B], NaN past each lane's count
-    const size_t B = c->B, nP = (size_t)c->d.n_state * (c->d.order + 1);
-    for (uint64_t s = 0; s < S; ++s)
-        for (size_t l = 0; l < B; ++l) {
-            const bool ok = s < cnt[l];
-            const R *p = src.data() + (s * B + l) * nP;
-            for (size_t i = 0; i < nP; ++i) dst[(s * nP + i) * B + l] = ok ? p[i] : (R)NAN;
-        }
-}
 
 extern "C" {
 
@@ -549,49 +817,93 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
     c->high_accuracy = high_accuracy;
     *out = c;
     const hy_dims &d = c->d;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
-    CU(cudaEventCreate(&c->ev0));
-    CU(cudaEventCreate(&c->ev1));
+    if (common_init(c)) return 1;
     c->h_ops.assign(ops, ops + d.n_ops);
     if (d.n_terms) c->h_terms.assign(terms, terms + d.n_terms);
     c->h_levels.assign(level_start, level_start + d.n_levels + 1);
-    if (d.n_events) c->h_ev_ref.assign(ev_ref, ev_ref + d.n_events);
-    const size_t B = std::max<size_t>(1, batch), rb = c->rb;
-    CU(cudaMalloc(&c->d_state, B * d.n_state * rb));
-    CU(cudaMalloc(&c->d_pars, B * std::max<size_t>(1, d.n_par) * rb));
-    CU(cudaMalloc(&c->d_thi, B * rb));
-    CU(cudaMalloc(&c->d_tlo, B * rb));
-    CU(cudaMalloc(&c->d_lasth, B * rb));
-    CU(cudaMalloc(&c->d_tf, B * rb));
-    CU(cudaMalloc(&c->d_mdt, B * rb));
-    CU(cudaMalloc(&c->d_minh, B * rb));
-    CU(cudaMalloc(&c->d_maxh, B * rb));
-    CU(cudaMalloc(&c->d_outcome, B * sizeof(long long)));
-    CU(cudaMalloc(&c->d_nsteps, B * sizeof(unsigned long long)));
-    CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
-    CU(cudaMemset(c->d_state, 0, B * d.n_state * rb));
-    CU(cudaMemset(c->d_pars, 0, B * std::max<size_t>(1, d.n_par) * rb));
-    CU(cudaMemset(c->d_thi, 0, B * rb));
-    CU(cudaMemset(c->d_tlo, 0, B * rb));
-    CU(cudaMemset(c->d_lasth, 0, B * rb));
     if (d.n_events) {
-        const size_t ne = d.n_events, nte = std::max<size_t>(1, d.n_tevents);
-        CU(cudaMalloc(&c->d_ev_dir, ne * 4));
-        CU(cudaMemcpy(c->d_ev_dir, ev_dir, ne * 4, cudaMemcpyHostToDevice));
-        std::vector<double> cd(nte, -1.0);
-        for (size_t i = 0; i < d.n_tevents; ++i) cd[i] = ev_cooldown ? ev_cooldown[i] : -1.0;
-        CU(cudaMalloc(&c->d_ev_cd, nte * 8));
-        CU(cudaMemcpy(c->d_ev_cd, cd.data(), nte * 8, cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&c->d_cd_elapsed, B * nte * rb));
-        CU(cudaMalloc(&c->d_cd_total, B * nte * rb));
-        c->log_cap = std::min<unsigned long long>(std::max<unsigned long long>(1ULL << 20, 16ULL * B), 1ULL << 26);
-        CU(cudaMalloc(&c->d_log, c->log_cap * sizeof(hy_event_rec)));
-        CU(cudaMalloc(&c->d_log_count, 8));
-        CU(cudaMemset(c->d_log_count, 0, 8));
-        if (hy_reset_cooldowns(c, -1)) return 1;
+        c->h_ev_ref.assign(ev_ref, ev_ref + d.n_events);
+        c->h_ev_dir.assign(ev_dir, ev_dir + d.n_events);
+        c->h_ev_cd.assign(std::max<size_t>(1, d.n_tevents), -1.0);
+        for (size_t i = 0; i < d.n_tevents; ++i) c->h_ev_cd[i] = ev_cooldown ? ev_cooldown[i] : -1.0;
     }
+    if (alloc_lanes(c)) return 1;
+    if (d.n_events && hy_reset_cooldowns(c, -1)) return 1;
     if (choose_geometry(c)) return 1;
+    return 0;
+}
+
+/* Deep copy of a context onto `device` (reference: copy.deepcopy(ta) per ensemble iteration,
+ * _ensemble_impl.py:47).  The scheduled program is reused (no matching / scheduling), the lane
+ * data (state, pars, time, last_h, results, tc, cooldowns) is copied device-to-device. */
+int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
+{
+    if (!src || !out) return fail("hy_clone: null argument");
+    int ndev = 0;
+    if (hy_device_count(&ndev)) return 1;
+    if (device < 0) device = src->device;
+    if (device >= ndev) return fail("hy_clone: invalid device index");
+    CU(cudaSetDevice(src->device));
+    CU(cudaStreamSynchronize(src->stream));
+    CU(cudaSetDevice(device));
+    hy_ctx *c = new hy_ctx();
+    *out = c;
+    c->device = device;
+    c->fp_bits = src->fp_bits;
+    c->rb = src->rb;
+    c->d = src->d;
+    c->B = src->B;
+    c->tol = src->tol;
+    c->high_accuracy = src->high_accuracy;
+    c->h_ops = src->h_ops;
+    c->h_terms = src->h_terms;
+    c->h_levels = src->h_levels;
+    c->h_ev_ref = src->h_ev_ref;
+    c->h_ev_dir = src->h_ev_dir;
+    c->h_ev_cd = src->h_ev_cd;
+    c->prog = src->prog;
+    c->li = src->li;
+    c->TS = src->TS;
+    if (common_init(c)) return 1;
+    if (alloc_lanes(c)) return 1;
+    {
+        // a different device may have another SM count: keep the schedule, refit the grid
+        cudaDeviceProp prop{};
+        CU(cudaGetDeviceProperties(&prop, device));
+        c->li.n_sm = (uint32_t)prop.multiProcessorCount;
+        const uint32_t T = c->li.traj_per_cta;
+        c->li.ctas = std::max(1u, std::min((c->B + T - 1) / T, c->li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
+    }
+    if (upload_program(c)) return 1;
+    const hy_dims &d = c->d;
+    const size_t B = c->B, rb = c->rb;
+    auto cp = [&](void *dst, const void *s_, size_t bytes) -> cudaError_t {
+        if (!bytes || !dst || !s_) return cudaSuccess;
+        return cudaMemcpyPeerAsync(dst, device, s_, src->device, bytes, c->stream);
+    };
+    CU(cp(c->d_state, src->d_state, B * d.n_state * rb));
+    CU(cp(c->d_pars, src->d_pars, B * d.n_par * rb));
+    CU(cp(c->d_thi, src->d_thi, B * rb));
+    CU(cp(c->d_tlo, src->d_tlo, B * rb));
+    CU(cp(c->d_lasth, src->d_lasth, B * rb));
+    CU(cp(c->d_minh, src->d_minh, B * rb));
+    CU(cp(c->d_maxh, src->d_maxh, B * rb));
+    CU(cp(c->d_outcome, src->d_outcome, B * 8));
+    CU(cp(c->d_nsteps, src->d_nsteps, B * 8));
+    if (src->d_tc) {
+        if (ensure_tc(c)) return 1;
+        CU(cp(c->d_tc, src->d_tc, (size_t)d.n_state * (d.order + 1) * B * rb));
+    }
+    if (d.n_tevents) {
+        CU(cp(c->d_cd_elapsed, src->d_cd_elapsed, B * d.n_tevents * rb));
+        CU(cp(c->d_cd_total, src->d_cd_total, B * d.n_tevents * rb));
+    }
+    if (src->n_red) {
+        CU(cudaMalloc((void **)&c->d_red, src->n_red * 4));
+        CU(cp(c->d_red, src->d_red, src->n_red * 4));
+        c->n_red = src->n_red;
+    }
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -599,13 +911,14 @@ int hy_destroy(hy_ctx *c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet,   c->d_state,   c->d_pars,   c->d_thi,     c->d_tlo,
-                    c->d_lasth, c->d_tf,   c->d_mdt,    c->d_minh, c->d_maxh,    c->d_tc,     c->d_outcome, c->d_nsteps,
-                    c->d_counter, c->d_gws, c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo, c->d_cout_count,
-                    c->d_tmp_in, c->d_tmp_out, c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log,
-                    c->d_log_count};
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet, c->d_state, c->d_pars,
+                    c->d_thi /* block of the per-lane vectors */, c->d_tc, c->d_gws, c->d_tmp_in, c->d_tmp_out,
+                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    rec_free(c->rec);
+    rec_free(c->rec_spare);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -640,6 +953,17 @@ int hy_set_stream(hy_ctx *c, void *cuda_stream)
     return 0;
 }
 
+int hy_sync(hy_ctx *c)
+{
+    if (!c) return fail("null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Stream-ordered: the copies are queued on the context's stream and the call returns (pageable
+// sources are staged by the runtime before it returns; pinned sources must stay untouched until
+// the next synchronising call - every step/propagate/download call is one).
 int hy_upload(hy_ctx *c, const void *state, const void *pars, const void *t_hi, const void *t_lo)
 {
     if (!c) return fail("null ctx");
@@ -650,7 +974,6 @@ int hy_upload(hy_ctx *c, const void *state, const void *pars, const void *t_hi, 
     if (pars && c->d.n_par) CU(cudaMemcpyAsync(c->d_pars, pars, B * c->d.n_par * rb, cudaMemcpyHostToDevice, c->stream));
     if (t_hi) CU(cudaMemcpyAsync(c->d_thi, t_hi, B * rb, cudaMemcpyHostToDevice, c->stream));
     if (t_lo) CU(cudaMemcpyAsync(c->d_tlo, t_lo, B * rb, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -665,6 +988,7 @@ int hy_download(hy_ctx *c, void *state, void *t_hi, void *t_lo, void *last_h)
     if (t_lo) CU(cudaMemcpyAsync(t_lo, c->d_tlo, B * rb, cudaMemcpyDeviceToHost, c->stream));
     if (last_h) CU(cudaMemcpyAsync(last_h, c->d_lasth, B * rb, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    finish_timing(c);
     return 0;
 }
 
@@ -679,7 +1003,6 @@ int hy_upload_dev(hy_ctx *c, const void *d_state, const void *d_pars, const void
         CU(cudaMemcpyAsync(c->d_pars, d_pars, B * c->d.n_par * rb, cudaMemcpyDeviceToDevice, c->stream));
     if (d_t_hi) CU(cudaMemcpyAsync(c->d_thi, d_t_hi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
     if (d_t_lo) CU(cudaMemcpyAsync(c->d_tlo, d_t_lo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -692,6 +1015,50 @@ int hy_state_dev(hy_ctx *c, void **d_state, void **d_t_hi, void **d_t_lo)
     return 0;
 }
 
+/* Restore the device-side Taylor coefficients / last step sizes of a copied or unpickled
+ * integrator (expose_batch_integrators.cpp:665-669: copies carry tc and last_h). */
+int hy_set_tc(hy_ctx *c, const void *tc)
+{
+    if (!c || !tc) return fail("hy_set_tc: null argument");
+    CU(cudaSetDevice(c->device));
+    if (ensure_tc(c)) return 1;
+    const size_t bytes = (size_t)c->d.n_state * (c->d.order + 1) * c->B * c->rb;
+    if (bytes) CU(cudaMemcpyAsync(c->d_tc, tc, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hy_set_last_h(hy_ctx *c, const void *last_h)
+{
+    if (!c || !last_h) return fail("hy_set_last_h: null argument");
+    CU(cudaSetDevice(c->device));
+    if (c->B) CU(cudaMemcpyAsync(c->d_lasth, last_h, c->B * c->rb, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* The reference's callback.angle_reducer (expose_callbacks.cpp:67-72) as a device-side post-step
+ * op of the propagate_* calls: the listed state variables are reduced to [0, 2 pi) after every
+ * step.  n = 0 switches it off. */
+int hy_set_angle_reducer(hy_ctx *c, const uint32_t *idx, uint32_t n)
+{
+    if (!c) return fail("null ctx");
+    if (n && !idx) return fail("hy_set_angle_reducer: null index array");
+    for (uint32_t i = 0; i < n; ++i)
+        if (idx[i] >= c->d.n_state) return fail("hy_set_angle_reducer: state index out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_red) cudaFree(c->d_red);
+    c->d_red = nullptr;
+    c->n_red = 0;
+    if (n) {
+        CU(cudaMalloc((void **)&c->d_red, n * 4));
+        CU(cudaMemcpy(c->d_red, idx, n * 4, cudaMemcpyHostToDevice));
+        c->n_red = n;
+    }
+    return 0;
+}
+
 static int fetch_results(hy_ctx *c, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
 {
     const size_t B = c->B, rb = c->rb;
@@ -701,6 +1068,7 @@ static int fetch_results(hy_ctx *c, int64_t *outcome, void *min_h, void *max_h, 
     if (max_h) CU(cudaMemcpyAsync(max_h, c->d_maxh, B * rb, cudaMemcpyDeviceToHost, c->stream));
     if (n_steps) CU(cudaMemcpyAsync(n_steps, c->d_nsteps, B * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    finish_timing(c);
     return 0;
 }
 
@@ -710,96 +1078,110 @@ int hy_step(hy_ctx *c, const void *max_delta_t, int backward, int write_tc, int6
     CU(cudaSetDevice(c->device));
     const size_t B = c->B, rb = c->rb;
     if (max_delta_t && B) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
-    if (run_kernel(c, hy::MODE_STEP, backward, 1, max_delta_t != nullptr, write_tc)) return 1;
-    if (fetch_results(c, outcome, nullptr, nullptr, nullptr)) return 1;
-    if (h && B) {
-        CU(cudaMemcpyAsync(h, c->d_lasth, B * rb, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+    RunArgs a;
+    a.mode = hy::MODE_STEP;
+    a.backward = backward;
+    a.max_steps = 1;
+    a.have_mdt = max_delta_t != nullptr;
+    a.write_tc = write_tc;
+    if (run_kernel(c, a)) return 1;
+    if (h && B) CU(cudaMemcpyAsync(h, c->d_lasth, B * rb, cudaMemcpyDeviceToHost, c->stream));
+    return fetch_results(c, outcome, nullptr, nullptr, nullptr);
+}
+
+int hy_propagate_ex(hy_ctx *c, const hy_prop_args *pa, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
+{
+    if (!c || !pa) return fail("hy_propagate_ex: null argument");
+    const bool grid = pa->grid != nullptr;
+    if (!grid && !pa->t && c->B && !pa->resume) return fail("hy_propagate: null time array");
+    if (grid && (!pa->grid_out || pa->grid_k == 0)) return fail("hy_propagate_grid: null/empty grid");
+    if (grid && pa->c_output) return fail("hy_propagate_grid: no continuous output in grid mode");
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
+    if (B == 0) return 0;
+    RunArgs a;
+    a.mode = grid ? hy::MODE_GRID : (pa->is_delta ? hy::MODE_FOR : hy::MODE_UNTIL);
+    a.max_steps = pa->max_steps;
+    a.have_mdt = pa->max_delta_t != nullptr;
+    a.write_tc = pa->write_tc || pa->c_output || grid;
+    a.resume = pa->resume ? 1 : 0;
+    a.pause_on_nt = pa->pause_on_nt;
+    a.launch_steps = pa->launch_steps;
+    if (pa->max_delta_t) CU(cudaMemcpyAsync(c->d_mdt, pa->max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (pa->active) {
+        CU(cudaMemcpyAsync(c->d_active, pa->active, B, cudaMemcpyHostToDevice, c->stream));
+        a.use_active = true;
     }
-    return 0;
+    const unsigned th = 256, bl = (unsigned)((B + th - 1) / th);
+    if (grid) {
+        const size_t k = pa->grid_k;
+        if (ensure_tmp(c, k * B * rb, k * n * B * rb)) return 1;
+        if (!a.resume) {
+            CU(cudaMemcpyAsync(c->d_tmp_in, pa->grid, k * B * rb, cudaMemcpyHostToDevice, c->stream));
+            // NaN-fill: grid points past an early exit stay NaN (reference behaviour).
+            CU(cudaMemsetAsync(c->d_tmp_out, 0xff, k * n * B * rb, c->stream));
+        }
+        a.grid = c->d_tmp_in;
+        a.gout = c->d_tmp_out;
+        a.grid_k = (uint32_t)k;
+    } else if (!a.resume) {
+        CU(cudaMemcpyAsync(c->d_tf, pa->t, B * rb, cudaMemcpyHostToDevice, c->stream));
+        if (c->fp_bits == 64)
+            hy::prep_tf_kernel<double><<<bl, th, 0, c->stream>>>((const double *)c->d_tf, pa->is_delta,
+                                                                 (const double *)c->d_thi, (const double *)c->d_tlo,
+                                                                 (double *)c->d_tfhi, (double *)c->d_tflo, (uint32_t)B);
+        else
+            hy::prep_tf_kernel<float><<<bl, th, 0, c->stream>>>((const float *)c->d_tf, pa->is_delta,
+                                                                (const float *)c->d_thi, (const float *)c->d_tlo,
+                                                                (float *)c->d_tfhi, (float *)c->d_tflo, (uint32_t)B);
+        CU(cudaGetLastError());
+    }
+    if (pa->c_output) {
+        const bool append = pa->c_output == 2 && c->rec != nullptr;
+        if (!c->rec) {
+            if (c->rec_spare) {
+                c->rec = c->rec_spare;
+                c->rec_spare = nullptr;
+            } else if (rec_create(c, &c->rec)) {
+                rec_free(c->rec);
+                c->rec = nullptr;
+                return 1;
+            }
+        }
+        if (!append && rec_reset(c->rec, c->stream)) return 1;
+        c->rec->indexed = false;
+        a.rec_on = 1;
+        a.rec_append = append ? 1 : 0;
+    }
+    if (run_kernel(c, a)) return 1;
+    if (grid) CU(cudaMemcpyAsync(pa->grid_out, c->d_tmp_out, pa->grid_k * n * B * rb, cudaMemcpyDeviceToHost, c->stream));
+    return fetch_results(c, outcome, min_h, max_h, n_steps);
 }
 
 int hy_propagate(hy_ctx *c, const void *t, int is_delta, uint64_t max_steps, const void *max_delta_t, int write_tc,
                  int c_output, int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
 {
-    if (!c) return fail("null ctx");
-    if (!t && c->B) return fail("hy_propagate: null time array");
-    CU(cudaSetDevice(c->device));
-    const size_t B = c->B, rb = c->rb;
-    if (B) CU(cudaMemcpyAsync(c->d_tf, t, B * rb, cudaMemcpyHostToDevice, c->stream));
-    if (max_delta_t && B) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
-    const int mode = is_delta ? hy::MODE_FOR : hy::MODE_UNTIL;
-    if (!c_output || B == 0) {
-        if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, write_tc)) return 1;
-        return fetch_results(c, outcome, min_h, max_h, n_steps);
-    }
-    // Continuous output.  The number of steps is not known in advance and the
-    // stepping is deterministic, so: pass 1 counts the steps on a backup of the
-    // state, pass 2 (on the restored state) records exactly that many.
-    const size_t n = c->d.n_state, P1 = c->d.order + 1;
-    void *bk_state = nullptr, *bk_thi = nullptr, *bk_tlo = nullptr;
-    CU(cudaMalloc(&bk_state, B * n * rb));
-    CU(cudaMalloc(&bk_thi, B * rb));
-    CU(cudaMalloc(&bk_tlo, B * rb));
-    CU(cudaMemcpyAsync(bk_state, c->d_state, B * n * rb, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(bk_thi, c->d_thi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(bk_tlo, c->d_tlo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
-    if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, 0)) return 1;
-    double ms1 = c->last_ms;
-    std::vector<unsigned long long> ns(B);
-    CU(cudaMemcpy(ns.data(), c->d_nsteps, B * 8, cudaMemcpyDeviceToHost));
-    uint64_t S = 0;
-    for (auto v : ns) S = std::max<uint64_t>(S, v);
-    for (void *p : {c->d_cout_tcs, c->d_cout_thi, c->d_cout_tlo})
-        if (p) cudaFree(p);
-    c->d_cout_tcs = c->d_cout_thi = c->d_cout_tlo = nullptr;
-    if (!c->d_cout_count) CU(cudaMalloc(&c->d_cout_count, B * 8));
-    c->cout_S = S;
-    const size_t tcs_bytes = std::max<size_t>(8, S * B * n * P1 * rb), tm_bytes = (S + 1) * B * rb;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    if (tcs_bytes + 2 * tm_bytes > free_b)
-        return fail("hy_propagate: continuous output needs " + std::to_string((tcs_bytes + 2 * tm_bytes) >> 20) +
-                    " MiB of device memory but only " + std::to_string(free_b >> 20) + " MiB are free");
-    CU(cudaMalloc(&c->d_cout_tcs, tcs_bytes));
-    CU(cudaMalloc(&c->d_cout_thi, tm_bytes));
-    CU(cudaMalloc(&c->d_cout_tlo, tm_bytes));
-    CU(cudaMemcpyAsync(c->d_state, bk_state, B * n * rb, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_thi, bk_thi, B * rb, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_tlo, bk_tlo, B * rb, cudaMemcpyDeviceToDevice, c->stream));
-    RunExtras x;
-    x.record_cout = true;
-    if (run_kernel(c, mode, 0, max_steps, max_delta_t != nullptr, 1, x)) return 1;
-    c->last_ms += ms1;
-    c->last_launches = 2;
-    CU(cudaMemcpyAsync(c->d_cout_count, c->d_nsteps, B * 8, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    cudaFree(bk_state);
-    cudaFree(bk_thi);
-    cudaFree(bk_tlo);
-    return fetch_results(c, outcome, min_h, max_h, n_steps);
+    hy_prop_args a{};
+    a.t = t;
+    a.is_delta = is_delta;
+    a.max_steps = max_steps;
+    a.max_delta_t = max_delta_t;
+    a.write_tc = write_tc;
+    a.c_output = c_output ? 1 : 0;
+    return hy_propagate_ex(c, &a, outcome, min_h, max_h, n_steps);
 }
 
 int hy_propagate_grid(hy_ctx *c, const void *grid, size_t k, uint64_t max_steps, const void *max_delta_t, void *out,
                       int64_t *outcome, void *min_h, void *max_h, uint64_t *n_steps)
 {
-    if (!c) return fail("null ctx");
     if (!grid || !out || k == 0) return fail("hy_propagate_grid: null/empty grid");
-    CU(cudaSetDevice(c->device));
-    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
-    if (B == 0) return 0;
-    if (ensure_tmp(c, k * B * rb, k * n * B * rb)) return 1;
-    CU(cudaMemcpyAsync(c->d_tmp_in, grid, k * B * rb, cudaMemcpyHostToDevice, c->stream));
-    // NaN-fill: grid points past an early exit stay NaN (reference behaviour).
-    CU(cudaMemsetAsync(c->d_tmp_out, 0xff, k * n * B * rb, c->stream));
-    if (max_delta_t) CU(cudaMemcpyAsync(c->d_mdt, max_delta_t, B * rb, cudaMemcpyHostToDevice, c->stream));
-    RunExtras x;
-    x.grid = c->d_tmp_in;
-    x.gout = c->d_tmp_out;
-    x.grid_k = (uint32_t)k;
-    if (run_kernel(c, hy::MODE_GRID, 0, max_steps, max_delta_t != nullptr, 1, x)) return 1;
-    CU(cudaMemcpyAsync(out, c->d_tmp_out, k * n * B * rb, cudaMemcpyDeviceToHost, c->stream));
-    return fetch_results(c, outcome, min_h, max_h, n_steps);
+    hy_prop_args a{};
+    a.max_steps = max_steps;
+    a.max_delta_t = max_delta_t;
+    a.grid = grid;
+    a.grid_k = k;
+    a.grid_out = out;
+    return hy_propagate_ex(c, &a, outcome, min_h, max_h, n_steps);
 }
 
 int hy_last_timing(hy_ctx *c, double *kernel_ms, uint64_t *launches)
@@ -845,81 +1227,96 @@ int hy_dense_eval(hy_ctx *c, const void *t, int rel_time, void *out)
     return 0;
 }
 
-int hy_cout_info(hy_ctx *c, uint64_t *n_steps, uint64_t *max_steps)
+/* ---- continuous output ---- */
+int hy_cout_detach(hy_ctx *c, hy_cout **out)
 {
-    if (!c) return fail("null ctx");
+    if (!c || !out) return fail("hy_cout_detach: null argument");
+    *out = nullptr;
+    if (!c->rec) return 0;
     CU(cudaSetDevice(c->device));
-    if (max_steps) *max_steps = c->d_cout_tcs ? c->cout_S : 0;
-    if (n_steps && c->B) {
-        if (!c->d_cout_count) {
-            std::memset(n_steps, 0, c->B * 8);
-        } else {
-            CU(cudaMemcpy(n_steps, c->d_cout_count, c->B * 8, cudaMemcpyDeviceToHost));
-        }
-    }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c->rec;
+    c->rec = nullptr;
     return 0;
 }
 
-int hy_cout_get(hy_ctx *c, void *tcs, void *times_hi, void *times_lo, uint64_t S)
+int hy_cout_free(hy_cout *r, hy_ctx *recycle_into)
 {
-    if (!c) return fail("null ctx");
-    if (!c->d_cout_tcs) return fail("hy_cout_get: no continuous output was recorded");
-    if (S != c->cout_S) return fail("hy_cout_get: S does not match the recorded number of steps");
-    CU(cudaSetDevice(c->device));
-    const size_t B = c->B, rb = c->rb, nP = (size_t)c->d.n_state * (c->d.order + 1);
-    std::vector<unsigned long long> cnt(B);
-    CU(cudaMemcpy(cnt.data(), c->d_cout_count, B * 8, cudaMemcpyDeviceToHost));
-    if (tcs && S) {
-        if (c->fp_bits == 64) {
-            std::vector<double> tmp(S * B * nP);
-            CU(cudaMemcpy(tmp.data(), c->d_cout_tcs, tmp.size() * rb, cudaMemcpyDeviceToHost));
-            cout_transpose<double>(c, tmp, cnt, (double *)tcs, S);
-        } else {
-            std::vector<float> tmp(S * B * nP);
-            CU(cudaMemcpy(tmp.data(), c->d_cout_tcs, tmp.size() * rb, cudaMemcpyDeviceToHost));
-            cout_transpose<float>(c, tmp, cnt, (float *)tcs, S);
-        }
+    if (!r) return 0;
+    hy_ctx *c = recycle_into;
+    if (c && !c->rec_spare && c->device == r->device && c->rb == r->rb && c->B == r->B && c->d.n_state == r->n &&
+        c->d.order + 1 == r->P1) {
+        c->rec_spare = r; // the next recording of this context reuses the pool: no cudaMalloc in steady state
+        return 0;
     }
-    for (int which = 0; which < 2; ++which) {
-        void *dst = which ? times_lo : times_hi;
-        if (!dst) continue;
-        CU(cudaMemcpy(dst, which ? c->d_cout_tlo : c->d_cout_thi, (S + 1) * B * rb, cudaMemcpyDeviceToHost));
-        for (uint64_t s = 0; s <= S; ++s)
-            for (size_t l = 0; l < B; ++l)
-                if (s > cnt[l]) {
-                    if (c->fp_bits == 64)
-                        ((double *)dst)[s * B + l] = NAN;
-                    else
-                        ((float *)dst)[s * B + l] = NAN;
-                }
-    }
+    rec_free(r);
     return 0;
 }
 
-int hy_cout_eval(hy_ctx *c, const void *t, size_t k, void *out)
+int hy_cout_info(hy_cout *r, uint64_t *n_steps, uint64_t *max_steps)
 {
-    if (!c || !t || !out) return fail("hy_cout_eval: null argument");
-    if (!c->d_cout_tcs) return fail("hy_cout_eval: no continuous output was recorded");
-    CU(cudaSetDevice(c->device));
-    const size_t B = c->B, rb = c->rb, n = c->d.n_state;
+    if (!r) return fail("hy_cout_info: null record");
+    CU(cudaSetDevice(r->device));
+    std::vector<uint32_t> cnt(r->B);
+    if (r->B) CU(cudaMemcpy(cnt.data(), r->d_count, (size_t)r->B * 4, cudaMemcpyDeviceToHost));
+    uint64_t mx = 0;
+    for (uint32_t l = 0; l < r->B; ++l) {
+        if (n_steps) n_steps[l] = cnt[l];
+        mx = std::max<uint64_t>(mx, cnt[l]);
+    }
+    if (max_steps) *max_steps = mx;
+    return 0;
+}
+
+int hy_cout_get(hy_cout *r, void *tcs, void *times_hi, void *times_lo, uint64_t S)
+{
+    if (!r) return fail("hy_cout_get: null record");
+    CU(cudaSetDevice(r->device));
+    if (rec_index(r)) return 1;
+    const size_t B = r->B, rb = r->rb, nP = (size_t)r->n * r->P1;
+    const size_t tcs_bytes = tcs ? S * nP * B * rb : 0, tm_bytes = (S + 1) * B * rb;
+    if (rec_ensure_tmp(r, 2 * tm_bytes, std::max<size_t>(8, tcs_bytes))) return 1;
+    const unsigned th = 128;
+    const unsigned bl = (unsigned)(((S + 1) * B + th - 1) / th);
+    char *thi = (char *)r->d_tmp_in, *tlo = thi + tm_bytes;
+    if (rb == 8)
+        hy::rec_gather_kernel<double><<<bl, th, 0, r->stream>>>(rec_dev<double>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                                tcs ? (double *)r->d_tmp_out : nullptr, (double *)thi,
+                                                                (double *)tlo, r->n, r->P1 - 1, r->B, (uint32_t)S);
+    else
+        hy::rec_gather_kernel<float><<<bl, th, 0, r->stream>>>(rec_dev<float>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                               tcs ? (float *)r->d_tmp_out : nullptr, (float *)thi,
+                                                               (float *)tlo, r->n, r->P1 - 1, r->B, (uint32_t)S);
+    CU(cudaGetLastError());
+    if (tcs && tcs_bytes) CU(cudaMemcpyAsync(tcs, r->d_tmp_out, tcs_bytes, cudaMemcpyDeviceToHost, r->stream));
+    if (times_hi) CU(cudaMemcpyAsync(times_hi, thi, tm_bytes, cudaMemcpyDeviceToHost, r->stream));
+    if (times_lo) CU(cudaMemcpyAsync(times_lo, tlo, tm_bytes, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+int hy_cout_eval(hy_cout *r, const void *t, size_t k, void *out)
+{
+    if (!r || !t || !out) return fail("hy_cout_eval: null argument");
+    CU(cudaSetDevice(r->device));
+    const size_t B = r->B, rb = r->rb, n = r->n;
     if (B == 0 || k == 0) return 0;
-    if (ensure_tmp(c, k * B * rb, k * n * B * rb)) return 1;
-    CU(cudaMemcpyAsync(c->d_tmp_in, t, k * B * rb, cudaMemcpyHostToDevice, c->stream));
+    if (rec_index(r)) return 1;
+    if (rec_ensure_tmp(r, k * B * rb, k * n * B * rb)) return 1;
+    CU(cudaMemcpyAsync(r->d_tmp_in, t, k * B * rb, cudaMemcpyHostToDevice, r->stream));
     const unsigned th = 128;
     const unsigned bl = (unsigned)((k * B + th - 1) / th);
-    if (c->fp_bits == 64)
-        hy::cout_eval_kernel<double><<<bl, th, 0, c->stream>>>(
-            (const double *)c->d_cout_tcs, (const double *)c->d_cout_thi, (const double *)c->d_cout_tlo,
-            c->d_cout_count, (const double *)c->d_tmp_in, (double *)c->d_tmp_out, (uint32_t)n, c->d.order,
-            (uint32_t)B, (uint32_t)k);
+    if (rb == 8)
+        hy::cout_eval_kernel<double><<<bl, th, 0, r->stream>>>(rec_dev<double>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                               (const double *)r->d_tmp_in, (double *)r->d_tmp_out,
+                                                               (uint32_t)n, r->P1 - 1, (uint32_t)B, (uint32_t)k);
     else
-        hy::cout_eval_kernel<float><<<bl, th, 0, c->stream>>>(
-            (const float *)c->d_cout_tcs, (const float *)c->d_cout_thi, (const float *)c->d_cout_tlo,
-            c->d_cout_count, (const float *)c->d_tmp_in, (float *)c->d_tmp_out, (uint32_t)n, c->d.order, (uint32_t)B,
-            (uint32_t)k);
+        hy::cout_eval_kernel<float><<<bl, th, 0, r->stream>>>(rec_dev<float>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                              (const float *)r->d_tmp_in, (float *)r->d_tmp_out,
+                                                              (uint32_t)n, r->P1 - 1, (uint32_t)B, (uint32_t)k);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, c->d_tmp_out, k * n * B * rb, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(out, r->d_tmp_out, k * n * B * rb, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
     return 0;
 }
 
@@ -930,7 +1327,8 @@ int hy_events_count(hy_ctx *c, uint64_t *n)
     if (!c->d_log_count) return 0;
     CU(cudaSetDevice(c->device));
     unsigned long long v = 0;
-    CU(cudaMemcpy(&v, c->d_log_count, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(&v, c->d_log_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     if (v > c->log_cap)
         return fail("the device event log overflowed (" + std::to_string(v) + " events, capacity " +
                     std::to_string(c->log_cap) + "): propagate in shorter segments");
@@ -945,10 +1343,13 @@ int hy_events_drain(hy_ctx *c, hy_event_rec *recs, uint64_t cap, uint64_t *n)
     if (!c->d_log_count) return 0;
     uint64_t have = 0;
     if (hy_events_count(c, &have)) return 1;
-    const uint64_t m = std::min<uint64_t>(have, cap);
-    if (m && recs) CU(cudaMemcpy(recs, c->d_log, m * sizeof(hy_event_rec), cudaMemcpyDeviceToHost));
-    CU(cudaMemset(c->d_log_count, 0, 8));
-    *n = m;
+    if (have > cap)
+        return fail("hy_events_drain: " + std::to_string(have) + " events are logged but the buffer holds " +
+                    std::to_string(cap) + " (nothing was dropped: call again with a larger buffer)");
+    if (have && recs) CU(cudaMemcpyAsync(recs, c->d_log, have * sizeof(hy_event_rec), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemsetAsync(c->d_log_count, 0, 8, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n = have;
     return 0;
 }
 
@@ -958,8 +1359,9 @@ int hy_get_cooldowns(hy_ctx *c, void *elapsed, void *total)
     if (!c->d.n_tevents) return 0;
     CU(cudaSetDevice(c->device));
     const size_t bytes = (size_t)c->B * c->d.n_tevents * c->rb;
-    if (elapsed) CU(cudaMemcpy(elapsed, c->d_cd_elapsed, bytes, cudaMemcpyDeviceToHost));
-    if (total) CU(cudaMemcpy(total, c->d_cd_total, bytes, cudaMemcpyDeviceToHost));
+    if (elapsed) CU(cudaMemcpyAsync(elapsed, c->d_cd_elapsed, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (total) CU(cudaMemcpyAsync(total, c->d_cd_total, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -969,8 +1371,9 @@ int hy_set_cooldowns(hy_ctx *c, const void *elapsed, const void *total)
     if (!c->d.n_tevents) return 0;
     CU(cudaSetDevice(c->device));
     const size_t bytes = (size_t)c->B * c->d.n_tevents * c->rb;
-    if (elapsed) CU(cudaMemcpy(c->d_cd_elapsed, elapsed, bytes, cudaMemcpyHostToDevice));
-    if (total) CU(cudaMemcpy(c->d_cd_total, total, bytes, cudaMemcpyHostToDevice));
+    if (elapsed) CU(cudaMemcpyAsync(c->d_cd_elapsed, elapsed, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (total) CU(cudaMemcpyAsync(c->d_cd_total, total, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -985,12 +1388,15 @@ int hy_reset_cooldowns(hy_ctx *c, int64_t lane)
     // total = -1 (not in cooldown), elapsed = 0
     if (c->fp_bits == 64) {
         std::vector<double> m1(count * nte, -1.0);
-        CU(cudaMemcpy((double *)c->d_cd_total + first * nte, m1.data(), m1.size() * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync((double *)c->d_cd_total + first * nte, m1.data(), m1.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     } else {
         std::vector<float> m1(count * nte, -1.0f);
-        CU(cudaMemcpy((float *)c->d_cd_total + first * nte, m1.data(), m1.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync((float *)c->d_cd_total + first * nte, m1.data(), m1.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     }
-    CU(cudaMemset((char *)c->d_cd_elapsed + first * nte * c->rb, 0, count * nte * c->rb));
+    CU(cudaMemsetAsync((char *)c->d_cd_elapsed + first * nte * c->rb, 0, count * nte * c->rb, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -998,6 +1404,13 @@ int hy_get_launch_info(hy_ctx *c, hy_launch_info *info)
 {
     if (!c || !info) return fail("null argument");
     *info = c->li;
+    return 0;
+}
+
+int hy_get_device(hy_ctx *c, int *device)
+{
+    if (!c || !device) return fail("null argument");
+    *device = c->device;
     return 0;
 }
 

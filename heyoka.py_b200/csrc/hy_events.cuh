@@ -176,10 +176,11 @@ template <typename R> __device__ inline int ev_find_roots(const R *c_in, int p, 
 template <typename R>
 static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, uint32_t n_events, uint32_t n_tevents,
                                      int p, R h, R t_hi, R t_lo, uint32_t traj, unsigned long long step_idx,
-                                     const EvParams<R> E, R &h_out, int &term_out)
+                                     const EvParams<R> E, R &h_out, int &term_out, int &nt_out)
 {
     h_out = h;
     term_out = -1;
+    nt_out = 0;
     if (h == (R)0 || !(h == h)) return;
     R q[EV_MAXP1];
     R roots[EV_MAXROOTS];
@@ -263,7 +264,10 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
     };
     for (int i = 0; i < nc; ++i) {
         const R at = cand_tau[i] < 0 ? -cand_tau[i] : cand_tau[i];
-        if (best_ev < 0 || at < best_tau_abs) push(cand_ev[i], cand_tau[i], cand_sg[i]);
+        if (best_ev < 0 || at < best_tau_abs) {
+            push(cand_ev[i], cand_tau[i], cand_sg[i]);
+            ++nt_out;
+        }
     }
     if (best_ev >= 0) {
         push(best_ev, best_tau, best_sg);

@@ -76,6 +76,37 @@ struct ProgDims {
     uint32_t ws_len, par_off, one_off, n_spill; // device workspace layout (hy_schedule.hpp)
 };
 
+// Internal outcome: the lane stopped inside a launch and can be resumed by the next one (per-launch
+// step budget, a non-terminal event whose callback must run on the host, recorder pool exhausted).
+// Never shown to callers of the Python API.
+// HY_OUTCOME_PAUSED is declared in include/hy_cuda.h (the host loop of the front end sees it);
+// HY_OUTCOME_PAUSED_POOL never leaves libhy_cuda: the lane ran out of recorder pool and is
+// resumed by hy_propagate_ex itself after it has grown the pool.
+#define HY_OUTCOME_PAUSED_POOL (-4294967401LL)
+
+// Continuous-output recorder (single pass): every lane appends its steps to a linked list of
+// fixed-size CHUNKS taken from a pool by bump allocation.  A chunk holds HY_REC_CH step records
+// of rec_len elements (n*(p+1) Taylor coefficients, then the end time (hi, lo) of the step),
+// preceded by a 2-element header (element 0: id of the next chunk, as an integer).
+constexpr uint32_t HY_REC_CH = 8;
+constexpr uint32_t HY_REC_NONE = 0xffffffffu;
+template <typename R> struct RecDev {
+    R *const *seg;          // [n_seg] segment base pointers (device array)
+    uint32_t seg_chunks;    // chunks per segment
+    uint32_t cap_chunks;    // chunks in all segments
+    unsigned int *next;     // bump counter
+    uint32_t *head, *tail;  // [B] first / last chunk of the lane
+    uint32_t *count;        // [B] recorded steps
+    uint32_t *nchunks;      // [B] chunks owned by the lane (>= ceil(count / HY_REC_CH))
+    R *t0_hi, *t0_lo;       // [B] time at which the lane's record starts
+    uint32_t rec_len, chunk_len;
+    int on, append;
+    __device__ __forceinline__ R *chunk(uint32_t cid) const
+    {
+        return seg[cid / seg_chunks] + (size_t)(cid % seg_chunks) * chunk_len;
+    }
+};
+
 template <typename R> struct KParams {
     hy_dims d;
     const void *prog;            // [ops | terms | imm] in the smem layout
@@ -88,15 +119,20 @@ template <typename R> struct KParams {
     R *state;      // [n][B]
     const R *pars; // [m][B]
     R *t_hi, *t_lo, *last_h;
-    const R *tf;  // [B] final time / delta (unused in MODE_STEP)
+    const R *tf_hi, *tf_lo;      // [B] absolute final time, double-length (MODE_UNTIL / MODE_FOR)
     const R *mdt; // [B] or nullptr
+    const unsigned char *active; // [B] lanes taking part in this launch (nullptr: all)
+    uint32_t *gidx;              // [B] next grid point of the lane (MODE_GRID; kept for resumed launches)
+    int resume;                  // lanes continue from the counters / grid index of the previous launch
+    int pause_on_nt;             // stop a lane (PAUSED) after a step that logged a non-terminal event
+    unsigned long long launch_steps; // per-launch step budget (0: none): the lane stops with PAUSED
+    const uint32_t *red_idx;     // [n_red] state variables reduced to [0, 2 pi) after every step
+    uint32_t n_red;
+    RecDev<R> rec;               // continuous-output recorder (rec.on)
     long long *outcome;
     R *min_h, *max_h;
     unsigned long long *n_steps;
     R *tc; // [n][p+1][B] or nullptr
-    // continuous output recording (device layout: tcs [S][B][n*(p+1)], times [S+1][B])
-    R *cout_tcs, *cout_thi, *cout_tlo;
-    uint32_t cout_cap;
     // propagate_grid: grid [K][B] in, gout [K][n][B] out
     const R *grid;
     R *gout;
@@ -904,6 +940,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     R hi = 0, lo = 0, mdt = 0, tf_hi = 0, tf_lo = 0;
     uint32_t gi = 0; // next grid point to emit (MODE_GRID)
     uint32_t cc = 0; // recorded continuous-output steps
+    uint32_t rtail = HY_REC_NONE; // recorder: id of the lane's last chunk
+    uint32_t rnch = 0;            // recorder: chunks the lane owns
+    R *rchunk = nullptr;          // recorder: its address
+    unsigned long long ls = 0;    // steps taken in this launch
     long long oc = HY_OUTCOME_TIME_LIMIT;
     R mn = r_inf<R>(), mx = 0, h = 0;
     unsigned long long ns = 0;
@@ -919,7 +959,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // ---- fetch the next trajectory for this group ----
             if (sub == 0) traj = (WGX && wg >= P.wgx_wgs) ? P.B : atomicAdd(P.counter, 1u);
             if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
-            if (traj < P.B) {
+            if (traj < P.B && (!P.active || P.active[traj])) {
                 have = true;
                 for (uint32_t i = sub; i < n; i += G) {
                     const R x0 = P.state[(size_t)i * P.B + traj];
@@ -932,18 +972,17 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
                 tf_hi = 0;
                 tf_lo = 0;
-                if (P.mode == MODE_FOR) {
-                    tf_hi = hi;
-                    tf_lo = lo;
-                    time_add(tf_hi, tf_lo, P.tf[traj]);
-                } else if (P.mode == MODE_UNTIL) {
-                    tf_hi = P.tf[traj];
+                if (P.mode == MODE_FOR || P.mode == MODE_UNTIL) {
+                    // (absolute final times: written by prep_tf_kernel before the first launch)
+                    tf_hi = P.tf_hi[traj];
+                    tf_lo = P.tf_lo[traj];
                 } else if (P.mode == MODE_GRID) {
                     tf_hi = P.grid[(size_t)(P.grid_k - 1) * P.B + traj];
                 }
-                gi = 0;
+                gi = P.resume ? P.gidx[traj] : 0u;
                 cc = 0;
-                if (P.mode == MODE_GRID) {
+                ls = 0;
+                if (P.mode == MODE_GRID && !P.resume) {
                     // Grid points at (or before) the starting time take the current state.
                     const R dir = tf_hi - hi;
                     while (gi < P.grid_k) {
@@ -955,9 +994,20 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         ++gi;
                     }
                 }
-                if (P.cout_tcs && sub == 0) {
-                    P.cout_thi[traj] = hi;
-                    P.cout_tlo[traj] = lo;
+                rtail = HY_REC_NONE;
+                rchunk = nullptr;
+                rnch = 0;
+                if (P.rec.on) {
+                    if (P.rec.append) {
+                        cc = P.rec.count[traj];
+                        rnch = P.rec.nchunks[traj];
+                        rtail = P.rec.tail[traj];
+                        if (rtail != HY_REC_NONE) rchunk = P.rec.chunk(rtail);
+                    } else if (sub == 0) {
+                        P.rec.t0_hi[traj] = hi;
+                        P.rec.t0_lo[traj] = lo;
+                        P.rec.head[traj] = HY_REC_NONE;
+                    }
                 }
                 if (P.mode != MODE_STEP) mdt = r_abs(mdt);
                 oc = HY_OUTCOME_TIME_LIMIT;
@@ -965,6 +1015,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 mx = 0;
                 h = 0;
                 ns = 0;
+                if (P.resume) {
+                    mn = P.min_h[traj];
+                    mx = P.max_h[traj];
+                    ns = P.n_steps[traj];
+                    h = P.last_h[traj];
+                }
                 if (G > 1) __syncwarp(gmask);
             }
         }
@@ -991,6 +1047,30 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 fin = true; // already there: nothing to integrate
             }
             lim = r_abs(rem) < mdt ? rem : r_copysign(mdt, rem);
+        }
+        // ---- recorder: the step needs a slot; take a new chunk from the pool when the lane's
+        // chunks are full.  Pool exhausted: the lane stops (PAUSED) BEFORE the step; the host adds
+        // a segment and resumes it.
+        if (P.rec.on && have && !fin && cc / HY_REC_CH >= rnch) {
+            uint32_t cid = 0;
+            if (sub == 0) cid = atomicAdd(P.rec.next, 1u);
+            if (G > 1) cid = __shfl_sync(gmask, cid, 0, G);
+            if (cid >= P.rec.cap_chunks) {
+                oc = HY_OUTCOME_PAUSED_POOL;
+                fin = true;
+            } else {
+                R *nc = P.rec.chunk(cid);
+                if (sub == 0) {
+                    *reinterpret_cast<uint32_t *>(nc) = HY_REC_NONE;
+                    if (rtail == HY_REC_NONE)
+                        P.rec.head[traj] = cid;
+                    else
+                        *reinterpret_cast<uint32_t *>(rchunk) = cid;
+                }
+                rtail = cid;
+                rchunk = nc;
+                ++rnch;
+            }
         }
         const bool stepping = have && !fin;
 
@@ -1152,14 +1232,16 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 
             // ---- event detection: may truncate the step at a terminal event ----
             int term_ev = -1;
+            int nt_fired = 0; // non-terminal events logged in this step
             if (NB == 0 && d.n_events) {
                 R h_eff = h;
                 if (sub == 0)
                     detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
-                                     term_ev);
+                                     term_ev, nt_fired);
                 if (G > 1) {
                     h_eff = __shfl_sync(gmask, h_eff, 0, G);
                     term_ev = __shfl_sync(gmask, term_ev, 0, G);
+                    nt_fired = __shfl_sync(gmask, nt_fired, 0, G);
                 }
                 if (term_ev >= 0) {
                     h = h_eff;
@@ -1169,13 +1251,14 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             }
 
             // ---- optional tc write, then the state update ----
-            if (stepping && (P.write_tc || P.cout_tcs || P.mode == MODE_GRID)) {
+            if (stepping && (P.write_tc || P.rec.on || P.mode == MODE_GRID)) {
                 if (P.write_tc && P.tc) {
                     for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
                     if (G > 1) __syncwarp(gmask);
                 }
-                if (P.cout_tcs && cc < P.cout_cap) {
-                    R *dstc = P.cout_tcs + ((size_t)cc * P.B + traj) * (size_t)(n * P1);
+                if (P.rec.on) {
+                    // step record: [n][p+1] coefficients (the end time follows after the time update)
+                    R *dstc = rchunk + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
                 }
                 if (P.mode == MODE_GRID) {
@@ -1283,18 +1366,45 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #if defined(HY_WGX_PROF) && defined(HY_TAIL_PROF)
             prof_rel += clock64() - prof_c;
 #endif
+            // ---- angle reduction (the reference's callback.angle_reducer, expose_callbacks.cpp:67-72,
+            // as a device-side post-step op): x <- x - 2 pi floor(x / (2 pi)) for the selected variables.
+            // Runs in the propagate modes only (step callbacks are not part of step()).
+            if (P.n_red && P.mode != MODE_STEP) {
+                if constexpr (NB != 0) {
+                    __syncwarp();
+                } else {
+                    if (G > 1) __syncwarp(gmask);
+                }
+                if (stepping) {
+                    const R two_pi = (R)6.283185307179586476925286766559;
+                    for (uint32_t q = sub; q < P.n_red; q += G) {
+                        const uint32_t i = P.red_idx[q];
+                        const R x = w[s_srow[i]];
+                        const R y = x - two_pi * floor(x / two_pi);
+                        w[s_srow[i]] = y;
+                        if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = y;
+                    }
+                }
+                if constexpr (NB != 0) {
+                    __syncwarp();
+                } else {
+                    if (G > 1) __syncwarp(gmask);
+                }
+            }
             if (stepping) {
                 time_add(hi, lo, h);
                 ++ns;
                 if (!finite) so = HY_OUTCOME_ERR_NF_STATE;
-                if (P.cout_tcs && cc < P.cout_cap) {
-                    ++cc;
+                if (P.rec.on) {
                     if (sub == 0) {
                         const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
-                        P.cout_thi[(size_t)cc * P.B + traj] = fin_ ? tf_hi : hi;
-                        P.cout_tlo[(size_t)cc * P.B + traj] = fin_ ? tf_lo : lo;
+                        R *dstt = rchunk + 2u + (cc % HY_REC_CH) * P.rec.rec_len + n * P1;
+                        dstt[0] = fin_ ? tf_hi : hi;
+                        dstt[1] = fin_ ? tf_lo : lo;
                     }
+                    ++cc;
                 }
+                ++ls;
 
                 // ---- does the trajectory end here? ----
                 if (P.mode == MODE_STEP || so == HY_OUTCOME_ERR_NF_STATE || term_ev >= 0) {
@@ -1314,6 +1424,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         fin = true;
                     } else if (P.max_steps && ns >= P.max_steps) {
                         oc = HY_OUTCOME_STEP_LIMIT;
+                        fin = true;
+                    } else if ((P.launch_steps && ls >= P.launch_steps) || (P.pause_on_nt && nt_fired)) {
+                        // the host wants the lane back (step callback / non-terminal event callback)
+                        oc = HY_OUTCOME_PAUSED;
                         fin = true;
                     }
                 }
@@ -1336,6 +1450,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 P.min_h[traj] = mn;
                 P.max_h[traj] = mx;
                 P.n_steps[traj] = ns;
+                if (P.gidx) P.gidx[traj] = gi;
+                if (P.rec.on) {
+                    P.rec.count[traj] = cc;
+                    P.rec.tail[traj] = rtail;
+                    P.rec.nchunks[traj] = rnch;
+                }
             }
             have = false;
             if (G > 1) __syncwarp(gmask);
@@ -1372,43 +1492,116 @@ __global__ void dense_eval_kernel(const R *__restrict__ tc, const R *__restrict_
     }
 }
 
-// ---- continuous output evaluation (reference continuous_output_batch::operator(),
-// taylor_expose_c_output.cpp:297-412): per-lane bisection over the recorded step
-// times + Horner.  tcs [S][B][n*(p+1)], times [S+1][B], t [K][B], out [K][n][B].
+// ---- absolute final times of propagate_until / propagate_for (double-length), one thread per lane ----
 template <typename R>
-__global__ void cout_eval_kernel(const R *__restrict__ tcs, const R *__restrict__ thi, const R *__restrict__ tlo,
-                                 const unsigned long long *__restrict__ count, const R *__restrict__ t,
-                                 R *__restrict__ out, uint32_t n, uint32_t p, uint32_t B, uint32_t K)
+__global__ void prep_tf_kernel(const R *__restrict__ t, int is_delta, const R *__restrict__ t_hi,
+                               const R *__restrict__ t_lo, R *__restrict__ tf_hi, R *__restrict__ tf_lo, uint32_t B)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= B) return;
+    R hi = t[l], lo = 0;
+    if (is_delta) {
+        hi = t_hi[l];
+        lo = t_lo[l];
+        time_add(hi, lo, t[l]);
+    }
+    tf_hi[l] = hi;
+    tf_lo[l] = lo;
+}
+
+// ---- continuous output (reference continuous_output_batch, taylor_expose_c_output.cpp:260-526) ----
+// The recorder leaves per-lane linked lists of chunks; rec_index_kernel flattens them into a
+// directory (dir[dir_off[l] + j] = id of the lane's j-th chunk) so that a step is found in O(1).
+template <typename R>
+__global__ void rec_index_kernel(const RecDev<R> rec, uint32_t *__restrict__ dir_off, uint32_t *__restrict__ dir,
+                                 unsigned int *__restrict__ dir_next, uint32_t B)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= B) return;
+    const uint32_t nch = (rec.count[l] + HY_REC_CH - 1u) / HY_REC_CH;
+    const uint32_t off = nch ? atomicAdd(dir_next, nch) : 0u;
+    dir_off[l] = off;
+    uint32_t cid = rec.head[l];
+    for (uint32_t j = 0; j < nch; ++j) {
+        dir[off + j] = cid;
+        cid = *reinterpret_cast<const uint32_t *>(rec.chunk(cid));
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ const R *rec_step(const RecDev<R> &rec, const uint32_t *dir, uint32_t off, uint32_t s)
+{
+    return rec.chunk(dir[off + s / HY_REC_CH]) + 2u + (s % HY_REC_CH) * rec.rec_len;
+}
+
+// Evaluation: per-lane bisection over the recorded end times + Horner.
+// t [K][B], out [K][n][B]; a lane without a record evaluates to NaN.
+template <typename R>
+__global__ void cout_eval_kernel(const RecDev<R> rec, const uint32_t *__restrict__ dir_off,
+                                 const uint32_t *__restrict__ dir, const R *__restrict__ t, R *__restrict__ out,
+                                 uint32_t n, uint32_t p, uint32_t B, uint32_t K)
 {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)K * B) return;
     const uint32_t l = (uint32_t)(gid % B), q = (uint32_t)(gid / B);
-    const uint32_t S = (uint32_t)count[l], P1 = p + 1;
+    const uint32_t S = rec.count[l], P1 = p + 1, nP = n * P1;
     const R tq = t[(size_t)q * B + l];
     if (S == 0) {
         for (uint32_t i = 0; i < n; ++i) out[((size_t)q * n + i) * B + l] = tq - tq + (R)NAN;
         return;
     }
-    const bool fwd = thi[(size_t)S * B + l] >= thi[l];
+    const uint32_t off = dir_off[l];
+    const bool fwd = rec_step(rec, dir, off, S - 1)[nP] >= rec.t0_hi[l];
     // first step s whose end time is beyond tq (clamped to the recorded range)
     uint32_t lo = 0, hi = S - 1;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const R te = thi[(size_t)(mid + 1) * B + l];
+        const R te = rec_step(rec, dir, off, mid)[nP];
         const bool before = fwd ? (tq < te) : (tq > te);
         if (before)
             hi = mid;
         else
             lo = mid + 1;
     }
-    const uint32_t s = lo;
-    const R tau = (tq - thi[(size_t)s * B + l]) - tlo[(size_t)s * B + l];
-    const R *base = tcs + ((size_t)s * B + l) * (size_t)(n * P1);
+    const uint32_t sidx = lo;
+    R t0h = rec.t0_hi[l], t0l = rec.t0_lo[l];
+    if (sidx > 0) {
+        const R *pr = rec_step(rec, dir, off, sidx - 1);
+        t0h = pr[nP];
+        t0l = pr[nP + 1];
+    }
+    const R tau = (tq - t0h) - t0l;
+    const R *base = rec_step(rec, dir, off, sidx);
     for (uint32_t i = 0; i < n; ++i) {
         const R *x = base + i * P1;
         R acc = x[p];
         for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k]);
         out[((size_t)q * n + i) * B + l] = acc;
+    }
+}
+
+// Dense copies in the reference's layouts: tcs [S][n][p+1][B] and times (hi, lo) [S+1][B], NaN past a
+// lane's own count (taylor_expose_c_output.cpp:449-451).  One thread per (step, lane).
+template <typename R>
+__global__ void rec_gather_kernel(const RecDev<R> rec, const uint32_t *__restrict__ dir_off,
+                                  const uint32_t *__restrict__ dir, R *__restrict__ tcs, R *__restrict__ thi,
+                                  R *__restrict__ tlo, uint32_t n, uint32_t p, uint32_t B, uint32_t S)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)(S + 1) * B) return;
+    const uint32_t l = (uint32_t)(gid % B), s = (uint32_t)(gid / B);
+    const uint32_t cnt = rec.count[l], nP = n * (p + 1);
+    const R nan = (R)NAN;
+    if (s == 0) {
+        thi[l] = rec.t0_hi[l];
+        tlo[l] = rec.t0_lo[l];
+    }
+    if (s < S) {
+        const R *src = s < cnt ? rec_step(rec, dir, dir_off[l], s) : nullptr;
+        if (tcs)
+            for (uint32_t i = 0; i < nP; ++i) tcs[((size_t)s * nP + i) * B + l] = src ? src[i] : nan;
+        thi[(size_t)(s + 1) * B + l] = src ? src[nP] : nan;
+        tlo[(size_t)(s + 1) * B + l] = src ? src[nP + 1] : nan;
     }
 }
 

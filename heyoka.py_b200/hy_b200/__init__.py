@@ -22,6 +22,7 @@ from .c_output import continuous_output_batch_dbl, continuous_output_batch_flt
 from .ensemble import (
     ensemble_propagate_until, ensemble_propagate_for, ensemble_propagate_grid,
     ensemble_propagate_until_batch, ensemble_propagate_for_batch, ensemble_propagate_grid_batch,
+    set_serialization_backend, get_serialization_backend,
 )
 
 __version__ = "0.1.0"
@@ -62,4 +63,4 @@ def recommended_simd_size(fp_type=float):
     GPU a "batch" is a whole shard; one warp's worth of lanes is the natural
     minimum granule."""
     _fp_to_suffix(fp_type)
-    return 32
+    return 32  # one warp of lanes, whatever the precision (a GPU has no host-SIMD-width notion)

@@ -65,6 +65,28 @@ class event_rec_t(C.Structure):
     ]
 
 
+class prop_args_t(C.Structure):
+    """hy_prop_args (include/hy_cuda.h)."""
+
+    _fields_ = [
+        ("t", C.c_void_p),
+        ("is_delta", C.c_int),
+        ("max_steps", C.c_uint64),
+        ("max_delta_t", C.c_void_p),
+        ("write_tc", C.c_int),
+        ("c_output", C.c_int),
+        ("active", C.c_void_p),
+        ("resume", C.c_int),
+        ("launch_steps", C.c_uint64),
+        ("pause_on_nt", C.c_int),
+        ("grid", C.c_void_p),
+        ("grid_k", C.c_size_t),
+        ("grid_out", C.c_void_p),
+    ]
+
+
+OUTCOME_PAUSED = -4294967400
+
 event_rec_dtype = np.dtype(
     [("lane", "<u4"), ("ev_idx", "<u4"), ("d_sgn", "<i4"), ("step", "<u4"), ("t", "<f8")]
 )
@@ -75,6 +97,15 @@ SYMBOLS = [
     "hy_device_count",
     "hy_create",
     "hy_destroy",
+    "hy_clone",
+    "hy_get_device",
+    "hy_sync",
+    "hy_set_tc",
+    "hy_set_last_h",
+    "hy_propagate_ex",
+    "hy_set_angle_reducer",
+    "hy_cout_detach",
+    "hy_cout_free",
     "hy_host_alloc",
     "hy_host_free",
     "hy_set_stream",
@@ -163,12 +194,26 @@ class PinnedArray:
             pass
 
 
+def _vp(a):
+    return None if a is None else a.ctypes.data
+
+
 class Context:
     """Owner of one hy_ctx."""
 
     def __init__(self, dc, fp_bits, batch, tol, high_accuracy, device=0, n_tevents=0,
-                 ev_dir=None, ev_cooldown=None):
+                 ev_dir=None, ev_cooldown=None, _handle=None):
+        import threading
+
         self._ctx = C.c_void_p()
+        self._lock = threading.Lock()  # guards the context's recorder against a recycling __del__
+        self.batch = batch
+        self.fp_bits = fp_bits
+        self.device = device
+        self._dc = dc
+        if _handle is not None:
+            self._ctx = _handle
+            return
         self.dims = dims_t(
             dc.n_state,
             dc.n_par,
@@ -200,13 +245,23 @@ class Context:
                 C.c_uint32(batch),
             )
         )
-        self.batch = batch
-        self.fp_bits = fp_bits
+
+    def clone(self, device=-1):
+        """hy_clone: deep copy onto `device` (no re-scheduling of the tape)."""
+        h = C.c_void_p()
+        rc = lib().hy_clone(self._ctx, C.byref(h), C.c_int(int(device)))
+        if rc != 0:
+            if h.value:
+                lib().hy_destroy(h)
+            check(rc)
+        dev = self.device if device < 0 else int(device)
+        return Context(self._dc, self.fp_bits, self.batch, 0.0, False, device=dev, _handle=h)
 
     def close(self):
         if self._ctx is not None and self._ctx.value:
-            lib().hy_destroy(self._ctx)
-            self._ctx = None
+            with self._lock:
+                h, self._ctx = self._ctx, None
+            lib().hy_destroy(h)
 
     def __del__(self):
         try:
@@ -217,11 +272,24 @@ class Context:
     def set_stream(self, cuda_stream):
         check(lib().hy_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
+    def sync(self):
+        check(lib().hy_sync(self._ctx))
+
     def upload(self, state=None, pars=None, t_hi=None, t_lo=None):
         check(lib().hy_upload(self._ctx, ptr(state), ptr(pars), ptr(t_hi), ptr(t_lo)))
 
     def download(self, state=None, t_hi=None, t_lo=None, last_h=None):
         check(lib().hy_download(self._ctx, ptr(state), ptr(t_hi), ptr(t_lo), ptr(last_h)))
+
+    def set_tc(self, tc):
+        check(lib().hy_set_tc(self._ctx, ptr(tc)))
+
+    def set_last_h(self, last_h):
+        check(lib().hy_set_last_h(self._ctx, ptr(last_h)))
+
+    def set_angle_reducer(self, idx):
+        arr = np.ascontiguousarray(idx, dtype=np.uint32)
+        check(lib().hy_set_angle_reducer(self._ctx, ptr(arr) if arr.size else None, C.c_uint32(arr.size)))
 
     def step(self, max_delta_t, backward, write_tc, outcome, h):
         check(
@@ -233,13 +301,28 @@ class Context:
 
     def propagate(self, t, is_delta, max_steps, max_delta_t, write_tc, c_output, outcome,
                   min_h, max_h, n_steps):
-        check(
-            lib().hy_propagate(
+        with self._lock:
+            rc = lib().hy_propagate(
                 self._ctx, ptr(t), C.c_int(int(is_delta)), C.c_uint64(int(max_steps)),
                 ptr(max_delta_t), C.c_int(int(write_tc)), C.c_int(int(c_output)), ptr(outcome),
                 ptr(min_h), ptr(max_h), ptr(n_steps),
             )
+        check(rc)
+
+    def propagate_ex(self, outcome, min_h, max_h, n_steps, t=None, is_delta=False, max_steps=0,
+                     max_delta_t=None, write_tc=False, c_output=0, active=None, resume=False,
+                     launch_steps=0, pause_on_nt=False, grid=None, grid_out=None):
+        """hy_propagate_ex: propagate_until/for/grid with an active-lane mask, resumable
+        launches and an appendable continuous output (include/hy_cuda.h)."""
+        a = prop_args_t(
+            _vp(t), int(is_delta), int(max_steps), _vp(max_delta_t), int(write_tc), int(c_output),
+            _vp(active), int(resume), int(launch_steps), int(pause_on_nt), _vp(grid),
+            0 if grid is None else int(grid.shape[0]), _vp(grid_out),
         )
+        with self._lock:
+            rc = lib().hy_propagate_ex(self._ctx, C.byref(a), ptr(outcome), ptr(min_h), ptr(max_h),
+                                       ptr(n_steps))
+        check(rc)
 
     def propagate_grid(self, grid, k, max_steps, max_delta_t, out, outcome, min_h, max_h, n_steps):
         check(
@@ -261,16 +344,16 @@ class Context:
     def dense_eval(self, t, rel_time, out):
         check(lib().hy_dense_eval(self._ctx, ptr(t), C.c_int(int(rel_time)), ptr(out)))
 
-    def cout_info(self, n_steps):
-        mx = C.c_uint64(0)
-        check(lib().hy_cout_info(self._ctx, ptr(n_steps), C.byref(mx)))
-        return mx.value
-
-    def cout_get(self, tcs, thi, tlo, S):
-        check(lib().hy_cout_get(self._ctx, ptr(tcs), ptr(thi), ptr(tlo), C.c_uint64(int(S))))
-
-    def cout_eval(self, t, k, out):
-        check(lib().hy_cout_eval(self._ctx, ptr(t), C.c_size_t(int(k)), ptr(out)))
+    def cout_detach(self):
+        """The continuous output recorded by the last propagate(c_output) call, as an object of
+        its own (None if nothing was recorded)."""
+        h = C.c_void_p()
+        with self._lock:
+            rc = lib().hy_cout_detach(self._ctx, C.byref(h))
+        check(rc)
+        if not h.value:
+            return None
+        return CoutRecord(h, self)
 
     def events_drain(self):
         n = C.c_uint64(0)
@@ -295,6 +378,47 @@ class Context:
         li = launch_info_t()
         check(lib().hy_get_launch_info(self._ctx, C.byref(li)))
         return {k: getattr(li, k) for k, _ in launch_info_t._fields_}
+
+
+class CoutRecord:
+    """Owner of one hy_cout (a recorded continuous output in device memory)."""
+
+    def __init__(self, handle, ctx):
+        import weakref
+
+        self._h = handle
+        self._ctx_ref = weakref.ref(ctx)
+
+    def info(self, n_steps):
+        mx = C.c_uint64(0)
+        check(lib().hy_cout_info(self._h, ptr(n_steps), C.byref(mx)))
+        return mx.value
+
+    def get(self, tcs, thi, tlo, S):
+        check(lib().hy_cout_get(self._h, ptr(tcs), ptr(thi), ptr(tlo), C.c_uint64(int(S))))
+
+    def eval(self, t, k, out):
+        check(lib().hy_cout_eval(self._h, ptr(t), C.c_size_t(int(k)), ptr(out)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            ctx = self._ctx_ref()
+            # give the pool back to the context it came from, if that is alive and idle
+            if (ctx is not None and ctx._ctx is not None and ctx._ctx.value
+                    and ctx._lock.acquire(False)):
+                try:
+                    lib().hy_cout_free(self._h, ctx._ctx)
+                finally:
+                    ctx._lock.release()
+            else:
+                lib().hy_cout_free(self._h, None)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def tape_kernel_variant(dc):

@@ -15,6 +15,7 @@ import math
 import numpy as np
 
 from . import _cabi
+from . import _devctx
 from . import decompose as _dec
 from . import _expression as _E
 from .enums import taylor_outcome, code_model, _outcome_from_int
@@ -130,7 +131,17 @@ class taylor_adaptive_batch_impl:
         self._compact_mode = bool(compact_mode)
         self._parallel_mode = bool(parallel_mode)
         self._llvm_kw = {k: v for k, v in kw.items() if k in _LLVM_KW}
-        self._device = int(kw.get("device", 0))
+        # device: a CUDA device index, or "all" / a list of indices to split the lanes of THIS
+        # integrator over several GPUs by contiguous trajectory range
+        dev = kw.get("device", 0)
+        if isinstance(dev, str):
+            if dev != "all":
+                raise ValueError("device must be an index, a list of indices or 'all'")
+        elif isinstance(dev, (list, tuple)):
+            dev = [int(x) for x in dev]
+        else:
+            dev = int(dev)
+        self._device = dev
         self._t_events = t_events
         self._nt_events = nt_events
         ev_exprs = [e.expression for e in t_events] + [e.expression for e in nt_events]
@@ -174,26 +185,18 @@ class taylor_adaptive_batch_impl:
 
     # ------------------------------------------------------------------
     def _alloc(self, state, pars, t_hi, t_lo):
-        """Create the device context and the pinned host mirrors."""
-        fp, B, n, m, p = self._fp, self._B, self._n, self._dc.n_par, self._order
-        ev_dir = [int(e.direction) for e in self._t_events + self._nt_events]
-        ev_cd = [float(e.cooldown) for e in self._t_events]
-        self._ctx = _cabi.Context(
-            self._dc,
-            64 if fp == np.float64 else 32,
-            B,
-            self._tol,
-            self._high_accuracy,
-            device=self._device,
-            n_tevents=len(self._t_events),
-            ev_dir=ev_dir if ev_dir else None,
-            ev_cooldown=ev_cd if ev_cd else None,
-        )
-        self._p_state = _cabi.PinnedArray((n, B), fp)
-        self._p_pars = _cabi.PinnedArray((m, B), fp)
-        self._p_thi = _cabi.PinnedArray((B,), fp)
-        self._p_tlo = _cabi.PinnedArray((B,), fp)
-        self._p_lasth = _cabi.PinnedArray((B,), fp)
+        """Create the host mirrors.  The device context is created on first use (or taken from
+        the pool of idle contexts / cloned from the integrator this one was copied from)."""
+        fp, B, n, m = self._fp, self._B, self._n, self._dc.n_par
+        self._ctx_obj = None
+        self._ctx_src = None      # context to clone from (hy_clone: no re-scheduling)
+        self._snap = None         # device-only data to restore into a new context
+        self._reducer_idx = ()    # device-side angle reduction currently configured
+        self._p_state = _devctx.host_array((n, B), fp)
+        self._p_pars = _devctx.host_array((m, B), fp)
+        self._p_thi = _devctx.host_array((B,), fp)
+        self._p_tlo = _devctx.host_array((B,), fp)
+        self._p_lasth = _devctx.host_array((B,), fp)
         self._p_tc = None
         self._p_dout = None
         self._p_state.array[...] = state
@@ -209,6 +212,91 @@ class taylor_adaptive_batch_impl:
         self._step_res = [(taylor_outcome.success, fp(0))] * B
         self._prop_res = [(taylor_outcome.success, fp(0), fp(0), 0)] * B
         self._tc_valid = False
+        self._tc_written = False
+        if not getattr(self, "_lazy_ctx", False):
+            self._ensure_ctx()  # the constructor fails loudly without libhy_cuda / a CUDA device
+
+    # ---- device context ----
+    def _ctx_key(self, device):
+        return (id(self._dc), self._fp, self._B, self._tol, self._high_accuracy, device,
+                tuple(int(e.direction) for e in self._t_events + self._nt_events),
+                tuple(float(e.cooldown) for e in self._t_events))
+
+    def _devices(self):
+        d = self._device
+        if d == "all":
+            return list(range(max(1, _cabi.device_count())))
+        return d if isinstance(d, list) else None
+
+    def _ensure_ctx(self):
+        if self._ctx_obj is not None:
+            return self._ctx_obj
+        fp, B = self._fp, self._B
+        fp_bits = 64 if fp == np.float64 else 32
+        ev_dir = [int(e.direction) for e in self._t_events + self._nt_events]
+        ev_cd = [float(e.cooldown) for e in self._t_events]
+        devs = self._devices()
+        ctx = None
+        if devs is not None and len(devs) > 1:
+            ctx = _devctx.MultiContext(self._dc, fp_bits, B, self._tol, self._high_accuracy, devs,
+                                       n_tevents=len(self._t_events), ev_dir=ev_dir or None,
+                                       ev_cooldown=ev_cd or None)
+        else:
+            dev = devs[0] if devs else self._device
+            ctx = _devctx.POOL.acquire(self._ctx_key(dev))
+            if ctx is None and self._ctx_src is not None and not isinstance(self._ctx_src, _devctx.MultiContext) \
+                    and self._ctx_src._ctx is not None and self._ctx_src._ctx.value:
+                ctx = self._ctx_src.clone(dev)
+            if ctx is None:
+                ctx = _cabi.Context(self._dc, fp_bits, B, self._tol, self._high_accuracy, device=dev,
+                                    n_tevents=len(self._t_events), ev_dir=ev_dir or None,
+                                    ev_cooldown=ev_cd or None)
+            else:
+                # a recycled / cloned context carries another integrator's device-only data
+                if self._t_events:
+                    ctx.reset_cooldowns(-1)
+                ctx.set_angle_reducer(())
+        self._ctx_src = None
+        self._ctx_obj = ctx
+        self._reducer_idx = ()
+        snap, self._snap = self._snap, None
+        if snap:
+            if snap.get("cooldowns") is not None and self._t_events:
+                ctx.set_cooldowns(np.ascontiguousarray(snap["cooldowns"][0]),
+                                  np.ascontiguousarray(snap["cooldowns"][1]))
+            if snap.get("tc") is not None:
+                ctx.set_tc(np.ascontiguousarray(snap["tc"]))
+                self._tc_written = True
+        # last_h lives on the device too (dense output reads it)
+        if np.any(self._p_lasth.array != 0):
+            ctx.set_last_h(self._p_lasth.array)
+        return ctx
+
+    @property
+    def _ctx(self):
+        return self._ensure_ctx()
+
+    def _release_ctx(self):
+        """Detach the device context (ensemble driver: the finished iteration keeps only its
+        host data; the context goes back to the pool for the next iteration)."""
+        ctx = self._ctx_obj
+        if ctx is None:
+            return
+        self._snap = self._device_snapshot()
+        self._ctx_obj = None
+        if isinstance(ctx, _devctx.MultiContext):
+            ctx.close()
+        else:
+            _devctx.POOL.release(self._ctx_key(ctx.device), ctx)
+
+    def _device_snapshot(self):
+        """Host copy of what lives only on the device: cooldowns, and tc if it was ever written."""
+        if self._ctx_obj is None:
+            return self._snap
+        snap = {"cooldowns": self._get_cooldown_arrays(), "tc": None}
+        if self._tc_written:
+            snap["tc"] = np.array(self.tc)
+        return snap
 
     # ---- read-only / writable views (expose_batch_integrators.cpp:394-518) ----
     @staticmethod
@@ -240,16 +328,19 @@ class taylor_adaptive_batch_impl:
     @property
     def tc(self):
         if self._p_tc is None:
-            self._p_tc = _cabi.PinnedArray((self._n, self._order + 1, self._B), self._fp)
+            self._p_tc = _devctx.host_array((self._n, self._order + 1, self._B), self._fp)
         if not self._tc_valid:
-            self._ctx.get_tc(self._p_tc.array)
+            if self._ctx_obj is None and self._snap and self._snap.get("tc") is not None:
+                self._p_tc.array[...] = self._snap["tc"]
+            elif self._ctx_obj is not None or self._tc_written:
+                self._ctx.get_tc(self._p_tc.array)
             self._tc_valid = True
         return self._ro(self._p_tc.array)
 
     @property
     def d_output(self):
         if self._p_dout is None:
-            self._p_dout = _cabi.PinnedArray((self._n, self._B), self._fp)
+            self._p_dout = _devctx.host_array((self._n, self._B), self._fp)
         return self._ro(self._p_dout.array)
 
     def set_time(self, tm):
@@ -479,9 +570,12 @@ class taylor_adaptive_batch_impl:
         self._do_step(None, True, write_tc)
 
     def _do_step(self, mdt, backward, write_tc):
+        self._set_reducer(())
         self._push()
         self._ctx.step(mdt, backward, write_tc, self._outcome_s, self._h)
         self._pull()
+        if write_tc:
+            self._tc_written = True
         self._step_res = None
         term = self._dispatch_events()
         if term:
@@ -497,6 +591,27 @@ class taylor_adaptive_batch_impl:
 
         return _normalise_callbacks(callback)
 
+    def _set_reducer(self, idx):
+        idx = tuple(int(i) for i in idx)
+        if idx != self._reducer_idx:
+            self._ctx.set_angle_reducer(idx)
+            self._reducer_idx = idx
+
+    def _split_builtin_callbacks(self, cbs):
+        """Step callbacks that exist as device-side post-step ops (the reference implements
+        angle_reducer in C++, expose_callbacks.cpp:67-72: no Python runs per step) are taken out
+        of the host loop.  Returns (host callbacks, state indices to reduce) - only when ALL
+        callbacks are builtins may the propagation stay on the device for more than one step."""
+        from .callback import angle_reducer
+
+        if cbs and all(isinstance(cb, angle_reducer) for cb in cbs):
+            idx = []
+            for cb in cbs:
+                cb.pre_hook(self)
+                idx += [i for i in cb._idx if i not in idx]
+            return [], idx
+        return cbs, []
+
     def _propagate(self, t, is_delta, max_steps, max_delta_t, callback, write_tc, c_output):
         fp, B = self._fp, self._B
         tt = self._vec_arg(t, "delta_t" if is_delta else "t")
@@ -505,18 +620,14 @@ class taylor_adaptive_batch_impl:
                 "A non-finite time was passed to the propagate_{}() function of an adaptive "
                 "Taylor integrator in batch mode".format("for" if is_delta else "until")
             )
-        mdt = self._vec_arg(max_delta_t, "max_delta_t", allow_empty=True)
-        if mdt is not None:
-            if np.any(np.isnan(mdt)):
-                raise ValueError("A nan max_delta_t was passed to propagate_for/until()")
-            if np.any(mdt <= 0):
-                raise ValueError("A non-positive max_delta_t was passed to propagate_for/until()")
-        if not isinstance(max_steps, (int, np.integer)) or isinstance(max_steps, bool) or max_steps < 0:
-            raise TypeError("max_steps must be a non-negative integer")
+        mdt = self._check_mdt(max_delta_t)
+        self._check_max_steps(max_steps)
         cbs, cb_ret = self._wrap_callbacks(callback)
         from .c_output import continuous_output_batch_impl
 
-        host_loop = bool(cbs) or self._needs_host_events()
+        host_cbs, red = self._split_builtin_callbacks(cbs)
+        self._set_reducer(red)
+        host_loop = bool(host_cbs) or self._needs_host_events()
         self._push()
         if not host_loop:
             self._ctx.propagate(tt, is_delta, max_steps, mdt, write_tc or c_output, c_output,
@@ -524,73 +635,71 @@ class taylor_adaptive_batch_impl:
             self._pull()
             self._dispatch_events()
         else:
-            self._propagate_host_loop(tt, is_delta, max_steps, mdt, cbs, write_tc, c_output)
+            self._propagate_host_loop(host_cbs, max_steps, mdt, write_tc, c_output, t=tt,
+                                      is_delta=is_delta)
+        if write_tc or c_output:
+            self._tc_written = True
         self._prop_res = None
         cout = None
         if c_output:
             cout = continuous_output_batch_impl._from_integrator(self)
         return (cout, cb_ret)
 
+    def _check_mdt(self, max_delta_t):
+        mdt = self._vec_arg(max_delta_t, "max_delta_t", allow_empty=True)
+        if mdt is not None:
+            if np.any(np.isnan(mdt)):
+                raise ValueError("A nan max_delta_t was passed to propagate_for/until/grid()")
+            if np.any(mdt <= 0):
+                raise ValueError("A non-positive max_delta_t was passed to propagate_for/until/grid()")
+        return mdt
+
+    @staticmethod
+    def _check_max_steps(max_steps):
+        if not isinstance(max_steps, (int, np.integer)) or isinstance(max_steps, bool) or max_steps < 0:
+            raise TypeError("max_steps must be a non-negative integer")
+
     def _needs_host_events(self):
         return any(e.callback is not None for e in self._t_events) or bool(self._nt_events)
 
-    def _propagate_host_loop(self, tt, is_delta, max_steps, mdt, cbs, write_tc, c_output):
-        """Step-by-step driver used when Python must run between steps (step
-        callbacks: step_cb_utils.cpp:70-98; event callbacks:
-        taylor_expose_events.cpp:109-138).  One kernel launch per batch step."""
-        fp, B = self._fp, self._B
-        if is_delta:
-            # Fix the absolute final times once (double-length).
-            hi = self._p_thi.array.copy()
-            lo = self._p_tlo.array.copy()
-            s = hi + tt
-            bb = s - hi
-            err = (hi - (s - bb)) + (tt - bb) + lo
-            tf = (s + err).astype(fp)
-        else:
-            tf = tt
+    def _propagate_host_loop(self, cbs, max_steps, mdt, write_tc, c_output, t=None, is_delta=False,
+                             grid=None, grid_out=None):
+        """Driver used when Python must run between steps (step callbacks:
+        step_cb_utils.cpp:70-98; event callbacks: taylor_expose_events.cpp:109-138).
+
+        The device keeps everything between launches (final times, step counters, min/max h,
+        grid position, the continuous output being recorded): a launch runs every ACTIVE lane
+        until it finishes or needs the host - after ONE step if there are step callbacks, else
+        after a step that logged a non-terminal event, or at a terminal event - and hands the
+        lane back with the internal outcome PAUSED.  The next launch resumes the lanes that go
+        on; finished lanes are masked out and keep their results."""
+        B = self._B
         for cb in cbs:
             if hasattr(cb, "pre_hook"):
                 cb.pre_hook(self)
-        tot_n = np.zeros(B, dtype=np.uint64)
-        mn = np.full(B, np.inf, dtype=fp)
-        mx = np.zeros(B, dtype=fp)
-        final = np.full(B, int(taylor_outcome.time_limit), dtype=np.int64)
-        active = np.ones(B, dtype=bool)
-        oc1 = np.zeros(B, dtype=np.int64)
-        a1 = np.zeros(B, dtype=fp)
-        b1 = np.zeros(B, dtype=fp)
-        n1 = np.zeros(B, dtype=np.uint64)
+        active = np.ones(B, dtype=np.uint8)
         first = True
+        stopped = None
         while np.any(active):
             if not first:
-                self._push()
+                self._push()  # callbacks may have edited state / pars
+            self._ctx.propagate_ex(
+                self._outcome, self._min_h, self._max_h, self._nsteps, t=t, is_delta=is_delta,
+                max_steps=max_steps, max_delta_t=mdt, write_tc=bool(write_tc or c_output),
+                c_output=(1 if first else 2) if c_output else 0, active=active, resume=not first,
+                launch_steps=1 if cbs else 0, pause_on_nt=bool(self._nt_events), grid=grid,
+                grid_out=grid_out)
             first = False
-            # Inactive lanes are parked by asking them to go nowhere.
-            target = np.where(active, tf, self._p_thi.array).astype(fp)
-            if np.any(~active):
-                self._park = True
-            self._ctx.propagate(target, 0, 1, mdt, write_tc or c_output, c_output,
-                                oc1, a1, b1, n1)
             self._pull()
             term = self._dispatch_events() or {}
-            stepped = active & (n1 > 0)
-            tot_n[stepped] += n1[stepped]
-            succ = stepped & np.isfinite(a1) & (b1 > 0)
-            mn = np.where(succ & (a1 < mn), a1, mn).astype(fp)
-            mx = np.where(succ & (b1 > mx), b1, mx).astype(fp)
-            done = active & (oc1 != int(taylor_outcome.step_limit))
+            act = active.astype(bool)
+            done = act & (self._outcome != _cabi.OUTCOME_PAUSED)
             for lane, (ev, keep) in term.items():
-                if keep and active[lane]:
-                    # continuing terminal event: the lane goes on (unless it also
-                    # reached its final time, which the next launch reports)
+                if keep and act[lane]:
+                    # continuing terminal event: the lane goes on (if it also sits at its final
+                    # time the next launch reports time_limit without stepping)
                     done[lane] = False
-            final[done] = oc1[done]
-            active &= ~done
-            if max_steps:
-                lim = active & (tot_n >= max_steps)
-                final[lim] = int(taylor_outcome.step_limit)
-                active &= ~lim
+            active[done] = 0
             stop = False
             for cb in cbs:
                 r = cb(self)
@@ -602,12 +711,10 @@ class taylor_adaptive_batch_impl:
                 if not r:
                     stop = True
             if stop:
-                final[active] = int(taylor_outcome.cb_stop)
+                stopped = active.astype(bool)
                 break
-        self._outcome[...] = final
-        self._min_h[...] = mn
-        self._max_h[...] = mx
-        self._nsteps[...] = tot_n
+        if stopped is not None:
+            self._outcome[stopped] = int(taylor_outcome.cb_stop)
 
     def _dispatch_events(self):
         """Drain the device event log and run the Python callbacks in
@@ -653,18 +760,21 @@ class taylor_adaptive_batch_impl:
             d = np.diff(g, axis=0)
             if not (np.all(d > 0) or np.all(d < 0)):
                 raise ValueError("A non-monotonic time grid was passed to propagate_grid()")
-        mdt = self._vec_arg(max_delta_t, "max_delta_t", allow_empty=True)
+        mdt = self._check_mdt(max_delta_t)
+        self._check_max_steps(max_steps)
         cbs, cb_ret = self._wrap_callbacks(callback)
-        if cbs or self._needs_host_events():
-            raise NotImplementedError(
-                "propagate_grid() with step/event callbacks is not available in this build"
-            )
+        host_cbs, red = self._split_builtin_callbacks(cbs)
+        self._set_reducer(red)
         out = np.empty((g.shape[0], n, B), dtype=fp)
         self._push()
-        self._ctx.propagate_grid(g, g.shape[0], max_steps, mdt, out, self._outcome, self._min_h,
-                                 self._max_h, self._nsteps)
-        self._pull()
-        self._dispatch_events()
+        if host_cbs or self._needs_host_events():
+            self._propagate_host_loop(host_cbs, max_steps, mdt, True, False, grid=g, grid_out=out)
+        else:
+            self._ctx.propagate_grid(g, g.shape[0], max_steps, mdt, out, self._outcome, self._min_h,
+                                     self._max_h, self._nsteps)
+            self._pull()
+            self._dispatch_events()
+        self._tc_written = True
         self._prop_res = None
         return (cb_ret, out)
 
@@ -672,7 +782,7 @@ class taylor_adaptive_batch_impl:
     def update_d_output(self, t, rel_time=False):
         tt = self._vec_arg(t, "t")
         if self._p_dout is None:
-            self._p_dout = _cabi.PinnedArray((self._n, self._B), self._fp)
+            self._p_dout = _devctx.host_array((self._n, self._B), self._fp)
         # Times may have been edited through set_time(): push them.
         self._ctx.upload(None, None, self._p_thi.array, self._p_tlo.array)
         self._ctx.dense_eval(tt, rel_time, self._p_dout.array)
@@ -706,6 +816,7 @@ class taylor_adaptive_batch_impl:
 
     # ---- copy / pickle (expose_batch_integrators.cpp:665-669) ----
     def _state_dict(self):
+        """Everything a copy needs, as host data (pickle_wrappers.hpp:35-73)."""
         return dict(
             fp=self._fp,
             sys=self._vsys if self._vsys is not None else self._sys,
@@ -722,78 +833,67 @@ class taylor_adaptive_batch_impl:
             nt_events=self._nt_events,
             llvm_kw=self._llvm_kw,
             device=self._device,
-            step_res=self.step_res,
-            prop_res=self.propagate_res,
+            step_res=self._step_res,
+            prop_res=self._prop_res,
             outcome_s=self._outcome_s.copy(),
             h=self._h.copy(),
             res_arrays=(self._outcome.copy(), self._min_h.copy(), self._max_h.copy(),
                         self._nsteps.copy()),
-            tc=np.array(self.tc),
-            cooldowns=self._get_cooldown_arrays(),
+            snap=self._device_snapshot(),
         )
 
     def _get_cooldown_arrays(self):
         nte = len(self._t_events)
         if not nte:
             return None
+        if self._ctx_obj is None:
+            return self._snap.get("cooldowns") if self._snap else None
         el = np.zeros((self._B, nte), dtype=self._fp)
         tot = np.zeros((self._B, nte), dtype=self._fp)
-        self._ctx.get_cooldowns(el, tot)
+        self._ctx_obj.get_cooldowns(el, tot)
         return el, tot
 
-    @classmethod
-    def _from_state_dict(cls, sd, dyn=None, deep=True):
-        fp = sd["fp"]
-        tev = _copy.deepcopy(sd["t_events"]) if deep else list(sd["t_events"])
-        ntev = _copy.deepcopy(sd["nt_events"]) if deep else list(sd["nt_events"])
-        ta = cls(
-            sd["sys"], sd["state"], time=sd["t_hi"], pars=sd["pars"] if sd["pars"].shape[0] else None,
-            tol=fp(sd["tol"]), high_accuracy=sd["high_accuracy"], compact_mode=sd["compact_mode"],
-            t_events=tev, nt_events=ntev, parallel_mode=sd["parallel_mode"], device=sd["device"],
-            **sd["llvm_kw"],
-        )
-        ta._p_tlo.array[...] = sd["t_lo"]
-        ta._p_lasth.array[...] = sd["last_h"]
-        ta._step_res = list(sd["step_res"])
-        ta._prop_res = list(sd["prop_res"])
-        ta._outcome_s[...] = sd["outcome_s"]
-        ta._h[...] = sd["h"]
-        for dst, src in zip((ta._outcome, ta._min_h, ta._max_h, ta._nsteps), sd["res_arrays"]):
-            dst[...] = src
-        ta._restore_device_extras(sd)
-        if dyn:
-            ta.__dict__.update(dyn)
+    def _copy_impl(self, deep, memo=None):
+        """Copy WITHOUT re-running the decomposition or touching the device: the copy shares the
+        immutable tape, owns host copies of the lane data and gets its device context on first
+        use - cloned from this integrator's (hy_clone) or taken from the pool of idle contexts."""
+        cls = type(self)
+        ta = cls.__new__(cls)
+        for k in ("_vsys", "_sys", "_tol", "_order", "_high_accuracy", "_compact_mode",
+                  "_parallel_mode", "_llvm_kw", "_device", "_dc", "_B", "_n"):
+            setattr(ta, k, getattr(self, k))
+        if deep:
+            ta._t_events = _copy.deepcopy(self._t_events, memo)
+            ta._nt_events = _copy.deepcopy(self._nt_events, memo)
+        else:
+            ta._t_events = list(self._t_events)
+            ta._nt_events = list(self._nt_events)
+        ta._lazy_ctx = True
+        ta._alloc(self._p_state.array, self._p_pars.array, self._p_thi.array, self._p_tlo.array)
+        ta._p_lasth.array[...] = self._p_lasth.array
+        ta._outcome[...] = self._outcome
+        ta._outcome_s[...] = self._outcome_s
+        ta._h[...] = self._h
+        ta._min_h[...] = self._min_h
+        ta._max_h[...] = self._max_h
+        ta._nsteps[...] = self._nsteps
+        ta._step_res = None if self._step_res is None else list(self._step_res)
+        ta._prop_res = None if self._prop_res is None else list(self._prop_res)
+        ta._snap = self._device_snapshot()
+        ta._tc_written = self._tc_written
+        ta._ctx_src = self._ctx_obj
+        if hasattr(self, "_tstate"):
+            ta._tstate = self._tstate.copy()
+        for k, v in self.__dict__.items():
+            if not k.startswith("_"):
+                ta.__dict__[k] = _copy.deepcopy(v, memo) if deep else v
         return ta
 
-    def _restore_device_extras(self, sd):
-        """tc / last_h / cooldowns live on the device: push them back."""
-        from . import _cabi as cabi
-
-        cds = sd.get("cooldowns")
-        if cds is not None and self._t_events:
-            self._ctx.set_cooldowns(np.ascontiguousarray(cds[0]), np.ascontiguousarray(cds[1]))
-        self._saved_tc = sd.get("tc")
-        if self._saved_tc is not None:
-            if self._p_tc is None:
-                self._p_tc = cabi.PinnedArray((self._n, self._order + 1, self._B), self._fp)
-            self._p_tc.array[...] = self._saved_tc
-            self._tc_valid = True
-
-    _OWN = None
-
-    def _dyn_attrs(self):
-        own = type(self)._OWN
-        return {k: v for k, v in self.__dict__.items() if not k.startswith("_") or k not in own}
-
     def __copy__(self):
-        sd = self._state_dict()
-        dyn = {k: v for k, v in self.__dict__.items() if not k.startswith("_")}
-        return type(self)._from_state_dict(sd, dyn, deep=False)
+        return self._copy_impl(False)
 
     def __deepcopy__(self, memo):
-        sd = self._state_dict()
-        dyn = {k: _copy.deepcopy(v, memo) for k, v in self.__dict__.items() if not k.startswith("_")}
-        return type(self)._from_state_dict(sd, dyn, deep=True)
+        return self._copy_impl(True, memo)
 
     def __getstate__(self):
         sd = self._state_dict()
@@ -802,10 +902,25 @@ class taylor_adaptive_batch_impl:
 
     def __setstate__(self, st):
         sd, dyn = st
-        other = type(self)._from_state_dict(sd, dyn, deep=False)
-        self.__dict__.update(other.__dict__)
-        # `other` must not free the context we just adopted.
-        other.__dict__.clear()
+        fp = sd["fp"]
+        self._lazy_ctx = True
+        type(self).__init__(
+            self, sd["sys"], sd["state"], time=sd["t_hi"],
+            pars=sd["pars"] if sd["pars"].shape[0] else None, tol=fp(sd["tol"]),
+            high_accuracy=sd["high_accuracy"], compact_mode=sd["compact_mode"],
+            t_events=list(sd["t_events"]), nt_events=list(sd["nt_events"]),
+            parallel_mode=sd["parallel_mode"], device=sd["device"], **sd["llvm_kw"])
+        self._p_tlo.array[...] = sd["t_lo"]
+        self._p_lasth.array[...] = sd["last_h"]
+        self._step_res = None if sd["step_res"] is None else list(sd["step_res"])
+        self._prop_res = None if sd["prop_res"] is None else list(sd["prop_res"])
+        self._outcome_s[...] = sd["outcome_s"]
+        self._h[...] = sd["h"]
+        for dst, src in zip((self._outcome, self._min_h, self._max_h, self._nsteps), sd["res_arrays"]):
+            dst[...] = src
+        self._snap = sd.get("snap")
+        self._tc_written = bool(self._snap and self._snap.get("tc") is not None)
+        self.__dict__.update(dyn)
 
     def __repr__(self):
         return (

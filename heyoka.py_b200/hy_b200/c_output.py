@@ -25,12 +25,18 @@ class continuous_output_batch_impl:
     def _from_integrator(cls, ta):
         co = (continuous_output_batch_dbl if ta._fp == np.float64 else continuous_output_batch_flt)()
         B = ta._B
+        # the record is an object of its own (like the reference's continuous_output_batch): it
+        # stays valid after the integrator moves on or is destroyed
+        rec = ta._ctx.cout_detach()
+        if rec is None:
+            return None
         ns = np.zeros(B, dtype=np.uint64)
-        S = ta._ctx.cout_info(ns)
+        S = rec.info(ns)
         if S == 0:
+            rec.close()
             return None
         co._ta = ta
-        co._ctx = ta._ctx
+        co._rec = rec
         co._n = ta._n
         co._B = B
         co._order = ta._order
@@ -48,7 +54,7 @@ class continuous_output_batch_impl:
             self._tcs = np.zeros((S, self._n, self._order + 1, self._B), dtype=fp)
             self._thi = np.zeros((S + 1, self._B), dtype=fp)
             self._tlo = np.zeros((S + 1, self._B), dtype=fp)
-            self._ctx.cout_get(self._tcs, self._thi, self._tlo, S)
+            self._rec.get(self._tcs, self._thi, self._tlo, S)
 
     def __call__(self, t):
         self._check()
@@ -63,7 +69,7 @@ class continuous_output_batch_impl:
                     )
                 tt = np.ascontiguousarray(arr.astype(fp)).reshape(1, B)
                 out = np.zeros((1, n, B), dtype=fp)
-                self._ctx.cout_eval(tt, 1, out)
+                self._rec.eval(tt, 1, out)
                 self._out = out[0]
                 v = self._out.view()
                 v.flags.writeable = False
@@ -78,7 +84,7 @@ class continuous_output_batch_impl:
                 out = np.zeros((k, n, B), dtype=fp)
                 if k:
                     tt = np.ascontiguousarray(arr.astype(fp))
-                    self._ctx.cout_eval(tt, k, out)
+                    self._rec.eval(tt, k, out)
                 return out
             raise ValueError(
                 "Invalid time array passed to a continuous_output_batch object: the number of "
@@ -86,7 +92,7 @@ class continuous_output_batch_impl:
             )
         tt = np.full((1, B), t, dtype=fp)
         out = np.zeros((1, n, B), dtype=fp)
-        self._ctx.cout_eval(tt, 1, out)
+        self._rec.eval(tt, 1, out)
         self._out = out[0]
         v = self._out.view()
         v.flags.writeable = False

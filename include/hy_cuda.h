@@ -109,8 +109,13 @@ typedef struct hy_dims {
 #define HY_OUTCOME_TIME_LIMIT (-4294967299LL)
 #define HY_OUTCOME_ERR_NF_STATE (-4294967300LL)
 #define HY_OUTCOME_CB_STOP (-4294967301LL)
+/* Not a reference value: returned by hy_propagate_ex for a lane that stopped inside a launch
+ * and can be resumed by the next one (per-launch step budget reached, or a non-terminal event
+ * fired and the caller asked to get the lane back to run its callback). */
+#define HY_OUTCOME_PAUSED (-4294967400LL)
 
 typedef struct hy_ctx hy_ctx;
+typedef struct hy_cout hy_cout; /* a recorded continuous output (device memory) */
 
 /* One record of the device event log (hy_events_drain). */
 typedef struct hy_event_rec {
@@ -136,6 +141,16 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
               uint32_t batch);
 int hy_destroy(hy_ctx *ctx);
 
+/* Deep copy of a context onto `device` (< 0: the source's device).  Replaces what
+ * copy.deepcopy(ta) does once per ensemble iteration in the reference
+ * (_ensemble_impl.py:47; copy_wrapper/deepcopy_wrapper, common_utils.hpp): the scheduled
+ * program is reused - no tape matching, no scheduling - and the lane data (state, pars,
+ * time, last_h, results, tc, cooldowns) is copied device to device (peer copy across GPUs). */
+int hy_clone(const hy_ctx *src, hy_ctx **out, int device);
+int hy_get_device(hy_ctx *ctx, int *device);
+/* Wait for everything queued on the context's stream. */
+int hy_sync(hy_ctx *ctx);
+
 /* Page-locked host buffers for the numpy mirrors of state/pars/time (the
  * reference's views alias integrator memory, expose_batch_integrators.cpp:
  * 394-518; here they alias pinned memory the DMA engines can reach). */
@@ -151,6 +166,12 @@ int hy_set_stream(hy_ctx *ctx, void *cuda_stream);
 int hy_upload(hy_ctx *ctx, const void *state, const void *pars, const void *t_hi,
               const void *t_lo);
 int hy_download(hy_ctx *ctx, void *state, void *t_hi, void *t_lo, void *last_h);
+
+/* Device-side Taylor coefficients [n, order+1, B] / last step sizes [B] of a copied or
+ * unpickled integrator (the reference's copies carry tc and last_h:
+ * expose_batch_integrators.cpp:665-669, pickle_wrappers.hpp:35-73). */
+int hy_set_tc(hy_ctx *ctx, const void *tc);
+int hy_set_last_h(hy_ctx *ctx, const void *last_h);
 
 /* Device-resident variants (pointers are device addresses of the same
  * layouts); used when the ensemble already lives in HBM. */
@@ -174,6 +195,40 @@ int hy_propagate(hy_ctx *ctx, const void *t, int is_delta, uint64_t max_steps,
                  const void *max_delta_t, int write_tc, int c_output, int64_t *outcome,
                  void *min_h, void *max_h, uint64_t *n_steps);
 
+/* The general form behind hy_propagate / hy_propagate_grid.  It adds what the front end
+ * needs to run Python between launches without re-integrating or re-uploading anything
+ * (step callbacks: step_cb_utils.cpp:70-98; event callbacks: taylor_expose_events.cpp:109-138):
+ *  - `active` [B] bytes (NULL: all): only these lanes take part; the others keep their state,
+ *    time and results;
+ *  - `resume`: the lanes continue the previous call (final times, step counters, min/max h,
+ *    grid position are kept on the device; `t` / `grid` are not read again);
+ *  - `launch_steps` > 0: a lane gives control back after that many steps, `pause_on_nt`: after
+ *    a step that logged a non-terminal event; its outcome is then HY_OUTCOME_PAUSED;
+ *  - `c_output`: 0 off, 1 record into a fresh continuous output, 2 append to the current one;
+ *  - `grid` != NULL selects propagate_grid (t/is_delta ignored). */
+typedef struct hy_prop_args {
+    const void *t;           /* [B] final times or time intervals                       */
+    int is_delta;
+    uint64_t max_steps;      /* per lane over the whole (resumed) call, 0 = unlimited    */
+    const void *max_delta_t; /* [B] or NULL                                             */
+    int write_tc;
+    int c_output;
+    const uint8_t *active;
+    int resume;
+    uint64_t launch_steps;
+    int pause_on_nt;
+    const void *grid;        /* [grid_k, B] or NULL                                     */
+    size_t grid_k;
+    void *grid_out;          /* [grid_k, n, B]                                          */
+} hy_prop_args;
+int hy_propagate_ex(hy_ctx *ctx, const hy_prop_args *args, int64_t *outcome, void *min_h, void *max_h,
+                    uint64_t *n_steps);
+
+/* The reference's callback.angle_reducer (expose_callbacks.cpp:67-72), a C++ builtin there,
+ * as a device-side post-step op here: the listed state variables are reduced to [0, 2 pi)
+ * after every step of the propagate_* calls.  n = 0 switches it off. */
+int hy_set_angle_reducer(hy_ctx *ctx, const uint32_t *state_idx, uint32_t n);
+
 /* propagate_grid (expose_batch_integrators.cpp:315-392): `grid` is [k, B]
  * host; `out` is [k, n, B] host, NaN-filled past an early exit. */
 int hy_propagate_grid(hy_ctx *ctx, const void *grid, size_t k, uint64_t max_steps,
@@ -194,14 +249,22 @@ int hy_get_tc(hy_ctx *ctx, void *tc);
 int hy_dense_eval(hy_ctx *ctx, const void *t, int rel_time, void *out);
 
 /* Continuous output recorded by hy_propagate(c_output=1)
- * (reference continuous_output_batch, taylor_expose_c_output.cpp:260-526).
+ * (reference continuous_output_batch, taylor_expose_c_output.cpp:260-526).  The propagate
+ * kernel records in ONE pass: every lane appends its steps (Taylor coefficients + end time)
+ * to a per-lane list of fixed-size chunks taken from a device pool (ragged storage: a lane
+ * costs what it recorded).  The record is an object of its own, like the reference's:
+ * hy_cout_detach hands it to the caller (NULL if nothing was recorded), and it stays valid
+ * after the integrator moves on.  hy_cout_free(rec, ctx) gives the pool back to `ctx` for its
+ * next recording (no cudaMalloc in steady state), hy_cout_free(rec, NULL) frees it.
  * hy_cout_info: per-lane number of recorded steps and max over lanes.
  * hy_cout_get:  tcs [S, n, order+1, B] and times (hi, lo) [S+1, B], padded
- *               with NaN past each lane's own count.
+ *               with NaN past each lane's own count (the +1 row: :449-451).
  * hy_cout_eval: out[i, :, :] = x(t[i, :]) for i < k; t is [k, B], out is [k, n, B]. */
-int hy_cout_info(hy_ctx *ctx, uint64_t *n_steps, uint64_t *max_steps);
-int hy_cout_get(hy_ctx *ctx, void *tcs, void *times_hi, void *times_lo, uint64_t S);
-int hy_cout_eval(hy_ctx *ctx, const void *t, size_t k, void *out);
+int hy_cout_detach(hy_ctx *ctx, hy_cout **out);
+int hy_cout_free(hy_cout *rec, hy_ctx *recycle_into);
+int hy_cout_info(hy_cout *rec, uint64_t *n_steps, uint64_t *max_steps);
+int hy_cout_get(hy_cout *rec, void *tcs, void *times_hi, void *times_lo, uint64_t S);
+int hy_cout_eval(hy_cout *rec, const void *t, size_t k, void *out);
 
 /* Events (taylor_expose_events.cpp:185-317; integrator side
  * expose_batch_integrators.cpp:651-656).  The device appends one record per

@@ -300,7 +300,17 @@ class NpTaylorBatch:
             h = np.where(clamp, lim, h).astype(T)
         outcome = np.where(clamp, OUT_TIME_LIMIT, OUT_SUCCESS).astype(np.int64)
         if self.ev_spec:
-            for l in np.nonzero(mask)[0]:
+            # Rigorous pre-filter (not the product's interval Horner): with q(s) = g(h s),
+            # |q(s) - q_0| <= sum_{k>=1} |q_k| on [0, 1], so |q_0| > sum_{k>=1} |q_k| excludes
+            # a root in the step.  Lanes with a running cooldown clock are always visited.
+            with np.errstate(all="ignore"):
+                hp = np.abs(h.astype(np.float64))[None, :] ** np.arange(self.order + 1)[:, None]
+                q = np.abs(EV.astype(np.float64)) * hp[None, :, :]
+                maybe = ~(q[:, 0, :] > 1.0000001 * q[:, 1:, :].sum(axis=1))
+            need = mask & np.any(maybe, axis=0)
+            for (l_, _e) in self.cd:
+                need[l_] = need[l_] or mask[l_]
+            for l in np.nonzero(need)[0]:
                 h[l], te = self._detect_lane(int(l), EV[:, :, l], h[l])
                 if te >= 0:
                     outcome[l] = -te - 1
