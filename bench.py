@@ -48,15 +48,38 @@ def parse():
     ap.add_argument("--steps", type=int, default=7)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--traj-per-gpu", type=int, default=125000)
-    ap.add_argument("--horizon", type=float, default=1e4, help="years")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configuration (2 = the headline outer Solar System ensemble)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --total trajectories split over the GPUs (default: every N runs THE "
+                         "configuration); weak: --traj-per-gpu on every GPU")
+    ap.add_argument("--total", type=int, default=0, help="trajectories in total (strong scaling)")
+    ap.add_argument("--traj-per-gpu", type=int, default=0, help="trajectories per GPU (weak scaling)")
+    ap.add_argument("--horizon", type=float, default=0.0, help="final time of the configuration (0: its own)")
     ap.add_argument("--segment", type=float, default=0.0,
-                    help="years per bench step (default horizon/10)")
+                    help="time per bench step (default horizon/10)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0,
                     help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+# trajectories of the configuration as BASELINE.json states it, and the largest shard one GPU takes
+# (cfg 3: the continuous output of 4M lanes is ~400 GB - it exists only sharded over 8 GPUs;
+#  cfg 4: the tape interpreter needs minutes for 1M lanes - an eighth is one GPU's share)
+CFG_TOTAL = {2: 1000000, 3: 4000000, 4: 1000000, 5: 1000000}
+CFG_MAX_PER_GPU = {2: 1000000, 3: 500000, 4: 125000, 5: 125000}
+
+
+def shard_size(args, world, rank):
+    from hy_b200.shard import shard_bounds
+
+    if args.scaling == "weak":
+        return args.traj_per_gpu or CFG_MAX_PER_GPU[args.config] // (8 if args.config == 2 else 1)
+    total = args.total or min(CFG_TOTAL[args.config], CFG_MAX_PER_GPU[args.config] * world)
+    lo, hi = shard_bounds(total, rank, world)
+    return hi - lo
 
 
 def dist_env():
@@ -126,10 +149,11 @@ class ClockSampler:
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel, per
-    launch, from the committed `ncu --set full` capture of this workload
-    (profiles/r01_ncu_full_bench_kernel.txt, lines `name [unit] = value`); None if
-    the summary is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel from the committed
+    `ncu --set full` capture of the SAME kernel on a smaller launch (profiles/r01_ncu_full_bench_kernel.txt,
+    a 6.4 ms launch over 125 000 trajectories x 1 step-segment) - a file read, not a measurement of the
+    timed launch; HBM traffic of this kernel is the state in/out only, so it does not grow with the
+    number of steps.  None if the summary is missing."""
     try:
         tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_kernel.txt")):
@@ -344,14 +368,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
+    import ctypes as C
     import hy_b200 as hy
     from hy_b200 import _cabi, decompose as D
+    from hy_b200.shard import reduce_throughput
 
-    B, horizon = args.traj_per_gpu, args.horizon
-    seg = args.segment if args.segment > 0 else horizon / 10.0
-    sys_, ic = workload(B, rank)
+    B = shard_size(args, world, rank)
+    cfgd = make_config(args.config, B, rank, args.horizon, args.segment)
+    sys_, ic, seg = cfgd["sys"], cfgd["ic"], cfgd["segment"]
     fp = np.float64
-    order = D.taylor_order(float(np.finfo(fp).eps))
+    eps = float(np.finfo(fp).eps)
+    order = D.taylor_order(eps)
+    n = ic.shape[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -360,8 +388,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm ("value") ----------------
-    dc = D.decompose(sys_, order)
-    ctx = _cabi.Context(dc, 64, B, float(np.finfo(fp).eps), False, device=local)
+    evs = cfgd["events"] or []
+    dc = D.decompose(sys_, order, events=evs)
+    ctx = _cabi.Context(dc, 64, B, eps, False, device=local, n_tevents=len(evs),
+                        ev_dir=[0] * len(evs) if evs else None, ev_cooldown=[-1.0] * len(evs) if evs else None)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     li = ctx.launch_info()
@@ -371,80 +401,110 @@ def main():
     oc = np.zeros(B, dtype=np.int64)
     nst = np.zeros(B, dtype=np.uint64)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    import ctypes as C
+    K = cfgd["grid_eval"]
+    tq = np.repeat(np.linspace(0.0, cfgd["horizon"], K), B).reshape(K, B) if K else None
+    gout = np.empty((K, n, B)) if K else None
 
     def reset_dev():
         _cabi.check(_cabi.lib().hy_upload_dev(
             ctx._ctx, C.c_void_p(d_ic.data_ptr()), None, C.c_void_p(d_zero.data_ptr()),
             C.c_void_p(d_zero.data_ptr())))
+        if evs:
+            ctx.reset_cooldowns(-1)
+
+    launches = [0]
 
     def one_step():
         l2_flush.zero_()
-        ctx.propagate(tf, 1, 0, None, 0, 0, oc, None, None, nst)  # propagate_for(seg)
-        return int(nst.sum()), ctx.last_timing()[0]
+        if cfgd["reset_each_step"]:
+            reset_dev()
+            ctx.propagate(tf, 0, 0, None, 0, 1 if cfgd["c_output"] else 0, oc, None, None, nst)
+        else:
+            ctx.propagate(tf, 1, 0, None, 0, 0, oc, None, None, nst)  # propagate_for(seg)
+        ms, nl = ctx.last_timing()
+        launches[0] += nl
+        if cfgd["c_output"]:
+            rec = ctx.cout_detach()
+            rec.eval(tq, K, gout)          # K x B dense evaluations (one more launch)
+            launches[0] += 2               # chunk directory + evaluation kernels
+            rec.close()                    # the pool goes back to the context
+        return int(nst.sum()), ms
 
     reset_dev()
-
     for _ in range(args.warmup):
         one_step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
+    launches[0] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     t0 = time.perf_counter()
     tot_steps, kern_ms = 0, 0.0
     for _ in range(args.steps):
-        s, ms = one_step()
-        tot_steps += s
+        s_, ms = one_step()
+        tot_steps += s_
         kern_ms += ms
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    assert np.all(oc == int(hy.taylor_outcome.time_limit)), "some trajectories did not finish"
+    gpu_launches = launches[0]
+    if not evs:
+        assert np.all(oc == int(hy.taylor_outcome.time_limit)), "some trajectories did not finish"
     # Sanity of what was timed (outside the timed region): the final state of the device arm
-    # conserves the energy of every trajectory.
-    from hy_b200 import workloads as W
-
+    # conserves the invariant of every trajectory.
     st_end = np.empty_like(ic)
     ctx.download(state=st_end)
-    e0_, e1_ = W.oss_energy(ic), W.oss_energy(st_end)
-    energy_drift = float(np.max(np.abs((e1_ - e0_) / e0_)))
-    assert energy_drift < 1e-10, energy_drift
-
-    from hy_b200.shard import reduce_throughput
+    drift = cfgd["check"](ic, st_end)
+    assert drift < cfgd["check_tol"], drift
 
     value, t_max, steps_all = reduce_throughput(dev_ms * 1e-3, tot_steps, dist if world > 1 else None, dev)
 
     # ---------------- end-to-end arm through the public API ----------------
     e2e = None
     if not args.no_e2e:
-        ta = hy.taylor_adaptive_batch(sys_, ic, device=local)
+        kw = {}
+        if evs:
+            kw["t_events"] = [hy.t_event_batch(e) for e in evs]
+        ta = hy.taylor_adaptive_batch(sys_, ic, device=local, **kw)
         ta._ctx.set_stream(stream.cuda_stream)
+
+        def e2e_step():
+            if cfgd["reset_each_step"]:
+                ta.state[:] = ic
+                ta.set_time(0.0)
+                if evs:
+                    ta.reset_cooldowns()
+                c_out, _ = ta.propagate_until(seg, c_output=cfgd["c_output"])
+                if cfgd["c_output"]:
+                    c_out(tq)
+                    del c_out
+            else:
+                ta.propagate_for(seg)
+            return int(ta.propagate_res_arrays[3].sum())
+
         ta.state[:] = ic
         ta.set_time(0.0)
         for _ in range(min(args.warmup, 1)):
-            ta.propagate_for(seg)  # warm-up (the device arm above already warmed the GPU)
+            e2e_step()  # warm-up (the device arm above already warmed the GPU)
         barrier()
         t0 = time.perf_counter()
         e_steps = 0
         for _ in range(args.steps):
             # host (pinned) state -> H2D, kernel, D2H of state/time/results
-            ta.propagate_for(seg)
-            e_steps += int(ta.propagate_res_arrays[3].sum())
+            e_steps += e2e_step()
         barrier()
         e_wall = time.perf_counter() - t0
         e_val, _, _ = reduce_throughput(e_wall, e_steps, dist if world > 1 else None, dev)
-        n, m = dc.n_state, dc.n_par
+        m = dc.n_par
         e2e = {
             "value": e_val,
             "unit": UNIT,
-            "h2d_bytes_per_step": int(B * 8 * (n + m + 2 + 1)),       # state, pars, t_hi, t_lo, t_final
-            "d2h_bytes_per_step": int(B * 8 * (n + 3 + 4)),           # state, t_hi, t_lo, last_h, results
+            "h2d_bytes_per_step": int(B * 8 * (n + m + 2 + 1 + K)),      # state, pars, t_hi, t_lo, t_final (+ query times)
+            "d2h_bytes_per_step": int(B * 8 * (n + 3 + 4 + K * n)),     # state, t_hi, t_lo, last_h, results (+ dense output)
         }
         del ta
 
@@ -461,7 +521,11 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
         achieved_tf = steps_rank * fl / k_s / 1e12
-        alg_bytes = 8.0 * (2 * dc.n_state + dc.n_par + 4 + 4) * B      # per launch: state in/out, time, results
+        rec_bytes = 8.0 * (n * (order + 1) + 2) * (steps_rank / args.steps) if cfgd["c_output"] else 0.0
+        alg_bytes = 8.0 * (2 * dc.n_state + dc.n_par + 4 + 4) * B + rec_bytes     # per launch
+        variant = li.get("kernel_variant", 0)
+        kname = {0: " (tape interpreter)", 203: " (register-resident CR3BP jets, hy_cr3bp_reg.cuh)"}.get(
+            variant, " (register-resident N-body jets, hy_nbody_reg.cuh)")
         roof = {
             "bound": "fp64-fma",
             "achieved": achieved_tf,
@@ -470,54 +534,61 @@ def main():
             "frac": achieved_tf / fma_peak if fma_peak else None,
             "peak_source": "measured DFMA microbenchmark (hy_measure_fma_peak) on this GPU; "
                            "MEASURED_PEAKS.json holds no FP64 figure",
-            "kernel": "hy::propagate_kernel<double,{},true,{}>{}".format(
-                li["group"], li.get("kernel_variant", 0),
-                " (register-resident N-body jets, hy_nbody_reg.cuh)" if li.get("kernel_variant") else
-                " (tape interpreter)"),
+            "kernel": "hy::propagate_kernel<double,{},true,{}>{}".format(li["group"], variant, kname),
             "kernel_ms_per_launch": kern_ms / args.steps,
             "flops_per_trajectory_step": fl,
-            "traffic": ncu_traffic(),
+            "traffic": ncu_traffic() if args.config == 2 else None,
+            "traffic_note": "ncu --set full capture of the same kernel on a 125 000-trajectory, 6.4 ms launch "
+                            "(profiles/r01_ncu_full_bench_kernel.txt); the kernel's HBM traffic is the state "
+                            "in/out and does not depend on the number of steps" if args.config == 2 else None,
             "hbm": {
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_gbs": alg_bytes * args.steps / k_s / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": hbm_src,
-                "note": "jets stay in shared memory: HBM carries only the initial/final state",
+                "note": "jets stay on chip: HBM carries the initial/final state"
+                        + (" and the continuous-output record" if cfgd["c_output"] else ""),
             },
             "smem": {
                 "operand_loads_per_trajectory_step": lo,
                 "achieved_gbs": steps_rank * lo * 8 / k_s / 1e9,
                 "peak_gbs": 128.0 * li["n_sm"] * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                "note": "operand loads of the tape (what the tape INTERPRETER would read from shared memory; "
+                "note": "operand loads of the tape (what the tape INTERPRETER reads from shared memory; "
                         "with kernel_variant > 0 the convolution operands are registers and shared memory "
-                        "carries only the state jets; the pair products travel by warp shuffle)",
+                        "carries only the state jets)",
             },
         }
         cpu = None
         if not args.no_cpu_baseline:
-            cpu, _, _ = cpu_baseline(sys_, order, horizon, args.cpu_seconds)
+            cpu, _, _ = cpu_baseline(cfgd, order, args.cpu_seconds)
+        total = int(round(steps_all / max(1, tot_steps) * B)) if world > 1 else B
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": "outer Solar System 6-body (model.nbody(6)) ensemble, FP64, tol=eps "
-                            "(order 20), ICs x(1+U(-1e-12,1e-12)) recentred, propagate_until "
-                            "{:g} yr".format(horizon),
-                "trajectories_per_gpu": B, "trajectories_total": B * world, "horizon_yr": horizon,
-                "step": "propagate_for({:g} yr) over the whole shard, continuing from the "
-                        "previous step (W+K = 10 steps cover the 1e4 yr horizon)".format(seg),
+                "workload": cfgd["name"] + ", final time {:g}".format(cfgd["horizon"]),
+                "config_id": args.config,
+                "trajectories_this_gpu": B,
+                "trajectories_total": (args.total or min(CFG_TOTAL[args.config], CFG_MAX_PER_GPU[args.config] * world))
+                if args.scaling == "strong" else B * world,
+                "trajectories_in_BASELINE_config": CFG_TOTAL[args.config],
+                "scaling_note": ("strong: the total is split over the GPUs by trajectory range; "
+                                 "at N = 1 one GPU runs the largest shard it can hold ({} trajectories)".format(
+                                     CFG_MAX_PER_GPU[args.config]))
+                if args.scaling == "strong" else "weak: every GPU runs --traj-per-gpu trajectories",
+                "horizon": cfgd["horizon"],
+                "step": cfgd["step_desc"] + " (default W+K = 10 steps cover the horizon once)",
                 "parallelism": "trajectory-range shards, no collective",
                 "l2": "flushed between iterations (256 MiB memset)",
                 "launch": li,
                 "wall_s_timed_region": wall,
-                "check": {"max_rel_energy_drift_after_timed_steps": energy_drift,
-                          "all_outcomes_time_limit": True},
+                "check": {cfgd["check_name"] + "_after_timed_steps": drift},
             },
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": args.steps,
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
             "trajectory_steps_per_step": steps_all / args.steps,
         }
