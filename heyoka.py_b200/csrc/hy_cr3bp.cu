@@ -3,36 +3,30 @@
 
 namespace hy {
 
-template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+template <typename R> cudaError_t launch_cr3bp_kernel(const KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx)
 {
-    auto kern = propagate_kernel<R, 2, true, -1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
-    if (e != cudaSuccess) return e;
-    kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
-    return cudaGetLastError();
+    if (fx) return launch_kernel_fn(propagate_kernel<R, 2, true, -1, false, NBR_PMAX, true>, P, li, s);
+    return launch_kernel_fn(propagate_kernel<R, 2, true, -1, false, NBR_PMAX, false>, P, li, s);
 }
 template <typename R> int regs_cr3bp_kernel()
 {
     cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, propagate_kernel<R, 2, true, -1>) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&a, propagate_kernel<R, 2, true, -1, false, NBR_PMAX, false>) != cudaSuccess) return 0;
     return a.numRegs;
 }
-cudaError_t launch_cr3bp_kernel_p22(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s)
+cudaError_t launch_cr3bp_kernel_p22(const KParams<double> &P, const hy_launch_info &li, cudaStream_t s, bool fx)
 {
-    auto kern = propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem_bytes);
-    if (e != cudaSuccess) return e;
-    kern<<<li.ctas, li.threads, li.smem_bytes, s>>>(P);
-    return cudaGetLastError();
+    if (fx) return launch_kernel_fn(propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI, true>, P, li, s);
+    return launch_kernel_fn(propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI, false>, P, li, s);
 }
 int regs_cr3bp_kernel_p22()
 {
     cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI>) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&a, propagate_kernel<double, 2, true, -1, false, CRB_PMAX_HI, false>) != cudaSuccess) return 0;
     return a.numRegs;
 }
-template cudaError_t launch_cr3bp_kernel<double>(const KParams<double> &, const hy_launch_info &, cudaStream_t);
-template cudaError_t launch_cr3bp_kernel<float>(const KParams<float> &, const hy_launch_info &, cudaStream_t);
+template cudaError_t launch_cr3bp_kernel<double>(const KParams<double> &, const hy_launch_info &, cudaStream_t, bool);
+template cudaError_t launch_cr3bp_kernel<float>(const KParams<float> &, const hy_launch_info &, cudaStream_t, bool);
 template int regs_cr3bp_kernel<double>();
 template int regs_cr3bp_kernel<float>();
 

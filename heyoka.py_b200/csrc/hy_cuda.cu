@@ -129,24 +129,24 @@ cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStre
     return cudaGetLastError();
 }
 
-template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s)
+template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx)
 {
     // register-resident N-body kernels (hy_nbody_reg.cuh)
     switch (li.kernel_variant) { // instantiated in hy_nb3.cu ... hy_nb6.cu
     case 0: break;
-    case 3: return hy::launch_nbody_kernel<R, 3>(P, li, s);
-    case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s);
-    case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s);
-    case 6: return hy::launch_nbody_kernel<R, 6>(P, li, s);
+    case 3: return hy::launch_nbody_kernel<R, 3>(P, li, s, fx);
+    case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s, fx);
+    case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s, fx);
+    case 6: return hy::launch_nbody_kernel<R, 6>(P, li, s, fx);
     case hy::NBR_VARIANT_P22: // 6 bodies, unrolled to order 22 (hy_nb6.cu)
-        if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_p22(P, li, s);
+        if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_p22(P, li, s, fx);
         return cudaErrorInvalidValue;
-    case 106: // warpgroup rotation (experimental)
-        if constexpr (std::is_same<R, double>::value) return hy::launch_nbody_kernel_wgx(P, li, s);
+    case 106: // warpgroup rotation (experimental: the plain build only)
+        if constexpr (std::is_same<R, double>::value) return fx ? cudaErrorNotSupported : hy::launch_nbody_kernel_wgx(P, li, s);
         return cudaErrorInvalidValue;
-    case hy::CRB_VARIANT: return hy::launch_cr3bp_kernel<R>(P, li, s); // hy_cr3bp.cu
+    case hy::CRB_VARIANT: return hy::launch_cr3bp_kernel<R>(P, li, s, fx); // hy_cr3bp.cu
     case hy::CRB_VARIANT_P22:
-        if constexpr (std::is_same<R, double>::value) return hy::launch_cr3bp_kernel_p22(P, li, s);
+        if constexpr (std::is_same<R, double>::value) return hy::launch_cr3bp_kernel_p22(P, li, s, fx);
         return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
@@ -254,9 +254,9 @@ int choose_geometry(hy_ctx *c)
         const uint32_t RS = (pr.ws_len + 1u) / 2u * 2u + 2u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
-        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 2) {
+        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 2) {
             bestG = 16;
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), (wgx ? 384u : max_threads) / 16u) & ~1u;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), (wgx ? 384u : max_threads) / 16u) & ~1u;
             bestRS = RS;
             best_smem = true;
             best = pr;
@@ -290,10 +290,10 @@ int choose_geometry(hy_ctx *c)
         while (RS % 4u != 2u) ++RS;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 2, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
-        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb) >= 16) {
+        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 16) {
             bestG = 2;
             const uint32_t mt = (uint32_t)hy::hy_max_threads(2, true, -1, (int)c->rb);
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb), mt / 2u) & ~15u;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), mt / 2u) & ~15u;
             bestRS = RS;
             best_smem = true;
             best = pr;
@@ -313,7 +313,7 @@ int choose_geometry(hy_ctx *c)
         const uint32_t fixed = L0.total + 64;
         if (fixed > (uint32_t)smem_optin) continue;
         const uint32_t budget = (uint32_t)smem_optin - fixed;
-        uint32_t Tfit = budget / (RS * (uint32_t)c->rb);
+        uint32_t Tfit = budget / (RS * (uint32_t)c->rb + 4u);
         bool smem = Tfit >= 1 && !force_global;
         if (!smem && G != 1) continue; // the global-workspace fallback kernel exists for G = 1 only
         const uint32_t mt = (uint32_t)hy::hy_max_threads((int)G, smem, 0); // 512 for the small-group interpreter variants
@@ -487,7 +487,6 @@ template <typename R> hy::RecDev<R> rec_dev(const hy_cout *r, int on, int append
     d.head = r->d_head;
     d.tail = r->d_tail;
     d.count = r->d_count;
-    d.nchunks = r->d_nch;
     d.t0_hi = (R *)r->d_t0hi;
     d.t0_lo = (R *)r->d_t0lo;
     d.rec_len = r->rec_len;
@@ -666,11 +665,13 @@ int ensure_tmp(hy_ctx *c, size_t in_bytes, size_t out_bytes)
 int launch_once(hy_ctx *c, const RunArgs &a)
 {
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+    // the plain build serves an uninterrupted propagate / step; anything else needs the FX build
+    const bool fx = a.rec_on || a.use_active || a.resume || a.pause_on_nt || a.launch_steps || c->n_red;
     cudaError_t e;
     if (c->fp_bits == 64)
-        e = launch<double>(make_params<double>(c, a), c->li, c->stream);
+        e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx);
     else
-        e = launch<float>(make_params<float>(c, a), c->li, c->stream);
+        e = launch<float>(make_params<float>(c, a), c->li, c->stream, fx);
     if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
     ++c->last_launches;
     return 0;

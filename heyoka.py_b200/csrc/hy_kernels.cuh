@@ -97,7 +97,6 @@ template <typename R> struct RecDev {
     unsigned int *next;     // bump counter
     uint32_t *head, *tail;  // [B] first / last chunk of the lane
     uint32_t *count;        // [B] recorded steps
-    uint32_t *nchunks;      // [B] chunks owned by the lane (>= ceil(count / HY_REC_CH))
     R *t0_hi, *t0_lo;       // [B] time at which the lane's record starts
     uint32_t rec_len, chunk_len;
     int on, append;
@@ -769,7 +768,7 @@ template <typename R> __device__ __forceinline__ R time_sub(R ahi, R alo, R bhi,
 // Shared-memory carve-up (dynamic smem):
 //   [ops | terms | imm | phase_slot | ev_ref | rk | ws]
 struct SmemLayout {
-    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_srow, off_ssp, off_rk, off_ws, total;
+    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_srow, off_ssp, off_ns0, off_rk, off_ws, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -795,6 +794,8 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     o += d.n_state * 4u;
     L.off_ssp = o;
     o += d.n_state * 4u;
+    L.off_ns0 = o;
+    o += T * 4u; // step count of every resident trajectory at the start of the launch
     o = align_up(o, 8);
     L.off_rk = o;
     o += (d.order + 2) * real_bytes;
@@ -824,7 +825,11 @@ __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB, int r
 // between the warpgroups at the phase boundaries of the step.
 // PM: the order the register-resident N-body jets are unrolled to (NBR_PMAX, or NBR_LMAX for the
 // high-accuracy 6-body build).
-template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false, int PM = NBR_PMAX>
+// FX: extended features - active-lane mask, resumed launches, per-launch step budget / pause on
+// non-terminal events, the continuous-output recorder, the device-side angle reducer, events on
+// the register-resident kernels.  The plain build (FX = false) of the register-resident kernels
+// is what an uninterrupted propagate_for/until/grid or step() runs: it carries none of that code.
+template <typename R, int G, bool SMEM, int NB = 0, bool WGX = false, int PM = NBR_PMAX, bool FX = (NB == 0)>
 __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)sizeof(R)), 1) propagate_kernel(const KParams<R> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -837,6 +842,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     uint32_t *s_ev = reinterpret_cast<uint32_t *>(smem_raw + L.off_ev);
     uint32_t *s_srow = reinterpret_cast<uint32_t *>(smem_raw + L.off_srow);
     int32_t *s_ssp = reinterpret_cast<int32_t *>(smem_raw + L.off_ssp);
+    uint32_t *s_ns0 = reinterpret_cast<uint32_t *>(smem_raw + L.off_ns0);
     R *s_rk = reinterpret_cast<R *>(smem_raw + L.off_rk);
     const uint32_t RS = P.TS; // workspace stride between trajectories (odd)
 
@@ -940,10 +946,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     R hi = 0, lo = 0, mdt = 0, tf_hi = 0, tf_lo = 0;
     uint32_t gi = 0; // next grid point to emit (MODE_GRID)
     uint32_t cc = 0; // recorded continuous-output steps
-    uint32_t rtail = HY_REC_NONE; // recorder: id of the lane's last chunk
-    uint32_t rnch = 0;            // recorder: chunks the lane owns
-    R *rchunk = nullptr;          // recorder: its address
-    unsigned long long ls = 0;    // steps taken in this launch
+    // (recorder state other than the step count `cc` is NOT kept in registers across the jets: the id of
+    //  the lane's last chunk is re-read from P.rec.tail once per recorded step; the per-launch step
+    //  budget is checked against the step count at fetch time, kept in shared memory)
     long long oc = HY_OUTCOME_TIME_LIMIT;
     R mn = r_inf<R>(), mx = 0, h = 0;
     unsigned long long ns = 0;
@@ -959,7 +964,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // ---- fetch the next trajectory for this group ----
             if (sub == 0) traj = (WGX && wg >= P.wgx_wgs) ? P.B : atomicAdd(P.counter, 1u);
             if (G > 1) traj = __shfl_sync(gmask, traj, 0, G);
-            if (traj < P.B && (!P.active || P.active[traj])) {
+            if (traj < P.B && (!FX || !P.active || P.active[traj])) {
                 have = true;
                 for (uint32_t i = sub; i < n; i += G) {
                     const R x0 = P.state[(size_t)i * P.B + traj];
@@ -979,10 +984,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 } else if (P.mode == MODE_GRID) {
                     tf_hi = P.grid[(size_t)(P.grid_k - 1) * P.B + traj];
                 }
-                gi = P.resume ? P.gidx[traj] : 0u;
+                gi = (FX && P.resume) ? P.gidx[traj] : 0u;
                 cc = 0;
-                ls = 0;
-                if (P.mode == MODE_GRID && !P.resume) {
+                if (P.mode == MODE_GRID && !(FX && P.resume)) {
                     // Grid points at (or before) the starting time take the current state.
                     const R dir = tf_hi - hi;
                     while (gi < P.grid_k) {
@@ -994,19 +998,14 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         ++gi;
                     }
                 }
-                rtail = HY_REC_NONE;
-                rchunk = nullptr;
-                rnch = 0;
-                if (P.rec.on) {
+                if ((FX && P.rec.on)) {
                     if (P.rec.append) {
                         cc = P.rec.count[traj];
-                        rnch = P.rec.nchunks[traj];
-                        rtail = P.rec.tail[traj];
-                        if (rtail != HY_REC_NONE) rchunk = P.rec.chunk(rtail);
                     } else if (sub == 0) {
                         P.rec.t0_hi[traj] = hi;
                         P.rec.t0_lo[traj] = lo;
                         P.rec.head[traj] = HY_REC_NONE;
+                        P.rec.tail[traj] = HY_REC_NONE;
                     }
                 }
                 if (P.mode != MODE_STEP) mdt = r_abs(mdt);
@@ -1015,12 +1014,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 mx = 0;
                 h = 0;
                 ns = 0;
-                if (P.resume) {
+                if ((FX && P.resume)) {
                     mn = P.min_h[traj];
                     mx = P.max_h[traj];
                     ns = P.n_steps[traj];
                     h = P.last_h[traj];
                 }
+                if ((FX && P.launch_steps) && sub == 0) s_ns0[slot] = (uint32_t)ns; // step count at the start of the launch
                 if (G > 1) __syncwarp(gmask);
             }
         }
@@ -1051,26 +1051,25 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         // ---- recorder: the step needs a slot; take a new chunk from the pool when the lane's
         // chunks are full.  Pool exhausted: the lane stops (PAUSED) BEFORE the step; the host adds
         // a segment and resumes it.
-        if (P.rec.on && have && !fin && cc / HY_REC_CH >= rnch) {
+        if ((FX && P.rec.on) && have && !fin && (cc % HY_REC_CH) == 0u) {
+            // (a chunk is taken exactly when the step that fills its first slot is about to run, so
+            //  "cc is a multiple of the chunk size" == "the lane's chunks are full")
             uint32_t cid = 0;
             if (sub == 0) cid = atomicAdd(P.rec.next, 1u);
             if (G > 1) cid = __shfl_sync(gmask, cid, 0, G);
             if (cid >= P.rec.cap_chunks) {
                 oc = HY_OUTCOME_PAUSED_POOL;
                 fin = true;
-            } else {
-                R *nc = P.rec.chunk(cid);
-                if (sub == 0) {
-                    *reinterpret_cast<uint32_t *>(nc) = HY_REC_NONE;
-                    if (rtail == HY_REC_NONE)
-                        P.rec.head[traj] = cid;
-                    else
-                        *reinterpret_cast<uint32_t *>(rchunk) = cid;
-                }
-                rtail = cid;
-                rchunk = nc;
-                ++rnch;
+            } else if (sub == 0) {
+                *reinterpret_cast<uint32_t *>(P.rec.chunk(cid)) = HY_REC_NONE;
+                const uint32_t rtail = P.rec.tail[traj];
+                if (rtail == HY_REC_NONE)
+                    P.rec.head[traj] = cid;
+                else
+                    *reinterpret_cast<uint32_t *>(P.rec.chunk(rtail)) = cid;
+                P.rec.tail[traj] = cid;
             }
+            if (G > 1) __syncwarp(gmask); // (the group reads P.rec.tail below)
         }
         const bool stepping = have && !fin;
 
@@ -1251,14 +1250,14 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             }
 
             // ---- optional tc write, then the state update ----
-            if (stepping && (P.write_tc || P.rec.on || P.mode == MODE_GRID)) {
+            if (stepping && (P.write_tc || (FX && P.rec.on) || P.mode == MODE_GRID)) {
                 if (P.write_tc && P.tc) {
                     for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
                     if (G > 1) __syncwarp(gmask);
                 }
-                if (P.rec.on) {
+                if ((FX && P.rec.on)) {
                     // step record: [n][p+1] coefficients (the end time follows after the time update)
-                    R *dstc = rchunk + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
+                    R *dstc = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
                 }
                 if (P.mode == MODE_GRID) {
@@ -1369,7 +1368,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // ---- angle reduction (the reference's callback.angle_reducer, expose_callbacks.cpp:67-72,
             // as a device-side post-step op): x <- x - 2 pi floor(x / (2 pi)) for the selected variables.
             // Runs in the propagate modes only (step callbacks are not part of step()).
-            if (P.n_red && P.mode != MODE_STEP) {
+            if (FX && P.n_red && P.mode != MODE_STEP) {
                 if constexpr (NB != 0) {
                     __syncwarp();
                 } else {
@@ -1395,16 +1394,15 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 time_add(hi, lo, h);
                 ++ns;
                 if (!finite) so = HY_OUTCOME_ERR_NF_STATE;
-                if (P.rec.on) {
+                if ((FX && P.rec.on)) {
                     if (sub == 0) {
                         const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
-                        R *dstt = rchunk + 2u + (cc % HY_REC_CH) * P.rec.rec_len + n * P1;
+                        R *dstt = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len + n * P1;
                         dstt[0] = fin_ ? tf_hi : hi;
                         dstt[1] = fin_ ? tf_lo : lo;
                     }
                     ++cc;
                 }
-                ++ls;
 
                 // ---- does the trajectory end here? ----
                 if (P.mode == MODE_STEP || so == HY_OUTCOME_ERR_NF_STATE || term_ev >= 0) {
@@ -1425,7 +1423,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     } else if (P.max_steps && ns >= P.max_steps) {
                         oc = HY_OUTCOME_STEP_LIMIT;
                         fin = true;
-                    } else if ((P.launch_steps && ls >= P.launch_steps) || (P.pause_on_nt && nt_fired)) {
+                    } else if (((FX && P.launch_steps) && (uint32_t)ns - s_ns0[slot] >= (uint32_t)P.launch_steps) ||
+                               (FX && P.pause_on_nt && nt_fired)) {
                         // the host wants the lane back (step callback / non-terminal event callback)
                         oc = HY_OUTCOME_PAUSED;
                         fin = true;
@@ -1450,12 +1449,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 P.min_h[traj] = mn;
                 P.max_h[traj] = mx;
                 P.n_steps[traj] = ns;
-                if (P.gidx) P.gidx[traj] = gi;
-                if (P.rec.on) {
-                    P.rec.count[traj] = cc;
-                    P.rec.tail[traj] = rtail;
-                    P.rec.nchunks[traj] = rnch;
-                }
+                if (FX && P.gidx) P.gidx[traj] = gi;
+                if ((FX && P.rec.on)) P.rec.count[traj] = cc;
             }
             have = false;
             if (G > 1) __syncwarp(gmask);

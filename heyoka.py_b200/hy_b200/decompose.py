@@ -718,3 +718,107 @@ def _fuse(uv, n, sv_src, ev_u):
                 u.op = "mulsh_out"
                 u.imm = op_u.id
                 u.args = ()
+
+
+# --------------------------------------------------------------------------------------
+# Event tape: the event functions ALONE, as functions of the state jets.
+# --------------------------------------------------------------------------------------
+class EventTape:
+    """Second tape for the register-resident kernels (csrc/hy_evtape.cuh): those keep the jets
+    of the ODE's sub-expressions in registers, so event functions cannot share u-variables with
+    the ODE; they are decomposed on their own, one event at a time (no sub-expression is shared
+    between two events: event e is evaluated by lane e mod G without synchronisation).
+
+    Row references: a state variable i is ``(i * (order + 1)) | REF_JET`` as in the main tape;
+    every other row lives in the "event workspace", numbered from ``n_state * (order + 1)``.
+    """
+
+    def __init__(self):
+        self.ops = np.zeros(0, dtype=op_dtype)
+        self.terms = np.zeros(0, dtype=term_dtype)
+        self.ev_ref = np.zeros(0, dtype=np.uint32)
+        self.op_start = np.zeros(1, dtype=np.uint32)
+        self.n_rows = 0       # rows of the event workspace
+        self.n_par = 0
+        self.n_events = 0
+
+
+def decompose_event_tape(events, names, order):
+    """Lower ``events`` (expressions in the state variables ``names``) to an :class:`EventTape`,
+    or return None if they use runtime parameters (the register-resident kernels hold none)."""
+    n, P1 = len(names), order + 1
+    base0 = n * P1
+    dummy = [(E.expression(nm), E.expression(0.0)) for nm in names]
+    ops_all, terms_all, ev_ref, op_start = [], [], [], [0]
+    next_row = base0
+    for ev in events:
+        dc = decompose(dummy, order, events=[ev])
+        if dc.n_par:
+            return None
+        rowmap = {}
+
+        def remap(ref, jet=None):
+            nonlocal next_row
+            ref = int(ref)
+            if ref == REF_ONE:
+                return REF_ONE
+            b = ref & 0x7FFFFFFF
+            is_jet = bool(ref & REF_JET) if jet is None else jet
+            if b < base0:
+                return ref  # a state jet
+            if b not in rowmap:
+                rowmap[b] = next_row
+                next_row += P1 if is_jet else 1
+            return rowmap[b] | (REF_JET if is_jet else 0)
+
+        for o in dc.ops:
+            oc, fl = int(o["opcode"]), int(o["flags"])
+            if not (fl & OPF_EVENT) or (fl & OPF_SVD) or oc == OP_SVD:
+                continue
+            q = np.zeros(1, dtype=op_dtype)[0]
+            q["opcode"], q["flags"], q["n"], q["imm"] = oc, fl & (OPF_NEGA | OPF_NEGB), o["n"], o["imm"]
+            if oc in (OP_LINCOMB, OP_SUMSQ, OP_MULSH):
+                q["b"] = len(terms_all)
+                for t in dc.terms[int(o["b"]): int(o["b"]) + int(o["n"])]:
+                    if int(t["par"]) >= 0:
+                        return None
+                    terms_all.append((remap(t["src"]), -1, float(t["coef"]),
+                                      remap(t["dst"]) if oc == OP_MULSH else 0, 0))
+                if oc == OP_MULSH:
+                    q["a"] = remap(o["a"])
+                else:
+                    q["dst"] = remap(o["dst"])
+            else:
+                q["dst"] = remap(o["dst"])
+                if oc != OP_TIME:
+                    q["a"] = remap(o["a"])
+                if oc in (OP_MUL, OP_DIV, OP_ADDSUB):
+                    q["b"] = remap(o["b"])
+                if oc == OP_SINCOS:
+                    q["dst2"] = remap(o["dst2"])
+                elif oc in (OP_DIV, OP_POW, OP_SQRT, OP_LOG):
+                    q["dst2"] = remap(int(o["dst2"]) & 0x7FFFFFFF, jet=False)
+            ops_all.append(q)
+        r = int(dc.ev_ref[0])
+        if (r & 0x7FFFFFFF) < base0:
+            # an event on a bare state variable: copy the jet into the workspace so that the root
+            # finder sees a unit-stride polynomial like any other
+            q = np.zeros(1, dtype=op_dtype)[0]
+            q["opcode"], q["n"], q["b"] = OP_LINCOMB, 1, len(terms_all)
+            terms_all.append((r, -1, 1.0, 0, 0))
+            dst = next_row | REF_JET
+            next_row += P1
+            q["dst"] = dst
+            ops_all.append(q)
+            ev_ref.append(dst)
+        else:
+            ev_ref.append(remap(r, jet=True))
+        op_start.append(len(ops_all))
+    et = EventTape()
+    et.ops = np.array(ops_all, dtype=op_dtype) if ops_all else np.zeros(0, dtype=op_dtype)
+    et.terms = np.array(terms_all, dtype=term_dtype) if terms_all else np.zeros(0, dtype=term_dtype)
+    et.ev_ref = np.array(ev_ref, dtype=np.uint32)
+    et.op_start = np.array(op_start, dtype=np.uint32)
+    et.n_rows = next_row - base0
+    et.n_events = len(events)
+    return et
