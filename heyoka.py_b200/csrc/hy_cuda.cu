@@ -15,6 +15,7 @@
 #include "hy_nbody_match.hpp"
 #include "hy_cr3bp_match.hpp"
 #include "hy_nb_launch.hpp"
+#include "hy_evtape_host.hpp"
 
 namespace {
 
@@ -78,6 +79,19 @@ struct hy_ctx {
     uint32_t *d_phase = nullptr;
     uint32_t *d_ev = nullptr;       // remapped event jet rows (device layout)
     std::vector<uint32_t> h_ev_ref; // ABI event references
+    // events on the register-resident kernels: the ODE-only tape (for the matchers) and the event tape
+    hy_dims d_ode{};
+    std::vector<hy_op> h_ops_ode;
+    std::vector<hy_term> h_terms_ode;
+    std::vector<hy_op> h_evt_ops;
+    std::vector<hy_term> h_evt_terms;
+    std::vector<uint32_t> h_evt_ref, h_evt_start;
+    uint32_t evt_rows = 0;
+    bool have_evt = false; // the caller supplied both tapes
+    bool use_evt = false;  // ... and the ODE tape was matched: the event tape is in use
+    void *d_evt = nullptr;
+    hy::EvtDev evt_dev{};
+    std::vector<unsigned char> evt_blob;
     std::vector<int32_t> h_ev_dir;
     std::vector<double> h_ev_cd;
     uint32_t *d_srow = nullptr;
@@ -202,8 +216,8 @@ uint32_t env_u32(const char *name, uint32_t dflt)
 
 hy::ProgDims prog_dims(const hy::Program &p)
 {
-    return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases,
-                        p.ws_len,  p.par_off,  p.one_off,              p.n_spill};
+    return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases, p.ws_len,
+                        p.par_off, p.one_off,  p.n_spill,              p.evt_bytes};
 }
 
 int upload_program(hy_ctx *c);
@@ -231,9 +245,37 @@ int choose_geometry(hy_ctx *c)
     li.kernel_variant = 0;
     // Register-resident kernel for N-body tapes (hy_nbody_reg.cuh): the jets of the pair
     // interactions live in registers, the state jets + a small exchange buffer in shared memory.
+    // With events the matchers look at the ODE-only tape; the event functions then run from the
+    // event tape (hy_evtape.cuh).  Without the two extra tapes an event-carrying system stays on the
+    // interpreter (the matchers reject n_events != 0).
+    const bool evt_ok = c->have_evt && env_u32("HY_CUDA_NO_REG_EVENTS", 0) == 0;
+    const hy_dims &md = evt_ok ? c->d_ode : d;
+    const hy_op *mops = evt_ok ? c->h_ops_ode.data() : c->h_ops.data();
+    const hy_term *mterms = evt_ok ? c->h_terms_ode.data() : c->h_terms.data();
+    c->use_evt = false;
+    std::string evt_err;
+    // Append the event workspace / interval scratch to the column of a matched tape.
+    auto attach_events = [&](hy::Program &pr) -> bool {
+        if (!evt_ok) return true;
+        hy::EvtProgram ep;
+        evt_err = hy::build_event_program(d.n_state, d.order, c->h_evt_ops, c->h_evt_terms, c->h_evt_ref,
+                                          c->h_evt_start, c->evt_rows, ep);
+        if (!evt_err.empty()) return false;
+        const uint32_t ews_off = (pr.ws_len + 1u) & ~1u;
+        const uint32_t eiv_off = ews_off + ((c->evt_rows + 1u) & ~1u);
+        pr.ws_len = eiv_off + 2u * (d.n_state + ep.n_slots);
+        pr.par_off = pr.one_off = pr.ws_len;
+        pr.ev_ref.clear();
+        for (uint32_t off : ep.ev_off) pr.ev_ref.push_back(ews_off + off);
+        pr.evt_bytes = (uint32_t)ep.blob.size();
+        c->evt_blob = ep.blob;
+        c->evt_dev = hy::EvtDev{nullptr, ep.n_ops, ep.n_terms, ep.n_imm, d.n_events, ews_off, eiv_off, ep.n_slots,
+                                (uint32_t)ep.blob.size()};
+        return true;
+    };
     hy::NbMatch nbm;
     if (!force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
-        hy::match_nbody(d, c->h_ops.data(), c->h_terms.data(), nbm) &&
+        hy::match_nbody(md, mops, mterms, nbm) &&
         hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits)) {
         hy::Program pr;
         pr.G = 16;
@@ -250,11 +292,13 @@ int choose_geometry(hy_ctx *c)
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = nbm.n_pairs;
         pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
+        const bool ev_att = attach_events(pr) && !(wgx && evt_ok);
         // column stride: even (16-byte aligned vectors); + 2 spreads the two trajectories of a warp over the banks
         const uint32_t RS = (pr.ws_len + 1u) / 2u * 2u + 2u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
-        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 2) {
+        if (ev_att && fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 2) {
+            c->use_evt = evt_ok;
             bestG = 16;
             bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), (wgx ? 384u : max_threads) / 16u) & ~1u;
             bestRS = RS;
@@ -271,7 +315,7 @@ int choose_geometry(hy_ctx *c)
     // [order][variable] in shared memory.
     hy::CrbMatch crm;
     if (!li.kernel_variant && !force_global && !Genv && env_u32("HY_CUDA_NO_CR3BP_REG", 0) == 0 &&
-        hy::match_cr3bp(d, c->h_ops.data(), c->h_terms.data(), c->fp_bits, crm)) {
+        hy::match_cr3bp(md, mops, mterms, c->fp_bits, crm)) {
         hy::Program pr;
         pr.G = 2;
         pr.n_phases = 0;
@@ -284,13 +328,15 @@ int choose_geometry(hy_ctx *c)
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = 2;
         pr.lane_utilisation = 1.0;
+        const bool ev_att = attach_events(pr);
         // column stride = 2 * odd: the 16 lanes of a half-warp (8 trajectories x 2 lanes, three
         // elements apart) hit 16 different 64-bit banks
         uint32_t RS = pr.ws_len;
         while (RS % 4u != 2u) ++RS;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 2, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
-        if (fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 16) {
+        if (ev_att && fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 16) {
+            c->use_evt = evt_ok;
             bestG = 2;
             const uint32_t mt = (uint32_t)hy::hy_max_threads(2, true, -1, (int)c->rb);
             bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), mt / 2u) & ~15u;
@@ -392,6 +438,13 @@ int upload_program(hy_ctx *c)
     if (!li.ws_in_smem) {
         if (c->d_gws) cudaFree(c->d_gws);
         CU(cudaMalloc(&c->d_gws, (size_t)li.ctas * T * RS * c->rb));
+    }
+    if (c->d_evt) cudaFree(c->d_evt);
+    c->d_evt = nullptr;
+    if (c->use_evt) {
+        CU(cudaMalloc(&c->d_evt, c->evt_blob.size()));
+        CU(cudaMemcpy(c->d_evt, c->evt_blob.data(), c->evt_blob.size(), cudaMemcpyHostToDevice));
+        c->evt_dev.blob = c->d_evt;
     }
     return 0;
 }
@@ -595,6 +648,7 @@ template <typename R> hy::KParams<R> make_params(hy_ctx *c, const RunArgs &a)
     P.red_idx = c->d_red;
     P.n_red = c->n_red;
     P.rec = rec_dev<R>(c->rec, a.rec_on, a.rec_append);
+    P.evt = c->use_evt ? c->evt_dev : hy::EvtDev{};
     P.outcome = c->d_outcome;
     P.min_h = (R *)c->d_minh;
     P.max_h = (R *)c->d_maxh;
@@ -666,7 +720,7 @@ int launch_once(hy_ctx *c, const RunArgs &a)
 {
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
     // the plain build serves an uninterrupted propagate / step; anything else needs the FX build
-    const bool fx = a.rec_on || a.use_active || a.resume || a.pause_on_nt || a.launch_steps || c->n_red;
+    const bool fx = a.rec_on || a.use_active || a.resume || a.pause_on_nt || a.launch_steps || c->n_red || c->use_evt;
     cudaError_t e;
     if (c->fp_bits == 64)
         e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx);
@@ -792,17 +846,22 @@ int hy_device_count(int *count)
     return 0;
 }
 
-int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const hy_op *ops, const hy_term *terms,
-              const uint32_t *level_start, const uint32_t *ev_ref, const int32_t *ev_dir, const double *ev_cooldown,
-              double tol, int high_accuracy, uint32_t batch)
+int hy_create2(hy_ctx **out, int device, int fp_bits, const hy_tape *full, const hy_tape *ode, const hy_event_tape *evt,
+               const int32_t *ev_dir, const double *ev_cooldown, double tol, int high_accuracy, uint32_t batch)
 {
-    if (!out || !dims || !ops || !level_start) return fail("hy_create: null argument");
+    if (!out || !full || !full->dims || !full->ops || !full->level_start) return fail("hy_create: null argument");
+    const hy_dims *dims = full->dims;
+    const uint32_t *ev_ref = full->ev_ref;
     if (fp_bits != 32 && fp_bits != 64) return fail("hy_create: fp_bits must be 32 or 64");
     if (dims->order < 2 || dims->order > 62) return fail("hy_create: unsupported Taylor order");
     if (dims->n_events && dims->order + 1 > (uint32_t)hy::EV_MAXP1)
         return fail("hy_create: event detection supports Taylor orders up to 31");
     if (dims->n_tevents > dims->n_events) return fail("hy_create: n_tevents > n_events");
     if (dims->n_events && (!ev_ref || !ev_dir)) return fail("hy_create: null event arrays");
+    if ((ode != nullptr) != (evt != nullptr)) return fail("hy_create2: the ODE tape and the event tape come together");
+    if (ode && (!ode->dims || !ode->ops || ode->dims->n_events != 0 || ode->dims->n_state != dims->n_state ||
+                ode->dims->order != dims->order || evt->n_events != dims->n_events || !evt->ev_ref || !evt->op_start))
+        return fail("hy_create2: inconsistent ODE / event tapes");
     int ndev = 0;
     if (hy_device_count(&ndev)) return 1;
     if (ndev == 0) return fail("hy_create: no CUDA device is visible (libhy_cuda has no CPU fallback)");
@@ -819,19 +878,39 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
     *out = c;
     const hy_dims &d = c->d;
     if (common_init(c)) return 1;
-    c->h_ops.assign(ops, ops + d.n_ops);
-    if (d.n_terms) c->h_terms.assign(terms, terms + d.n_terms);
-    c->h_levels.assign(level_start, level_start + d.n_levels + 1);
+    c->h_ops.assign(full->ops, full->ops + d.n_ops);
+    if (d.n_terms) c->h_terms.assign(full->terms, full->terms + d.n_terms);
+    c->h_levels.assign(full->level_start, full->level_start + d.n_levels + 1);
     if (d.n_events) {
         c->h_ev_ref.assign(ev_ref, ev_ref + d.n_events);
         c->h_ev_dir.assign(ev_dir, ev_dir + d.n_events);
         c->h_ev_cd.assign(std::max<size_t>(1, d.n_tevents), -1.0);
         for (size_t i = 0; i < d.n_tevents; ++i) c->h_ev_cd[i] = ev_cooldown ? ev_cooldown[i] : -1.0;
     }
+    if (ode && d.n_events) {
+        c->d_ode = *ode->dims;
+        c->h_ops_ode.assign(ode->ops, ode->ops + c->d_ode.n_ops);
+        if (c->d_ode.n_terms) c->h_terms_ode.assign(ode->terms, ode->terms + c->d_ode.n_terms);
+        if (evt->n_ops) c->h_evt_ops.assign(evt->ops, evt->ops + evt->n_ops);
+        if (evt->n_terms) c->h_evt_terms.assign(evt->terms, evt->terms + evt->n_terms);
+        c->h_evt_ref.assign(evt->ev_ref, evt->ev_ref + evt->n_events);
+        c->h_evt_start.assign(evt->op_start, evt->op_start + evt->n_events + 1);
+        c->evt_rows = evt->n_rows;
+        c->have_evt = true;
+    }
     if (alloc_lanes(c)) return 1;
     if (d.n_events && hy_reset_cooldowns(c, -1)) return 1;
     if (choose_geometry(c)) return 1;
     return 0;
+}
+
+int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const hy_op *ops, const hy_term *terms,
+              const uint32_t *level_start, const uint32_t *ev_ref, const int32_t *ev_dir, const double *ev_cooldown,
+              double tol, int high_accuracy, uint32_t batch)
+{
+    if (!dims) return fail("hy_create: null argument");
+    hy_tape full{dims, ops, terms, level_start, ev_ref};
+    return hy_create2(out, device, fp_bits, &full, nullptr, nullptr, ev_dir, ev_cooldown, tol, high_accuracy, batch);
 }
 
 /* Deep copy of a context onto `device` (reference: copy.deepcopy(ta) per ensemble iteration,
@@ -865,6 +944,18 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
     c->prog = src->prog;
     c->li = src->li;
     c->TS = src->TS;
+    c->d_ode = src->d_ode;
+    c->h_ops_ode = src->h_ops_ode;
+    c->h_terms_ode = src->h_terms_ode;
+    c->h_evt_ops = src->h_evt_ops;
+    c->h_evt_terms = src->h_evt_terms;
+    c->h_evt_ref = src->h_evt_ref;
+    c->h_evt_start = src->h_evt_start;
+    c->evt_rows = src->evt_rows;
+    c->have_evt = src->have_evt;
+    c->use_evt = src->use_evt;
+    c->evt_dev = src->evt_dev;
+    c->evt_blob = src->evt_blob;
     if (common_init(c)) return 1;
     if (alloc_lanes(c)) return 1;
     {
@@ -915,7 +1006,7 @@ int hy_destroy(hy_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet, c->d_state, c->d_pars,
                     c->d_thi /* block of the per-lane vectors */, c->d_tc, c->d_gws, c->d_tmp_in, c->d_tmp_out,
-                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red};
+                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     rec_free(c->rec);

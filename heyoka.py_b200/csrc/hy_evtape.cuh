@@ -142,7 +142,7 @@ static __device__ __noinline__ R evt_wconv(const R *__restrict__ pa, int sa, con
 }
 
 // math wrappers (defined in hy_kernels.cuh)
-template <typename R> __device__ R pow0(R x, double alpha);
+template <typename R> __device__ __noinline__ R pow0(R x, double alpha);
 
 // One op of the event tape at order k (same recurrences as exec_op in hy_kernels.cuh).
 template <typename R, int XS>
@@ -273,6 +273,53 @@ __device__ __forceinline__ void evt_exec(const EOp &o, const ETerm *__restrict__
     } break;
     default: break;
     }
+}
+
+// One op at EVERY order 0..p (pass A of the event evaluation).  Linear combinations - the common
+// case: shifted coordinates such as x - mu - keep their operand pointers in registers and run one
+// tight loop over the orders; everything else goes through evt_exec order by order.
+template <typename R, int XS>
+__device__ __forceinline__ void evt_exec_all(const EOp &o, const ETerm *__restrict__ terms, const EvtCtx<R, XS> &C,
+                                             const uint32_t p)
+{
+    if (o.opcode == HY_OP_LINCOMB && o.n <= 4 && (o.dst & ER_KIND) == ER_JET) {
+        const R *src[4];
+        int st[4];
+        R cf[4], c0 = 0; // c0: the constant (terms on the unit jet) - enters at order 0 only
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            src[i] = C.rk + 1; // (a finite value: unused slots contribute 0 * 1)
+            st[i] = 0;
+            cf[i] = 0;
+        }
+        bool ok = true;
+        for (uint32_t i = 0; i < o.n; ++i) {
+            const ETerm t = terms[o.b + i];
+            if ((t.src & ER_KIND) == ER_ONE) {
+                // exec_op adds the terms in order with an FMA; a constant in any position other than the
+                // last would change the rounding of the order-0 sum: fall back to the generic path then
+                if (i + 1 != o.n) ok = false;
+                c0 = (R)t.coef;
+            } else {
+                src[i] = C.base(t.src, st[i]);
+                cf[i] = (R)t.coef;
+                if (st[i] == 0) ok = false; // (a single-row operand: generic path)
+            }
+        }
+        if (ok) {
+            R *dst = C.ews + (o.dst & 0x3fff);
+#pragma unroll 1
+            for (uint32_t k = 0; k <= p; ++k) {
+                R acc = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc = evt_fma(cf[i], src[i][(int)k * st[i]], acc);
+                dst[k] = k == 0 ? evt_fma(c0, (R)1, acc) : acc;
+            }
+            return;
+        }
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k <= p; ++k) evt_exec<R, XS>(o, terms, C, k);
 }
 
 // ---- interval arithmetic (round-to-nearest + widening: every result is pushed outwards by 4 ulps

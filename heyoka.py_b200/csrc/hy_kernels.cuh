@@ -25,6 +25,7 @@
 #include "../../include/hy_cuda.h"
 #include "hy_schedule.hpp"
 #include "hy_events.cuh"
+#include "hy_evtape.cuh"
 #include "hy_nbody_reg.cuh"
 #include "hy_cr3bp_reg.cuh"
 
@@ -74,6 +75,7 @@ enum { MODE_UNTIL = 0, MODE_FOR = 1, MODE_STEP = 2, MODE_GRID = 3 };
 struct ProgDims {
     uint32_t n_slots, n_tslots, n_imm, n_phases;
     uint32_t ws_len, par_off, one_off, n_spill; // device workspace layout (hy_schedule.hpp)
+    uint32_t evt_bytes;                          // event tape staged in shared memory (hy_evtape.cuh), or 0
 };
 
 // Internal outcome: the lane stopped inside a launch and can be resumed by the next one (per-launch
@@ -128,6 +130,7 @@ template <typename R> struct KParams {
     const uint32_t *red_idx;     // [n_red] state variables reduced to [0, 2 pi) after every step
     uint32_t n_red;
     RecDev<R> rec;               // continuous-output recorder (rec.on)
+    EvtDev evt;                  // event tape of the register-resident kernels (evt.n_events)
     long long *outcome;
     R *min_h, *max_h;
     unsigned long long *n_steps;
@@ -768,7 +771,7 @@ template <typename R> __device__ __forceinline__ R time_sub(R ahi, R alo, R bhi,
 // Shared-memory carve-up (dynamic smem):
 //   [ops | terms | imm | phase_slot | ev_ref | rk | ws]
 struct SmemLayout {
-    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_srow, off_ssp, off_ns0, off_rk, off_ws, total;
+    uint32_t off_ops, off_terms, off_imm, off_phase, off_ev, off_srow, off_ssp, off_ns0, off_rk, off_evt, off_ws, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -799,6 +802,9 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
     o = align_up(o, 8);
     L.off_rk = o;
     o += (d.order + 2) * real_bytes;
+    o = align_up(o, 16);
+    L.off_evt = o;
+    o += pd.evt_bytes;
     o = align_up(o, 16);
     L.off_ws = o;
     if (ws_in_smem) o += T * RS * real_bytes;
@@ -860,8 +866,21 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         }
         for (uint32_t i = threadIdx.x; i < d.order + 2; i += blockDim.x)
             s_rk[i] = i == 0 ? (R)0 : (R)(1.0 / (double)i);
+        if constexpr (FX && NB != 0) {
+            const uint32_t *es = reinterpret_cast<const uint32_t *>(P.evt.blob);
+            uint32_t *ed = reinterpret_cast<uint32_t *>(smem_raw + L.off_evt);
+            for (uint32_t i = threadIdx.x; i < P.pd.evt_bytes / 4; i += blockDim.x) ed[i] = es[i];
+        }
     }
     __syncthreads();
+    // event tape of the register-resident kernels (FX builds): ops | terms | imm | op ranges | event slots
+    const EOp *s_eops = reinterpret_cast<const EOp *>(smem_raw + L.off_evt);
+    const ETerm *s_eterms = reinterpret_cast<const ETerm *>(s_eops + P.evt.n_ops);
+    const double *s_eimm = reinterpret_cast<const double *>(s_eterms + P.evt.n_terms);
+    const uint32_t *s_estart = reinterpret_cast<const uint32_t *>(s_eimm + P.evt.n_imm);
+    const uint32_t *s_eslot = s_estart + P.evt.n_events + 1;
+    const uint32_t *s_eused = s_eslot + P.evt.n_events;
+    const bool reg_events = FX && NB != 0 && P.evt.n_events != 0;
 
     const uint32_t p = d.order, P1 = p + 1, n = d.n_state;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1141,7 +1160,35 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     }
                 }
             }
-
+            // ---- event functions on the register-resident kernels (hy_evtape.cuh): lane e mod G
+            // evaluates event e from the state jets.  Linear ops at every order, products / squares
+            // whose history nobody reads at orders 0, p-1, p (all the step-size norms need).
+            if constexpr (FX && NB != 0) {
+                if (reg_events) {
+                    const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+                    for (uint32_t e = sub; e < P.evt.n_events; e += G) {
+                        const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
+                        // pass A: the ops that are needed at every order, op by op (they never read a
+                        // three-order op, and an op's order k needs its operands at orders <= k only)
+#pragma unroll 1
+                        for (uint32_t i = o0; i < o1; ++i) {
+                            const EOp o = s_eops[i];
+                            if (o.flags & EOF_ALL) evt_exec_all<R, (int)XS>(o, s_eterms, ec, p);
+                        }
+                        // pass B: the rest at orders 0, p-1, p, order by order
+#pragma unroll 1
+                        for (uint32_t q = 0; q < 3; ++q) {
+                            const uint32_t k = q == 0 ? 0u : p - 2u + q;
+#pragma unroll 1
+                            for (uint32_t i = o0; i < o1; ++i) {
+                                const EOp o = s_eops[i];
+                                if (!(o.flags & EOF_ALL)) evt_exec<R, (int)XS>(o, s_eterms, ec, k);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
         }
 
         // ---- the rest of the step ----
@@ -1170,6 +1217,15 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     n0 = nan_max(nan_max(nan_max(n0, r_abs(a.x)), r_abs(a.y)), r_abs(a.z));
                     n1 = nan_max(nan_max(nan_max(n1, r_abs(b.x)), r_abs(b.y)), r_abs(b.z));
                     n2 = nan_max(nan_max(nan_max(n2, r_abs(c.x)), r_abs(c.y)), r_abs(c.z));
+                }
+                if constexpr (FX) {
+                    if (reg_events) // the event functions take part in the norms
+                        for (uint32_t e = sub; e < P.evt.n_events; e += G) {
+                            const R *x = &w[s_ev[e]];
+                            n0 = nan_max(n0, r_abs(x[0]));
+                            n1 = nan_max(n1, r_abs(x[p - 1]));
+                            n2 = nan_max(n2, r_abs(x[p]));
+                        }
                 }
             } else {
                 for (uint32_t i = sub; i < n + d.n_events; i += G) {
@@ -1247,6 +1303,60 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     so = -(long long)term_ev - 1;
                 }
                 if (sub == 0 && d.n_tevents) advance_cooldowns<R>(traj, d.n_tevents, h, P.ev);
+            }
+
+            if constexpr (FX && NB != 0) {
+                if (reg_events) {
+                    // ---- can an event happen in [0, h] at all?  Interval Horner enclosures of the state
+                    // polynomials over the step, pushed through the event tape in interval arithmetic.
+                    R *iv = w + P.evt.eiv_off;
+                    for (uint32_t i = sub; i < n; i += G) {
+                        if (!s_eused[i]) continue; // (no event reads this state variable)
+                        const Ival<R> v = iv_horner<R>(w + s_srow[i], (int)XS, (int)p, h);
+                        iv[2 * i] = v.lo;
+                        iv[2 * i + 1] = v.hi;
+                    }
+                    __syncwarp();
+                    bool maybe = false;
+                    for (uint32_t e = sub; e < P.evt.n_events; e += G) {
+                        const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
+#pragma unroll 1
+                        for (uint32_t i = o0; i < o1; ++i) evt_interval<R>(s_eops[i], s_eterms, iv, s_eimm, hi, h);
+                        const R glo = iv[2 * s_eslot[e]], ghi = iv[2 * s_eslot[e] + 1];
+                        if (!(glo > (R)0 || ghi < (R)0)) maybe = true; // 0 inside the enclosure (or NaN)
+                    }
+                    const unsigned mb = __ballot_sync(TM_FULL, maybe && stepping);
+                    const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+                    if ((mb >> (lane & ~(uint32_t)(G - 1))) & gbits) {
+                        // ---- rare: the remaining orders of the event jets, then the root finder ----
+                        const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+                        for (uint32_t e = sub; e < P.evt.n_events; e += G) {
+                            const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
+#pragma unroll 1
+                            for (uint32_t k = 1; k + 1 < p; ++k)
+#pragma unroll 1
+                                for (uint32_t i = o0; i < o1; ++i) {
+                                    const EOp o = s_eops[i];
+                                    if (!(o.flags & EOF_ALL)) evt_exec<R, (int)XS>(o, s_eterms, ec, k);
+                                }
+                        }
+                        __syncwarp(gmask);
+                        R h_eff = h;
+                        if (sub == 0)
+                            detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
+                                             term_ev, nt_fired);
+                        h_eff = __shfl_sync(gmask, h_eff, 0, G);
+                        term_ev = __shfl_sync(gmask, term_ev, 0, G);
+                        nt_fired = __shfl_sync(gmask, nt_fired, 0, G);
+                        if (term_ev >= 0) {
+                            h = h_eff;
+                            hn = h_eff;
+                            so = -(long long)term_ev - 1;
+                        }
+                    }
+                    if (stepping && sub == 0 && d.n_tevents) advance_cooldowns<R>(traj, d.n_tevents, h, P.ev);
+                    __syncwarp();
+                }
             }
 
             // ---- optional tc write, then the state update ----

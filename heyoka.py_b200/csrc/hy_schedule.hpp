@@ -80,6 +80,7 @@ struct Program {
     // device workspace layout (per trajectory column)
     uint32_t ws_len = 0, par_off = 0, one_off = 0;
     uint32_t n_spill = 0;              // state jets kept in the global scratch
+    uint32_t evt_bytes = 0;            // event tape of the register-resident kernels (hy_evtape.cuh)
     std::vector<uint32_t> state_row;   // [n_state] device row: jet base (resident) or ping-pong base (spilled)
     std::vector<int32_t> state_spill;  // [n_state] spill slot or -1
     std::vector<uint32_t> ev_ref;      // [n_events] remapped event jet references

@@ -65,6 +65,26 @@ class event_rec_t(C.Structure):
     ]
 
 
+class tape_t(C.Structure):
+    """hy_tape (include/hy_cuda.h)."""
+
+    _fields_ = [("dims", C.c_void_p), ("ops", C.c_void_p), ("terms", C.c_void_p),
+                ("level_start", C.c_void_p), ("ev_ref", C.c_void_p)]
+
+
+class event_tape_t(C.Structure):
+    """hy_event_tape (include/hy_cuda.h)."""
+
+    _fields_ = [("n_ops", C.c_uint32), ("n_terms", C.c_uint32), ("n_rows", C.c_uint32),
+                ("n_events", C.c_uint32), ("ops", C.c_void_p), ("terms", C.c_void_p),
+                ("ev_ref", C.c_void_p), ("op_start", C.c_void_p)]
+
+
+def _dims_of(dc, n_tevents, n_events=None):
+    return dims_t(dc.n_state, dc.n_par, dc.order, dc.n_rows, len(dc.ops), len(dc.terms),
+                  len(dc.level_start) - 1, dc.n_events if n_events is None else n_events, n_tevents)
+
+
 class prop_args_t(C.Structure):
     """hy_prop_args (include/hy_cuda.h)."""
 
@@ -96,6 +116,7 @@ SYMBOLS = [
     "hy_last_error",
     "hy_device_count",
     "hy_create",
+    "hy_create2",
     "hy_destroy",
     "hy_clone",
     "hy_get_device",
@@ -202,7 +223,7 @@ class Context:
     """Owner of one hy_ctx."""
 
     def __init__(self, dc, fp_bits, batch, tol, high_accuracy, device=0, n_tevents=0,
-                 ev_dir=None, ev_cooldown=None, _handle=None):
+                 ev_dir=None, ev_cooldown=None, _handle=None, dc_ode=None, evt=None):
         import threading
 
         self._ctx = C.c_void_p()
@@ -228,6 +249,20 @@ class Context:
         self._keep = (dc.ops, dc.terms, dc.level_start, dc.ev_ref)
         evd = None if ev_dir is None else np.ascontiguousarray(ev_dir, dtype=np.int32)
         evc = None if ev_cooldown is None else np.ascontiguousarray(ev_cooldown, dtype=np.float64)
+        if dc_ode is not None and evt is not None and dc.n_events:
+            # event-carrying system: hand over the ODE-only tape and the event tape as well, so that
+            # a matched ODE runs on its register-resident kernel (hy_create2)
+            self._keep += (dc_ode.ops, dc_ode.terms, dc_ode.level_start, evt.ops, evt.terms, evt.ev_ref,
+                           evt.op_start)
+            d_ode = _dims_of(dc_ode, 0, 0)
+            full = tape_t(C.addressof(self.dims), _vp(dc.ops), _vp(dc.terms), _vp(dc.level_start), _vp(dc.ev_ref))
+            ode = tape_t(C.addressof(d_ode), _vp(dc_ode.ops), _vp(dc_ode.terms), _vp(dc_ode.level_start), None)
+            et = event_tape_t(len(evt.ops), len(evt.terms), evt.n_rows, evt.n_events, _vp(evt.ops),
+                              _vp(evt.terms), _vp(evt.ev_ref), _vp(evt.op_start))
+            check(lib().hy_create2(C.byref(self._ctx), C.c_int(device), C.c_int(fp_bits), C.byref(full),
+                                   C.byref(ode), C.byref(et), ptr(evd), ptr(evc), C.c_double(tol),
+                                   C.c_int(int(high_accuracy)), C.c_uint32(batch)))
+            return
         check(
             lib().hy_create(
                 C.byref(self._ctx),

@@ -146,6 +146,12 @@ class taylor_adaptive_batch_impl:
         self._nt_events = nt_events
         ev_exprs = [e.expression for e in t_events] + [e.expression for e in nt_events]
         self._dc = _dec.decompose(self._sys, self._order, events=ev_exprs)
+        # event-carrying systems: the ODE alone and the events alone, for the register-resident kernels
+        self._dc_ode = self._evt = None
+        if ev_exprs:
+            self._evt = _dec.decompose_event_tape(ev_exprs, [l.name for l, _ in self._sys], self._order)
+            if self._evt is not None:
+                self._dc_ode = _dec.decompose(self._sys, self._order)
         m = self._dc.n_par
 
         if pars is not None:
@@ -240,7 +246,7 @@ class taylor_adaptive_batch_impl:
         if devs is not None and len(devs) > 1:
             ctx = _devctx.MultiContext(self._dc, fp_bits, B, self._tol, self._high_accuracy, devs,
                                        n_tevents=len(self._t_events), ev_dir=ev_dir or None,
-                                       ev_cooldown=ev_cd or None)
+                                       ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt)
         else:
             dev = devs[0] if devs else self._device
             ctx = _devctx.POOL.acquire(self._ctx_key(dev))
@@ -250,7 +256,7 @@ class taylor_adaptive_batch_impl:
             if ctx is None:
                 ctx = _cabi.Context(self._dc, fp_bits, B, self._tol, self._high_accuracy, device=dev,
                                     n_tevents=len(self._t_events), ev_dir=ev_dir or None,
-                                    ev_cooldown=ev_cd or None)
+                                    ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt)
             else:
                 # a recycled / cloned context carries another integrator's device-only data
                 if self._t_events:
@@ -860,7 +866,7 @@ class taylor_adaptive_batch_impl:
         cls = type(self)
         ta = cls.__new__(cls)
         for k in ("_vsys", "_sys", "_tol", "_order", "_high_accuracy", "_compact_mode",
-                  "_parallel_mode", "_llvm_kw", "_device", "_dc", "_B", "_n"):
+                  "_parallel_mode", "_llvm_kw", "_device", "_dc", "_dc_ode", "_evt", "_B", "_n"):
             setattr(ta, k, getattr(self, k))
         if deep:
             ta._t_events = _copy.deepcopy(self._t_events, memo)

@@ -141,6 +141,37 @@ int hy_create(hy_ctx **out, int device, int fp_bits, const hy_dims *dims, const 
               uint32_t batch);
 int hy_destroy(hy_ctx *ctx);
 
+/* hy_create with the two extra tapes that let EVENT-carrying systems run on the
+ * register-resident kernels (those keep the jets of the ODE's sub-expressions in registers, so
+ * event functions cannot share u-variables with the ODE):
+ *  - `ode`: the tape of the ODE alone (no event functions; dims->n_events = 0) - what the
+ *    N-body / CR3BP matchers look at;
+ *  - `evt`: the event functions alone, as functions of the state jets, one event after the
+ *    other without shared sub-expressions (ops [op_start[e], op_start[e+1]) belong to event e).
+ *    Row references: state variable i = (i * (order + 1)) | HY_REF_JET as in the main tape,
+ *    everything else is numbered from n_state * (order + 1) ("event workspace", n_rows rows).
+ * `full` is the combined tape hy_create takes (used by the tape interpreter whenever the ODE
+ * tape is not matched).  `ode` and `evt` may be NULL (then this is hy_create).
+ * Reference: events are part of the integrator's construction,
+ * expose_batch_integrators.cpp:166-208 (t_events / nt_events keyword arguments). */
+typedef struct hy_tape {
+    const hy_dims *dims;
+    const hy_op *ops;
+    const hy_term *terms;
+    const uint32_t *level_start;
+    const uint32_t *ev_ref;
+} hy_tape;
+typedef struct hy_event_tape {
+    uint32_t n_ops, n_terms, n_rows, n_events;
+    const hy_op *ops;
+    const hy_term *terms;
+    const uint32_t *ev_ref;   /* [n_events] jet of every event function                 */
+    const uint32_t *op_start; /* [n_events + 1]                                         */
+} hy_event_tape;
+int hy_create2(hy_ctx **out, int device, int fp_bits, const hy_tape *full, const hy_tape *ode,
+               const hy_event_tape *evt, const int32_t *ev_dir, const double *ev_cooldown, double tol,
+               int high_accuracy, uint32_t batch);
+
 /* Deep copy of a context onto `device` (< 0: the source's device).  Replaces what
  * copy.deepcopy(ta) does once per ensemble iteration in the reference
  * (_ensemble_impl.py:47; copy_wrapper/deepcopy_wrapper, common_utils.hpp): the scheduled
