@@ -92,6 +92,7 @@ struct hy_ctx {
     void *d_evt = nullptr;
     hy::EvtDev evt_dev{};
     std::vector<unsigned char> evt_blob;
+    unsigned long long *d_evstats = nullptr;
     std::vector<int32_t> h_ev_dir;
     std::vector<double> h_ev_cd;
     uint32_t *d_srow = nullptr;
@@ -445,6 +446,12 @@ int upload_program(hy_ctx *c)
         CU(cudaMalloc(&c->d_evt, c->evt_blob.size()));
         CU(cudaMemcpy(c->d_evt, c->evt_blob.data(), c->evt_blob.size(), cudaMemcpyHostToDevice));
         c->evt_dev.blob = c->d_evt;
+        c->evt_dev.stats = nullptr;
+        if (env_u32("HY_CUDA_EVENT_STATS", 0)) {
+            if (!c->d_evstats) CU(cudaMalloc((void **)&c->d_evstats, 16));
+            CU(cudaMemset(c->d_evstats, 0, 16));
+            c->evt_dev.stats = c->d_evstats;
+        }
     }
     return 0;
 }
@@ -1006,7 +1013,7 @@ int hy_destroy(hy_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet, c->d_state, c->d_pars,
                     c->d_thi /* block of the per-lane vectors */, c->d_tc, c->d_gws, c->d_tmp_in, c->d_tmp_out,
-                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt};
+                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt, c->d_evstats};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     rec_free(c->rec);
@@ -1496,6 +1503,22 @@ int hy_get_launch_info(hy_ctx *c, hy_launch_info *info)
 {
     if (!c || !info) return fail("null argument");
     *info = c->li;
+    return 0;
+}
+
+/* Debug counters of the event path of the register-resident kernels (HY_CUDA_EVENT_STATS=1 at
+ * hy_create time): steps taken, and steps whose interval enclosure could not exclude an event. */
+int hy_get_event_stats(hy_ctx *c, uint64_t *steps, uint64_t *full_evals)
+{
+    if (!c) return fail("null ctx");
+    unsigned long long v[2] = {0, 0};
+    if (c->d_evstats) {
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(v, c->d_evstats, 16, cudaMemcpyDeviceToHost));
+    }
+    if (steps) *steps = v[0];
+    if (full_evals) *full_evals = v[1];
     return 0;
 }
 

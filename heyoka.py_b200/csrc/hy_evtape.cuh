@@ -58,6 +58,8 @@ struct EvtDev {
     uint32_t eiv_off;      // offset of the interval scratch: 2 x (n_state + n_slots) elements
     uint32_t n_slots;
     uint32_t bytes;        // size of the blob
+    unsigned long long *stats; // optional counters (HY_CUDA_EVENT_STATS=1): [0] steps, [1] steps whose
+                               // enclosure contained 0 (remaining orders + root finder run)
 };
 
 template <typename R, int XS> struct EvtCtx {

@@ -1327,7 +1327,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     }
                     const unsigned mb = __ballot_sync(TM_FULL, maybe && stepping);
                     const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
-                    if ((mb >> (lane & ~(uint32_t)(G - 1))) & gbits) {
+                    const bool gmaybe = ((mb >> (lane & ~(uint32_t)(G - 1))) & gbits) != 0u;
+                    if (P.evt.stats && sub == 0 && stepping) {
+                        atomicAdd(P.evt.stats, 1ULL);
+                        if (gmaybe) atomicAdd(P.evt.stats + 1, 1ULL);
+                    }
+                    if (gmaybe) {
                         // ---- rare: the remaining orders of the event jets, then the root finder ----
                         const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
                         for (uint32_t e = sub; e < P.evt.n_events; e += G) {

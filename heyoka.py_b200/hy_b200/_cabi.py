@@ -120,6 +120,7 @@ SYMBOLS = [
     "hy_destroy",
     "hy_clone",
     "hy_get_device",
+    "hy_get_event_stats",
     "hy_sync",
     "hy_set_tc",
     "hy_set_last_h",
@@ -408,6 +409,11 @@ class Context:
 
     def reset_cooldowns(self, lane=-1):
         check(lib().hy_reset_cooldowns(self._ctx, C.c_int64(int(lane))))
+
+    def event_stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().hy_get_event_stats(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_info(self):
         li = launch_info_t()

@@ -179,6 +179,10 @@ int hy_create2(hy_ctx **out, int device, int fp_bits, const hy_tape *full, const
  * time, last_h, results, tc, cooldowns) is copied device to device (peer copy across GPUs). */
 int hy_clone(const hy_ctx *src, hy_ctx **out, int device);
 int hy_get_device(hy_ctx *ctx, int *device);
+/* Debug counters of the event path on the register-resident kernels (enabled by
+ * HY_CUDA_EVENT_STATS=1 when the context is created): steps taken, and steps in which the
+ * interval enclosure over the step could not exclude an event (full evaluation + root finder). */
+int hy_get_event_stats(hy_ctx *ctx, uint64_t *steps, uint64_t *full_evals);
 /* Wait for everything queued on the context's stream. */
 int hy_sync(hy_ctx *ctx);
 

@@ -16,6 +16,7 @@ evs = [(x - mu) ** 2 + y * y + z * z - 0.012 ** 2, (x - mu + 1.0) ** 2 + y * y +
 rng = np.random.default_rng(20251022)
 ic = np.array([-0.80, 0, 0, 0, -0.6276410653920693, 0])[:, None] * np.ones((1, B))
 ic[0] += rng.uniform(-1e-2, 1e-2, B); ic[4] += rng.uniform(-1e-2, 1e-2, B)
+os.environ["HY_CUDA_EVENT_STATS"] = "1"
 for mode in ("reg", "interp", "noevents"):
     if mode == "interp":
         os.environ["HY_CUDA_NO_REG_EVENTS"] = "1"
@@ -31,4 +32,4 @@ for mode in ("reg", "interp", "noevents"):
         ns = ta.propagate_res_arrays[3].sum()
     oc = ta.propagate_res_arrays[0]
     print(mode, "variant", li["kernel_variant"], "T", li["traj_per_cta"], "threads", li["threads"], "smem", li["smem_bytes"],
-          "steps %.3e" % ns, "kernel ms %.1f" % ms, "steps/s %.3e" % (ns / ms * 1e3), "hits", int((oc > -10).sum()), flush=True)
+          "stats", ta._ctx.event_stats() if mode == "reg" else "", "steps %.3e" % ns, "kernel ms %.1f" % ms, "steps/s %.3e" % (ns / ms * 1e3), "hits", int((oc > -10).sum()), flush=True)
