@@ -16,6 +16,7 @@
 #include "hy_cr3bp_match.hpp"
 #include "hy_nb_launch.hpp"
 #include "hy_evtape_host.hpp"
+#include "hy_jit.hpp"
 
 namespace {
 
@@ -68,6 +69,7 @@ struct hy_ctx {
     uint32_t B = 0;
     double tol = 0;
     int high_accuracy = 0;
+    int no_jit = 0; // compact_mode: stay on the tape interpreter
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // tape (host copies: kept for re-scheduling and for hy_clone)
@@ -126,6 +128,9 @@ struct hy_ctx {
     // launch geometry
     hy_launch_info li{};
     uint32_t TS = 0;
+    // run-time compiled kernel (hy_jit.hpp; li.kernel_variant == HY_VARIANT_JIT)
+    hy::jit::Image jit_img;
+    hy::jit::Loaded jit_k;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0;
@@ -144,11 +149,15 @@ cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStre
     return cudaGetLastError();
 }
 
-template <typename R> cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx)
+template <typename R>
+cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx, const hy::jit::Loaded *jk)
 {
     // register-resident N-body kernels (hy_nbody_reg.cuh)
     switch (li.kernel_variant) { // instantiated in hy_nb3.cu ... hy_nb6.cu
     case 0: break;
+    case HY_VARIANT_JIT: // generated from the tape and compiled at hy_create time (hy_jit.hpp)
+        if (!jk || !jk->func) return cudaErrorInvalidValue;
+        return hy::jit::launch(*jk, P, li.ctas, li.threads, li.smem_bytes, s);
     case 3: return hy::launch_nbody_kernel<R, 3>(P, li, s, fx);
     case 4: return hy::launch_nbody_kernel<R, 4>(P, li, s, fx);
     case 5: return hy::launch_nbody_kernel<R, 5>(P, li, s, fx);
@@ -219,6 +228,49 @@ hy::ProgDims prog_dims(const hy::Program &p)
 {
     return hy::ProgDims{p.n_slots, p.n_tslots, (uint32_t)p.imm.size(), p.n_phases, p.ws_len,
                         p.par_off, p.one_off,  p.n_spill,              p.evt_bytes};
+}
+
+// Plan, generate and compile (or fetch from the cache) the run-time compiled kernel of a tape.
+// Returns 1: `pr` / `img` hold the kernel (row offsets of `pr` pre-multiplied for the interleaved
+// workspace), 0: the tape is served better by the interpreter, -1: failure (`err`).
+int jit_plan(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uint32_t *ev_ref, int fp_bits, uint32_t B,
+             uint32_t n_sm, uint32_t smem_optin, bool force, hy::Program &pr, bool &smem, uint32_t &T, hy::jit::Image &img,
+             std::string &err)
+{
+    const uint32_t rb = (uint32_t)fp_bits / 8u;
+    err = hy::build_program(d, ops, terms, ev_ref, 1, false, pr, false);
+    if (!err.empty()) return -1;
+    const size_t col_bytes = (size_t)pr.ws_len * rb;
+    if (!force && col_bytes <= env_u32("HY_CUDA_JIT_MIN_BYTES", 3072)) return 0;
+    hy::ProgDims pd0 = prog_dims(pr);
+    pd0.n_slots = pd0.n_tslots = 0; // (the program is code: no ops / terms are staged)
+    hy::SmemLayout L0 = hy::make_layout(d, pd0, 1, 0, pr.ws_len, rb, 0);
+    const uint32_t fixed = L0.total + 64;
+    const uint32_t fit = fixed < smem_optin ? (uint32_t)((smem_optin - fixed) / col_bytes) & ~31u : 0u;
+    smem = fit >= env_u32("HY_CUDA_JIT_SMEM_MIN_THREADS", 128);
+    T = smem ? std::min(fit, 256u) : (std::max(32u, env_u32("HY_CUDA_JIT_THREADS", 128)) & ~31u);
+    // do not keep more trajectories resident than the batch can feed
+    const uint32_t need = std::max(1u, (B + n_sm - 1) / n_sm);
+    T = std::max(32u, std::min(T, (need + 31u) & ~31u));
+    hy::jit::Gen gen(d, pr);
+    const std::string src = gen.source(fp_bits, smem, T);
+    if (src.empty()) {
+        err = "op without a generator";
+        return -1;
+    }
+    err = hy::jit::build(src, hy::jit::kernel_name(fp_bits, smem), img);
+    if (!err.empty()) return -1;
+    // the kernel indexes the interleaved workspace in elements: pre-multiply the row offsets
+    for (auto &r : pr.state_row) r *= hy::jit::WS;
+    for (auto &r : pr.ev_ref) r *= hy::jit::WS;
+    pr.par_off *= hy::jit::WS;
+    pr.one_off *= hy::jit::WS;
+    pr.n_slots = pr.n_tslots = 0; // nothing to stage: the program is code
+    pr.ops.clear();
+    pr.terms.clear();
+    pr.n_phases = 0;
+    pr.phase_slot = {0};
+    return 1;
 }
 
 int upload_program(hy_ctx *c);
@@ -347,6 +399,32 @@ int choose_geometry(hy_ctx *c)
             li.kernel_variant = hy::cr3bp_kernel_variant(d.order, c->fp_bits);
         }
     }
+    // Run-time compiled kernel (hy_jit.hpp): one thread per trajectory, the order sweep generated from
+    // the tape.  HY_CUDA_JIT = 0: never, 1: always, 2 (default): for tapes whose workspace is too large
+    // for the small-group interpreter variants (those would run with 16-lane groups or from global
+    // memory, far below their roofline); hy_create's `compact_mode` flag (reference kwarg) selects the
+    // interpreter as well.
+    bool jit_smem = false;
+    uint32_t jit_T = 0;
+    const uint32_t jit_mode = c->no_jit ? 0u : env_u32("HY_CUDA_JIT", 2);
+    if (!li.kernel_variant && jit_mode && !force_global && !Genv) {
+        hy::Program pr;
+        std::string jerr;
+        const int jr = jit_plan(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), c->fp_bits, c->B, li.n_sm,
+                                (uint32_t)smem_optin, jit_mode == 1, pr, jit_smem, jit_T, c->jit_img, jerr);
+        if (jr > 0) {
+            bestG = 1;
+            bestT = jit_T;
+            bestRS = pr.ws_len;
+            best_smem = jit_smem;
+            best = pr;
+            li.kernel_variant = HY_VARIANT_JIT;
+        } else if (jr < 0) {
+            if (jit_mode == 1) return fail("hy_create: " + jerr);
+            if (env_u32("HY_CUDA_JIT_VERBOSE", 0))
+                std::fprintf(stderr, "hy_cuda: run-time compilation failed, using the tape interpreter: %s\n", jerr.c_str());
+        }
+    }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
         if (li.kernel_variant) break;
         if (Genv && G != Genv) continue;
@@ -384,6 +462,7 @@ int choose_geometry(hy_ctx *c)
     // Do not keep more trajectories resident than the batch can feed.
     uint32_t per_cta_needed = std::max(1u, (c->B + li.n_sm - 1) / li.n_sm);
     T = std::max(1u, std::min(T, per_cta_needed));
+    if (li.kernel_variant == HY_VARIANT_JIT) T = jit_T; // whole warps, the CTA size the kernel was compiled for
     if (li.kernel_variant) T = (T + 1u) & ~1u; // whole warps: the two trajectories of a warp step in lockstep
     if (li.kernel_variant == 106) T = 24;      // whole warpgroups
     if (li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22)
@@ -393,12 +472,22 @@ int choose_geometry(hy_ctx *c)
     li.threads = ((T * G + 31) / 32) * 32;
     uint32_t ctas = (c->B + T - 1) / T;
     li.ctas = std::max(1u, std::min(ctas, li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
+    if (li.kernel_variant == HY_VARIANT_JIT && !li.ws_in_smem)
+        li.ctas = std::max(1u, std::min(ctas, li.n_sm * env_u32("HY_CUDA_JIT_CTAS_PER_SM", 1)));
     const uint32_t RS = bestRS;
     c->TS = RS;
     c->prog = best;
     hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
     li.smem_bytes = L.total;
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
+    if (li.kernel_variant == HY_VARIANT_JIT) {
+        CU(cudaSetDevice(c->device));
+        hy::jit::unload(c->jit_k);
+        const std::string lerr = hy::jit::load(c->jit_img, li.smem_bytes, !li.ws_in_smem, c->jit_k);
+        if (!lerr.empty()) return fail("hy_create: " + lerr);
+        li.regs_per_thread = (uint32_t)c->jit_k.regs;
+        return upload_program(c);
+    }
     li.regs_per_thread = (uint32_t)(c->fp_bits == 64 ? regs_for_group<double>(G, li.ws_in_smem, li.kernel_variant)
                                                      : regs_for_group<float>(G, li.ws_in_smem, li.kernel_variant));
     return upload_program(c);
@@ -730,9 +819,9 @@ int launch_once(hy_ctx *c, const RunArgs &a)
     const bool fx = a.rec_on || a.use_active || a.resume || a.pause_on_nt || a.launch_steps || c->n_red || c->use_evt;
     cudaError_t e;
     if (c->fp_bits == 64)
-        e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx);
+        e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx, &c->jit_k);
     else
-        e = launch<float>(make_params<float>(c, a), c->li, c->stream, fx);
+        e = launch<float>(make_params<float>(c, a), c->li, c->stream, fx, &c->jit_k);
     if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
     ++c->last_launches;
     return 0;
@@ -881,7 +970,8 @@ int hy_create2(hy_ctx **out, int device, int fp_bits, const hy_tape *full, const
     c->d = *dims;
     c->B = batch;
     c->tol = tol;
-    c->high_accuracy = high_accuracy;
+    c->high_accuracy = (high_accuracy & HY_CREATE_HIGH_ACCURACY) ? 1 : 0;
+    c->no_jit = (high_accuracy & HY_CREATE_COMPACT) ? 1 : 0;
     *out = c;
     const hy_dims &d = c->d;
     if (common_init(c)) return 1;
@@ -963,6 +1053,8 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
     c->use_evt = src->use_evt;
     c->evt_dev = src->evt_dev;
     c->evt_blob = src->evt_blob;
+    c->no_jit = src->no_jit;
+    c->jit_img = src->jit_img;
     if (common_init(c)) return 1;
     if (alloc_lanes(c)) return 1;
     {
@@ -972,6 +1064,10 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
         c->li.n_sm = (uint32_t)prop.multiProcessorCount;
         const uint32_t T = c->li.traj_per_cta;
         c->li.ctas = std::max(1u, std::min((c->B + T - 1) / T, c->li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
+    }
+    if (c->li.kernel_variant == HY_VARIANT_JIT) {
+        const std::string lerr = hy::jit::load(c->jit_img, c->li.smem_bytes, !c->li.ws_in_smem, c->jit_k);
+        if (!lerr.empty()) return fail("hy_clone: " + lerr);
     }
     if (upload_program(c)) return 1;
     const hy_dims &d = c->d;
@@ -1016,6 +1112,7 @@ int hy_destroy(hy_ctx *c)
                     c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt, c->d_evstats};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    hy::jit::unload(c->jit_k);
     rec_free(c->rec);
     rec_free(c->rec_spare);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1539,6 +1636,26 @@ int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term 
     hy::CrbMatch cm; // (FP64 order, then FP32 order: the introspection call does not know the precision)
     if (!*variant && (hy::match_cr3bp(*dims, ops, terms, 64, cm) || hy::match_cr3bp(*dims, ops, terms, 32, cm)))
         *variant = hy::cr3bp_kernel_variant(dims->order, 64);
+    return 0;
+}
+
+/* Generate and compile the kernel of a tape without a device (fills the on-disk cache; the build
+ * step runs it for the BASELINE tapes so that the GPU box starts warm). */
+int hy_jit_precompile(int fp_bits, const hy_tape *full, uint32_t batch, int *from_cache, double *compile_s)
+{
+    if (!full || !full->dims || !full->ops) return fail("hy_jit_precompile: null argument");
+    if (fp_bits != 32 && fp_bits != 64) return fail("hy_jit_precompile: fp_bits must be 32 or 64");
+    hy::Program pr;
+    hy::jit::Image img;
+    bool smem = false;
+    uint32_t T = 0;
+    std::string err;
+    // (sm_100a: 148 SMs, 227 KB of shared memory per CTA)
+    const int r = jit_plan(*full->dims, full->ops, full->terms, full->ev_ref, fp_bits, batch, 148u, 232448u,
+                           env_u32("HY_CUDA_JIT", 2) == 1, pr, smem, T, img, err);
+    if (r < 0) return fail("hy_jit_precompile: " + err);
+    if (from_cache) *from_cache = r == 0 ? -1 : (img.from_cache ? 1 : 0);
+    if (compile_s) *compile_s = img.compile_s;
     return 0;
 }
 

@@ -173,7 +173,8 @@ template <typename R> __device__ inline int ev_find_roots(const R *c_in, int p, 
 // Returns the (possibly truncated) step in h_out and the index of the terminal
 // event that truncated it (-1: none).  Non-terminal events before the
 // truncation point and the terminal event itself are appended to the log.
-template <typename R>
+// GS: element stride between the orders of an event jet (1 for a trajectory column).
+template <typename R, int GS = 1>
 static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev_ref, uint32_t n_events, uint32_t n_tevents,
                                      int p, R h, R t_hi, R t_lo, uint32_t traj, unsigned long long step_idx,
                                      const EvParams<R> E, R &h_out, int &term_out, int &nt_out)
@@ -198,19 +199,20 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
         // shared-memory carve-out at its maximum, local memory lives in L2): interval Horner of
         // g over tau in [0, h] (or [h, 0]).
         {
-            R lo = g[p], hi = g[p];
+            R lo = g[p * GS], hi = g[p * GS];
             for (int k = p - 1; k >= 0; --k) {
                 const R a = lo * h, b = hi * h; // (h < 0 swaps the ends)
                 const R mn = a < b ? a : b, mx = a < b ? b : a;
-                lo = (mn < 0 ? mn : (R)0) + g[k];
-                hi = (mx > 0 ? mx : (R)0) + g[k];
+                const R gk = g[k * GS];
+                lo = (mn < 0 ? mn : (R)0) + gk;
+                hi = (mx > 0 ? mx : (R)0) + gk;
             }
             if (lo > (R)0 || hi < (R)0) continue;
         }
         // q(s) = g(h s)
         R hk = 1;
         for (int k = 0; k <= p; ++k) {
-            q[k] = g[k] * hk;
+            q[k] = g[k * GS] * hk;
             hk *= h;
         }
         // second exclusion on the scaled polynomial: enclosure of q over [0, 1]
@@ -275,13 +277,13 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
         term_out = best_ev;
         // start the cooldown of the event that fired
         const R *g = w + (ev_ref[best_ev] & 0x7fffffffu);
-        R f = g[p], df = 0, gm = 0, hk = 1;
+        R f = g[p * GS], df = 0, gm = 0, hk = 1;
         for (int k = p - 1; k >= 0; --k) {
             df = fma(df, best_tau, f);
-            f = fma(f, best_tau, g[k]);
+            f = fma(f, best_tau, g[k * GS]);
         }
         for (int k = 0; k <= p; ++k) {
-            const R a = g[k] * hk;
+            const R a = g[k * GS] * hk;
             gm = (a < 0 ? -a : a) > gm ? (a < 0 ? -a : a) : gm;
             hk *= h;
         }

@@ -1,0 +1,548 @@
+// hy_jit.hpp - run-time compiled kernels: the order sweep of ANY tape as straight-line CUDA.
+//
+// The reference JIT-compiles every ODE system to native code in the taylor_adaptive_batch
+// constructor ([UPSTREAM] LLVM, called from /root/reference/heyoka/expose_batch_integrators.cpp:166-208).
+// The B200 counterpart: hy_create lowers the scheduled program (hy_schedule.hpp, one lane per
+// trajectory) to CUDA source - every op of the tape becomes one statement with literal row offsets,
+// coefficients and term counts, the convolutions are the bodies of hy_kernels.cuh - and compiles it
+// with NVRTC for sm_100a together with the persistent propagate kernel (hy_kernels.cuh, built with
+// HY_JIT): the same step-size control, event detection, dense / continuous output and bookkeeping
+// code as the precompiled kernels, with the tape interpreter replaced by the generated function.
+//
+// Execution model of the generated kernels: ONE THREAD PER TRAJECTORY.  The 32 trajectories of a
+// warp execute the same instruction stream (no divergence between op kinds, no group
+// synchronisation), their workspace is interleaved row by row (row r of lane l at [r * 32 + l]):
+// every access of a warp is one contiguous 256-byte (FP64) segment - conflict-free in shared
+// memory, fully coalesced in global memory.  Small systems keep the workspace in shared memory;
+// systems whose jets do not fit stream them from global memory (L1/L2).
+//
+// Compiled kernels are cached on disk (cubin + lowered kernel name, keyed by a hash of the source
+// and the options): <directory of libhy_cuda.so>/jit_cache, or $HY_CUDA_JIT_CACHE.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/hy_cuda.h"
+#include "hy_schedule.hpp"
+
+namespace hy {
+namespace jit {
+
+constexpr uint32_t WS = 32; // element stride between rows of the warp-interleaved workspace
+
+// --------------------------------------------------------------------------------------------
+// Code generation
+// --------------------------------------------------------------------------------------------
+struct Gen {
+    const hy_dims &d;
+    const Program &pr;
+    std::ostringstream os;
+    Gen(const hy_dims &d_, const Program &p_) : d(d_), pr(p_) {}
+
+    static std::string lit(double v)
+    {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%a", v);
+        std::string s(buf);
+        if (s.find("inf") != std::string::npos || s.find("nan") != std::string::npos) {
+            // (coefficients of a tape are finite; keep the generator total anyway)
+            return v != v ? "(0.0/0.0)" : (v > 0 ? "(1.0/0.0)" : "(-1.0/0.0)");
+        }
+        return "(R)" + s;
+    }
+    // row expression at order k: base (+ k for jets)
+    static std::string row(uint32_t base, bool jet, const char *k = "k")
+    {
+        std::string s = std::to_string(base);
+        if (jet) s += std::string(" + ") + k;
+        return s;
+    }
+    static std::string Wr(uint32_t base, bool jet, const char *k = "k") { return "W(" + row(base, jet, k) + ")"; }
+    static std::string ptr(uint32_t base) { return "(w + " + std::to_string(base) + " * HY_WS)"; }
+    static std::string ptrk(uint32_t base, const char *k = "k")
+    {
+        return "(w + (" + std::to_string(base) + " + " + k + ") * HY_WS)";
+    }
+
+    void store(const DOp &o, const std::string &val)
+    {
+        if (o.opcode == HY_OP_SVD || (o.flags & HY_OPF_SVD))
+            os << "        W(" << o.dst << " + k + 1) = (" << val << ") * rk[k + 1];\n";
+        else
+            os << "        " << Wr(o.dst, o.flags & DF_JDST) << " = " << val << ";\n";
+    }
+
+    // One op at order k (k: a variable of the generated code).  Mirrors exec_op (hy_kernels.cuh)
+    // statement by statement so that both paths round identically.
+    bool emit_op(const DOp &o)
+    {
+        const DTerm *t = pr.terms.data() + o.b; // (G = 1: the lane's stream is the term array)
+        os << "      { // op " << (int)o.opcode << "\n";
+        switch (o.opcode) {
+        case HY_OP_LINCOMB: {
+            const bool nopar = (o.pad & DP_NOPAR) != 0;
+            // (blocks of 8 terms: operands first, then one FMA chain in term order - as exec_op)
+            os << "        R acc = 0;\n";
+            for (uint32_t i0 = 0; i0 < o.n; i0 += 8) {
+                const uint32_t m = std::min<uint32_t>(8, o.n - i0);
+                for (uint32_t u = 0; u < m; ++u) {
+                    const DTerm &tt = t[i0 + u];
+                    const uint32_t mask = tt.aux >> 16;
+                    os << "        const R v" << i0 + u << " = " << Wr(tt.src, mask == 0xffffu) << ";\n";
+                }
+                for (uint32_t u = 0; u < m; ++u) {
+                    const DTerm &tt = t[i0 + u];
+                    const uint32_t mult = tt.aux & 0xffffu;
+                    if (nopar || mult == pr.one_off)
+                        os << "        acc = r_fma(" << lit(tt.coef) << ", v" << i0 + u << ", acc);\n";
+                    else
+                        os << "        acc = r_fma(" << lit(tt.coef) << " * W(" << mult << "), v" << i0 + u << ", acc);\n";
+                }
+            }
+            store(o, "acc");
+        } break;
+        case HY_OP_ADDSUB: {
+            os << "        const R a = " << ((o.flags & HY_OPF_NEGA) ? "-" : "") << Wr(o.a, o.flags & DF_JA) << ";\n";
+            os << "        const R b = " << ((o.flags & HY_OPF_NEGB) ? "-" : "") << Wr(o.b, o.flags & DF_JB) << ";\n";
+            store(o, "a + b");
+        } break;
+        case HY_OP_SVD: store(o, Wr(o.a, o.flags & DF_JA)); break;
+        case HY_OP_MUL:
+            store(o, "conv_wide<R, HY_WS>(" + ptr(o.a) + ", " + ptrk(o.b) + ", (int)k + 1)");
+            break;
+        case HY_OP_SQUARE:
+            os << "        const R *a = " << ptr(o.a) << ";\n";
+            os << "        R acc = conv_wide<R, HY_WS>(a, a + k * HY_WS, (int)((k + 1) >> 1));\n";
+            os << "        acc = acc + acc;\n";
+            os << "        if ((k & 1u) == 0) { const R m = a[(k >> 1) * HY_WS]; acc = r_fma(m, m, acc); }\n";
+            store(o, "acc");
+            break;
+        case HY_OP_SUMSQ:
+            os << "        const int half = (int)((k + 1) >> 1);\n        R acc = 0, acc2 = 0;\n";
+            for (uint32_t i = 0; i < o.n; ++i) {
+                os << "        { const R *a = " << ptr(t[i].src & 0x3fffffffu) << ";\n";
+                os << "          acc += conv_wide<R, HY_WS>(a, a + k * HY_WS, half);\n";
+                os << "          if ((k & 1u) == 0) { const R m = a[(k >> 1) * HY_WS]; acc2 = r_fma(m, m, acc2); } }\n";
+            }
+            store(o, "(acc + acc) + acc2");
+            break;
+        case HY_OP_MULSH: {
+            os << "        const R *b = " << ptrk(o.a) << ";\n        const int n = (int)k + 1;\n";
+            auto dstref = [&](const DTerm &ti) { return Wr(ti.aux & 0x3fffffffu, ti.aux & HY_DREF_JET); };
+            if (o.n == 3) {
+                os << "        R s0, s1, s2;\n";
+                os << "        conv3_wide<R, HY_WS>(" << ptr(t[0].src & 0x3fffffffu) << ", " << ptr(t[1].src & 0x3fffffffu) << ", "
+                   << ptr(t[2].src & 0x3fffffffu) << ", b, n, s0, s1, s2);\n";
+                for (int i = 0; i < 3; ++i) os << "        " << dstref(t[i]) << " = s" << i << ";\n";
+            } else {
+                for (uint32_t i = 0; i < o.n; ++i)
+                    os << "        " << dstref(t[i]) << " = conv_wide<R, HY_WS>(" << ptr(t[i].src & 0x3fffffffu) << ", b, n);\n";
+            }
+        } break;
+        case HY_OP_DIV:
+            os << "        const R *b = " << ptr(o.b) << ";\n        R *c = " << ptr(o.dst) << ";\n";
+            os << "        if (k == 0) W(" << o.dst2 << ") = (R)1 / b[0];\n";
+            os << "        R acc = " << Wr(o.a, o.flags & DF_JA) << ";\n";
+            os << "        if (k > 0) acc -= conv_wide<R, HY_WS>(b + HY_WS, c + (k - 1) * HY_WS, (int)k);\n";
+            os << "        c[k * HY_WS] = acc * W(" << o.dst2 << ");\n";
+            break;
+        case HY_OP_POW:
+        case HY_OP_SQRT: {
+            const double alpha = o.opcode == HY_OP_SQRT ? 0.5 : pr.imm[o.imm];
+            char ab[64];
+            std::snprintf(ab, sizeof ab, "%a", alpha);
+            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
+            os << "        const double alpha = " << ab << ";\n";
+            os << "        if (k == 0) {\n          W(" << o.dst2 << ") = (R)1 / a[0];\n";
+            if (o.opcode == HY_OP_SQRT)
+                os << "          c[0] = r_sqrt(a[0]);\n";
+            else
+                os << "          c[0] = pow0<R>(a[0], alpha);\n";
+            os << "        } else {\n          const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;\n";
+            os << "          c[k * HY_WS] = (conv_pow<R, HY_WS>(a + k * HY_WS, c, (int)k, al1, kal) * rk[k]) * W(" << o.dst2
+               << ");\n        }\n";
+        } break;
+        case HY_OP_EXP:
+            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
+            os << "        if (k == 0) {\n          c[0] = r_exp(a[0]);\n        } else {\n          R acc = 0, jr = 1;\n";
+            os << "          _Pragma(\"unroll 1\") for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * a[j * HY_WS], c[(k "
+                  "- j) * HY_WS], acc);\n";
+            os << "          c[k * HY_WS] = acc * rk[k];\n        }\n";
+            break;
+        case HY_OP_LOG:
+            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
+            os << "        if (k == 0) {\n          W(" << o.dst2 << ") = (R)1 / a[0];\n          c[0] = r_log(a[0]);\n";
+            os << "        } else {\n          R acc = 0, jr = 1;\n";
+            os << "          _Pragma(\"unroll 1\") for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * c[j * HY_WS], a[(k "
+                  "- j) * HY_WS], acc);\n";
+            os << "          c[k * HY_WS] = r_fma(-acc, rk[k], a[k * HY_WS]) * W(" << o.dst2 << ");\n        }\n";
+            break;
+        case HY_OP_SINCOS:
+            os << "        const R *a = " << ptr(o.a) << ";\n        R *s = " << ptr(o.dst) << ", *c = " << ptr(o.dst2) << ";\n";
+            os << "        if (k == 0) {\n          R sv, cv;\n          r_sincos(a[0], &sv, &cv);\n          s[0] = sv;\n          c[0] = cv;\n";
+            os << "        } else {\n          R sa0 = 0, ca0 = 0, sa1 = 0, ca1 = 0, jr = 1;\n          uint32_t j = 1;\n";
+            os << "          _Pragma(\"unroll 1\") for (; j + 1 <= k; j += 2, jr += (R)2) {\n";
+            os << "            const R ja0 = jr * a[j * HY_WS], ja1 = (jr + (R)1) * a[(j + 1) * HY_WS];\n";
+            os << "            const R c0 = c[(k - j) * HY_WS], s0 = s[(k - j) * HY_WS], c1 = c[(k - j - 1) * HY_WS], s1 = s[(k - j - 1) * "
+                  "HY_WS];\n";
+            os << "            sa0 = r_fma(ja0, c0, sa0);\n            ca0 = r_fma(ja0, s0, ca0);\n";
+            os << "            sa1 = r_fma(ja1, c1, sa1);\n            ca1 = r_fma(ja1, s1, ca1);\n          }\n";
+            os << "          if (j <= k) {\n            const R ja = jr * a[j * HY_WS];\n";
+            os << "            sa0 = r_fma(ja, c[(k - j) * HY_WS], sa0);\n            ca0 = r_fma(ja, s[(k - j) * HY_WS], ca0);\n          }\n";
+            os << "          s[k * HY_WS] = (sa0 + sa1) * rk[k];\n          c[k * HY_WS] = -((ca0 + ca1) * rk[k]);\n        }\n";
+            break;
+        case HY_OP_TIME: os << "        W(" << o.dst << " + k) = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);\n"; break;
+        case OP_NOP: break;
+        default: return false; // (fused pair ops are not generated: the program is built without fusion)
+        }
+        os << "      }\n";
+        return true;
+    }
+
+    // The whole translation unit.  Returns "" if the program holds an op the generator does not know.
+    std::string source(int fp_bits, bool smem, uint32_t threads)
+    {
+        os << "// generated by hy_jit.hpp: " << d.n_state << " state variables, order " << d.order << ", " << pr.n_slots
+           << " ops, " << pr.ws_len << " workspace rows\n";
+        os << "#define HY_JIT 1\n#define HY_WS " << WS << "\n#define HY_JIT_THREADS " << threads << "\n";
+        os << "#include \"hy_kernels.cuh\"\n";
+        os << "#define W(r) w[(r) * HY_WS]\n";
+        os << "namespace hy {\n";
+        os << "template <typename R> __device__ __forceinline__ void hy_gen_jets(R *__restrict__ w, const R *__restrict__ rk, const R tm)\n{\n";
+        os << "    _Pragma(\"unroll 1\") for (uint32_t k = 0; k < " << d.order << "u; ++k) {\n";
+        for (uint32_t i = 0; i < pr.n_slots; ++i)
+            if (!emit_op(pr.ops[i])) return "";
+        os << "    }\n}\n";
+        os << "template <typename R> __device__ __forceinline__ void hy_gen_ev_sweep(R *__restrict__ w, const R *__restrict__ rk, const R tm)\n{\n";
+        os << "    const uint32_t k = " << d.order << "u;\n    (void)k; (void)rk; (void)tm; (void)w;\n";
+        if (d.n_events)
+            for (uint32_t i = 0; i < pr.n_slots; ++i) {
+                const DOp &o = pr.ops[i];
+                if (!(o.flags & HY_OPF_EVENT) || (o.flags & HY_OPF_SVD) || o.opcode == HY_OP_SVD) continue;
+                if (!emit_op(o)) return "";
+            }
+        os << "}\n";
+        const char *R = fp_bits == 64 ? "double" : "float";
+        os << "template __global__ void propagate_kernel<" << R << ", 1, " << (smem ? "true" : "false")
+           << ", 0, false, NBR_PMAX, true>(const KParams<" << R << ">);\n";
+        os << "} // namespace hy\n";
+        return os.str();
+    }
+};
+
+inline std::string kernel_name(int fp_bits, bool smem)
+{
+    return std::string("hy::propagate_kernel<") + (fp_bits == 64 ? "double" : "float") + ", 1, " + (smem ? "true" : "false") +
+           ", 0, false, hy::NBR_PMAX, true>";
+}
+
+// --------------------------------------------------------------------------------------------
+// NVRTC (loaded on first use: libhy_cuda.so itself does not depend on it)
+// --------------------------------------------------------------------------------------------
+struct Nvrtc {
+    void *h = nullptr;
+    int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    int (*DestroyProgram)(void **) = nullptr;
+    int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+    int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+    int (*GetProgramLog)(void *, char *) = nullptr;
+    int (*GetCUBINSize)(void *, size_t *) = nullptr;
+    int (*GetCUBIN)(void *, char *) = nullptr;
+    int (*AddNameExpression)(void *, const char *) = nullptr;
+    int (*GetLoweredName)(void *, const char *, const char **) = nullptr;
+    int (*Version)(int *, int *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool load()
+    {
+        if (h) return true;
+        for (const char *nm : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+            h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (h) break;
+        }
+        if (!h) {
+            err = "libnvrtc not found";
+            return false;
+        }
+#define HY_NVRTC_SYM(f)                                                        \
+    f = reinterpret_cast<decltype(f)>(dlsym(h, "nvrtc" #f));                   \
+    if (!f) {                                                                  \
+        err = "nvrtc" #f " missing";                                           \
+        return false;                                                          \
+    }
+        HY_NVRTC_SYM(CreateProgram)
+        HY_NVRTC_SYM(DestroyProgram)
+        HY_NVRTC_SYM(CompileProgram)
+        HY_NVRTC_SYM(GetProgramLogSize)
+        HY_NVRTC_SYM(GetProgramLog)
+        HY_NVRTC_SYM(GetCUBINSize)
+        HY_NVRTC_SYM(GetCUBIN)
+        HY_NVRTC_SYM(AddNameExpression)
+        HY_NVRTC_SYM(GetLoweredName)
+        HY_NVRTC_SYM(Version)
+        HY_NVRTC_SYM(GetErrorString)
+#undef HY_NVRTC_SYM
+        return true;
+    }
+};
+inline Nvrtc &nvrtc()
+{
+    static Nvrtc n;
+    return n;
+}
+
+// directory of libhy_cuda.so (the kernel headers are read from there; the cache lives below it)
+inline std::string lib_dir()
+{
+    Dl_info info{};
+    if (dladdr(reinterpret_cast<const void *>(&lib_dir), &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        const size_t s = p.rfind('/');
+        return s == std::string::npos ? std::string(".") : p.substr(0, s);
+    }
+    return ".";
+}
+inline std::string cache_dir()
+{
+    const char *e = std::getenv("HY_CUDA_JIT_CACHE");
+    return (e && *e) ? std::string(e) : lib_dir() + "/jit_cache";
+}
+
+inline uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ULL)
+{
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ULL;
+    }
+    return h;
+}
+
+inline std::string read_file(const std::string &path)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return "";
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// A compiled kernel: cubin image + lowered (mangled) name of the kernel in it.
+struct Image {
+    std::vector<char> cubin;
+    std::string name;
+    bool from_cache = false;
+    double compile_s = 0;
+};
+
+// Stubs of the system headers the kernel sources include (NVRTC has none of them).
+inline const char *stub_stdint()
+{
+    return "#pragma once\n"
+           "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;\n"
+           "typedef int int32_t; typedef unsigned int uint32_t; typedef long int64_t; typedef unsigned long uint64_t;\n"
+           "typedef unsigned long uintptr_t; typedef long intptr_t;\n";
+}
+
+// The headers of the kernel translation unit: their content is part of the cache key.
+inline const std::vector<std::string> &kernel_headers()
+{
+    static const std::vector<std::string> v = {"hy_kernels.cuh",    "hy_devprog.h",     "hy_events.cuh", "hy_evtape.cuh",
+                                               "hy_nbody_reg.cuh",  "hy_cr3bp_reg.cuh", "../../include/hy_cuda.h"};
+    return v;
+}
+
+inline std::string options_string(const std::vector<std::string> &opts)
+{
+    std::string s;
+    for (auto &o : opts) s += o + " ";
+    return s;
+}
+
+// Compile `src` (or fetch it from the cache).  Returns "" on success.
+inline std::string build(const std::string &src, const std::string &kname, Image &out)
+{
+    const std::string dir = lib_dir();
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-I" + dir,
+                                     "-I" + dir + "/../../include"};
+    // cache key: generated source + kernel headers + options + compiler version
+    uint64_t h = fnv1a(src);
+    for (auto &hn : kernel_headers()) {
+        const std::string body = read_file(dir + "/" + hn);
+        if (body.empty()) return "cannot read kernel header " + dir + "/" + hn;
+        h = fnv1a(body, h);
+    }
+    h = fnv1a(options_string(opts) + kname, h);
+    Nvrtc &nv = nvrtc();
+    int vmaj = 0, vmin = 0;
+    const bool have_nvrtc = nv.load();
+    if (have_nvrtc) nv.Version(&vmaj, &vmin);
+    char keybuf[64];
+    std::snprintf(keybuf, sizeof keybuf, "%016" PRIx64, h);
+    const std::string cdir = cache_dir();
+    const std::string cpath = cdir + "/" + keybuf + ".hyjit";
+    {
+        const std::string blob = read_file(cpath);
+        if (blob.size() > 12 && std::memcmp(blob.data(), "HYJ1", 4) == 0) {
+            uint32_t nl = 0;
+            std::memcpy(&nl, blob.data() + 4, 4);
+            if (8 + (size_t)nl < blob.size()) {
+                out.name.assign(blob.data() + 8, nl);
+                out.cubin.assign(blob.begin() + 8 + nl, blob.end());
+                out.from_cache = true;
+                return "";
+            }
+        }
+    }
+    if (!have_nvrtc) return "NVRTC unavailable (" + nv.err + ") and no cached kernel " + cpath;
+    static std::mutex mtx; // (NVRTC is thread-safe, but one compilation at a time keeps the memory bounded)
+    std::lock_guard<std::mutex> lk(mtx);
+    timespec t0{}, t1{};
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    void *prog = nullptr;
+    const char *hdr_names[] = {"stdint.h", "cstdint", "stddef.h", "cuda_runtime.h"};
+    const std::string stddef_stub = "#pragma once\ntypedef unsigned long size_t;\n";
+    const std::string cstdint_stub = std::string("#pragma once\n#include <stdint.h>\n");
+    const char *hdr_src[] = {stub_stdint(), cstdint_stub.c_str(), stddef_stub.c_str(), "#pragma once\n"};
+    int rc = nv.CreateProgram(&prog, src.c_str(), "hy_jit_kernel.cu", 4, hdr_src, hdr_names);
+    if (rc) return std::string("nvrtcCreateProgram: ") + nv.GetErrorString(rc);
+    nv.AddNameExpression(prog, kname.c_str());
+    std::vector<const char *> copts;
+    for (auto &o : opts) copts.push_back(o.c_str());
+    rc = nv.CompileProgram(prog, (int)copts.size(), copts.data());
+    if (rc) {
+        size_t ls = 0;
+        nv.GetProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) nv.GetProgramLog(prog, &log[0]);
+        nv.DestroyProgram(&prog);
+        if (const char *dump = std::getenv("HY_CUDA_JIT_DUMP")) {
+            std::ofstream f(std::string(dump) + "/hy_jit_failed.cu");
+            f << src;
+        }
+        if (log.size() > 4000) log.resize(4000);
+        return std::string("NVRTC compilation failed: ") + nv.GetErrorString(rc) + "\n" + log;
+    }
+    const char *lowered = nullptr;
+    rc = nv.GetLoweredName(prog, kname.c_str(), &lowered);
+    if (rc || !lowered) {
+        nv.DestroyProgram(&prog);
+        return "nvrtcGetLoweredName failed";
+    }
+    out.name = lowered;
+    size_t cs = 0;
+    nv.GetCUBINSize(prog, &cs);
+    out.cubin.resize(cs);
+    nv.GetCUBIN(prog, out.cubin.data());
+    nv.DestroyProgram(&prog);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    out.compile_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    out.from_cache = false;
+    if (const char *dump = std::getenv("HY_CUDA_JIT_DUMP")) {
+        std::ofstream f(std::string(dump) + "/hy_jit_" + keybuf + ".cu");
+        f << src;
+    }
+    // store (best effort; atomic rename so that concurrent processes never see a partial file)
+    ::mkdir(cdir.c_str(), 0777);
+    {
+        const std::string tmp = cpath + ".tmp" + std::to_string((long)::getpid());
+        std::ofstream f(tmp, std::ios::binary);
+        if (f) {
+            const uint32_t nl = (uint32_t)out.name.size();
+            f.write("HYJ1", 4);
+            f.write(reinterpret_cast<const char *>(&nl), 4);
+            f.write(out.name.data(), nl);
+            f.write(out.cubin.data(), (std::streamsize)out.cubin.size());
+            f.close();
+            if (::rename(tmp.c_str(), cpath.c_str()) != 0) ::unlink(tmp.c_str());
+        }
+    }
+    return "";
+}
+
+// --------------------------------------------------------------------------------------------
+// Driver API entry points (through the runtime: no link-time dependency on libcuda)
+// --------------------------------------------------------------------------------------------
+struct Driver {
+    int (*ModuleLoadData)(void **, const void *) = nullptr;
+    int (*ModuleUnload)(void *) = nullptr;
+    int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+    int (*FuncSetAttribute)(void *, int, int) = nullptr;
+    int (*FuncGetAttribute)(int *, int, void *) = nullptr;
+    int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
+    std::string err;
+    bool ok = false;
+    bool load()
+    {
+        if (ok) return true;
+        auto get = [&](const char *nm, void **fp) {
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint(nm, fp, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !*fp) {
+                err = std::string("driver entry point ") + nm + " not found";
+                return false;
+            }
+            return true;
+        };
+        ok = get("cuModuleLoadData", (void **)&ModuleLoadData) && get("cuModuleUnload", (void **)&ModuleUnload) &&
+             get("cuModuleGetFunction", (void **)&ModuleGetFunction) && get("cuFuncSetAttribute", (void **)&FuncSetAttribute) &&
+             get("cuFuncGetAttribute", (void **)&FuncGetAttribute) && get("cuLaunchKernel", (void **)&LaunchKernel);
+        return ok;
+    }
+};
+inline Driver &driver()
+{
+    static Driver d;
+    return d;
+}
+
+// A kernel loaded into the current device's primary context.
+struct Loaded {
+    void *module = nullptr;
+    void *func = nullptr;
+    int regs = 0;
+};
+
+inline std::string load(const Image &img, uint32_t smem_bytes, bool prefer_l1, Loaded &out)
+{
+    Driver &dr = driver();
+    if (!dr.load()) return dr.err;
+    cudaFree(nullptr); // make sure the primary context exists and is current
+    int rc = dr.ModuleLoadData(&out.module, img.cubin.data());
+    if (rc) return "cuModuleLoadData failed (" + std::to_string(rc) + ")";
+    rc = dr.ModuleGetFunction(&out.func, out.module, img.name.c_str());
+    if (rc) return "cuModuleGetFunction(" + img.name + ") failed (" + std::to_string(rc) + ")";
+    // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8, PREFERRED_SHARED_MEMORY_CARVEOUT = 9, NUM_REGS = 4
+    rc = dr.FuncSetAttribute(out.func, 8, (int)smem_bytes);
+    if (rc) return "cuFuncSetAttribute(max dynamic shared memory) failed (" + std::to_string(rc) + ")";
+    if (prefer_l1) dr.FuncSetAttribute(out.func, 9, 0); // jets in global memory: all of L1 for them
+    dr.FuncGetAttribute(&out.regs, 4, out.func);
+    return "";
+}
+
+inline void unload(Loaded &l)
+{
+    if (l.module && driver().ok) driver().ModuleUnload(l.module);
+    l.module = l.func = nullptr;
+}
+
+template <typename KP>
+inline cudaError_t launch(const Loaded &l, const KP &P, uint32_t ctas, uint32_t threads, uint32_t smem, cudaStream_t s)
+{
+    void *args[] = {const_cast<KP *>(&P)};
+    const int rc = driver().LaunchKernel(l.func, ctas, 1, 1, threads, 1, 1, smem, (void *)s, args, nullptr);
+    return rc == 0 ? cudaSuccess : cudaErrorLaunchFailure;
+}
+
+} // namespace jit
+} // namespace hy

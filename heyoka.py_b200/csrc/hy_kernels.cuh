@@ -23,13 +23,30 @@
 #include <stdint.h>
 
 #include "../../include/hy_cuda.h"
+#ifdef __CUDACC_RTC__
+#include "hy_devprog.h" // run-time compiled kernels (hy_jit.hpp): no host code in the translation unit
+#else
 #include "hy_schedule.hpp"
+#endif
 #include "hy_events.cuh"
 #include "hy_evtape.cuh"
 #include "hy_nbody_reg.cuh"
 #include "hy_cr3bp_reg.cuh"
 
+// Run-time compiled kernels (hy_jit.hpp) define HY_JIT and HY_WS = 32: one thread per trajectory,
+// workspace interleaved over the lanes of a warp (row r of lane l at [r * 32 + l]), the order
+// sweep generated from the tape (hy_gen_jets) instead of interpreted.
+#ifndef HY_WS
+#define HY_WS 1
+#endif
+
 namespace hy {
+
+#ifdef HY_JIT
+// generated per tape: orders 0 .. p-1 of every op / the event-function ops at order p
+template <typename R> __device__ __forceinline__ void hy_gen_jets(R *__restrict__ w, const R *__restrict__ rk, const R tm);
+template <typename R> __device__ __forceinline__ void hy_gen_ev_sweep(R *__restrict__ w, const R *__restrict__ rk, const R tm);
+#endif
 
 // ---- precision-generic math wrappers ----
 __device__ __forceinline__ double r_fma(double a, double b, double c) { return fma(a, b, c); }
@@ -192,7 +209,10 @@ template <typename R> __device__ __noinline__ R pow0(R x, double alpha)
 // address arithmetic (immediate offsets from two base registers).
 // ---------------------------------------------------------------------------
 // sum_{j=0}^{n-1} pa[j] * pb[-j]
-template <typename R> __device__ __forceinline__ R conv(const R *__restrict__ pa, const R *__restrict__ pb, int n)
+// (S: element stride of the workspace - 1 for a trajectory column, HY_WS for the warp-interleaved
+//  workspace of the run-time compiled kernels)
+template <typename R, int S = 1>
+__device__ __forceinline__ R conv(const R *__restrict__ pa, const R *__restrict__ pb, int n)
 {
     R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll 1
@@ -202,8 +222,8 @@ template <typename R> __device__ __forceinline__ R conv(const R *__restrict__ pa
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const bool v = u < m;
-            a[u] = v ? pa[j0 + u] : (R)0;
-            b[u] = v ? pb[-(j0 + u)] : (R)0;
+            a[u] = v ? pa[(j0 + u) * S] : (R)0;
+            b[u] = v ? pb[-(j0 + u) * S] : (R)0;
         }
         s0 = r_fma(a[0], b[0], s0);
         s1 = r_fma(a[1], b[1], s1);
@@ -217,8 +237,42 @@ template <typename R> __device__ __forceinline__ R conv(const R *__restrict__ pa
     return (s0 + s1) + (s2 + s3);
 }
 
+#ifdef HY_JIT
+// Run-time compiled kernels: the operands come from global memory (L1/L2/HBM), so a convolution
+// must have ALL its loads in flight before the first FMA waits on one - every block of the loop
+// above costs one memory latency.  Same terms, same four chains in the same order as conv():
+// identical rounding.  Out of line: the generated sweep calls it once per product (small code,
+// the instruction cache holds the whole sweep).
+template <typename R, int S, int NT> __device__ __forceinline__ R conv_wide_n(const R *__restrict__ pa, const R *__restrict__ pb, int n)
+{
+    R a[NT], b[NT];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        const bool v = u < n;
+        a[u] = v ? pa[u * S] : (R)0;
+        b[u] = v ? pb[-u * S] : (R)0;
+    }
+    R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int u = 0; u < NT; u += 4) {
+        s0 = r_fma(a[u], b[u], s0);
+        s1 = r_fma(a[u + 1], b[u + 1], s1);
+        s2 = r_fma(a[u + 2], b[u + 2], s2);
+        s3 = r_fma(a[u + 3], b[u + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+template <typename R, int S> __device__ __noinline__ R conv_wide(const R *__restrict__ pa, const R *__restrict__ pb, int n)
+{
+    if (n <= 8) return conv_wide_n<R, S, 8>(pa, pb, n);
+    if (n <= 16) return conv_wide_n<R, S, 16>(pa, pb, n);
+    if (n <= 24) return conv_wide_n<R, S, 24>(pa, pb, n);
+    return conv<R, S>(pa, pb, n);
+}
+#endif
+
 // Three products sharing the operand b:  o_i = sum_{j<n} a_i[j] * pb[-j]
-template <typename R>
+template <typename R, int S = 1>
 __device__ __forceinline__ void conv3(const R *__restrict__ a0, const R *__restrict__ a1, const R *__restrict__ a2,
                                       const R *__restrict__ pb, int n, R &o0, R &o1, R &o2)
 {
@@ -230,10 +284,10 @@ __device__ __forceinline__ void conv3(const R *__restrict__ a0, const R *__restr
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const bool v = u < m;
-            b[u] = v ? pb[-(j0 + u)] : (R)0;
-            x[u] = v ? a0[j0 + u] : (R)0;
-            y[u] = v ? a1[j0 + u] : (R)0;
-            z[u] = v ? a2[j0 + u] : (R)0;
+            b[u] = v ? pb[-(j0 + u) * S] : (R)0;
+            x[u] = v ? a0[(j0 + u) * S] : (R)0;
+            y[u] = v ? a1[(j0 + u) * S] : (R)0;
+            z[u] = v ? a2[(j0 + u) * S] : (R)0;
         }
         s0a = r_fma(x[0], b[0], s0a);
         s1a = r_fma(y[0], b[0], s1a);
@@ -253,8 +307,43 @@ __device__ __forceinline__ void conv3(const R *__restrict__ a0, const R *__restr
     o2 = s2a + s2b;
 }
 
+#ifdef HY_JIT
+// conv3 with 12-term blocks (48 loads in flight); chains as in conv3: even / odd terms.
+template <typename R, int S>
+__device__ __noinline__ void conv3_wide(const R *__restrict__ a0, const R *__restrict__ a1, const R *__restrict__ a2,
+                                        const R *__restrict__ pb, int n, R &o0, R &o1, R &o2)
+{
+    R s0a = 0, s1a = 0, s2a = 0, s0b = 0, s1b = 0, s2b = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += 12) {
+        R x[12], y[12], z[12], b[12];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const bool v = u < m;
+            b[u] = v ? pb[-(j0 + u) * S] : (R)0;
+            x[u] = v ? a0[(j0 + u) * S] : (R)0;
+            y[u] = v ? a1[(j0 + u) * S] : (R)0;
+            z[u] = v ? a2[(j0 + u) * S] : (R)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 12; u += 2) {
+            s0a = r_fma(x[u], b[u], s0a);
+            s1a = r_fma(y[u], b[u], s1a);
+            s2a = r_fma(z[u], b[u], s2a);
+            s0b = r_fma(x[u + 1], b[u + 1], s0b);
+            s1b = r_fma(y[u + 1], b[u + 1], s1b);
+            s2b = r_fma(z[u + 1], b[u + 1], s2b);
+        }
+    }
+    o0 = s0a + s0b;
+    o1 = s1a + s1b;
+    o2 = s2a + s2b;
+}
+#endif
+
 // pow recurrence sum:  sum_{j<n} (kal - j*al1) * ak[-j] * c[j]
-template <typename R>
+template <typename R, int S = 1>
 __device__ __forceinline__ R conv_pow(const R *__restrict__ ak, const R *__restrict__ c, int n, const R al1, const R kal)
 {
     R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -266,8 +355,8 @@ __device__ __forceinline__ R conv_pow(const R *__restrict__ ak, const R *__restr
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const bool v = u < m;
-            a[u] = v ? ak[-(j0 + u)] : (R)0;
-            b[u] = v ? c[j0 + u] : (R)0;
+            a[u] = v ? ak[-(j0 + u) * S] : (R)0;
+            b[u] = v ? c[(j0 + u) * S] : (R)0;
         }
 #pragma unroll
         for (int u = 0; u < 8; u += 4) {
@@ -821,6 +910,9 @@ __host__ __device__ inline SmemLayout make_layout(const hy_dims &d, const ProgDi
 // (rb: bytes per real.  The FP32 CR3BP kernel holds 5 x 9 jet registers: more warps instead.)
 __host__ __device__ constexpr int hy_max_threads(int G, bool smem, int NB, int rb = 8)
 {
+#ifdef HY_JIT_THREADS
+    return HY_JIT_THREADS; // run-time compiled kernels: the CTA size is a compile-time constant of the build
+#endif
     return (NB < 0 && rb == 4) ? HY_CRB_F32_THREADS : ((NB == 0 && smem && G < 16) ? 512 : 256);
 }
 
@@ -893,19 +985,28 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     const unsigned wmask = __ballot_sync(0xffffffffu, slot < P.T);
     if (slot >= P.T) return;
     R *w;
+#ifdef HY_JIT
+    // warp-interleaved workspace: warp q of the CTA owns rows [q * RS, (q + 1) * RS) x 32 lanes
+    w = (SMEM ? reinterpret_cast<R *>(smem_raw + L.off_ws) : P.gws + (size_t)blockIdx.x * P.T * RS) +
+        (size_t)(threadIdx.x >> 5) * RS * 32u + lane;
+#else
     if (SMEM)
         w = reinterpret_cast<R *>(smem_raw + L.off_ws) + (size_t)slot * RS;
     else
         w = P.gws + ((size_t)blockIdx.x * P.T + slot) * RS;
+#endif
     // global scratch of this trajectory slot's spilled state jets
     R *gj = P.gjet + ((size_t)blockIdx.x * P.T + slot) * (size_t)P.pd.n_spill * P1;
     // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
 // (NB > 0: the orders of a state variable are NBR_JS elements apart, see hy_nbody_reg.cuh)
-    constexpr uint32_t XS = NB > 0 ? (uint32_t)NBR_JS : (NB < 0 ? (uint32_t)CRB_XS : 1u);
+    // (HY_JIT: the rows of the interleaved workspace are HY_WS elements apart; state_row, ev_ref, par_off
+    //  and one_off arrive pre-multiplied)
+    constexpr uint32_t XS = NB > 0 ? (uint32_t)NBR_JS : (NB < 0 ? (uint32_t)CRB_XS : (uint32_t)HY_WS);
+    constexpr uint32_t ES = NB == 0 ? (uint32_t)HY_WS : 1u; // order stride of an event jet
 #define XJ(i, j) (s_ssp[i] >= 0 ? __ldcg(&gj[(uint32_t)s_ssp[i] * P1 + (j)]) : w[s_srow[i] + (j) * XS])
     // unit jet [1, 0, ..., 0] (never changes)
     if constexpr (NB == 0)
-        for (uint32_t i = sub; i < P1; i += G) w[one_off + i] = i == 0 ? (R)1 : (R)0;
+        for (uint32_t i = sub; i < P1; i += G) w[one_off + i * XS] = i == 0 ? (R)1 : (R)0;
     // register-resident N-body path: per-lane constants (pair, exchange slots, body)
     NbrLane<(NB > 0 ? NB : 2)> nl{};
     if constexpr (NB > 0) {
@@ -990,7 +1091,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     w[s_srow[i]] = x0;
                     if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = x0;
                 }
-                for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i] = P.pars[(size_t)i * P.B + traj];
+                for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i * XS] = P.pars[(size_t)i * P.B + traj];
                 hi = P.t_hi[traj];
                 lo = P.t_lo[traj];
                 mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
@@ -1137,6 +1238,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 else
                     crb_jets<R, CPM, false>(w, cl, p);
             } else {
+#ifdef HY_JIT
+                hy_gen_jets<R>(w, s_rk, hi);
+                if (d.n_events) hy_gen_ev_sweep<R>(w, s_rk, hi);
+#else
                 const DOp *lops = s_ops + sub;
                 const DTerm *lterms = s_terms + sub;
                 const uint32_t n_ph = P.pd.n_phases;
@@ -1159,6 +1264,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         if (G > 1) __syncwarp(gmask);
                     }
                 }
+#endif
             }
             // ---- event functions on the register-resident kernels (hy_evtape.cuh): lane e mod G
             // evaluates event e from the state jets.  Linear ops at every order, products / squares
@@ -1237,8 +1343,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     } else {
                         const R *x = &w[s_ev[i - n]];
                         x0 = x[0];
-                        x1 = x[p - 1];
-                        x2 = x[p];
+                        x1 = x[(p - 1) * ES];
+                        x2 = x[p * ES];
                     }
                     n0 = nan_max(n0, r_abs(x0));
                     n1 = nan_max(n1, r_abs(x1));
@@ -1291,8 +1397,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             if (NB == 0 && d.n_events) {
                 R h_eff = h;
                 if (sub == 0)
-                    detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
-                                     term_ev, nt_fired);
+                    detect_events<R, (int)ES>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
+                                              term_ev, nt_fired);
                 if (G > 1) {
                     h_eff = __shfl_sync(gmask, h_eff, 0, G);
                     term_ev = __shfl_sync(gmask, term_ev, 0, G);

@@ -151,6 +151,7 @@ SYMBOLS = [
     "hy_reset_cooldowns",
     "hy_get_launch_info",
     "hy_tape_kernel_variant",
+    "hy_jit_precompile",
     "hy_measure_fma_peak",
 ]
 
@@ -183,6 +184,17 @@ def ptr(a):
     if a is None:
         return None
     return a.ctypes.data_as(C.c_void_p)
+
+
+def jit_precompile(dc, fp_bits=64, batch=1 << 20, n_tevents=0):
+    """hy_jit_precompile: generate + compile the run-time kernel of a tape without a device (warms
+    the on-disk kernel cache).  Returns (from_cache, compile_seconds); from_cache is -1 when the
+    tape is served by the interpreter."""
+    dims = _dims_of(dc, n_tevents)
+    full = tape_t(C.addressof(dims), _vp(dc.ops), _vp(dc.terms), _vp(dc.level_start), _vp(dc.ev_ref))
+    fc, cs = C.c_int(0), C.c_double(0.0)
+    check(lib().hy_jit_precompile(C.c_int(fp_bits), C.byref(full), C.c_uint32(batch), C.byref(fc), C.byref(cs)))
+    return fc.value, cs.value
 
 
 def device_count():
@@ -224,8 +236,11 @@ class Context:
     """Owner of one hy_ctx."""
 
     def __init__(self, dc, fp_bits, batch, tol, high_accuracy, device=0, n_tevents=0,
-                 ev_dir=None, ev_cooldown=None, _handle=None, dc_ode=None, evt=None):
+                 ev_dir=None, ev_cooldown=None, _handle=None, dc_ode=None, evt=None, compact_mode=False):
         import threading
+
+        # hy_create's flag word: HY_CREATE_HIGH_ACCURACY | HY_CREATE_COMPACT (include/hy_cuda.h)
+        high_accuracy = (1 if high_accuracy else 0) | (2 if compact_mode else 0)
 
         self._ctx = C.c_void_p()
         self._lock = threading.Lock()  # guards the context's recorder against a recycling __del__

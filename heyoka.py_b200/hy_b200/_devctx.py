@@ -111,7 +111,7 @@ class MultiContext:
     """Lane-sharded context over several devices with the interface of ``_cabi.Context``."""
 
     def __init__(self, dc, fp_bits, batch, tol, high_accuracy, devices, n_tevents=0, ev_dir=None,
-                 ev_cooldown=None, dc_ode=None, evt=None):
+                 ev_cooldown=None, dc_ode=None, evt=None, compact_mode=False):
         self.devices = list(devices)
         G = len(self.devices)
         self.batch = batch
@@ -127,12 +127,13 @@ class MultiContext:
         self._pool = ThreadPoolExecutor(max_workers=len(self.bounds))
         first = _cabi.Context(dc, fp_bits, self.bounds[0][1] - self.bounds[0][0], tol, high_accuracy,
                               device=self.devices[0], n_tevents=n_tevents, ev_dir=ev_dir,
-                              ev_cooldown=ev_cooldown, dc_ode=dc_ode, evt=evt)
+                              ev_cooldown=ev_cooldown, dc_ode=dc_ode, evt=evt, compact_mode=compact_mode)
         self.parts = [first]
         for (lo, hi), dev in zip(self.bounds[1:], self.devices[1:]):
             self.parts.append(_cabi.Context(dc, fp_bits, hi - lo, tol, high_accuracy, device=dev,
                                             n_tevents=n_tevents, ev_dir=ev_dir,
-                                            ev_cooldown=ev_cooldown, dc_ode=dc_ode, evt=evt))
+                                            ev_cooldown=ev_cooldown, dc_ode=dc_ode, evt=evt,
+                                            compact_mode=compact_mode))
         # per-shard contiguous staging buffers (page-locked): the caller's arrays are [rows, B]
         # with the lane index fastest, so a shard is a strided slice of them
         self._st = [dict() for _ in self.parts]

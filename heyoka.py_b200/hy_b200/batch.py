@@ -224,7 +224,7 @@ class taylor_adaptive_batch_impl:
 
     # ---- device context ----
     def _ctx_key(self, device):
-        return (id(self._dc), self._fp, self._B, self._tol, self._high_accuracy, device,
+        return (id(self._dc), self._fp, self._B, self._tol, self._high_accuracy, self._compact_mode, device,
                 tuple(int(e.direction) for e in self._t_events + self._nt_events),
                 tuple(float(e.cooldown) for e in self._t_events))
 
@@ -246,7 +246,8 @@ class taylor_adaptive_batch_impl:
         if devs is not None and len(devs) > 1:
             ctx = _devctx.MultiContext(self._dc, fp_bits, B, self._tol, self._high_accuracy, devs,
                                        n_tevents=len(self._t_events), ev_dir=ev_dir or None,
-                                       ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt)
+                                       ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt,
+                                       compact_mode=self._compact_mode)
         else:
             dev = devs[0] if devs else self._device
             ctx = _devctx.POOL.acquire(self._ctx_key(dev))
@@ -256,7 +257,8 @@ class taylor_adaptive_batch_impl:
             if ctx is None:
                 ctx = _cabi.Context(self._dc, fp_bits, B, self._tol, self._high_accuracy, device=dev,
                                     n_tevents=len(self._t_events), ev_dir=ev_dir or None,
-                                    ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt)
+                                    ev_cooldown=ev_cd or None, dc_ode=self._dc_ode, evt=self._evt,
+                                    compact_mode=self._compact_mode)
             else:
                 # a recycled / cloned context carries another integrator's device-only data
                 if self._t_events:

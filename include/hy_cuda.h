@@ -312,6 +312,16 @@ int hy_set_cooldowns(hy_ctx *ctx, const void *elapsed, const void *total); /* re
 int hy_reset_cooldowns(hy_ctx *ctx, int64_t lane);             /* -1 = all lanes */
 
 /* Introspection for benches/tests: launch geometry chosen for the tape. */
+/* kernel_variant of a kernel generated from the tape and compiled at hy_create time with NVRTC
+ * (csrc/hy_jit.hpp): one thread per trajectory, the order sweep as straight-line code.  This is
+ * the counterpart of the reference's LLVM JIT (expose_batch_integrators.cpp:166-208). */
+#define HY_VARIANT_JIT 1000u
+/* Bits of hy_create's `high_accuracy` argument.  HY_CREATE_COMPACT is the reference's
+ * `compact_mode=True` (expose_batch_integrators.cpp:198): no per-system code generation - the
+ * tape interpreter runs the system. */
+#define HY_CREATE_HIGH_ACCURACY 1
+#define HY_CREATE_COMPACT 2
+
 typedef struct hy_launch_info {
     uint32_t group;          /* threads cooperating on one trajectory        */
     uint32_t traj_per_cta;   /* trajectories resident per CTA                */
@@ -343,6 +353,12 @@ int hy_get_launch_info(hy_ctx *ctx, hy_launch_info *info);
  * orders 21..22) or 9 (FP32), no events or parameters (hy_cr3bp_match.hpp). */
 int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term *terms,
                            uint32_t *variant);
+
+/* Generate and compile the run-time kernel of a tape ahead of time, without a device: fills the
+ * on-disk kernel cache (csrc/jit_cache, or $HY_CUDA_JIT_CACHE) that hy_create looks up first.
+ * *from_cache: 1 the kernel was already cached, 0 it was compiled now (*compile_s seconds), -1 the
+ * tape is served by the interpreter (no kernel is generated for it). */
+int hy_jit_precompile(int fp_bits, const hy_tape *full, uint32_t batch, int *from_cache, double *compile_s);
 
 /* DFMA/FFMA peak microbenchmark used as the compute roof (no peak for
  * FP64/FP32 FMA is in MEASURED_PEAKS.json): returns TFLOP/s. */
