@@ -49,7 +49,31 @@ struct Gen {
     const hy_dims &d;
     const Program &pr;
     std::ostringstream os;
-    Gen(const hy_dims &d_, const Program &p_) : d(d_), pr(p_) {}
+    // order blocking (blockconv_core, hy_kernels.cuh): block size M (0: off), first scratch row of
+    // every blocked op (M - 1 rows per output), number of scratch rows
+    uint32_t M = 0;
+    uint32_t pf_dist = 0, pf_level = 1; // software prefetch: ops ahead (0: off), cache level
+    std::vector<int64_t> qbase;
+    uint32_t q_rows = 0;
+    Gen(const hy_dims &d_, const Program &p_, uint32_t blk) : d(d_), pr(p_)
+    {
+        qbase.assign(pr.n_slots, -1);
+        if (blk >= 2 && d.order >= 2 * blk) {
+            M = blk;
+            uint32_t next = pr.ws_len;
+            for (uint32_t i = 0; i < pr.n_slots; ++i) {
+                const DOp &o = pr.ops[i];
+                uint32_t outs = 0;
+                if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV) outs = 1;
+                if (o.opcode == HY_OP_MULSH && o.n >= 2 && o.n <= 4) outs = o.n;
+                if (outs && next + outs * (M - 1) < 65535u) {
+                    qbase[i] = next;
+                    next += outs * (M - 1);
+                }
+            }
+            q_rows = next - pr.ws_len;
+        }
+    }
 
     static std::string lit(double v)
     {
@@ -84,11 +108,46 @@ struct Gen {
             os << "        " << Wr(o.dst, o.flags & DF_JDST) << " = " << val << ";\n";
     }
 
-    // One op at order k (k: a variable of the generated code).  Mirrors exec_op (hy_kernels.cuh)
-    // statement by statement so that both paths round identically.
-    bool emit_op(const DOp &o)
+    // Prefetch the operand rows of op `o` at order k (plain sweep: the full history of every
+    // convolution operand, the current row of the others).
+    void emit_prefetch(const DOp &o, int lvl)
+    {
+        const DTerm *t = pr.terms.data() + o.b;
+        const std::string L = std::to_string(lvl);
+        auto jet = [&](uint32_t base) {
+            os << "        pf_rows<R, HY_WS, " << L << ">(" << ptr(base) << ", (int)k + 1);\n";
+        };
+        auto cur = [&](uint32_t base, bool j) {
+            os << "        pf_rows<R, HY_WS, " << L << ">(" << (j ? ptrk(base) : ptr(base)) << ", 1);\n";
+        };
+        switch (o.opcode) {
+        case HY_OP_LINCOMB:
+            for (uint32_t i = 0; i < o.n; ++i) cur(t[i].src, (t[i].aux >> 16) == 0xffffu);
+            break;
+        case HY_OP_ADDSUB: cur(o.a, o.flags & DF_JA); cur(o.b, o.flags & DF_JB); break;
+        case HY_OP_SVD: cur(o.a, o.flags & DF_JA); break;
+        case HY_OP_MUL: jet(o.a); jet(o.b); break;
+        case HY_OP_SQUARE: jet(o.a); break;
+        case HY_OP_SUMSQ: for (uint32_t i = 0; i < o.n; ++i) jet(t[i].src & 0x3fffffffu); break;
+        case HY_OP_MULSH: jet(o.a); for (uint32_t i = 0; i < o.n; ++i) jet(t[i].src & 0x3fffffffu); break;
+        case HY_OP_DIV: jet(o.b); jet(o.dst); cur(o.a, o.flags & DF_JA); break;
+        case HY_OP_POW: case HY_OP_SQRT: case HY_OP_EXP: case HY_OP_LOG: jet(o.a); jet(o.dst); break;
+        case HY_OP_SINCOS: jet(o.a); jet(o.dst); jet(o.dst2); break;
+        default: break;
+        }
+    }
+
+    // One op at order k (k: a variable of the generated code).  Linear ops are emitted inline (a few
+    // loads and FMAs); everything with a convolution is a call to an out-of-line body (jop_*,
+    // hy_kernels.cuh) with literal row numbers.  The unblocked arithmetic is exec_op's.
+    bool emit_op(const DOp &o, uint32_t slot = 0, bool sweep = false)
     {
         const DTerm *t = pr.terms.data() + o.b; // (G = 1: the lane's stream is the term array)
+        const bool blocked = sweep && M && qbase[slot] >= 0;
+        const std::string Ms = std::to_string(blocked ? M : 1u);
+        const std::string bi = blocked ? "bi" : "HY_NOBLK";
+        const uint32_t qb = blocked ? (uint32_t)qbase[slot] : 0u;
+        auto rowk = [&](uint32_t base, bool jet) { return row(base, jet); };
         os << "      { // op " << (int)o.opcode << "\n";
         switch (o.opcode) {
         case HY_OP_LINCOMB: {
@@ -120,88 +179,51 @@ struct Gen {
         } break;
         case HY_OP_SVD: store(o, Wr(o.a, o.flags & DF_JA)); break;
         case HY_OP_MUL:
-            store(o, "conv_wide<R, HY_WS>(" + ptr(o.a) + ", " + ptrk(o.b) + ", (int)k + 1)");
+            os << "        jop_mul<R, HY_WS, " << Ms << ">(w, k, " << bi << ", " << o.a << ", " << o.b << ", "
+               << rowk(o.dst, o.flags & DF_JDST) << ", " << qb << ");\n";
             break;
         case HY_OP_SQUARE:
-            os << "        const R *a = " << ptr(o.a) << ";\n";
-            os << "        R acc = conv_wide<R, HY_WS>(a, a + k * HY_WS, (int)((k + 1) >> 1));\n";
-            os << "        acc = acc + acc;\n";
-            os << "        if ((k & 1u) == 0) { const R m = a[(k >> 1) * HY_WS]; acc = r_fma(m, m, acc); }\n";
-            store(o, "acc");
+            os << "        jop_square<R, HY_WS>(w, k, " << o.a << ", " << rowk(o.dst, o.flags & DF_JDST) << ");\n";
             break;
         case HY_OP_SUMSQ:
-            os << "        const int half = (int)((k + 1) >> 1);\n        R acc = 0, acc2 = 0;\n";
-            for (uint32_t i = 0; i < o.n; ++i) {
-                os << "        { const R *a = " << ptr(t[i].src & 0x3fffffffu) << ";\n";
-                os << "          acc += conv_wide<R, HY_WS>(a, a + k * HY_WS, half);\n";
-                os << "          if ((k & 1u) == 0) { const R m = a[(k >> 1) * HY_WS]; acc2 = r_fma(m, m, acc2); } }\n";
-            }
+            os << "        R acc = 0, acc2 = 0;\n";
+            for (uint32_t i = 0; i < o.n; ++i)
+                os << "        jop_sumsq_term<R, HY_WS>(w, k, " << (t[i].src & 0x3fffffffu) << ", acc, acc2);\n";
             store(o, "(acc + acc) + acc2");
             break;
         case HY_OP_MULSH: {
-            os << "        const R *b = " << ptrk(o.a) << ";\n        const int n = (int)k + 1;\n";
-            auto dstref = [&](const DTerm &ti) { return Wr(ti.aux & 0x3fffffffu, ti.aux & HY_DREF_JET); };
-            if (o.n == 3) {
-                os << "        R s0, s1, s2;\n";
-                os << "        conv3_wide<R, HY_WS>(" << ptr(t[0].src & 0x3fffffffu) << ", " << ptr(t[1].src & 0x3fffffffu) << ", "
-                   << ptr(t[2].src & 0x3fffffffu) << ", b, n, s0, s1, s2);\n";
-                for (int i = 0; i < 3; ++i) os << "        " << dstref(t[i]) << " = s" << i << ";\n";
+            // (the fusion pass builds groups of 2..4 products; anything else falls back to single products)
+            if (o.n >= 1 && o.n <= 4) {
+                os << "        const JRows<R, HY_WS, " << Ms << ", " << o.n << "> r = {{";
+                for (uint32_t i = 0; i < o.n; ++i) os << (i ? ", " : "") << (t[i].src & 0x3fffffffu);
+                os << "}, {";
+                for (uint32_t i = 0; i < o.n; ++i) os << (i ? ", " : "") << rowk(t[i].aux & 0x3fffffffu, t[i].aux & HY_DREF_JET);
+                os << "}};\n";
+                os << "        jop_mulsh<R, HY_WS, " << Ms << ", " << o.n << ">(w, k, " << bi << ", " << o.a << ", r, " << qb << ");\n";
             } else {
                 for (uint32_t i = 0; i < o.n; ++i)
-                    os << "        " << dstref(t[i]) << " = conv_wide<R, HY_WS>(" << ptr(t[i].src & 0x3fffffffu) << ", b, n);\n";
+                    os << "        jop_mul<R, HY_WS, 1>(w, k, HY_NOBLK, " << (t[i].src & 0x3fffffffu) << ", " << o.a << ", "
+                       << rowk(t[i].aux & 0x3fffffffu, t[i].aux & HY_DREF_JET) << ", 0);\n";
             }
         } break;
         case HY_OP_DIV:
-            os << "        const R *b = " << ptr(o.b) << ";\n        R *c = " << ptr(o.dst) << ";\n";
-            os << "        if (k == 0) W(" << o.dst2 << ") = (R)1 / b[0];\n";
-            os << "        R acc = " << Wr(o.a, o.flags & DF_JA) << ";\n";
-            os << "        if (k > 0) acc -= conv_wide<R, HY_WS>(b + HY_WS, c + (k - 1) * HY_WS, (int)k);\n";
-            os << "        c[k * HY_WS] = acc * W(" << o.dst2 << ");\n";
+            os << "        jop_div<R, HY_WS, " << Ms << ">(w, k, " << bi << ", " << rowk(o.a, o.flags & DF_JA) << ", " << o.b << ", "
+               << o.dst << ", " << o.dst2 << ", " << qb << ");\n";
             break;
         case HY_OP_POW:
         case HY_OP_SQRT: {
             const double alpha = o.opcode == HY_OP_SQRT ? 0.5 : pr.imm[o.imm];
             char ab[64];
             std::snprintf(ab, sizeof ab, "%a", alpha);
-            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
-            os << "        const double alpha = " << ab << ";\n";
-            os << "        if (k == 0) {\n          W(" << o.dst2 << ") = (R)1 / a[0];\n";
-            if (o.opcode == HY_OP_SQRT)
-                os << "          c[0] = r_sqrt(a[0]);\n";
-            else
-                os << "          c[0] = pow0<R>(a[0], alpha);\n";
-            os << "        } else {\n          const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;\n";
-            os << "          c[k * HY_WS] = (conv_pow<R, HY_WS>(a + k * HY_WS, c, (int)k, al1, kal) * rk[k]) * W(" << o.dst2
-               << ");\n        }\n";
+            os << "        jop_pow<R, HY_WS>(w, rk, k, " << o.a << ", " << o.dst << ", " << o.dst2 << ", " << ab << ", "
+               << (o.opcode == HY_OP_SQRT ? 1 : 0) << ");\n";
         } break;
-        case HY_OP_EXP:
-            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
-            os << "        if (k == 0) {\n          c[0] = r_exp(a[0]);\n        } else {\n          R acc = 0, jr = 1;\n";
-            os << "          _Pragma(\"unroll 1\") for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * a[j * HY_WS], c[(k "
-                  "- j) * HY_WS], acc);\n";
-            os << "          c[k * HY_WS] = acc * rk[k];\n        }\n";
-            break;
+        case HY_OP_EXP: os << "        jop_exp<R, HY_WS>(w, rk, k, " << o.a << ", " << o.dst << ");\n"; break;
         case HY_OP_LOG:
-            os << "        const R *a = " << ptr(o.a) << ";\n        R *c = " << ptr(o.dst) << ";\n";
-            os << "        if (k == 0) {\n          W(" << o.dst2 << ") = (R)1 / a[0];\n          c[0] = r_log(a[0]);\n";
-            os << "        } else {\n          R acc = 0, jr = 1;\n";
-            os << "          _Pragma(\"unroll 1\") for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * c[j * HY_WS], a[(k "
-                  "- j) * HY_WS], acc);\n";
-            os << "          c[k * HY_WS] = r_fma(-acc, rk[k], a[k * HY_WS]) * W(" << o.dst2 << ");\n        }\n";
+            os << "        jop_log<R, HY_WS>(w, rk, k, " << o.a << ", " << o.dst << ", " << o.dst2 << ");\n";
             break;
         case HY_OP_SINCOS:
-            os << "        const R *a = " << ptr(o.a) << ";\n        R *s = " << ptr(o.dst) << ", *c = " << ptr(o.dst2) << ";\n";
-            os << "        if (k == 0) {\n          R sv, cv;\n          r_sincos(a[0], &sv, &cv);\n          s[0] = sv;\n          c[0] = cv;\n";
-            os << "        } else {\n          R sa0 = 0, ca0 = 0, sa1 = 0, ca1 = 0, jr = 1;\n          uint32_t j = 1;\n";
-            os << "          _Pragma(\"unroll 1\") for (; j + 1 <= k; j += 2, jr += (R)2) {\n";
-            os << "            const R ja0 = jr * a[j * HY_WS], ja1 = (jr + (R)1) * a[(j + 1) * HY_WS];\n";
-            os << "            const R c0 = c[(k - j) * HY_WS], s0 = s[(k - j) * HY_WS], c1 = c[(k - j - 1) * HY_WS], s1 = s[(k - j - 1) * "
-                  "HY_WS];\n";
-            os << "            sa0 = r_fma(ja0, c0, sa0);\n            ca0 = r_fma(ja0, s0, ca0);\n";
-            os << "            sa1 = r_fma(ja1, c1, sa1);\n            ca1 = r_fma(ja1, s1, ca1);\n          }\n";
-            os << "          if (j <= k) {\n            const R ja = jr * a[j * HY_WS];\n";
-            os << "            sa0 = r_fma(ja, c[(k - j) * HY_WS], sa0);\n            ca0 = r_fma(ja, s[(k - j) * HY_WS], ca0);\n          }\n";
-            os << "          s[k * HY_WS] = (sa0 + sa1) * rk[k];\n          c[k * HY_WS] = -((ca0 + ca1) * rk[k]);\n        }\n";
+            os << "        jop_sincos<R, HY_WS>(w, rk, k, " << o.a << ", " << o.dst << ", " << o.dst2 << ");\n";
             break;
         case HY_OP_TIME: os << "        W(" << o.dst << " + k) = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);\n"; break;
         case OP_NOP: break;
@@ -222,8 +244,15 @@ struct Gen {
         os << "namespace hy {\n";
         os << "template <typename R> __device__ __forceinline__ void hy_gen_jets(R *__restrict__ w, const R *__restrict__ rk, const R tm)\n{\n";
         os << "    _Pragma(\"unroll 1\") for (uint32_t k = 0; k < " << d.order << "u; ++k) {\n";
-        for (uint32_t i = 0; i < pr.n_slots; ++i)
-            if (!emit_op(pr.ops[i])) return "";
+        if (M) {
+            // orders [M, floor(p / M) M) run in blocks of M; bi: position inside the block
+            os << "      const uint32_t bi = (k >= " << M << "u && k < " << (d.order / M) * M << "u) ? k % " << M
+               << "u : 0xffffffffu;\n";
+        }
+        for (uint32_t i = 0; i < pr.n_slots; ++i) {
+            if (pf_dist && i + pf_dist < pr.n_slots) emit_prefetch(pr.ops[i + pf_dist], pf_level);
+            if (!emit_op(pr.ops[i], i, true)) return "";
+        }
         os << "    }\n}\n";
         os << "template <typename R> __device__ __forceinline__ void hy_gen_ev_sweep(R *__restrict__ w, const R *__restrict__ rk, const R tm)\n{\n";
         os << "    const uint32_t k = " << d.order << "u;\n    (void)k; (void)rk; (void)tm; (void)w;\n";

@@ -342,6 +342,83 @@ __device__ __noinline__ void conv3_wide(const R *__restrict__ a0, const R *__res
 }
 #endif
 
+#ifdef HY_JIT
+// Software prefetch of the rows an upcoming op will read (rows [0, n) of a jet): needs no
+// registers, so the memory round trip of op i + D overlaps the arithmetic of ops i .. i + D - 1.
+template <typename R, int S, int LVL> __device__ __forceinline__ void pf_rows(const R *p, int n)
+{
+#pragma unroll 4
+    for (int u = 0; u < n; ++u) {
+        if (LVL == 1)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + u * S));
+        else
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + u * S));
+    }
+}
+// ---- order-blocked Cauchy products (run-time compiled kernels) ----
+// The jets of a large system stream from L2 / HBM: a plain sweep reads the whole history of both
+// operands of every product at every order.  Blocked in groups of M orders, the history is read once
+// per block: at the first order k0 of a block (k0 a multiple of M, k0 >= M) ONE pass over
+// s[jlo .. jhi] and the window operand computes, for i = 0 .. M-1, the part of the order-(k0+i) sum
+// whose two factors are both known already,
+//     O_i = sum_{j = jlo+i}^{jhi} s[j] * w[K + i - j],
+// O_0 is the complete sum of order k0; O_1 .. O_{M-1} are parked in scratch rows and completed at
+// their own order with the 2 i products that involve the new coefficients (shortsum below).
+//   product  c = a b :  s = a, w = b, jlo = 0, jhi = k0, K = k0
+//   quotient c = a / b (sum_{j>=1} b[j] c[k-j]) :  s = b, w = c, jlo = 1, jhi = k0, K = k0
+// NT streams share the window operand (MULSH).  Memory traffic of the products drops ~2.5x at
+// M = 4, the number of dependent memory round trips per step ~4x.  The summation order differs from
+// conv(): results agree with the interpreter to rounding, not bit for bit.
+template <typename R, int S, int M, int NT, int CH>
+__device__ __forceinline__ void blockconv_core(const R *const *ps, const R *__restrict__ pw, int n, R (&O)[NT][M])
+{
+    R wv[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) wv[i] = 0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int i = 0; i < M; ++i) O[t][i] = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += CH) {
+        R sv[NT][CH], wn[CH];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const bool v = u < m;
+            wn[u] = v ? pw[-(j0 + u) * S] : (R)0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) sv[t][u] = v ? ps[t][(j0 + u) * S] : (R)0;
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+#pragma unroll
+            for (int i = M - 1; i > 0; --i) wv[i] = wv[i - 1];
+            wv[0] = wn[u];
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int i = 0; i < M; ++i) O[t][i] = r_fma(sv[t][u], wv[i], O[t][i]);
+        }
+    }
+}
+// sum_{j<i} x[j] y[-j], i < M (all loads first, nothing branches)
+template <typename R, int S, int M> __device__ __forceinline__ R shortsum(const R *__restrict__ x, const R *__restrict__ y, uint32_t i)
+{
+    R xs[M > 1 ? M - 1 : 1], ys[M > 1 ? M - 1 : 1]; // (M = 1: never called, must still compile)
+#pragma unroll
+    for (int u = 0; u < M - 1; ++u) {
+        const bool v = (uint32_t)u < i;
+        xs[u] = v ? x[u * S] : (R)0;
+        ys[u] = v ? y[-u * S] : (R)0;
+    }
+    R acc = 0;
+#pragma unroll
+    for (int u = 0; u < M - 1; ++u) acc = r_fma(xs[u], ys[u], acc);
+    return acc;
+}
+#endif
+
 // pow recurrence sum:  sum_{j<n} (kal - j*al1) * ak[-j] * c[j]
 template <typename R, int S = 1>
 __device__ __forceinline__ R conv_pow(const R *__restrict__ ak, const R *__restrict__ c, int n, const R al1, const R kal)
@@ -398,6 +475,194 @@ __device__ __forceinline__ R conv_pow_from1(const R *__restrict__ ak, const R *_
     }
     return (s0 + s1) + (s2 + s3);
 }
+
+#ifdef HY_JIT
+// ---------------------------------------------------------------------------
+// Out-of-line op bodies of the run-time compiled kernels.  The generated sweep is a list of calls
+// with literal row numbers ("threaded code"): a few instructions per op, so the whole sweep stays
+// in the instruction cache however many ops the system has; the bodies below are shared by all
+// ops and all warps.  Rows are element rows of the interleaved workspace (element r at w[r * S]).
+// bi: position of the order inside a block of M (0xffffffff: this order is not blocked).
+// The unblocked paths repeat exec_op's arithmetic statement by statement (identical rounding).
+// ---------------------------------------------------------------------------
+#define HY_NOBLK 0xffffffffu
+template <typename R, int S, int M>
+__device__ __noinline__ void jop_mul(R *__restrict__ w, uint32_t k, uint32_t bi, uint32_t a, uint32_t b, uint32_t dst, uint32_t q)
+{
+    const R *pa = w + a * S, *pb = w + b * S;
+    if (M < 2 || bi == HY_NOBLK) {
+        w[dst * S] = conv_wide<R, S>(pa, pb + k * S, (int)k + 1);
+    } else if (bi == 0) {
+        const R *const ps[1] = {pa};
+        R O[1][M];
+        blockconv_core<R, S, M, 1, 16>(ps, pb + k * S, (int)k + 1, O);
+        w[dst * S] = O[0][0];
+#pragma unroll
+        for (int i = 1; i < M; ++i) w[(q + i - 1) * S] = O[0][i];
+    } else {
+        w[dst * S] = (w[(q + bi - 1) * S] + shortsum<R, S, M>(pa, pb + k * S, bi)) + shortsum<R, S, M>(pb, pa + k * S, bi);
+    }
+}
+// NT products sharing the operand b (MULSH): rows a[t] -> dst[t]; scratch rows q + t (M - 1)
+template <typename R, int S, int M, int NT> struct JRows {
+    uint32_t a[NT], dst[NT];
+};
+template <typename R, int S, int M, int NT>
+__device__ __noinline__ void jop_mulsh(R *__restrict__ w, uint32_t k, uint32_t bi, uint32_t b, const JRows<R, S, M, NT> r, uint32_t q)
+{
+    const R *pb = w + b * S;
+    if (M < 2 || bi == HY_NOBLK) {
+        if (NT == 3) {
+            R s0, s1, s2;
+            conv3_wide<R, S>(w + r.a[0] * S, w + r.a[1] * S, w + r.a[2 % NT] * S, pb + k * S, (int)k + 1, s0, s1, s2);
+            w[r.dst[0] * S] = s0;
+            w[r.dst[1] * S] = s1;
+            w[r.dst[2 % NT] * S] = s2;
+        } else {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) w[r.dst[t] * S] = conv_wide<R, S>(w + r.a[t] * S, pb + k * S, (int)k + 1);
+        }
+    } else if (bi == 0) {
+        const R *ps[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) ps[t] = w + r.a[t] * S;
+        R O[NT][M];
+        blockconv_core<R, S, M, NT, (NT == 1 ? 16 : (NT == 2 ? 12 : 8))>(ps, pb + k * S, (int)k + 1, O);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            w[r.dst[t] * S] = O[t][0];
+#pragma unroll
+            for (int i = 1; i < M; ++i) w[(q + t * (M - 1) + i - 1) * S] = O[t][i];
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const R *pa = w + r.a[t] * S;
+            w[r.dst[t] * S] = (w[(q + t * (M - 1) + bi - 1) * S] + shortsum<R, S, M>(pa, pb + k * S, bi)) +
+                              shortsum<R, S, M>(pb, pa + k * S, bi);
+        }
+    }
+}
+// c = a / b: num = row of a at this order, b / c = jet bases, inv = row holding 1 / b[0]
+template <typename R, int S, int M>
+__device__ __noinline__ void jop_div(R *__restrict__ w, uint32_t k, uint32_t bi, uint32_t num, uint32_t b, uint32_t c,
+                                     uint32_t inv, uint32_t q)
+{
+    const R *pb = w + b * S;
+    R *pc = w + c * S;
+    if (k == 0) w[inv * S] = (R)1 / pb[0];
+    if (M < 2 || bi == HY_NOBLK) {
+        R acc = w[num * S];
+        if (k > 0) acc -= conv_wide<R, S>(pb + S, pc + (k - 1) * S, (int)k);
+        pc[k * S] = acc * w[inv * S];
+    } else if (bi == 0) {
+        const R *const ps[1] = {pb + S};
+        R O[1][M];
+        blockconv_core<R, S, M, 1, 16>(ps, pc + (k - 1) * S, (int)k, O);
+#pragma unroll
+        for (int i = 1; i < M; ++i) w[(q + i - 1) * S] = O[0][i];
+        const R acc = w[num * S] - O[0][0];
+        pc[k * S] = acc * w[inv * S];
+    } else {
+        const R s = (w[(q + bi - 1) * S] + shortsum<R, S, M>(pb + S, pc + (k - 1) * S, bi)) + shortsum<R, S, M>(pc, pb + k * S, bi);
+        pc[k * S] = (w[num * S] - s) * w[inv * S];
+    }
+}
+template <typename R, int S> __device__ __noinline__ void jop_square(R *__restrict__ w, uint32_t k, uint32_t a, uint32_t dst)
+{
+    const R *pa = w + a * S;
+    R acc = conv_wide<R, S>(pa, pa + k * S, (int)((k + 1) >> 1));
+    acc = acc + acc;
+    if ((k & 1u) == 0) {
+        const R m = pa[(k >> 1) * S];
+        acc = r_fma(m, m, acc);
+    }
+    w[dst * S] = acc;
+}
+// one term of a sum of squares: acc += sum_{j<half} a[j] a[k-j]; acc2 = fma(a[k/2], a[k/2], acc2) for even k
+template <typename R, int S> __device__ __noinline__ void jop_sumsq_term(const R *__restrict__ w, uint32_t k, uint32_t a, R &acc, R &acc2)
+{
+    const R *pa = w + a * S;
+    acc += conv_wide<R, S>(pa, pa + k * S, (int)((k + 1) >> 1));
+    if ((k & 1u) == 0) {
+        const R m = pa[(k >> 1) * S];
+        acc2 = r_fma(m, m, acc2);
+    }
+}
+template <typename R, int S>
+__device__ __noinline__ void jop_pow(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t c, uint32_t inv,
+                                     double alpha, int is_sqrt)
+{
+    const R *pa = w + a * S;
+    R *pc = w + c * S;
+    if (k == 0) {
+        w[inv * S] = (R)1 / pa[0];
+        pc[0] = is_sqrt ? r_sqrt(pa[0]) : pow0<R>(pa[0], alpha);
+    } else {
+        const R al1 = (R)(alpha + 1.0), kal = (R)k * (R)alpha;
+        pc[k * S] = (conv_pow<R, S>(pa + k * S, pc, (int)k, al1, kal) * rk[k]) * w[inv * S];
+    }
+}
+template <typename R, int S> __device__ __noinline__ void jop_exp(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t c)
+{
+    const R *pa = w + a * S;
+    R *pc = w + c * S;
+    if (k == 0) {
+        pc[0] = r_exp(pa[0]);
+    } else {
+        R acc = 0, jr = 1;
+#pragma unroll 1
+        for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * pa[j * S], pc[(k - j) * S], acc);
+        pc[k * S] = acc * rk[k];
+    }
+}
+template <typename R, int S>
+__device__ __noinline__ void jop_log(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t c, uint32_t inv)
+{
+    const R *pa = w + a * S;
+    R *pc = w + c * S;
+    if (k == 0) {
+        w[inv * S] = (R)1 / pa[0];
+        pc[0] = r_log(pa[0]);
+    } else {
+        R acc = 0, jr = 1;
+#pragma unroll 1
+        for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * pc[j * S], pa[(k - j) * S], acc);
+        pc[k * S] = r_fma(-acc, rk[k], pa[k * S]) * w[inv * S];
+    }
+}
+template <typename R, int S>
+__device__ __noinline__ void jop_sincos(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t sr, uint32_t cr)
+{
+    const R *pa = w + a * S;
+    R *s = w + sr * S, *c = w + cr * S;
+    if (k == 0) {
+        R sv, cv;
+        r_sincos(pa[0], &sv, &cv);
+        s[0] = sv;
+        c[0] = cv;
+    } else {
+        R sa0 = 0, ca0 = 0, sa1 = 0, ca1 = 0, jr = 1;
+        uint32_t j = 1;
+#pragma unroll 1
+        for (; j + 1 <= k; j += 2, jr += (R)2) {
+            const R ja0 = jr * pa[j * S], ja1 = (jr + (R)1) * pa[(j + 1) * S];
+            const R c0 = c[(k - j) * S], s0 = s[(k - j) * S], c1 = c[(k - j - 1) * S], s1 = s[(k - j - 1) * S];
+            sa0 = r_fma(ja0, c0, sa0);
+            ca0 = r_fma(ja0, s0, ca0);
+            sa1 = r_fma(ja1, c1, sa1);
+            ca1 = r_fma(ja1, s1, ca1);
+        }
+        if (j <= k) {
+            const R ja = jr * pa[j * S];
+            sa0 = r_fma(ja, c[(k - j) * S], sa0);
+            ca0 = r_fma(ja, s[(k - j) * S], ca0);
+        }
+        s[k * S] = (sa0 + sa1) * rk[k];
+        c[k * S] = -((ca0 + ca1) * rk[k]);
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // Order-specialised body of the fused pair interaction (nd = 3): K is a

@@ -58,24 +58,29 @@ def nbody(n, masses=None, Gconst=1.0):
         raise ValueError("At least 2 bodies are needed to construct an N-body system")
     if masses is None:
         masses = [1.0] * n
-    masses = [float(m) for m in masses]
+    # masses are numbers or expressions (the reference accepts e.g. par[i]: runtime masses)
+    masses = [m if isinstance(m, E.expression) else float(m) for m in masses]
     if len(masses) > n:
         raise ValueError("Too many masses for an N-body system")
     masses = masses + [0.0] * (n - len(masses))
     G = float(Gconst)
     b = _nbody_vars(n)
     acc = [[[] for _ in range(3)] for _ in range(n)]
+
+    def _zero(m):
+        return not isinstance(m, E.expression) and m == 0.0
+
     for i in range(n):
         for j in range(i + 1, n):
-            if masses[i] == 0.0 and masses[j] == 0.0:
+            if _zero(masses[i]) and _zero(masses[j]):
                 continue
             d = [b[j][c] - b[i][c] for c in range(3)]
             w = E.pow(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], -1.5)
             for c in range(3):
                 f = d[c] * w
-                if masses[j] != 0.0:
+                if not _zero(masses[j]):
                     acc[i][c].append((G * masses[j]) * f)
-                if masses[i] != 0.0:
+                if not _zero(masses[i]):
                     acc[j][c].append((-G * masses[i]) * f)
     sys = []
     for i in range(n):

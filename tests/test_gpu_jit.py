@@ -1,0 +1,187 @@
+"""GPU: the run-time compiled kernels (csrc/hy_jit.hpp, kernel_variant 1000) against the tape
+interpreter (same integrator built with compact_mode=True) - bit for bit, every op kind and every
+API feature that runs inside the kernel - and against the C oracle.
+
+Reference: the reference JIT-compiles every system in the constructor
+(/root/reference/heyoka/expose_batch_integrators.cpp:166-208); `compact_mode` there trades
+code-generation time for run time (:198), here it selects the interpreter.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+import hy_b200 as hy
+from hy_b200 import decompose as D
+from hy_b200 import workloads as W
+from oracle.c_oracle import COracle
+
+pytestmark = pytest.mark.gpu
+
+JIT = 1000
+
+
+def _forced(make):
+    """Build with HY_CUDA_JIT=1 (every tape, however small, gets a compiled kernel)."""
+    old = os.environ.get("HY_CUDA_JIT")
+    os.environ["HY_CUDA_JIT"] = "1"
+    try:
+        ta = make()
+        ta._ctx
+    finally:
+        if old is None:
+            del os.environ["HY_CUDA_JIT"]
+        else:
+            os.environ["HY_CUDA_JIT"] = old
+    return ta
+
+
+def _pair(sys_, ic, **kw):
+    a = _forced(lambda: hy.taylor_adaptive_batch(sys_, ic, **kw))
+    b = hy.taylor_adaptive_batch(sys_, ic, compact_mode=True, **kw)
+    assert a._ctx.launch_info()["kernel_variant"] == JIT, a._ctx.launch_info()
+    assert b._ctx.launch_info()["kernel_variant"] == 0, b._ctx.launch_info()
+    return a, b
+
+
+def _same(a, b):
+    assert np.array_equal(a.state, b.state)
+    assert np.array_equal(a.time, b.time)
+    for x, y in zip(a.propagate_res_arrays, b.propagate_res_arrays):
+        assert np.array_equal(x, y)
+
+
+def test_config4_default_is_compiled_and_bitwise_equal_to_interpreter():
+    # 42 state variables, 191 ops: the default build of a large tape is the compiled kernel
+    vs = hy.var_ode_sys(W.kepler_j2_sys(), hy.var_args.vars)
+    ic = W.kepler_j2_ensemble(96, seed=5)
+    a = hy.taylor_adaptive_batch(vs, ic)
+    b = hy.taylor_adaptive_batch(vs, ic, compact_mode=True)
+    li = a._ctx.launch_info()
+    assert li["kernel_variant"] == JIT and li["group"] == 1 and li["ws_in_smem"] == 0
+    assert b._ctx.launch_info()["kernel_variant"] == 0
+    a.propagate_until(4000.0)
+    b.propagate_until(4000.0)
+    _same(a, b)
+    # and the oracle (step counts exact, state to 1e-11)
+    orc = COracle(D.decompose(vs.sys, a.order), W_full(vs, ic))
+    oc, mn, mx, ns, _ = orc.propagate_until(4000.0)
+    assert list(a.propagate_res_arrays[3]) == list(ns)
+    err = np.max(np.abs(a.state - orc.state) / np.maximum(1.0, np.abs(orc.state)))
+    assert err < 1e-11, err
+
+
+def W_full(vs, ic):
+    """Initial conditions of a variational system: the state plus the identity sensitivities."""
+    ta = hy.taylor_adaptive_batch(vs, ic, compact_mode=True)
+    return ta.state.copy()
+
+
+@pytest.mark.parametrize("fp", [np.float64, np.float32])
+def test_every_op_kind_bitwise(fp):
+    # sin/cos, exp, log, sqrt, pow, div, square, products, time, runtime parameters
+    x, v, s = hy.make_vars("x", "v", "s")
+    sys_ = [(x, v),
+            (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x) + 0.01 * hy.exp(-s * s) / (1.0 + x * x)),
+            (s, hy.log(2.0 + hy.cos(x)) * hy.sqrt(1.0 + v * v) - hy.par[1] * s + (1.5 + x * x) ** -1.5 + (x * v) * (s * v))]
+    rng = np.random.default_rng(3)
+    ic = rng.uniform(-0.5, 0.5, (3, 70)).astype(fp)
+    pars = np.stack([np.full(70, 0.1), np.linspace(0.2, 0.4, 70)]).astype(fp)
+    a, b = _pair(sys_, ic, fp_type=fp, pars=pars)
+    for ta in (a, b):
+        ta.propagate_until(fp(6.0))
+    _same(a, b)
+    # single steps with the Taylor coefficients, backward too
+    for ta in (a, b):
+        ta.step(write_tc=True)
+        ta.step_backward()
+    assert np.array_equal(a.tc, b.tc)
+    _same(a, b)
+    orc = COracle(D.decompose(sys_, a.order), ic, pars=pars, fp_type=fp)
+    orc.propagate_until(fp(6.0))
+
+
+def test_ragged_times_grid_and_continuous_output_bitwise():
+    sys_ = W.forced_pendulum_sys()
+    B = 45
+    ic = np.stack([np.linspace(0.0, 1.0, B), np.linspace(0.2, 0.3, B)])
+    pars = np.full((1, B), 0.05)
+    a, b = _pair(sys_, ic, pars=pars)
+    tf = np.linspace(2.0, 9.0, B)
+    for ta in (a, b):
+        ta.propagate_until(tf, max_delta_t=0.7)
+    _same(a, b)
+    grid = np.linspace(9.0, 14.0, 11)[:, None] * np.ones((1, B)) + np.linspace(0, 0.3, B)[None, :]
+    ga = a.propagate_grid(grid)
+    gb = b.propagate_grid(grid)
+    assert np.array_equal(ga, gb)
+    _same(a, b)
+    ca = a.propagate_for(3.0, c_output=True)
+    cb = b.propagate_for(3.0, c_output=True)
+    _same(a, b)
+    tq = np.linspace(14.4, 17.0, 9)[:, None] * np.ones((1, B))
+    assert np.array_equal(ca(tq), cb(tq))
+
+
+def test_events_bitwise_and_high_accuracy():
+    # terminal + non-terminal events share u-variables with the ODE; compensated update
+    x, v = hy.make_vars("x", "v")
+    sys_ = [(x, v), (v, -9.8 * hy.sin(x))]
+    B = 40
+    ic = np.stack([np.linspace(0.1, 1.2, B), np.linspace(-0.3, 0.3, B)])
+
+    def mk(**kw):
+        return dict(t_events=[hy.t_event_batch(v * v - 1.0, direction=hy.event_direction.positive)],
+                    nt_events=[hy.nt_event_batch(x, lambda ta, t, d, i: None)], high_accuracy=True, **kw)
+
+    a = _forced(lambda: hy.taylor_adaptive_batch(sys_, ic, **mk()))
+    b = hy.taylor_adaptive_batch(sys_, ic, compact_mode=True, **mk())
+    assert a._ctx.launch_info()["kernel_variant"] == JIT
+    for ta in (a, b):
+        ta.propagate_until(8.0)
+    _same(a, b)
+    assert (a.propagate_res_arrays[0] > -10).any()  # some lanes stopped on the terminal event
+
+
+def test_parametric_masses_nbody_runs_compiled_and_matches_oracle():
+    # an N-body system with the masses as runtime parameters is NOT matched by the register-resident
+    # kernel (hy_nbody_match.hpp) - the review's example of a system that fell back to the interpreter
+    from hy_b200 import model
+
+    sys_ = model.nbody(6, masses=[hy.par[i] for i in range(6)], Gconst=W.OSS_G)
+    B = 64
+    ic = W.oss_ensemble(B)
+    pars = W.OSS_MASSES[:, None] * np.ones((1, B))
+    a = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
+    li = a._ctx.launch_info()
+    assert li["kernel_variant"] == JIT, li
+    b = hy.taylor_adaptive_batch(sys_, ic, pars=pars, compact_mode=True)
+    for ta in (a, b):
+        ta.propagate_until(30.0)
+    _same(a, b)
+    orc = COracle(D.decompose(sys_, a.order), ic, pars=pars)
+    oc, mn, mx, ns, _ = orc.propagate_until(30.0)
+    assert list(a.propagate_res_arrays[3]) == list(ns)
+    err = np.max(np.abs(a.state - orc.state) / np.maximum(1.0, np.abs(orc.state)))
+    assert err < 1e-12, err
+
+
+def test_compiled_kernel_in_shared_memory_and_clone():
+    # a mid-size tape: the interleaved workspace fits in shared memory
+    sys_ = W.cr3bp_sys(0.01)
+    ic = W.cr3bp_ensemble(200)
+    os.environ["HY_CUDA_NO_CR3BP_REG"] = "1"
+    try:
+        a, b = _pair(sys_, ic)
+    finally:
+        del os.environ["HY_CUDA_NO_CR3BP_REG"]
+    assert a._ctx.launch_info()["ws_in_smem"] == 1
+    import copy
+
+    c = copy.deepcopy(a)  # hy_clone: the compiled kernel is loaded again for the copy
+    for ta in (a, b, c):
+        ta.propagate_until(3.0)
+    _same(a, b)
+    _same(c, b)
+    assert c._ctx.launch_info()["kernel_variant"] == JIT

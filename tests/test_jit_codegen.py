@@ -1,0 +1,74 @@
+"""CPU: the run-time kernel generator (csrc/hy_jit.hpp).  No device is needed to generate and
+compile a kernel: hy_jit_precompile lowers the tape to CUDA source, compiles it with NVRTC for
+sm_100a and stores the image in the kernel cache (what __graft_entry__.build() does for the
+BASELINE tapes).  Running the kernels is covered by tests/test_gpu_jit.py."""
+
+import glob
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import hy_b200 as hy
+from hy_b200 import _cabi
+from hy_b200 import decompose as D
+from hy_b200 import workloads as W
+
+
+@pytest.fixture()
+def jit_cache(tmp_path, monkeypatch):
+    monkeypatch.setenv("HY_CUDA_JIT_CACHE", str(tmp_path))
+    monkeypatch.setenv("HY_CUDA_JIT", "1")  # compile whatever the size of the tape
+    return tmp_path
+
+
+def _images(path):
+    out = []
+    for f in glob.glob(os.path.join(str(path), "*.hyjit")):
+        b = open(f, "rb").read()
+        assert b[:4] == b"HYJ1"
+        nl = struct.unpack("<I", b[4:8])[0]
+        out.append((b[8:8 + nl].decode(), b[8 + nl:]))
+    return out
+
+
+def test_every_op_kind_compiles_and_is_cached(jit_cache):
+    x, v, s = hy.make_vars("x", "v", "s")
+    sys_ = [(x, v),
+            (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x) + 0.01 * hy.exp(-s * s) / (1.0 + x * x)),
+            (s, hy.log(2.0 + hy.cos(x)) * hy.sqrt(1.0 + v * v) - hy.par[1] * s + (1.5 + x * x) ** -1.5 + (x * v) * (s * v))]
+    dc = D.decompose(sys_, 20, events=[v * v - 1.0])
+    kinds = {D.OP_NAMES[int(o["opcode"])] for o in dc.ops}
+    assert {"lincomb", "mul", "square", "div", "pow", "sqrt", "exp", "log", "sincos", "time"} <= kinds
+    for fp_bits in (64, 32):
+        fc, secs = _cabi.jit_precompile(dc, fp_bits, batch=4096, n_tevents=1)
+        assert fc == 0 and secs > 0.0          # compiled now
+        fc, secs = _cabi.jit_precompile(dc, fp_bits, batch=4096, n_tevents=1)
+        assert fc == 1                          # second time: from the cache
+    imgs = _images(jit_cache)
+    assert len(imgs) == 2
+    names = sorted(n for n, _ in imgs)
+    # the persistent propagate kernel, one thread per trajectory (G = 1), FP32 and FP64
+    assert all("propagate_kernel" in n for n in names), names
+    assert any("IdLi1E" in n for n in names) and any("IfLi1E" in n for n in names), names
+    for _, cubin in imgs:
+        assert cubin[:4] == b"\x7fELF"
+
+
+def test_small_tapes_stay_on_the_interpreter_by_default(jit_cache, monkeypatch):
+    monkeypatch.setenv("HY_CUDA_JIT", "2")
+    dc = D.decompose(W.pendulum_sys(), 20)
+    fc, _ = _cabi.jit_precompile(dc, 64)
+    assert fc == -1
+    assert _images(jit_cache) == []
+
+
+def test_order_blocking_variant_compiles(jit_cache, monkeypatch):
+    # HY_CUDA_JIT_BLOCK = 4: products / quotients in blocks of four orders (another kernel image)
+    vs = hy.var_ode_sys(W.kepler_j2_sys(), hy.var_args.vars)
+    dc = D.decompose(vs.sys, 20)
+    assert _cabi.jit_precompile(dc, 64, batch=64)[0] == 0
+    monkeypatch.setenv("HY_CUDA_JIT_BLOCK", "4")
+    assert _cabi.jit_precompile(dc, 64, batch=64)[0] == 0
+    assert len(_images(jit_cache)) == 2
