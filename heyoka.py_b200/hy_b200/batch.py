@@ -508,15 +508,41 @@ class taylor_adaptive_batch_impl:
         return self._ro(self._tstate)
 
     def eval_taylor_map(self, inputs):
+        """Reference: expose_batch_integrators.cpp:573-649 (argument checks and messages)."""
         self._need_var()
-        inputs = np.asarray(inputs, dtype=self._fp)
+        if isinstance(inputs, np.ndarray):
+            if inputs.dtype != self._fp:
+                raise TypeError(
+                    "Invalid dtype detected for the inputs of a Taylor map evaluation: the expected dtype "
+                    "is '{}', but the dtype of the inputs array is '{}' instead".format(
+                        np.dtype(self._fp), inputs.dtype))
+            if not inputs.flags.c_contiguous:
+                raise ValueError(
+                    "Invalid inputs array detected in a Taylor map evaluation: the array is not C-style "
+                    "contiguous, please consider using numpy.ascontiguousarray() to turn it into one")
+        else:
+            inputs = np.ascontiguousarray(inputs, dtype=self._fp)
         nv = len(self._vsys.vargs_list)
-        if inputs.shape != (nv, self._B):
+        if inputs.ndim != 2:
             raise ValueError(
-                "Invalid inputs array passed to eval_taylor_map(): the expected shape is "
-                "({}, {}) but the shape of the input is {}".format(nv, self._B, inputs.shape)
-            )
-        self._tstate = self._vsys.eval_taylor_map(self._p_state.array, inputs).astype(self._fp)
+                "The array of inputs provided for the evaluation of a Taylor map has {} dimension(s), "
+                "but it must have 2 dimensions instead".format(inputs.ndim))
+        if inputs.shape[0] != nv:
+            raise ValueError(
+                "The array of inputs provided for the evaluation of a Taylor map has {} row(s), "
+                "but it must have {} row(s) instead".format(inputs.shape[0], nv))
+        if inputs.shape[1] != self._B:
+            raise ValueError(
+                "The array of inputs provided for the evaluation of a Taylor map has {} column(s), "
+                "but it must have {} column(s) instead".format(inputs.shape[1], self._B))
+        if not hasattr(self, "_tstate"):
+            self._tstate = np.zeros((self.n_orig_sv, self._B), dtype=self._fp)
+        if np.may_share_memory(inputs, self._p_state.array) or np.may_share_memory(inputs, self._tstate):
+            raise ValueError(
+                "Invalid inputs array detected in a Taylor map evaluation: the array may overlap with the "
+                "internal data of the integrator")
+        # (written in place: tstate keeps referring to the same buffer, as in the reference)
+        self._tstate[...] = self._vsys.eval_taylor_map(self._p_state.array, inputs)
         return self.tstate
 
     # ---- host <-> device sync ----

@@ -690,14 +690,22 @@ def _fuse(uv, n, sv_src, ev_u):
             u.terms = [(s, -1, 1.0) for s in srcs]
             u.args = tuple(srcs)
 
-    # MULSH: group MULs by shared operand (greedy, most-shared first).
+    # MULSH: group MULs by shared operand (greedy, most-shared first).  Only products of the SAME
+    # dependency depth are grouped: a product that feeds another one sharing the operand
+    # ((s * d) * d in second-order variational equations) must not end up in the same op.
+    depth = {}
+    for u in uv:  # (u-variables are created in dependency order)
+        srcs = [a for a in u.args if a != ONE]
+        if u.terms:
+            srcs += [t[0] for t in u.terms if t[0] != ONE]
+        depth[u.id] = 1 + max([depth[a] for a in srcs] + [0]) if u.id >= n else 0
     muls = [u for u in uv[n:] if u.op == OP_MUL]
     by_operand = {}
     for u in muls:
         for a in set(u.args):
-            by_operand.setdefault(a, []).append(u)
+            by_operand.setdefault((a, depth[u.id]), []).append(u)
     taken = set()
-    for b, lst in sorted(by_operand.items(), key=lambda kv: (-len(kv[1]), kv[0])):
+    for (b, _), lst in sorted(by_operand.items(), key=lambda kv: (-len(kv[1]), kv[0])):
         grp = [u for u in lst if u.id not in taken]
         # Bound the register footprint of the fused op.
         while len(grp) >= 2:

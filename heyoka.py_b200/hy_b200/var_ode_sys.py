@@ -1,4 +1,4 @@
-"""First-order variational equations (``var_ode_sys``).
+"""Variational equations of arbitrary order (``var_ode_sys``).
 
 Mirror of /root/reference/heyoka/expose_var_ode_sys.cpp:29-58: the state is
 augmented with the sensitivities d x_i / d a_j of the solution w.r.t. the
@@ -7,7 +7,7 @@ augmented state follows the reference (_test_var_integrator.py:190-201): by
 total order, then by component, then reverse-lexicographic multi-index - for
 order 1 that is, for each component i, d x_i/d a_0, d x_i/d a_1, ...
 
-Only order 1 is built; higher orders raise.
+Any order is built by repeated total differentiation of the equations one order below.
 """
 
 import enum
@@ -24,15 +24,42 @@ class var_args(enum.IntFlag):
     all = 7
 
 
+def _mindices(na, m):
+    """All multi-indices of total order m over na arguments, in the reference's order
+    (descending lexicographic: (2,0), (1,1), (0,2))."""
+    out = []
+
+    def rec(pos, left, cur):
+        if pos == na - 1:
+            out.append(tuple(cur + [left]))
+            return
+        for v in range(left, -1, -1):
+            rec(pos + 1, left - v, cur + [v])
+
+    rec(0, m, [])
+    return out
+
+
+def _vname(base, alpha):
+    """Reference naming: the sparse multi-index, e.g. '∂[(0, 1), (1, 1)]x' (var_ode_sys.ipynb:229-262)."""
+    sp = ", ".join("({}, {})".format(j, a) for j, a in enumerate(alpha) if a)
+    return "∂[{}]{}".format(sp, base)
+
+
 class var_ode_sys:
+    """Variational equations of arbitrary order (reference: expose_var_ode_sys.cpp:29-58).
+
+    The augmented state is ordered by total differentiation order, then by component, then by
+    descending lexicographic multi-index (var_ode_sys.ipynb:361-529, _test_var_integrator.py:190-201).
+    The equation of d^alpha x_i is the total derivative, w.r.t. one of the arguments, of the
+    equation one order below: d/da_j g = sum_s (dg/ds) d_j s (+ dg/da_j for a parameter), where s
+    runs over the (variational) state symbols of g and d_j of the symbol d^beta x_k is the symbol
+    d^(beta + e_j) x_k."""
+
     def __init__(self, sys, args, order=1):
         sys = [(l, E._wrap(r)) for l, r in sys]
         if order < 1:
             raise ValueError("The 'order' argument to the var_ode_sys constructor must be nonzero")
-        if order != 1:
-            raise NotImplementedError(
-                "var_ode_sys: only first-order variational equations are available in this build"
-            )
         n = len(sys)
         names = [l.name for l, _ in sys]
         rhs = [r for _, r in sys]
@@ -52,6 +79,8 @@ class var_ode_sys:
                 al += [E.expression(nm) for nm in names]
             if args & var_args.params:
                 al += [E.par[i] for i in range(npar)]
+            if not al:
+                raise ValueError("Cannot formulate the variational equations with an empty list of arguments")
         else:
             al = list(args)
             if not al:
@@ -70,18 +99,49 @@ class var_ode_sys:
         self.order = order
         self._names = names
         na = len(al)
-        # Sensitivity variables, component-major.
-        svar = [[E.expression("d{}_d{}".format(names[i], _aname(a))) for a in al] for i in range(n)]
-        jac = [[E.diff(rhs[i], E.expression(names[k])) for k in range(n)] for i in range(n)]
-        eqs = list(sys)
-        for i in range(n):
-            for j, a in enumerate(al):
-                terms = [jac[i][k] * svar[k][j] for k in range(n)]
-                if a.kind == "par":
-                    terms.append(E.diff(rhs[i], a))
-                eqs.append((svar[i][j], E.sum(terms)))
-        self.sys = eqs
         self._na = na
+        # multi-indices per total order; position of every (order, component, alpha) in the state
+        self._mi = [[tuple([0] * na)]] + [_mindices(na, m) for m in range(1, order + 1)]
+        self._off = [0]
+        for m in range(order + 1):
+            self._off.append(self._off[-1] + n * len(self._mi[m]))
+        zero = tuple([0] * na)
+        sym = {(i, zero): E.expression(names[i]) for i in range(n)}
+        for m in range(1, order + 1):
+            for i in range(n):
+                for al_ in self._mi[m]:
+                    sym[(i, al_)] = E.expression(_vname(names[i], al_))
+        owner = {sym[k].name: k for k in sym}  # symbol name -> (component, alpha)
+
+        def total_diff(g, j):
+            a = al[j]
+            terms = []
+            for nm in E.get_variables([g]):
+                k, beta = owner[nm]
+                b2 = list(beta)
+                b2[j] += 1
+                dg = E.diff(g, sym[(k, beta)])
+                if dg.kind == "num" and dg.value == 0.0:
+                    continue
+                terms.append(dg * sym[(k, tuple(b2))])
+            if a.kind == "par":
+                dg = E.diff(g, a)
+                if not (dg.kind == "num" and dg.value == 0.0):
+                    terms.append(dg)
+            return E.sum(terms) if terms else E.expression(0.0)
+
+        eq = {(i, zero): rhs[i] for i in range(n)}
+        eqs = list(sys)
+        for m in range(1, order + 1):
+            for i in range(n):
+                for al_ in self._mi[m]:
+                    # differentiate the equation one order below w.r.t. the LAST argument of alpha
+                    j = max(q for q in range(na) if al_[q] > 0)
+                    lower = list(al_)
+                    lower[j] -= 1
+                    eq[(i, al_)] = total_diff(eq[(i, tuple(lower))], j)
+                    eqs.append((sym[(i, al_)], eq[(i, al_)]))
+        self.sys = eqs
 
     @property
     def vargs(self):
@@ -89,44 +149,53 @@ class var_ode_sys:
 
     def _initial_var_state(self, fp):
         n, na = self.n_orig_sv, self._na
-        ic = np.zeros(n * na, dtype=fp)
+        ic = np.zeros(self._off[-1] - n, dtype=fp)
         for i in range(n):
             for j, a in enumerate(self.vargs_list):
                 if a.kind == "var" and a.name == self._names[i]:
-                    ic[i * na + j] = 1
+                    ic[i * na + j] = 1  # order 1: d x_i / d x_i(0) = 1; every higher order starts at 0
         return ic
 
     def get_vslice(self, order, component=None):
-        n, na = self.n_orig_sv, self._na
+        n = self.n_orig_sv
         if order > self.order:
             raise ValueError(
                 "The derivative order {} is larger than the maximum order {}".format(order, self.order)
             )
         if component is not None and not (0 <= component < n):
             raise ValueError("Invalid component {}".format(component))
-        if order == 0:
-            return slice(0, n) if component is None else slice(component, component + 1)
+        nm = len(self._mi[order])
         if component is None:
-            return slice(n, n + n * na)
-        return slice(n + component * na, n + (component + 1) * na)
+            return slice(self._off[order], self._off[order + 1])
+        return slice(self._off[order] + component * nm, self._off[order] + (component + 1) * nm)
 
     def get_mindex(self, i):
-        n, na = self.n_orig_sv, self._na
-        if not (0 <= i < n + n * na):
+        if not (0 <= i < self._off[-1]):
             raise IndexError("Invalid index {} passed to get_mindex()".format(i))
-        if i < n:
-            return [i] + [0] * na
-        i -= n
-        comp, j = divmod(i, na)
-        mi = [0] * na
-        mi[j] = 1
-        return [comp] + mi
+        m = max(q for q in range(self.order + 1) if self._off[q] <= i)
+        comp, j = divmod(i - self._off[m], len(self._mi[m]))
+        return [comp] + list(self._mi[m][j])
 
     def eval_taylor_map(self, state, inputs):
-        """x_i + sum_j (d x_i / d a_j) * delta_j   (first order)."""
-        n, na = self.n_orig_sv, self._na
-        sens = state[n:].reshape(n, na, -1)
-        return state[:n] + np.einsum("ijb,jb->ib", sens, inputs)
+        """x_i + sum_{|alpha| >= 1} (d^alpha x_i / alpha!) delta^alpha
+        (reference: taylor map evaluation, var_ode_sys.ipynb:620-707)."""
+        import math
+
+        n = self.n_orig_sv
+        out = np.array(state[:n], dtype=state.dtype, copy=True)
+        for m in range(1, self.order + 1):
+            mis = self._mi[m]
+            for i in range(n):
+                base = self._off[m] + i * len(mis)
+                for j, al_ in enumerate(mis):
+                    mono = 1.0
+                    fact = 1.0
+                    for q, e in enumerate(al_):
+                        if e:
+                            mono = mono * inputs[q] ** e
+                            fact *= math.factorial(e)
+                    out[i] = out[i] + state[base + j] * mono / fact
+        return out
 
     def __repr__(self):
         return "var_ode_sys(order={}, n_orig_sv={}, vargs={})".format(

@@ -85,8 +85,26 @@ def test_var_ode_sys_layout():
     assert vs.get_mindex(0) == [0, 0, 0] and vs.get_mindex(2) == [0, 1, 0]
     assert vs.get_mindex(5) == [1, 0, 1]
     assert list(vs._initial_var_state(float)) == [1, 0, 0, 1]
-    with pytest.raises(NotImplementedError):
-        hy.var_ode_sys(sys_, hy.var_args.vars, order=2)
+    # order 2 (reference layout: var_ode_sys.ipynb:229-262, :529): by total order, component,
+    # descending lexicographic multi-index; the mixed derivative is built once
+    v2 = hy.var_ode_sys(sys_, hy.var_args.vars, order=2)
+    assert len(v2.sys) == 12 and v2.get_vslice(order=2) == slice(6, 12)
+    assert v2.get_vslice(order=2, component=1) == slice(9, 12)
+    assert [v2.get_mindex(i) for i in range(6, 12)] == [[0, 2, 0], [0, 1, 1], [0, 0, 2], [1, 2, 0], [1, 1, 1], [1, 0, 2]]
+    assert [l.name for l, _ in v2.sys[6:9]] == ["∂[(0, 2)]x", "∂[(0, 1), (1, 1)]x", "∂[(1, 2)]x"]
+    assert list(v2._initial_var_state(float)) == [1, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+    with pytest.raises(ValueError):
+        v2.get_vslice(order=3)
+    # w.r.t. the parameter as well: 3 arguments -> 2 * (3 + 6) sensitivities
+    v3 = hy.var_ode_sys(sys_, hy.var_args.vars | hy.var_args.params, order=2)
+    assert len(v3.sys) == 2 + 2 * 3 + 2 * 6 and len(v3.vargs) == 3
+    assert v3.get_mindex(2 + 6) == [0, 2, 0, 0] and v3.get_mindex(2 + 6 + 5) == [0, 0, 0, 2]
+    # the Taylor map is the truncated multivariate series
+    st = np.arange(1.0, 13.0)[:, None]
+    dx = np.array([[0.1], [-0.2]])
+    tm = v2.eval_taylor_map(st, dx)
+    ex0 = 1 + 3 * 0.1 + 4 * -0.2 + 7 * 0.01 / 2 + 8 * 0.1 * -0.2 + 9 * 0.04 / 2
+    assert abs(tm[0, 0] - ex0) < 1e-15
     # symbolic Jacobian against finite differences
     rhs = [r for _, r in sys_]
     pt = {"x": 0.3, "v": -0.2}

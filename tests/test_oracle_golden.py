@@ -183,3 +183,34 @@ def test_simd_baseline_matches_scalar_oracle():
     o = COracle(dc, g["ic"], pars=g["pars"])
     r = o.propagate_until([10.0, 11.0, 12.0, 13.0])
     assert np.array_equal(ns, r[3]) and np.max(np.abs(st - o.state)) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["np", "c"])
+def test_variational_order2_A12(kind):
+    # var_ode_sys.ipynb:361,529,707: second-order variational equations of the forced damped
+    # pendulum - the 12-vector at t = 3, the order-2 slice / multi-indices, the Taylor map.
+    g = G["var_pendulum_order2"]
+    x, v = hy.make_vars("x", "v")
+    sys_ = [(x, v), (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x))]
+    vs = hy.var_ode_sys(sys_, hy.var_args.vars, order=g["order"])
+    assert vs.order == 2 and vs.n_orig_sv == 2 and [a.name for a in vs.vargs] == ["x", "v"]
+    assert len(vs.sys) == 12
+    ic = np.zeros(12)
+    ic[:2] = g["ic"]
+    ic[2:] = vs._initial_var_state(float)
+    assert list(ic) == g["initial_state"]
+    sl = vs.get_vslice(2)
+    assert [sl.start, sl.stop] == g["order2_slice"]
+    assert [vs.get_mindex(i) for i in range(sl.start, sl.stop)] == g["order2_mindex"]
+    ta = make(kind, vs.sys, ic, pars=np.array([[g["par"]]]))
+    ta.propagate_until(g["t_end"])
+    st = ta.state[:, 0]
+    assert np.max(np.abs(st - np.array(g["final_state_8digits"]))) < 6e-9
+    assert np.max(np.abs(st[sl] - np.array(g["order2_values"])) / np.abs(g["order2_values"])) < 1e-13
+    tm = vs.eval_taylor_map(ta.state, np.array(g["taylor_map_inputs"])[:, None])[:, 0]
+    assert np.max(np.abs(tm - np.array(g["taylor_map_state_8digits"]))) < 6e-9
+    # the Taylor map against a run from the displaced initial conditions (the notebook prints 6.6e-13)
+    tb = make(kind, sys_, np.array(g["ic"]) + np.array(g["taylor_map_inputs"]), pars=np.array([[g["par"]]]))
+    tb.propagate_until(g["t_end"])
+    err = tm - tb.state[:, 0]
+    assert np.max(np.abs(err - np.array(g["taylor_map_error_vs_displaced_run"]))) < 5e-15
