@@ -405,32 +405,6 @@ int choose_geometry(hy_ctx *c)
             li.kernel_variant = hy::cr3bp_kernel_variant(d.order, c->fp_bits);
         }
     }
-    // Run-time compiled kernel (hy_jit.hpp): one thread per trajectory, the order sweep generated from
-    // the tape.  HY_CUDA_JIT = 0: never, 1: always, 2 (default): for tapes whose workspace is too large
-    // for the small-group interpreter variants (those would run with 16-lane groups or from global
-    // memory, far below their roofline); hy_create's `compact_mode` flag (reference kwarg) selects the
-    // interpreter as well.
-    bool jit_smem = false;
-    uint32_t jit_T = 0;
-    const uint32_t jit_mode = c->no_jit ? 0u : env_u32("HY_CUDA_JIT", 2);
-    if (!li.kernel_variant && jit_mode && !force_global && !Genv) {
-        hy::Program pr;
-        std::string jerr;
-        const int jr = jit_plan(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), c->fp_bits, c->B, li.n_sm,
-                                (uint32_t)smem_optin, jit_mode == 1, pr, jit_smem, jit_T, c->jit_img, jerr);
-        if (jr > 0) {
-            bestG = 1;
-            bestT = jit_T;
-            bestRS = pr.ws_len;
-            best_smem = jit_smem;
-            best = pr;
-            li.kernel_variant = HY_VARIANT_JIT;
-        } else if (jr < 0) {
-            if (jit_mode == 1) return fail("hy_create: " + jerr);
-            if (env_u32("HY_CUDA_JIT_VERBOSE", 0))
-                std::fprintf(stderr, "hy_cuda: run-time compilation failed, using the tape interpreter: %s\n", jerr.c_str());
-        }
-    }
     for (uint32_t G : {1u, 4u, 16u}) { // group sizes with compiled kernels
         if (li.kernel_variant) break;
         if (Genv && G != Genv) continue;
@@ -458,6 +432,35 @@ int choose_geometry(hy_ctx *c)
             best_smem = smem;
             best = pr;
             bestRS = RS;
+        }
+    }
+    // Run-time compiled kernel (hy_jit.hpp): one thread per trajectory, the order sweep generated from
+    // the tape.  HY_CUDA_JIT = 0: never, 1: always, 2 (default): when the interpreter would run the
+    // tape badly - its workspace does not fit in shared memory, or lane utilisation x resident threads
+    // (the score above) is low: few trajectories per SM and levels too narrow / too mixed for the
+    // group (config 4: 10 trajectories, 16-lane groups half idle).  Wide regular tapes (an N-body
+    // system with parametric masses) stay on the interpreter, which is faster for them (3.5e7 vs
+    // 2.5e7 steps/s).  hy_create's `compact_mode` flag (reference kwarg) selects the interpreter.
+    bool jit_smem = false;
+    uint32_t jit_T = 0;
+    const uint32_t jit_mode = c->no_jit ? 0u : env_u32("HY_CUDA_JIT", 2);
+    const bool interp_weak = !bestG || !best_smem || best_score < (double)env_u32("HY_CUDA_JIT_MAX_SCORE", 200);
+    if (!li.kernel_variant && !force_global && !Genv && (jit_mode == 1 || (jit_mode == 2 && interp_weak))) {
+        hy::Program pr;
+        std::string jerr;
+        const int jr = jit_plan(d, c->h_ops.data(), c->h_terms.data(), c->h_ev_ref.data(), c->fp_bits, c->B, li.n_sm,
+                                (uint32_t)smem_optin, jit_mode == 1, pr, jit_smem, jit_T, c->jit_img, jerr);
+        if (jr > 0) {
+            bestG = 1;
+            bestT = jit_T;
+            bestRS = pr.ws_len;
+            best_smem = jit_smem;
+            best = pr;
+            li.kernel_variant = HY_VARIANT_JIT;
+        } else if (jr < 0) {
+            if (jit_mode == 1) return fail("hy_create: " + jerr);
+            if (env_u32("HY_CUDA_JIT_VERBOSE", 0))
+                std::fprintf(stderr, "hy_cuda: run-time compilation failed, using the tape interpreter: %s\n", jerr.c_str());
         }
     }
     if (!bestG) return fail("hy_create: the program does not fit in shared memory for any group size");
