@@ -390,8 +390,13 @@ def main():
     # ---------------- device-resident arm ("value") ----------------
     evs = cfgd["events"] or []
     dc = D.decompose(sys_, order, events=evs)
+    # (event-carrying systems: the ODE-only tape and the event tape go along, as the front end does -
+    #  a matched ODE then keeps its register-resident kernel, hy_create2)
+    evt = D.decompose_event_tape(evs, [l.name for l, _ in sys_], order) if evs else None
+    dc_ode = D.decompose(sys_, order) if evt is not None else None
     ctx = _cabi.Context(dc, 64, B, eps, False, device=local, n_tevents=len(evs),
-                        ev_dir=[0] * len(evs) if evs else None, ev_cooldown=[-1.0] * len(evs) if evs else None)
+                        ev_dir=[0] * len(evs) if evs else None, ev_cooldown=[-1.0] * len(evs) if evs else None,
+                        dc_ode=dc_ode, evt=evt)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     li = ctx.launch_info()
@@ -524,7 +529,8 @@ def main():
         rec_bytes = 8.0 * (n * (order + 1) + 2) * (steps_rank / args.steps) if cfgd["c_output"] else 0.0
         alg_bytes = 8.0 * (2 * dc.n_state + dc.n_par + 4 + 4) * B + rec_bytes     # per launch
         variant = li.get("kernel_variant", 0)
-        kname = {0: " (tape interpreter)", 203: " (register-resident CR3BP jets, hy_cr3bp_reg.cuh)"}.get(
+        kname = {0: " (tape interpreter)", 203: " (register-resident CR3BP jets, hy_cr3bp_reg.cuh)",
+                 1000: " (generated from the tape and compiled at hy_create time with NVRTC, hy_jit.hpp)"}.get(
             variant, " (register-resident N-body jets, hy_nbody_reg.cuh)")
         roof = {
             "bound": "fp64-fma",
@@ -557,6 +563,23 @@ def main():
                         "carries only the state jets)",
             },
         }
+        if variant == 1000 and not li["ws_in_smem"]:
+            # Run-time compiled kernel with the jets in global memory: the operands of every recurrence
+            # stream through L1 / L2 / HBM, so memory - not the FP64 pipe - is the roof.  Algorithmic bytes
+            # per trajectory-step = 8 x (operand loads of the tape + rows written); the caches serve part of
+            # them (ncu, profiles/r02_ncu_jit_cfg4.txt: 277 kB read + 54 kB written per step at DRAM).
+            abytes = 8.0 * (lo + dc.n_rows)
+            roof = {
+                "bound": "hbm", "achieved": steps_rank * abytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": steps_rank * abytes / k_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "kernel": roof["kernel"], "kernel_ms_per_launch": roof["kernel_ms_per_launch"],
+                "algorithmic_bytes_per_trajectory_step": abytes,
+                "traffic": None,
+                "traffic_note": "per launch the kernel moves (operand loads + rows) x 8 B per trajectory-step "
+                                "through the memory hierarchy; DRAM sees what L1 (40 % hits) and L2 (20 %) miss",
+                "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": fma_peak,
+                         "frac": achieved_tf / fma_peak if fma_peak else None, "flops_per_trajectory_step": fl},
+            }
         cpu = None
         if not args.no_cpu_baseline:
             cpu, _, _ = cpu_baseline(cfgd, order, args.cpu_seconds)

@@ -303,6 +303,59 @@ def tan(a):
     return sin(a) / cos(a)
 
 
+# Hyperbolic functions, their inverses and the sigmoid, as compositions of exp / log / sqrt
+# (reference: expose_expression.cpp:288-306 exposes them as primitives; the Taylor coefficients of a
+# composition are those of the function, so the integrator sees the same right-hand side).
+def sinh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.sinh(a.value))
+    return 0.5 * (exp(a) - exp(-a))
+
+
+def cosh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.cosh(a.value))
+    return 0.5 * (exp(a) + exp(-a))
+
+
+def tanh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.tanh(a.value))
+    e2 = exp(2.0 * a)
+    return (e2 - 1.0) / (e2 + 1.0)
+
+
+def sigmoid(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(1.0 / (1.0 + math.exp(-a.value)))
+    return 1.0 / (1.0 + exp(-a))
+
+
+def asinh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.asinh(a.value))
+    return log(a + sqrt(a * a + 1.0))
+
+
+def acosh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.acosh(a.value))
+    return log(a + sqrt(a * a - 1.0))
+
+
+def atanh(a):
+    a = _wrap(a)
+    if _isnum(a):
+        return _num(math.atanh(a.value))
+    return 0.5 * log((1.0 + a) / (1.0 - a))
+
+
 def sum(terms):
     """N-ary sum (reference: expose_expression.cpp ``sum``)."""
     terms = [_wrap(t) for t in terms]

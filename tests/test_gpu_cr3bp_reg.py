@@ -53,8 +53,8 @@ def test_variant_selected():
     # tol = 1e-18 (order 22, the setting of the reference's CR3BP notebook): the FP64 order-22 build
     t22 = _make(sys_, ic, tol=1e-18)
     assert t22.order == 22 and t22._ctx.launch_info()["kernel_variant"] == 222
-    # orders above that and event-carrying systems keep the interpreter
-    assert _make(sys_, ic, tol=1e-21)._ctx.launch_info()["kernel_variant"] == 0
+    # orders above that are not served by the register kernel (interpreter, or a run-time compiled kernel)
+    assert _make(sys_, ic, tol=1e-21)._ctx.launch_info()["kernel_variant"] in (0, 1000)
     x = hy.make_vars("x")
     ev = hy.t_event_batch(x - 5.0)
     assert hy.taylor_adaptive_batch(sys_, ic, t_events=[ev])._ctx.launch_info()["kernel_variant"] == 0
