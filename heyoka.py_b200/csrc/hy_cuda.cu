@@ -247,6 +247,7 @@ int jit_plan(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uin
     pr.ws_len += gen.q_rows;
     gen.pf_dist = env_u32("HY_CUDA_JIT_PF_DIST", 0);
     gen.pf_level = env_u32("HY_CUDA_JIT_PF_LEVEL", 1);
+    gen.batch = env_u32("HY_CUDA_JIT_BATCH", 64);
     const size_t col_bytes = (size_t)pr.ws_len * rb;
     if (!force && col_bytes <= env_u32("HY_CUDA_JIT_MIN_BYTES", 3072)) return 0;
     hy::ProgDims pd0 = prog_dims(pr);

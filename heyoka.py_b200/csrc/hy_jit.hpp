@@ -29,7 +29,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <mutex>
+#include <numeric>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -53,6 +55,7 @@ struct Gen {
     // every blocked op (M - 1 rows per output), number of scratch rows
     uint32_t M = 0;
     uint32_t pf_dist = 0, pf_level = 1; // software prefetch: ops ahead (0: off), cache level
+    uint32_t batch = 0;                  // loads per batch of independent linear ops (0: program order, no batches)
     std::vector<int64_t> qbase;
     uint32_t q_rows = 0;
     Gen(const hy_dims &d_, const Program &p_, uint32_t blk) : d(d_), pr(p_)
@@ -137,6 +140,122 @@ struct Gen {
         }
     }
 
+    // ---- linear ops (LINCOMB / ADDSUB / SVD) in three phases, so that a batch of independent ops
+    // can issue all its loads before the first FMA waits on one (one memory round trip per batch
+    // instead of one per op).  Arithmetic as exec_op: one FMA chain in term order.
+    static bool is_linear(const DOp &o) { return o.opcode == HY_OP_LINCOMB || o.opcode == HY_OP_ADDSUB || o.opcode == HY_OP_SVD; }
+    uint32_t lin_nloads(const DOp &o) const
+    {
+        if (o.opcode == HY_OP_LINCOMB) {
+            uint32_t n = o.n;
+            const DTerm *t = pr.terms.data() + o.b;
+            if (!(o.pad & DP_NOPAR))
+                for (uint32_t i = 0; i < o.n; ++i) n += (t[i].aux & 0xffffu) != pr.one_off;
+            return n;
+        }
+        return o.opcode == HY_OP_ADDSUB ? 2u : 1u;
+    }
+    void lin_loads(const DOp &o, uint32_t id)
+    {
+        const DTerm *t = pr.terms.data() + o.b;
+        const std::string v = "v" + std::to_string(id) + "_";
+        if (o.opcode == HY_OP_LINCOMB) {
+            const bool nopar = (o.pad & DP_NOPAR) != 0;
+            for (uint32_t u = 0; u < o.n; ++u) {
+                const DTerm &tt = t[u];
+                os << "        const R " << v << u << " = " << Wr(tt.src, (tt.aux >> 16) == 0xffffu) << ";\n";
+                const uint32_t mult = tt.aux & 0xffffu;
+                if (!nopar && mult != pr.one_off) os << "        const R " << v << "m" << u << " = W(" << mult << ");\n";
+            }
+        } else if (o.opcode == HY_OP_ADDSUB) {
+            os << "        const R " << v << "a = " << ((o.flags & HY_OPF_NEGA) ? "-" : "") << Wr(o.a, o.flags & DF_JA) << ";\n";
+            os << "        const R " << v << "b = " << ((o.flags & HY_OPF_NEGB) ? "-" : "") << Wr(o.b, o.flags & DF_JB) << ";\n";
+        } else {
+            os << "        const R " << v << "a = " << Wr(o.a, o.flags & DF_JA) << ";\n";
+        }
+    }
+    void lin_math(const DOp &o, uint32_t id)
+    {
+        const DTerm *t = pr.terms.data() + o.b;
+        const std::string v = "v" + std::to_string(id) + "_";
+        if (o.opcode == HY_OP_LINCOMB) {
+            const bool nopar = (o.pad & DP_NOPAR) != 0;
+            os << "        R " << v << "acc = 0;\n";
+            for (uint32_t u = 0; u < o.n; ++u) {
+                const DTerm &tt = t[u];
+                const uint32_t mult = tt.aux & 0xffffu;
+                if (nopar || mult == pr.one_off)
+                    os << "        " << v << "acc = r_fma(" << lit(tt.coef) << ", " << v << u << ", " << v << "acc);\n";
+                else
+                    os << "        " << v << "acc = r_fma(" << lit(tt.coef) << " * " << v << "m" << u << ", " << v << u << ", " << v
+                       << "acc);\n";
+            }
+        } else if (o.opcode == HY_OP_ADDSUB) {
+            os << "        const R " << v << "acc = " << v << "a + " << v << "b;\n";
+        } else {
+            os << "        const R " << v << "acc = " << v << "a;\n";
+        }
+    }
+    void lin_store(const DOp &o, uint32_t id) { store(o, "v" + std::to_string(id) + "_acc"); }
+
+    // ---- same-sweep dependencies: the rows an op reads / writes at the CURRENT order ----
+    void cur_rows(const DOp &o, std::vector<uint32_t> &rd, std::vector<uint32_t> &wr) const
+    {
+        const DTerm *t = pr.terms.data() + o.b;
+        const bool writes_next = o.opcode == HY_OP_SVD || (o.flags & HY_OPF_SVD); // x[k+1]: next sweep
+        switch (o.opcode) {
+        case HY_OP_LINCOMB:
+            for (uint32_t i = 0; i < o.n; ++i) rd.push_back(t[i].src & 0x3fffffffu);
+            break;
+        case HY_OP_SUMSQ:
+            for (uint32_t i = 0; i < o.n; ++i) rd.push_back(t[i].src & 0x3fffffffu);
+            break;
+        case HY_OP_MULSH:
+            rd.push_back(o.a);
+            for (uint32_t i = 0; i < o.n; ++i) {
+                rd.push_back(t[i].src & 0x3fffffffu);
+                wr.push_back(t[i].aux & 0x3fffffffu);
+            }
+            break;
+        case HY_OP_ADDSUB: case HY_OP_MUL: case HY_OP_DIV:
+            rd.push_back(o.a);
+            rd.push_back(o.b);
+            break;
+        case HY_OP_TIME: case OP_NOP: break;
+        default: rd.push_back(o.a); break;
+        }
+        if (o.opcode != HY_OP_MULSH && o.opcode != OP_NOP && !writes_next) wr.push_back(o.dst);
+        if (o.opcode == HY_OP_SINCOS) wr.push_back(o.dst2);
+    }
+    // Slots in dependency-level order (ops of one level are independent), linear ops first inside a
+    // level, then grouped by kind.
+    std::vector<uint32_t> level_order() const
+    {
+        std::map<uint32_t, uint32_t> prod; // row base -> slot
+        std::vector<uint32_t> lvl(pr.n_slots, 0);
+        for (uint32_t i = 0; i < pr.n_slots; ++i) {
+            std::vector<uint32_t> rd, wr;
+            cur_rows(pr.ops[i], rd, wr);
+            uint32_t l = 0;
+            for (uint32_t r : rd) {
+                auto it = prod.find(r);
+                if (it != prod.end()) l = std::max(l, lvl[it->second] + 1);
+            }
+            lvl[i] = l;
+            for (uint32_t r : wr) prod[r] = i;
+        }
+        std::vector<uint32_t> idx(pr.n_slots);
+        std::iota(idx.begin(), idx.end(), 0u);
+        auto cls = [&](uint32_t i) { return is_linear(pr.ops[i]) ? 0u : 1u + pr.ops[i].opcode; };
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+            if (lvl[a] != lvl[b]) return lvl[a] < lvl[b];
+            return cls(a) < cls(b);
+        });
+        levels_ = lvl;
+        return idx;
+    }
+    mutable std::vector<uint32_t> levels_;
+
     // One op at order k (k: a variable of the generated code).  Linear ops are emitted inline (a few
     // loads and FMAs); everything with a convolution is a call to an out-of-line body (jop_*,
     // hy_kernels.cuh) with literal row numbers.  The unblocked arithmetic is exec_op's.
@@ -150,34 +269,13 @@ struct Gen {
         auto rowk = [&](uint32_t base, bool jet) { return row(base, jet); };
         os << "      { // op " << (int)o.opcode << "\n";
         switch (o.opcode) {
-        case HY_OP_LINCOMB: {
-            const bool nopar = (o.pad & DP_NOPAR) != 0;
-            // (blocks of 8 terms: operands first, then one FMA chain in term order - as exec_op)
-            os << "        R acc = 0;\n";
-            for (uint32_t i0 = 0; i0 < o.n; i0 += 8) {
-                const uint32_t m = std::min<uint32_t>(8, o.n - i0);
-                for (uint32_t u = 0; u < m; ++u) {
-                    const DTerm &tt = t[i0 + u];
-                    const uint32_t mask = tt.aux >> 16;
-                    os << "        const R v" << i0 + u << " = " << Wr(tt.src, mask == 0xffffu) << ";\n";
-                }
-                for (uint32_t u = 0; u < m; ++u) {
-                    const DTerm &tt = t[i0 + u];
-                    const uint32_t mult = tt.aux & 0xffffu;
-                    if (nopar || mult == pr.one_off)
-                        os << "        acc = r_fma(" << lit(tt.coef) << ", v" << i0 + u << ", acc);\n";
-                    else
-                        os << "        acc = r_fma(" << lit(tt.coef) << " * W(" << mult << "), v" << i0 + u << ", acc);\n";
-                }
-            }
-            store(o, "acc");
-        } break;
-        case HY_OP_ADDSUB: {
-            os << "        const R a = " << ((o.flags & HY_OPF_NEGA) ? "-" : "") << Wr(o.a, o.flags & DF_JA) << ";\n";
-            os << "        const R b = " << ((o.flags & HY_OPF_NEGB) ? "-" : "") << Wr(o.b, o.flags & DF_JB) << ";\n";
-            store(o, "a + b");
-        } break;
-        case HY_OP_SVD: store(o, Wr(o.a, o.flags & DF_JA)); break;
+        case HY_OP_LINCOMB:
+        case HY_OP_ADDSUB:
+        case HY_OP_SVD:
+            lin_loads(o, slot);
+            lin_math(o, slot);
+            lin_store(o, slot);
+            break;
         case HY_OP_MUL:
             os << "        jop_mul<R, HY_WS, " << Ms << ">(w, k, " << bi << ", " << o.a << ", " << o.b << ", "
                << rowk(o.dst, o.flags & DF_JDST) << ", " << qb << ");\n";
@@ -249,9 +347,36 @@ struct Gen {
             os << "      const uint32_t bi = (k >= " << M << "u && k < " << (d.order / M) * M << "u) ? k % " << M
                << "u : 0xffffffffu;\n";
         }
-        for (uint32_t i = 0; i < pr.n_slots; ++i) {
-            if (pf_dist && i + pf_dist < pr.n_slots) emit_prefetch(pr.ops[i + pf_dist], pf_level);
-            if (!emit_op(pr.ops[i], i, true)) return "";
+        if (!batch) {
+            for (uint32_t i = 0; i < pr.n_slots; ++i) {
+                if (pf_dist && i + pf_dist < pr.n_slots) emit_prefetch(pr.ops[i + pf_dist], pf_level);
+                if (!emit_op(pr.ops[i], i, true)) return "";
+            }
+        } else {
+            // dependency levels; the linear ops of a level in batches (loads, arithmetic, stores)
+            const std::vector<uint32_t> ord = level_order();
+            size_t i = 0;
+            while (i < ord.size()) {
+                const DOp &o = pr.ops[ord[i]];
+                if (!is_linear(o)) {
+                    if (!emit_op(o, ord[i], true)) return "";
+                    ++i;
+                    continue;
+                }
+                size_t j = i;
+                uint32_t loads = 0;
+                while (j < ord.size() && is_linear(pr.ops[ord[j]]) && levels_[ord[j]] == levels_[ord[i]] &&
+                       (j == i || loads + lin_nloads(pr.ops[ord[j]]) <= batch)) {
+                    loads += lin_nloads(pr.ops[ord[j]]);
+                    ++j;
+                }
+                os << "      { // " << (j - i) << " linear ops of level " << levels_[ord[i]] << "\n";
+                for (size_t q = i; q < j; ++q) lin_loads(pr.ops[ord[q]], ord[q]);
+                for (size_t q = i; q < j; ++q) lin_math(pr.ops[ord[q]], ord[q]);
+                for (size_t q = i; q < j; ++q) lin_store(pr.ops[ord[q]], ord[q]);
+                os << "      }\n";
+                i = j;
+            }
         }
         os << "    }\n}\n";
         os << "template <typename R> __device__ __forceinline__ void hy_gen_ev_sweep(R *__restrict__ w, const R *__restrict__ rk, const R tm)\n{\n";

@@ -1,5 +1,6 @@
-run() { echo "$@"; env "$@" QCHECK=0 QMODES=jit python tools/gpu_jit_cfg4.py 2>&1 | tail -1; }
-run HY_CUDA_JIT_THREADS=256 HY_CUDA_JIT_BLOCK=0 QB=4096 QT=60000
-run HY_CUDA_JIT_THREADS=32 HY_CUDA_JIT_BLOCK=0 QB=4736 QT=60000
-run HY_CUDA_JIT_THREADS=64 HY_CUDA_JIT_BLOCK=0 QB=9472 QT=60000
-run HY_CUDA_JIT_THREADS=1024 HY_CUDA_JIT_BLOCK=0 QB=151552 QT=20000
+QCHECK=1 QMODES= QB=64 python tools/gpu_jit_cfg4.py 2>&1 | grep "steps equal"
+run() { echo "$@"; env "$@" QCHECK=0 QMODES=jit QT=20000 python tools/gpu_jit_cfg4.py 2>&1 | tail -1; }
+run HY_CUDA_JIT_THREADS=512 HY_CUDA_JIT_BATCH=0
+run HY_CUDA_JIT_THREADS=512 HY_CUDA_JIT_BATCH=32
+run HY_CUDA_JIT_THREADS=512 HY_CUDA_JIT_BATCH=64
+run HY_CUDA_JIT_THREADS=256 HY_CUDA_JIT_BATCH=32
