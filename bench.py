@@ -286,9 +286,15 @@ def cpu_baseline(cfgd, order, target_s, rank_seed=0):
         "cores": cores,
         "kind": "port",
         "sample": "{} trajectories x t = {:g} = {} steps in {:.1f} s (SIMD-batched C port of the reference "
-                  "algorithm: 8 lanes/thread in lock-step, OpenMP over batches{})".format(
-                      traj, h, int(ns.sum()), dt, extra),
+                  "algorithm: 8 lanes/thread in lock-step, OpenMP over batches, built {}{})".format(
+                      traj, h, int(ns.sum()), dt, _c_oracle_flags(), extra),
     }, dt, int(ns.sum())
+
+
+def _c_oracle_flags():
+    from oracle import c_oracle
+
+    return c_oracle.SIMD_FLAGS
 
 
 def run_reference(args):

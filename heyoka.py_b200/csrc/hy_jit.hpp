@@ -129,7 +129,7 @@ struct Gen {
             break;
         case HY_OP_ADDSUB: cur(o.a, o.flags & DF_JA); cur(o.b, o.flags & DF_JB); break;
         case HY_OP_SVD: cur(o.a, o.flags & DF_JA); break;
-        case HY_OP_MUL: jet(o.a); jet(o.b); break;
+        case HY_OP_MUL: case HY_OP_INTG: jet(o.a); jet(o.b); break;
         case HY_OP_SQUARE: jet(o.a); break;
         case HY_OP_SUMSQ: for (uint32_t i = 0; i < o.n; ++i) jet(t[i].src & 0x3fffffffu); break;
         case HY_OP_MULSH: jet(o.a); for (uint32_t i = 0; i < o.n; ++i) jet(t[i].src & 0x3fffffffu); break;
@@ -217,7 +217,7 @@ struct Gen {
                 wr.push_back(t[i].aux & 0x3fffffffu);
             }
             break;
-        case HY_OP_ADDSUB: case HY_OP_MUL: case HY_OP_DIV:
+        case HY_OP_ADDSUB: case HY_OP_MUL: case HY_OP_DIV: case HY_OP_INTG:
             rd.push_back(o.a);
             rd.push_back(o.b);
             break;
@@ -322,6 +322,10 @@ struct Gen {
             break;
         case HY_OP_SINCOS:
             os << "        jop_sincos<R, HY_WS>(w, rk, k, " << o.a << ", " << o.dst << ", " << o.dst2 << ");\n";
+            break;
+        case HY_OP_INTG:
+            os << "        jop_intg<R, HY_WS>(w, rk, k, " << o.a << ", " << o.b << ", " << rowk(o.dst, o.flags & DF_JDST) << ", "
+               << (int)pr.imm[o.imm] << ");\n";
             break;
         case HY_OP_TIME: os << "        W(" << o.dst << " + k) = k == 0 ? tm : (k == 1 ? (R)1 : (R)0);\n"; break;
         case OP_NOP: break;

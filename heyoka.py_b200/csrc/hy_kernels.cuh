@@ -70,6 +70,15 @@ __device__ __forceinline__ float r_copysign(float a, float b) { return copysignf
 // scaled by e <= 1/2, so the result is good to ~1 ulp - at a third of the cost of pow().
 static __device__ __noinline__ double r_root(double x, double e) { return exp(log(x) * e); }
 static __device__ __noinline__ float r_root(float x, float e) { return expf(logf(x) * e); }
+// order 0 of the INTG functions (HY_OP_INTG: imm = 0 asin, 1 acos, 2 atan, 3 erf)
+static __device__ __noinline__ double r_intg0(double a, int code)
+{
+    return code == 0 ? asin(a) : (code == 1 ? acos(a) : (code == 2 ? atan(a) : erf(a)));
+}
+static __device__ __noinline__ float r_intg0(float a, int code)
+{
+    return code == 0 ? asinf(a) : (code == 1 ? acosf(a) : (code == 2 ? atanf(a) : erff(a)));
+}
 template <typename R> __device__ __forceinline__ R r_inf();
 template <> __device__ __forceinline__ double r_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
@@ -632,6 +641,20 @@ __device__ __noinline__ void jop_log(R *__restrict__ w, const R *__restrict__ rk
     }
 }
 template <typename R, int S>
+__device__ __noinline__ void jop_intg(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t b, uint32_t dst,
+                                      int code)
+{
+    const R *pa = w + a * S, *pb = w + b * S;
+    if (k == 0) {
+        w[dst * S] = r_intg0(pa[0], code);
+    } else {
+        R acc = 0, jr = 1;
+#pragma unroll 1
+        for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * pa[j * S], pb[(k - j) * S], acc);
+        w[dst * S] = acc * rk[k];
+    }
+}
+template <typename R, int S>
 __device__ __noinline__ void jop_sincos(R *__restrict__ w, const R *__restrict__ rk, uint32_t k, uint32_t a, uint32_t sr, uint32_t cr)
 {
     const R *pa = w + a * S;
@@ -1056,6 +1079,18 @@ __device__ __forceinline__ void exec_op(const DOp o, const DTerm *__restrict__ l
 #pragma unroll 1
             for (uint32_t j = 1; j < k; ++j, jr += (R)1) acc = r_fma(jr * c[j], a[k - j], acc);
             c[k] = r_fma(-acc, rk[k], a[k]) * w[o.dst2];
+        }
+    } break;
+    case HY_OP_INTG: {
+        // dst = F(a), dF/da = b:  dst[k] = (1/k) sum_{j=1..k} j a[j] b[k-j]
+        const R *a = w + o.a, *b = w + o.b;
+        if (k == 0) {
+            w[o.dst] = r_intg0(a[0], (int)s_imm[o.imm]);
+        } else {
+            R acc = 0, jr = 1;
+#pragma unroll 1
+            for (uint32_t j = 1; j <= k; ++j, jr += (R)1) acc = r_fma(jr * a[j], b[k - j], acc);
+            w[o.dst + ((o.flags & DF_JDST) ? k : 0u)] = acc * rk[k];
         }
     } break;
     case HY_OP_SINCOS: {

@@ -73,7 +73,8 @@ inline double op_cost(const hy_op &o)
     case HY_OP_POW:
     case HY_OP_SQRT: return 12 + 5 * k;
     case HY_OP_EXP:
-    case HY_OP_LOG: return 10 + 4 * k;
+    case HY_OP_LOG:
+    case HY_OP_INTG: return 10 + 4 * k;
     case HY_OP_SINCOS: return 12 + 6 * k;
     case HY_OP_TIME: return 3;
     case HY_OP_SVD: return 4;
@@ -135,7 +136,8 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
             if (o.opcode == HY_OP_MULSH) add_dep(i, o.a);
         } else if (o.opcode != HY_OP_TIME) {
             add_dep(i, o.a);
-            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB) add_dep(i, o.b);
+            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB || o.opcode == HY_OP_INTG)
+                add_dep(i, o.b);
         }
     }
     for (uint32_t i = 0; i < n_ops; ++i)
@@ -303,7 +305,7 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
     for (uint32_t i = 0; i < n_ops; ++i) {
         const hy_op &o = ops[i];
         switch (o.opcode) {
-        case HY_OP_MUL: mark_hist(o.a); mark_hist(o.b); break;
+        case HY_OP_MUL: case HY_OP_INTG: mark_hist(o.a); mark_hist(o.b); break;
         case HY_OP_SQUARE: case HY_OP_POW: case HY_OP_SQRT: case HY_OP_EXP: case HY_OP_LOG: case HY_OP_SINCOS:
             mark_hist(o.a); break;
         case HY_OP_DIV: mark_hist(o.b); break;
@@ -338,7 +340,8 @@ inline std::string build_program(const hy_dims &d, const hy_op *ops, const hy_te
             if (o.opcode == HY_OP_MULSH) add_block(o.a);
         } else if (o.opcode != HY_OP_TIME) {
             add_block(o.a);
-            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB) add_block(o.b);
+            if (o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV || o.opcode == HY_OP_ADDSUB || o.opcode == HY_OP_INTG)
+                add_block(o.b);
         }
     }
     std::vector<char> is_ev_state(n_state, 0);

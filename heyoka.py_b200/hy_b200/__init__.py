@@ -11,7 +11,7 @@ import numpy as _np
 from . import model, callback
 from ._expression import (
     expression, make_vars, par, time, sin, cos, exp, log, sqrt, pow, sum, prod, diff, square, tan,
-    sinh, cosh, tanh, sigmoid, asinh, acosh, atanh,
+    sinh, cosh, tanh, sigmoid, asinh, acosh, atanh, asin, acos, atan, erf,
 )
 from .enums import taylor_outcome, event_direction, code_model
 from .var_ode_sys import var_ode_sys, var_args

@@ -298,6 +298,12 @@ log = _unary("log", math.log)
 sqrt = _unary("sqrt", math.sqrt)
 
 
+asin = _unary("asin", math.asin)
+acos = _unary("acos", math.acos)
+atan = _unary("atan", math.atan)
+erf = _unary("erf", math.erf)
+
+
 def tan(a):
     a = _wrap(a)
     return sin(a) / cos(a)
@@ -512,6 +518,14 @@ def diff(e, x):
                 r = n * da[0]
             elif nm == "log":
                 r = da[0] / a[0]
+            elif nm == "asin":
+                r = da[0] * pow(1.0 - a[0] * a[0], -0.5)
+            elif nm == "acos":
+                r = -(da[0] * pow(1.0 - a[0] * a[0], -0.5))
+            elif nm == "atan":
+                r = da[0] / (1.0 + a[0] * a[0])
+            elif nm == "erf":
+                r = (2.0 / math.sqrt(math.pi)) * exp(-(a[0] * a[0])) * da[0]
             else:
                 raise NotImplementedError("diff() of '{}'".format(nm))
         d[id(n)] = r
@@ -552,7 +566,8 @@ def rebuild(n, args):
         return -args[0]
     if nm == "pow":
         return pow(args[0], args[1])
-    return {"sin": sin, "cos": cos, "exp": exp, "log": log, "sqrt": sqrt}[nm](args[0])
+    return {"sin": sin, "cos": cos, "exp": exp, "log": log, "sqrt": sqrt, "asin": asin, "acos": acos,
+            "atan": atan, "erf": erf}[nm](args[0])
 
 
 def eval_numpy(e, var_values, pars=None, tm=None):
@@ -586,6 +601,10 @@ def eval_numpy(e, var_values, pars=None, tm=None):
                 r = -a[0]
             elif nm == "pow":
                 r = np.power(a[0], a[1])
+            elif nm in ("asin", "acos", "atan"):
+                r = getattr(np, "arc" + nm[1:])(a[0])
+            elif nm == "erf":
+                r = np.vectorize(math.erf)(a[0]) if isinstance(a[0], np.ndarray) else math.erf(a[0])
             else:
                 r = getattr(np, nm)(a[0])
         val[id(n)] = r

@@ -27,7 +27,8 @@ from . import _expression as E
 
 # Opcodes: keep in sync with include/hy_cuda.h.
 OP_LINCOMB, OP_MUL, OP_SQUARE, OP_DIV, OP_POW, OP_SQRT, OP_EXP, OP_LOG = range(8)
-OP_SINCOS, OP_TIME, OP_SVD, OP_SUMSQ, OP_MULSH, OP_ADDSUB = 8, 9, 10, 11, 12, 13
+OP_SINCOS, OP_TIME, OP_SVD, OP_SUMSQ, OP_MULSH, OP_ADDSUB, OP_INTG = 8, 9, 10, 11, 12, 13, 14
+INTG_CODES = {"asin": 0, "acos": 1, "atan": 2, "erf": 3}
 OPF_EVENT, OPF_NEGA, OPF_NEGB, OPF_SVD = 0x1, 0x2, 0x4, 0x8
 REF_JET = 0x80000000
 REF_ONE = 0x7FFFFFFF
@@ -47,6 +48,7 @@ OP_NAMES = {
     OP_SUMSQ: "sumsq",
     OP_MULSH: "mulsh",
     OP_ADDSUB: "addsub",
+    OP_INTG: "intg",
 }
 
 op_dtype = np.dtype(
@@ -195,7 +197,7 @@ class Decomposition:
                 elif oc == OP_MULSH:
                     fl += n * 2 * (k + 1)
                     lo += (n + 1) * (k + 1)
-                elif oc in (OP_DIV, OP_EXP, OP_LOG):
+                elif oc in (OP_DIV, OP_EXP, OP_LOG, OP_INTG):
                     fl += 2 * k + 2
                     lo += 2 * k + 1
                 elif oc in (OP_POW, OP_SQRT):
@@ -401,6 +403,22 @@ def decompose(sys, order, events=(), fuse=True):
                 else:
                     s, c = sincos(materialise(a[0]))
                     L = _Lin.atom(s if nm == "sin" else c)
+            elif nm in INTG_CODES:
+                # F(a) with dF/da = g(a) built from existing ops: F[k] = (1/k) sum_j j a[j] g[k-j]
+                if a[0].is_num():
+                    L = _Lin.const(getattr(math, nm)(a[0].num()))
+                else:
+                    ua = materialise(a[0])
+                    sq = do_pow(_Lin.atom(ua), 2.0)
+                    if nm in ("asin", "acos"):
+                        g = do_pow(_Lin.const(1.0).add(sq, -1.0), -0.5)
+                        if nm == "acos":
+                            g = g.scale(-1.0)
+                    elif nm == "atan":
+                        g = do_pow(_Lin.const(1.0).add(sq), -1.0)
+                    else:
+                        g = _Lin.atom(nonlin(OP_EXP, (materialise(sq.scale(-1.0)),))).scale(2.0 / math.sqrt(math.pi))
+                    L = _Lin.atom(nonlin(OP_INTG, (ua, materialise(g)), float(INTG_CODES[nm])))
             else:
                 raise NotImplementedError(
                     "the function '{}' is not supported by the Taylor decomposition".format(nm)
@@ -435,7 +453,7 @@ def decompose(sys, order, events=(), fuse=True):
     for u in uv:
         if u.op in (OP_DIV, OP_POW, OP_SQRT, OP_EXP, OP_LOG, OP_SINCOS, "cos_of", OP_TIME):
             u.jet = True
-        if u.op in (OP_MUL, OP_SQUARE, OP_POW, OP_SQRT, OP_EXP, OP_LOG, OP_SINCOS, "cos_of"):
+        if u.op in (OP_MUL, OP_SQUARE, OP_POW, OP_SQRT, OP_EXP, OP_LOG, OP_SINCOS, "cos_of", OP_INTG):
             for a in u.args:
                 uv[a].jet = True
         if u.op == OP_DIV:
@@ -579,7 +597,7 @@ def decompose(sys, order, events=(), fuse=True):
             o["dst"] = ref(u.svd_of)
         elif u.op != OP_MULSH:
             o["dst"] = ref(u.id)
-        o["imm"] = u.imm if u.op == OP_POW else 0.0
+        o["imm"] = u.imm if u.op in (OP_POW, OP_INTG) else 0.0
         if u.op in (OP_LINCOMB, OP_SUMSQ):
             o["b"] = len(terms)
             o["n"] = len(u.terms)
@@ -783,6 +801,8 @@ def decompose_event_tape(events, names, order):
             oc, fl = int(o["opcode"]), int(o["flags"])
             if not (fl & OPF_EVENT) or (fl & OPF_SVD) or oc == OP_SVD:
                 continue
+            if oc == OP_INTG:
+                return None  # (not in the event evaluator of the register-resident kernels: shared tape)
             q = np.zeros(1, dtype=op_dtype)[0]
             q["opcode"], q["flags"], q["n"], q["imm"] = oc, fl & (OPF_NEGA | OPF_NEGB), o["n"], o["imm"]
             if oc in (OP_LINCOMB, OP_SUMSQ, OP_MULSH):

@@ -59,6 +59,10 @@ enum hy_opcode {
     HY_OP_SUMSQ = 11,  /* dst[k] = sum_i sum_j a_i[j] a_i[k-j]       (terms)   */
     HY_OP_MULSH = 12,  /* dst_i[k] = sum_j a_i[j] b[k-j], i<n (terms=a_i,dst_i)*/
     HY_OP_ADDSUB = 13, /* dst[k] = (+-)a[k] (+-)b[k]   (signs: HY_OPF_NEGA/NEGB)  */
+    HY_OP_INTG = 14,   /* dst = F(a) for a function with dF/da = b (both jets):
+                          dst[0] = F(a[0]), dst[k] = (1/k) sum_{j=1..k} j a[j] b[k-j];
+                          imm selects F: 0 asin, 1 acos, 2 atan, 3 erf - b is built
+                          by earlier ops: +-(1-a^2)^(-1/2), 1/(1+a^2), 2/sqrt(pi) exp(-a^2) */
     HY_OP_COUNT
 };
 
@@ -78,7 +82,7 @@ typedef struct hy_op {
     uint32_t a;    /* first operand row reference                             */
     uint32_t b;    /* second operand row reference, or first term index       */
     uint32_t n;    /* number of terms (LINCOMB / SUMSQ / MULSH)               */
-    double imm;    /* POW exponent                                            */
+    double imm;    /* POW exponent; INTG: code of the function                */
 } hy_op; /* 32 bytes */
 
 typedef struct hy_term {

@@ -135,6 +135,28 @@ class COracle:
 
 
 _SIMD = None
+SIMD_FLAGS = "portable (-O3 -mavx2 -mfma)"
+
+
+def _simd_native():
+    """The CPU baseline compiled for the host it runs on (-O3 -march=native: AVX-512 where the
+    host has it), into a temporary directory; None if that fails (the portable in-tree build is
+    used then).  The in-tree .so must run on any x86-64 box, so it cannot be -march=native."""
+    global SIMD_FLAGS
+    import tempfile
+
+    if os.environ.get("HY_BASELINE_PORTABLE"):
+        return None
+    try:
+        out = os.path.join(tempfile.mkdtemp(prefix="hy_baseline_"), "libhy_baseline_simd_native.so")
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O3", "-march=native", "-fPIC", "-shared", "-fopenmp", "-fno-fast-math",
+                               "-o", out, os.path.join(_HERE, "hy_baseline_simd.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        SIMD_FLAGS = "native (-O3 -march=native)"
+        return out
+    except Exception:
+        return None
 
 
 def simd_propagate_until(dc, state, t, pars=None, nthreads=0):
@@ -143,7 +165,7 @@ def simd_propagate_until(dc, state, t, pars=None, nthreads=0):
     global _SIMD
     if _SIMD is None:
         build()
-        _SIMD = C.CDLL(os.path.join(_HERE, "libhy_baseline_simd.so"))
+        _SIMD = C.CDLL(_simd_native() or os.path.join(_HERE, "libhy_baseline_simd.so"))
         _SIMD.ora_simd_propagate_until.restype = C.c_int
     st = np.ascontiguousarray(np.array(state, dtype=np.float64).reshape(dc.n_state, -1))
     B = st.shape[1]

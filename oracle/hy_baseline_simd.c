@@ -167,6 +167,20 @@ static void exec_op(const hy_op *o, const hy_term *T, double *ws, const double *
             FORL c[(size_t)k * W + l] = acc[l] * rk[k];
         }
     } break;
+    case HY_OP_INTG: {
+        const double *a = ROW(o->a & 0x7fffffffu), *b = ROW(o->b & 0x7fffffffu);
+        double *c = ROW(o->dst & 0x7fffffffu);
+        const int jet = (o->dst & 0x80000000u) != 0;
+        if (k == 0) {
+            const int code = (int)o->imm;
+            FORL c[l] = code == 0 ? asin(a[l]) : (code == 1 ? acos(a[l]) : (code == 2 ? atan(a[l]) : erf(a[l])));
+        } else {
+            vd acc;
+            FORL acc[l] = 0;
+            for (uint32_t j = 1; j <= k; ++j) FORL acc[l] = fma((double)j * a[(size_t)j * W + l], b[(size_t)(k - j) * W + l], acc[l]);
+            FORL c[(size_t)(jet ? k : 0) * W + l] = acc[l] * rk[k];
+        }
+    } break;
     case HY_OP_LOG: {
         const double *a = ROW(o->a & 0x7fffffffu);
         double *c = ROW(o->dst & 0x7fffffffu), *inv = ROW(o->dst2);

@@ -44,6 +44,10 @@
 #define R_LOG log
 #define R_SIN sin
 #define R_COS cos
+#define R_ASIN asin
+#define R_ACOS acos
+#define R_ATAN atan
+#define R_ERF erf
 #define R_ABS fabs
 #define R_COPYSIGN copysign
 #include "hy_oracle_impl.h"
@@ -56,6 +60,10 @@
 #undef R_LOG
 #undef R_SIN
 #undef R_COS
+#undef R_ASIN
+#undef R_ACOS
+#undef R_ATAN
+#undef R_ERF
 #undef R_ABS
 #undef R_COPYSIGN
 #undef JET
@@ -73,6 +81,10 @@
 #define R_LOG logf
 #define R_SIN sinf
 #define R_COS cosf
+#define R_ASIN asinf
+#define R_ACOS acosf
+#define R_ATAN atanf
+#define R_ERF erff
 #define R_ABS fabsf
 #define R_COPYSIGN copysignf
 #include "hy_oracle_impl.h"

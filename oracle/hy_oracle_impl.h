@@ -149,6 +149,18 @@ static void FN(exec_op)(const FN(ora_sys) * S, const hy_op *o, REAL *ws, const R
             c[k] = acc * S->rk[k];
         }
     } break;
+    case HY_OP_INTG: {
+        /* dst = F(a), dF/da = b (include/hy_cuda.h): dst[k] = (1/k) sum_{j=1..k} j a[j] b[k-j] */
+        const REAL *a = JET(o->a), *b = JET(o->b);
+        if (k == 0) {
+            const int code = (int)o->imm;
+            *FN(st)(ws, o->dst, 0) = code == 0 ? R_ASIN(a[0]) : (code == 1 ? R_ACOS(a[0]) : (code == 2 ? R_ATAN(a[0]) : R_ERF(a[0])));
+        } else {
+            REAL acc = 0;
+            for (uint32_t j = 1; j <= k; ++j) acc = R_FMA((REAL)j * a[j], b[k - j], acc);
+            *FN(st)(ws, o->dst, k) = acc * S->rk[k];
+        }
+    } break;
     case HY_OP_LOG: {
         const REAL *a = JET(o->a);
         REAL *c = JET(o->dst);

@@ -244,6 +244,53 @@ class NpTaylorBatch:
                                     C[k] = -ca / T(k)
                                 done[0] = k
                             J[k] = S[k] if nm == "sin" else C[k]
+                        elif nm in ("asin", "acos", "atan", "erf"):
+                            # F(a) with dF/da = g(a): F[k] = (1/k) sum_{j=1..k} j a[j] g[k-j]; the jet
+                            # of g is carried along with its own recurrences (square, pow / exp)
+                            key = id(nd)
+                            if key not in cosj:
+                                cosj[key] = [np.zeros((p + 1, B), dtype=T) for _ in range(3)]
+                            SQ, U, Gj = cosj[key]  # a^2, 1 -+ a^2 (or -a^2), g
+                            A = a[0]
+                            acc = np.zeros(B, dtype=T)
+                            for j in range(k + 1):
+                                acc = acc + A[j] * A[k - j]
+                            SQ[k] = acc
+                            if nm in ("asin", "acos"):
+                                U[k] = (T(1) if k == 0 else T(0)) - SQ[k]
+                                al = -0.5
+                            elif nm == "atan":
+                                U[k] = (T(1) if k == 0 else T(0)) + SQ[k]
+                                al = -1.0
+                            else:
+                                U[k] = -SQ[k]
+                            if nm == "erf":
+                                if k == 0:
+                                    Gj[0] = np.exp(U[0])
+                                else:
+                                    acc = np.zeros(B, dtype=T)
+                                    for j in range(1, k + 1):
+                                        acc = acc + T(j) * U[j] * Gj[k - j]
+                                    Gj[k] = acc / T(k)
+                                scale = T(2.0 / math.sqrt(math.pi))
+                            else:
+                                if k == 0:
+                                    Gj[0] = pow0(U[0], al, T)
+                                else:
+                                    acc = np.zeros(B, dtype=T)
+                                    for j in range(k):
+                                        acc = acc + T(k * al - j * (al + 1.0)) * U[k - j] * Gj[j]
+                                    Gj[k] = acc / (T(k) * U[0])
+                                scale = T(-1) if nm == "acos" else T(1)
+                            if k == 0:
+                                f0 = {"asin": np.arcsin, "acos": np.arccos, "atan": np.arctan,
+                                      "erf": np.vectorize(math.erf, otypes=[T])}[nm]
+                                J[0] = f0(A[0]).astype(T)
+                            else:
+                                acc = np.zeros(B, dtype=T)
+                                for j in range(1, k + 1):
+                                    acc = acc + T(j) * A[j] * (scale * Gj[k - j])
+                                J[k] = acc / T(k)
                         else:
                             raise NotImplementedError(nm)
                 # State recurrence x_i[k+1] = f_i[k] / (k+1).

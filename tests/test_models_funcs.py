@@ -91,3 +91,46 @@ def test_hyperbolic_functions_and_sigmoid():
         y += h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
         t += h
     assert abs(ta.state[0, 0] - y) < 1e-12
+
+
+def _intg_sys():
+    x, y = hy.make_vars("x", "y")
+    return [(x, hy.asin(0.5 * hy.sin(hy.time)) + hy.atan(y)),
+            (y, hy.erf(x) - 0.1 * hy.acos(0.3 * hy.cos(y)))]
+
+
+def test_asin_acos_atan_erf_tape_and_oracles():
+    # One new recurrence (HY_OP_INTG, include/hy_cuda.h) serves the four functions: F(a) with
+    # dF/da = g(a), g built from existing ops.  Reference: expose_expression.cpp:288-306.
+    import math
+    from hy_b200 import decompose as D
+    from oracle.c_oracle import COracle
+
+    x = hy.make_vars("x")
+    for f, g, pt in ((hy.asin, np.arcsin, 0.3), (hy.acos, np.arccos, 0.3), (hy.atan, np.arctan, 1.3),
+                     (hy.erf, math.erf, 0.4)):
+        assert abs(E.eval_numpy(f(x), {"x": pt}) - g(pt)) < 1e-15
+        d = E.eval_numpy(hy.diff(f(x), x), {"x": pt})
+        assert abs(d - (g(pt + 1e-6) - g(pt - 1e-6)) / 2e-6) < 1e-8
+        assert f(pt).kind == "num"
+    sys_ = _intg_sys()
+    dc = D.decompose(sys_, 20)
+    kinds = [D.OP_NAMES[int(o["opcode"])] for o in dc.ops]
+    assert kinds.count("intg") == 4
+    ic = np.array([[0.1, -0.2], [0.3, 0.5]])
+    a = NpTaylorBatch(sys_, ic)
+    a.propagate_until(3.0)
+    b = COracle(dc, ic)
+    b.propagate_until(3.0)
+    assert np.max(np.abs(a.state - b.state)) < 1e-13      # DAG walker vs tape interpreter
+
+    def rhs(t, s):
+        return np.array([math.asin(0.5 * math.sin(t)) + math.atan(s[1]),
+                         math.erf(s[0]) - 0.1 * math.acos(0.3 * math.cos(s[1]))])
+
+    s, t, h = ic[:, 0].copy(), 0.0, 2e-4
+    for _ in range(15000):
+        k1 = rhs(t, s); k2 = rhs(t + h / 2, s + h / 2 * k1); k3 = rhs(t + h / 2, s + h / 2 * k2); k4 = rhs(t + h, s + h * k3)
+        s = s + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        t += h
+    assert np.max(np.abs(s - a.state[:, 0])) < 1e-11
