@@ -444,7 +444,11 @@ int choose_geometry(hy_ctx *c)
     // 2.5e7 steps/s).  hy_create's `compact_mode` flag (reference kwarg) selects the interpreter.
     bool jit_smem = false;
     uint32_t jit_T = 0;
-    const uint32_t jit_mode = c->no_jit ? 0u : env_u32("HY_CUDA_JIT", 2);
+    uint32_t jit_mode = c->no_jit ? 0u : env_u32("HY_CUDA_JIT", 2);
+    // (the A/B switches that keep a matched tape "on the tape interpreter" mean exactly that)
+    if (jit_mode == 2 && (env_u32("HY_CUDA_NO_NBODY_REG", 0) || env_u32("HY_CUDA_NO_CR3BP_REG", 0) ||
+                          env_u32("HY_CUDA_NO_REG_EVENTS", 0)))
+        jit_mode = 0;
     const bool interp_weak = !bestG || !best_smem || best_score < (double)env_u32("HY_CUDA_JIT_MAX_SCORE", 200);
     if (!li.kernel_variant && !force_global && !Genv && (jit_mode == 1 || (jit_mode == 2 && interp_weak))) {
         hy::Program pr;

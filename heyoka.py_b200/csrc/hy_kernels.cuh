@@ -1773,13 +1773,18 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // ---- optional tc write, then the state update ----
             if (stepping && (P.write_tc || (FX && P.rec.on) || P.mode == MODE_GRID)) {
                 if (P.write_tc && P.tc) {
-                    for (uint32_t i = sub; i < n * P1; i += G) P.tc[(size_t)i * P.B + traj] = XJ(i / P1, i % P1);
+                    // (variable-major loops: no division per element)
+                    for (uint32_t v_ = 0; v_ < n; ++v_)
+                        for (uint32_t k_ = sub; k_ < P1; k_ += G) P.tc[(size_t)(v_ * P1 + k_) * P.B + traj] = XJ(v_, k_);
                     if (G > 1) __syncwarp(gmask);
                 }
                 if ((FX && P.rec.on)) {
                     // step record: [n][p+1] coefficients (the end time follows after the time update)
                     R *dstc = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
-                    for (uint32_t i = sub; i < n * P1; i += G) dstc[i] = XJ(i / P1, i % P1);
+                    for (uint32_t v_ = 0; v_ < n; ++v_) {
+                        R *dv = dstc + v_ * P1;
+                        for (uint32_t k_ = sub; k_ < P1; k_ += G) dv[k_] = XJ(v_, k_);
+                    }
                 }
                 if (P.mode == MODE_GRID) {
                     // Dense output at every grid point inside this step.

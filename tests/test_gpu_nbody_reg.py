@@ -53,7 +53,8 @@ def test_variant_selected():
     assert td.order == 22 and td._ctx.launch_info()["kernel_variant"] == 226
     te = _make(hy.model.nbody(5, masses=list(common.OSS_MASSES[:5]), Gconst=common.OSS_G),
                common.oss_ensemble(8)[:30].copy(), tol=1e-18)
-    assert te.order == 22 and te._ctx.launch_info()["kernel_variant"] == 0
+    # (not served by a register kernel: the interpreter, or a run-time compiled kernel)
+    assert te.order == 22 and te._ctx.launch_info()["kernel_variant"] in (0, 1000)
 
 
 @pytest.mark.parametrize("fp", [np.float64, np.float32])
