@@ -94,6 +94,7 @@ struct hy_ctx {
     void *d_evt = nullptr;
     hy::EvtDev evt_dev{};
     std::vector<unsigned char> evt_blob;
+    hy::EvtProgram evt_prog; // (kept for the event code generator, hy_jit.hpp)
     unsigned long long *d_evstats = nullptr;
     std::vector<int32_t> h_ev_dir;
     std::vector<double> h_ev_cd;
@@ -153,6 +154,9 @@ template <typename R>
 cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx, const hy::jit::Loaded *jk)
 {
     // register-resident N-body kernels (hy_nbody_reg.cuh)
+    // a register-resident kernel rebuilt at hy_create time with its event functions as generated code
+    if (fx && jk && jk->func && li.kernel_variant != HY_VARIANT_JIT)
+        return hy::jit::launch(*jk, P, li.ctas, li.threads, li.smem_bytes, s);
     switch (li.kernel_variant) { // instantiated in hy_nb3.cu ... hy_nb6.cu
     case 0: break;
     case HY_VARIANT_JIT: // generated from the tape and compiled at hy_create time (hy_jit.hpp)
@@ -329,6 +333,7 @@ int choose_geometry(hy_ctx *c)
         for (uint32_t off : ep.ev_off) pr.ev_ref.push_back(ews_off + off);
         pr.evt_bytes = (uint32_t)ep.blob.size();
         c->evt_blob = ep.blob;
+        c->evt_prog = ep;
         c->evt_dev = hy::EvtDev{nullptr, ep.n_ops, ep.n_terms, ep.n_imm, d.n_events, ews_off, eiv_off, ep.n_slots,
                                 (uint32_t)ep.blob.size()};
         return true;
@@ -494,6 +499,37 @@ int choose_geometry(hy_ctx *c)
     hy::SmemLayout L = hy::make_layout(d, prog_dims(c->prog), G, T, RS, (uint32_t)c->rb, (int)li.ws_in_smem);
     li.smem_bytes = L.total;
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
+    // Events on a register-resident kernel: rebuild the kernel (FX build) with the event functions as
+    // generated code (hy_jit.hpp, EvtGen).  HY_CUDA_JIT_EVT = 0: never (the event tape is interpreted),
+    // 1 (default): for the CR3BP kernels, 2: for the N-body kernels as well (their FX build takes
+    // minutes to compile).  A failed compilation leaves the interpreted event tape in place.
+    if (c->use_evt && li.kernel_variant != HY_VARIANT_JIT && !c->no_jit) {
+        const uint32_t ej = env_u32("HY_CUDA_JIT_EVT", 1);
+        const bool crb = li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
+        std::string kname;
+        const char *R = c->fp_bits == 64 ? "double" : "float";
+        if (crb && ej >= 1)
+            kname = std::string("hy::propagate_kernel<") + R + ", 2, true, -1, false, " +
+                    (li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22 ? "hy::CRB_PMAX_HI" : "hy::NBR_PMAX") + ", true>";
+        else if (!crb && ej >= 2 && li.kernel_variant >= 3 && li.kernel_variant <= 6)
+            kname = std::string("hy::propagate_kernel<") + R + ", 16, true, " + std::to_string(li.kernel_variant) +
+                    ", false, hy::NBR_PMAX, true>";
+        else if (!crb && ej >= 2 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
+            kname = "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
+        if (!kname.empty()) {
+            const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order);
+            hy::jit::Image img;
+            std::string jerr = hy::jit::build(src, kname, img);
+            if (jerr.empty()) {
+                CU(cudaSetDevice(c->device));
+                hy::jit::unload(c->jit_k);
+                jerr = hy::jit::load(img, li.smem_bytes, false, c->jit_k);
+                if (jerr.empty()) c->jit_img = img;
+            }
+            if (!jerr.empty() && env_u32("HY_CUDA_JIT_VERBOSE", 0))
+                std::fprintf(stderr, "hy_cuda: event code generation failed, the event tape is interpreted: %s\n", jerr.c_str());
+        }
+    }
     if (li.kernel_variant == HY_VARIANT_JIT) {
         CU(cudaSetDevice(c->device));
         hy::jit::unload(c->jit_k);
@@ -1067,6 +1103,7 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
     c->use_evt = src->use_evt;
     c->evt_dev = src->evt_dev;
     c->evt_blob = src->evt_blob;
+    c->evt_prog = src->evt_prog;
     c->no_jit = src->no_jit;
     c->jit_img = src->jit_img;
     if (common_init(c)) return 1;
@@ -1079,8 +1116,9 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
         const uint32_t T = c->li.traj_per_cta;
         c->li.ctas = std::max(1u, std::min((c->B + T - 1) / T, c->li.n_sm * env_u32("HY_CUDA_CTAS_PER_SM", 1)));
     }
-    if (c->li.kernel_variant == HY_VARIANT_JIT) {
-        const std::string lerr = hy::jit::load(c->jit_img, c->li.smem_bytes, !c->li.ws_in_smem, c->jit_k);
+    if (!c->jit_img.cubin.empty()) {
+        const bool whole = c->li.kernel_variant == HY_VARIANT_JIT;
+        const std::string lerr = hy::jit::load(c->jit_img, c->li.smem_bytes, whole && !c->li.ws_in_smem, c->jit_k);
         if (!lerr.empty()) return fail("hy_clone: " + lerr);
     }
     if (upload_program(c)) return 1;

@@ -124,6 +124,17 @@ static __device__ __noinline__ R evt_conv(const R *__restrict__ pa, int sa, cons
     return (s0 + s1) + (s2 + s3);
 }
 
+// The same sum with compile-time strides and length (generated event code, hy_jit.hpp: every load has
+// an immediate offset, nothing loops or branches).  Term u goes to chain u mod 4, as above.
+template <typename R, int SA, int SB, int N>
+__device__ __forceinline__ R evt_conv_ct(const R *__restrict__ pa, const R *__restrict__ pb)
+{
+    R s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < N; ++u) s[u & 3] = evt_fma(pa[u * SA], pb[-u * SB], s[u & 3]);
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+
 // sum_{j = j0}^{j1} (wk + j wj) * pa[j sa] * pb[(k - j) sb]  (the recurrences of pow / exp / log / sincos)
 template <typename R>
 static __device__ __noinline__ R evt_wconv(const R *__restrict__ pa, int sa, const R *__restrict__ pb, int sb, int k,
@@ -365,6 +376,22 @@ template <typename R> __device__ __forceinline__ Ival<R> iv_horner(const R *c, i
         lo = fmin(mn, (R)0) + ck;
         hi = fmax(mx, (R)0) + ck;
     }
+    return iv_widen<R>(lo, hi);
+}
+
+// A cheaper enclosure of the same polynomial (generated event code, hy_jit.hpp): the first-order term
+// exactly, the rest by absolute values - c0 + [min(0, c1 h), max(0, c1 h)] -+ sum_{k>=2} |c_k| |h|^k.
+// One FMA per coefficient instead of the ~12 instructions of an interval Horner step (FP64 min / max
+// are compare + select pairs); looser, but only the rare full evaluation pays for that.
+template <typename R, int S, int P> __device__ __forceinline__ Ival<R> iv_taylor_abs(const R *c, R h)
+{
+    const R ah = fabs(h);
+    R r = fabs(c[P * S]);
+#pragma unroll
+    for (int k = P - 1; k >= 2; --k) r = evt_fma(r, ah, fabs(c[k * S]));
+    r = r * ah * ah; // sum_{k>=2} |c_k| |h|^k
+    const R d1 = c[S] * h, c0 = c[0];
+    const R lo = c0 + fmin(d1, (R)0) - r, hi = c0 + fmax(d1, (R)0) + r;
     return iv_widen<R>(lo, hi);
 }
 

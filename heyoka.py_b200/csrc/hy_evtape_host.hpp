@@ -25,6 +25,11 @@ struct EvtProgram {
     uint32_t n_ops = 0, n_terms = 0, n_imm = 0, n_slots = 0;
     std::vector<uint32_t> ev_off; // [n_events] offset of every event jet inside the event workspace
     std::vector<uint32_t> state_used; // [n_state] 1: the event tape reads this state variable
+    // the lowered program itself (for the code generator of hy_jit.hpp: events as straight-line code)
+    std::vector<EOp> ops;
+    std::vector<ETerm> terms;
+    std::vector<double> imm;
+    std::vector<uint32_t> op_start, ev_slot;
 };
 
 inline std::string build_event_program(uint32_t n_state, uint32_t order, const std::vector<hy_op> &ops,
@@ -172,6 +177,11 @@ inline std::string build_event_program(uint32_t n_state, uint32_t order, const s
     }
     for (const ETerm &t : et)
         if ((t.src & ER_KIND) == ER_STATE) out.state_used[t.src & 0x3fff] = 1;
+    out.ops = eo;
+    out.terms = et;
+    out.imm = imm;
+    out.op_start = op_start;
+    for (uint32_t e = 0; e < n_ev; ++e) out.ev_slot.push_back(slot(ev_ref[e]));
     // blob: [ops | terms | imm | op_start | ev_slot | state_used]
     const size_t bytes =
         n_ops * sizeof(EOp) + et.size() * sizeof(ETerm) + imm.size() * 8 + (n_ev + 1) * 4 + n_ev * 4 + n_state * 4;

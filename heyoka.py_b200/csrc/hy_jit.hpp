@@ -38,6 +38,7 @@
 
 #include "../../include/hy_cuda.h"
 #include "hy_schedule.hpp"
+#include "hy_evtape_host.hpp"
 
 namespace hy {
 namespace jit {
@@ -399,6 +400,143 @@ struct Gen {
         return os.str();
     }
 };
+
+// --------------------------------------------------------------------------------------------
+// Event functions of a register-resident kernel as generated code.  The event tape
+// (hy_evtape_host.hpp) is evaluated by ONE lane per trajectory as straight-line code: literal ops
+// (the interpreter's switch and reference decoding fold away), the convolutions of the three orders
+// a step needs (0, p-1, p) fully unrolled with immediate offsets.
+// --------------------------------------------------------------------------------------------
+struct EvtGen {
+    const EvtProgram &ep;
+    const std::vector<uint32_t> &state_row;
+    uint32_t p;
+    std::ostringstream os;
+    EvtGen(const EvtProgram &e, const std::vector<uint32_t> &sr, uint32_t order) : ep(e), state_row(sr), p(order) {}
+
+    static std::string eop(const EOp &o)
+    {
+        std::ostringstream s;
+        s << "EOp{" << (int)o.opcode << ", " << (int)o.flags << ", " << o.n << ", " << o.dst << ", " << o.dst2 << ", " << o.a
+          << ", " << o.b << ", " << o.imm << ", " << o.sd << ", " << o.sd2 << ", " << o.sa << ", " << o.sb << ", {0, 0, 0, 0, 0}}";
+        return s.str();
+    }
+    // pointer to order 0 of a reference and its stride between orders (as source text)
+    std::string base(uint16_t ref, std::string &stride) const
+    {
+        const uint16_t kind = ref & ER_KIND, off = ref & 0x3fff;
+        if (kind == ER_STATE) {
+            stride = "XS";
+            return "(C.w + " + std::to_string(state_row[off]) + ")";
+        }
+        stride = kind == ER_JET ? "1" : "0";
+        return "(C.ews + " + std::to_string(off) + ")";
+    }
+    bool explicit_conv(const EOp &o) const
+    {
+        return o.opcode == HY_OP_MUL || o.opcode == HY_OP_SQUARE || o.opcode == HY_OP_SUMSQ || o.opcode == HY_OP_MULSH;
+    }
+    // a three-order op at the literal order K
+    void emit_at(const EOp &o, uint32_t K)
+    {
+        const ETerm *t = ep.terms.data() + o.b;
+        const std::string Ks = std::to_string(K);
+        auto sq = [&](uint16_t ref, const std::string &acc, const std::string &acc2) {
+            std::string st;
+            const std::string pa = base(ref, st);
+            const uint32_t half = (K + 1) >> 1;
+            os << "      { const R *a = " << pa << ";\n";
+            if (half) os << "        " << acc << " += evt_conv_ct<R, " << st << ", " << st << ", " << half << ">(a, a + " << Ks << " * " << st << ");\n";
+            if ((K & 1u) == 0) os << "        { const R m = a[" << (K >> 1) << " * " << st << "]; " << acc2 << " = evt_fma(m, m, " << acc2 << "); }\n";
+            os << "      }\n";
+        };
+        switch (o.opcode) {
+        case HY_OP_MUL: {
+            std::string sa, sb;
+            const std::string pa = base(o.a, sa), pb = base(o.b, sb);
+            os << "      C.st(" << o.dst << ", " << Ks << ", evt_conv_ct<R, " << sa << ", " << sb << ", " << K + 1 << ">(" << pa << ", "
+               << pb << " + " << Ks << " * " << sb << "));\n";
+        } break;
+        case HY_OP_SQUARE:
+            // evt_exec: acc = conv; acc = acc + acc; even k: acc = fma(m, m, acc)
+            os << "      { R acc = 0;\n";
+            {
+                std::string st;
+                const std::string pa = base(o.a, st);
+                const uint32_t half = (K + 1) >> 1;
+                if (half)
+                    os << "        acc = evt_conv_ct<R, " << st << ", " << st << ", " << half << ">(" << pa << ", " << pa << " + " << Ks
+                       << " * " << st << ");\n";
+            }
+            if ((K & 1u) == 0) {
+                std::string st;
+                const std::string pa = base(o.a, st);
+                os << "        acc = acc + acc; { const R m = " << pa << "[" << (K >> 1) << " * " << st << "]; acc = evt_fma(m, m, acc); }\n";
+            } else {
+                os << "        acc = acc + acc;\n";
+            }
+            os << "        C.st(" << o.dst << ", " << Ks << ", acc); }\n";
+            break;
+        case HY_OP_SUMSQ:
+            os << "      { R acc = 0, acc2 = 0;\n";
+            for (uint32_t i = 0; i < o.n; ++i) sq(t[i].src, "acc", "acc2");
+            os << "        C.st(" << o.dst << ", " << Ks << ", (acc + acc) + acc2); }\n";
+            break;
+        case HY_OP_MULSH: {
+            std::string sb;
+            const std::string pb = base(o.a, sb);
+            for (uint32_t i = 0; i < o.n; ++i) {
+                std::string sa;
+                const std::string pa = base(t[i].src, sa);
+                os << "      C.st(" << t[i].dst << ", " << Ks << ", evt_conv_ct<R, " << sa << ", " << sb << ", " << K + 1 << ">(" << pa
+                   << ", " << pb << " + " << Ks << " * " << sb << "));\n";
+            }
+        } break;
+        default: os << "      evt_exec<R, XS>(" << eop(o) << ", terms, C, " << Ks << "u);\n"; break;
+        }
+    }
+    std::string source()
+    {
+        os << "// event functions: " << ep.ops.size() << " ops, " << ep.ev_slot.size() << " events, order " << p << "\n";
+        os << "template <typename R, int XS> __device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm *terms)\n{\n";
+        for (const EOp &o : ep.ops)
+            if (o.flags & EOF_ALL) os << "    evt_exec_all<R, XS>(" << eop(o) << ", terms, C, " << p << "u);\n";
+        for (uint32_t K : {0u, p - 1u, p}) {
+            os << "    { // order " << K << "\n";
+            for (const EOp &o : ep.ops)
+                if (!(o.flags & EOF_ALL)) emit_at(o, K);
+            os << "    }\n";
+        }
+        os << "}\n";
+        os << "template <typename R, int XS>\n__device__ __forceinline__ void hy_gen_evt_order(const EvtCtx<R, XS> &C, const ETerm *terms, uint32_t k)\n{\n";
+        os << "    (void)C; (void)terms; (void)k;\n";
+        for (const EOp &o : ep.ops)
+            if (!(o.flags & EOF_ALL)) os << "    evt_exec<R, XS>(" << eop(o) << ", terms, C, k);\n";
+        os << "}\n";
+        os << "template <typename R, int XS>\n__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, "
+              "const double *imm, R t0, R h)\n{\n    (void)terms; (void)imm; (void)t0;\n";
+        for (size_t i = 0; i < ep.state_used.size(); ++i)
+            if (ep.state_used[i])
+                os << "    { const Ival<R> v = iv_taylor_abs<R, XS, " << p << ">(w + " << state_row[i] << ", h); iv[" << 2 * i
+                   << "] = v.lo; iv[" << 2 * i + 1 << "] = v.hi; }\n";
+        for (const EOp &o : ep.ops) os << "    evt_interval<R>(" << eop(o) << ", terms, iv, imm, t0, h);\n";
+        os << "    bool maybe = false;\n";
+        for (uint32_t sl : ep.ev_slot)
+            os << "    { const R glo = iv[" << 2 * sl << "], ghi = iv[" << 2 * sl + 1 << "]; if (!(glo > (R)0 || ghi < (R)0)) maybe = true; }\n";
+        os << "    return maybe;\n}\n";
+        return os.str();
+    }
+};
+
+// Translation unit of a register-resident kernel (FX build) with generated event functions.
+inline std::string evt_kernel_source(const EvtProgram &ep, const std::vector<uint32_t> &state_row, uint32_t order)
+{
+    EvtGen g(ep, state_row, order);
+    std::string s = "#define HY_JIT_EVT 1\n#include \"hy_kernels.cuh\"\nnamespace hy {\n";
+    s += g.source();
+    s += "} // namespace hy\n";
+    return s;
+}
 
 inline std::string kernel_name(int fp_bits, bool smem)
 {

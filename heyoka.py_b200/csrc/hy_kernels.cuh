@@ -42,6 +42,17 @@
 
 namespace hy {
 
+#ifdef HY_JIT_EVT
+// Event functions of a register-resident kernel as generated code (hy_jit.hpp): all events on the
+// first lane of the trajectory's group.  norms: the ops needed at every order over all orders, the
+// rest at orders 0, p-1, p; order: the rest at one more order (rare path: an event may happen);
+// interval: enclosures of the event functions over the step, true if one of them contains 0.
+template <typename R, int XS> __device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm *terms);
+template <typename R, int XS>
+__device__ __forceinline__ void hy_gen_evt_order(const EvtCtx<R, XS> &C, const ETerm *terms, uint32_t k);
+template <typename R, int XS>
+__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, const double *imm, R t0, R h);
+#endif
 #ifdef HY_JIT
 // generated per tape: orders 0 .. p-1 of every op / the event-function ops at order p
 template <typename R> __device__ __forceinline__ void hy_gen_jets(R *__restrict__ w, const R *__restrict__ rk, const R tm);
@@ -1572,6 +1583,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             if constexpr (FX && NB != 0) {
                 if (reg_events) {
                     const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+#ifdef HY_JIT_EVT
+                    if (sub == 0) hy_gen_evt_norms<R, (int)XS>(ec, s_eterms);
+#else
                     for (uint32_t e = sub; e < P.evt.n_events; e += G) {
                         const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
                         // pass A: the ops that are needed at every order, op by op (they never read a
@@ -1592,6 +1606,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                             }
                         }
                     }
+#endif
                     __syncwarp();
                 }
             }
@@ -1716,6 +1731,10 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     // ---- can an event happen in [0, h] at all?  Interval Horner enclosures of the state
                     // polynomials over the step, pushed through the event tape in interval arithmetic.
                     R *iv = w + P.evt.eiv_off;
+                    bool maybe = false;
+#ifdef HY_JIT_EVT
+                    if (sub == 0) maybe = hy_gen_evt_interval<R, (int)XS>(w, iv, s_eterms, s_eimm, hi, h);
+#else
                     for (uint32_t i = sub; i < n; i += G) {
                         if (!s_eused[i]) continue; // (no event reads this state variable)
                         const Ival<R> v = iv_horner<R>(w + s_srow[i], (int)XS, (int)p, h);
@@ -1723,7 +1742,6 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         iv[2 * i + 1] = v.hi;
                     }
                     __syncwarp();
-                    bool maybe = false;
                     for (uint32_t e = sub; e < P.evt.n_events; e += G) {
                         const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
 #pragma unroll 1
@@ -1731,6 +1749,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         const R glo = iv[2 * s_eslot[e]], ghi = iv[2 * s_eslot[e] + 1];
                         if (!(glo > (R)0 || ghi < (R)0)) maybe = true; // 0 inside the enclosure (or NaN)
                     }
+#endif
                     const unsigned mb = __ballot_sync(TM_FULL, maybe && stepping);
                     const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
                     const bool gmaybe = ((mb >> (lane & ~(uint32_t)(G - 1))) & gbits) != 0u;
@@ -1741,6 +1760,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     if (gmaybe) {
                         // ---- rare: the remaining orders of the event jets, then the root finder ----
                         const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+#ifdef HY_JIT_EVT
+                        if (sub == 0) {
+#pragma unroll 1
+                            for (uint32_t k = 1; k + 1 < p; ++k) hy_gen_evt_order<R, (int)XS>(ec, s_eterms, k);
+                        }
+#else
                         for (uint32_t e = sub; e < P.evt.n_events; e += G) {
                             const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
 #pragma unroll 1
@@ -1751,6 +1776,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                                     if (!(o.flags & EOF_ALL)) evt_exec<R, (int)XS>(o, s_eterms, ec, k);
                                 }
                         }
+#endif
                         __syncwarp(gmask);
                         R h_eff = h;
                         if (sub == 0)

@@ -9,7 +9,17 @@ import csv, re, subprocess, sys, os, tempfile, collections
 rep, so, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
-subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
+if so.endswith(".hyjit"):
+    # a run-time compiled kernel from the cache (hy_jit.hpp): [magic | name length | name | cubin]
+    import struct
+    blob = open(so, "rb").read()
+    nl = struct.unpack("<I", blob[4:8])[0]
+    open(os.path.join(tmp, "jit.cubin"), "wb").write(blob[8 + nl:])
+elif so.endswith(".cubin"):
+    import shutil
+    shutil.copy(so, os.path.join(tmp, "jit.cubin"))
+else:
+    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 # (one cubin per translation unit: take the one that holds the kernel)
 dis = []
 for f in sorted(os.listdir(tmp)):
