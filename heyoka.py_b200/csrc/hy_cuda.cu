@@ -500,9 +500,9 @@ int choose_geometry(hy_ctx *c)
     li.smem_bytes = L.total;
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
     // Events on a register-resident kernel: rebuild the kernel (FX build) with the event functions as
-    // generated code (hy_jit.hpp, EvtGen).  HY_CUDA_JIT_EVT = 0: never (the event tape is interpreted),
-    // 1 (default): for the CR3BP kernels, 2: for the N-body kernels as well (their FX build takes
-    // minutes to compile).  A failed compilation leaves the interpreted event tape in place.
+    // generated code (hy_jit.hpp, EvtGen; NVRTC compiles the one instantiation in 5-7 s).
+    // HY_CUDA_JIT_EVT = 0: never (the event tape is interpreted), 1 (default): always.  A failed
+    // compilation leaves the interpreted event tape in place.
     if (c->use_evt && li.kernel_variant != HY_VARIANT_JIT && !c->no_jit) {
         const uint32_t ej = env_u32("HY_CUDA_JIT_EVT", 1);
         const bool crb = li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
@@ -511,10 +511,10 @@ int choose_geometry(hy_ctx *c)
         if (crb && ej >= 1)
             kname = std::string("hy::propagate_kernel<") + R + ", 2, true, -1, false, " +
                     (li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22 ? "hy::CRB_PMAX_HI" : "hy::NBR_PMAX") + ", true>";
-        else if (!crb && ej >= 2 && li.kernel_variant >= 3 && li.kernel_variant <= 6)
+        else if (!crb && ej >= 1 && li.kernel_variant >= 3 && li.kernel_variant <= 6)
             kname = std::string("hy::propagate_kernel<") + R + ", 16, true, " + std::to_string(li.kernel_variant) +
                     ", false, hy::NBR_PMAX, true>";
-        else if (!crb && ej >= 2 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
+        else if (!crb && ej >= 1 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
             kname = "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
         if (!kname.empty()) {
             const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order);
