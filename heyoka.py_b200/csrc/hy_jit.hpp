@@ -564,9 +564,13 @@ struct Nvrtc {
     bool load()
     {
         if (h) return true;
-        for (const char *nm : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
-            h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-            if (h) break;
+        if (const char *e = std::getenv("HY_CUDA_NVRTC_LIB")) { // (explicit library; also how the tests take NVRTC away)
+            h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+        } else {
+            for (const char *nm : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+                h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+                if (h) break;
+            }
         }
         if (!h) {
             err = "libnvrtc not found";

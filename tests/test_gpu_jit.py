@@ -201,3 +201,25 @@ def test_compiled_kernel_global_workspace_mid_size_tape():
     for ta in (a, b):
         ta.propagate_until(3.0)
     _same(a, b)
+
+
+def test_without_nvrtc_the_interpreter_takes_over(tmp_path):
+    # no compiler and an empty cache: hy_create must not fail - the tape interpreter runs the system
+    # (a subprocess: the NVRTC handle is loaded once per process)
+    import subprocess
+    import sys
+
+    code = """
+import numpy as np, hy_b200 as hy
+from hy_b200 import workloads as W
+vs = hy.var_ode_sys(W.kepler_j2_sys(), hy.var_args.vars)
+ta = hy.taylor_adaptive_batch(vs, W.kepler_j2_ensemble(8))
+li = ta._ctx.launch_info()
+assert li["kernel_variant"] == 0, li
+ta.propagate_until(500.0)
+print("fallback ok", li["group"])
+"""
+    env = dict(os.environ, HY_CUDA_NVRTC_LIB="/nonexistent/libnvrtc.so", HY_CUDA_JIT_CACHE=str(tmp_path),
+               PYTHONPATH=os.pathsep.join(sys.path))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
