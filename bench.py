@@ -69,16 +69,17 @@ def parse():
 
 # trajectories of the configuration as BASELINE.json states it, and the largest shard one GPU takes
 # (cfg 3: the continuous output of 4M lanes is ~400 GB - it exists only sharded over 8 GPUs;
-#  cfg 4: the tape interpreter needs minutes for 1M lanes - an eighth is one GPU's share)
+#  cfgs 4 and 5 ran an eighth of their 10^6 lanes per GPU while they were on the tape interpreter; with
+#  the generated / register-resident kernels of round 2 one GPU takes the whole configuration)
 CFG_TOTAL = {2: 1000000, 3: 4000000, 4: 1000000, 5: 1000000}
-CFG_MAX_PER_GPU = {2: 1000000, 3: 500000, 4: 125000, 5: 125000}
+CFG_MAX_PER_GPU = {2: 1000000, 3: 500000, 4: 1000000, 5: 1000000}
 
 
 def shard_size(args, world, rank):
     from hy_b200.shard import shard_bounds
 
     if args.scaling == "weak":
-        return args.traj_per_gpu or CFG_MAX_PER_GPU[args.config] // (8 if args.config == 2 else 1)
+        return args.traj_per_gpu or CFG_MAX_PER_GPU[args.config] // (1 if args.config == 3 else 8)
     total = args.total or min(CFG_TOTAL[args.config], CFG_MAX_PER_GPU[args.config] * world)
     lo, hi = shard_bounds(total, rank, world)
     return hi - lo
@@ -600,18 +601,24 @@ def main():
         }
         if variant == 1000 and not li["ws_in_smem"]:
             # Run-time compiled kernel with the jets in global memory: the operands of every recurrence
-            # stream through L1 / L2 / HBM, so memory - not the FP64 pipe - is the roof.  Algorithmic bytes
-            # per trajectory-step = 8 x (operand loads of the tape + rows written); the caches serve part of
-            # them (ncu, profiles/r02_ncu_jit_cfg4.txt: 277 kB read + 54 kB written per step at DRAM).
-            abytes = 8.0 * (lo + dc.n_rows)
+            # stream through L1 / L2 / HBM, so memory - not the FP64 pipe - is the roof.  Algorithmic bytes per
+            # trajectory-step: every jet that is read with history is fetched once per order (k + 1 rows at
+            # order k, however many ops share it) and every workspace row is written once:
+            # 8 x (n_jets x p (p + 1) / 2 + n_rows).  ncu (profiles/r02_ncu_jit_cfg4.txt) measures 277 kB read +
+            # 54 kB written per step at the DRAM pins for config 4 (229 kB algorithmic): the caches do not hold a
+            # jet from one op that uses it to the next.
+            n_jets = sum(1 for u in dc.uvars if u.jet and u.row is not None)
+            abytes = 8.0 * (n_jets * order * (order + 1) / 2 + dc.n_rows)
             roof = {
                 "bound": "hbm", "achieved": steps_rank * abytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": steps_rank * abytes / k_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "kernel": roof["kernel"], "kernel_ms_per_launch": roof["kernel_ms_per_launch"],
                 "algorithmic_bytes_per_trajectory_step": abytes,
-                "traffic": None,
-                "traffic_note": "per launch the kernel moves (operand loads + rows) x 8 B per trajectory-step "
-                                "through the memory hierarchy; DRAM sees what L1 (40 % hits) and L2 (20 %) miss",
+                "traffic": 331e3 * steps_rank / args.steps if args.config == 4 else None,
+                "traffic_note": "DRAM bytes per launch = 331 kB per trajectory-step (ncu --set full capture of the same "
+                                "kernel, profiles/r02_ncu_jit_cfg4.txt) x the steps of one launch; operand loads of the "
+                                "tape: {:.0f} kB per step (L1 serves 38 % of them, L2 20 %)".format(8e-3 * (lo + dc.n_rows))
+                if args.config == 4 else None,
                 "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": fma_peak,
                          "frac": achieved_tf / fma_peak if fma_peak else None, "flops_per_trajectory_step": fl},
             }

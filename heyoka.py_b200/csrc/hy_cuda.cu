@@ -261,6 +261,21 @@ int jit_plan(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uin
     const uint32_t fit = fixed < smem_optin ? (uint32_t)((smem_optin - fixed) / col_bytes) & ~31u : 0u;
     smem = fit >= env_u32("HY_CUDA_JIT_SMEM_MIN_THREADS", 128);
     T = smem ? std::min(fit, 512u) : (std::max(32u, env_u32("HY_CUDA_JIT_THREADS", 512)) & ~31u);
+    if (!smem && !env_u32("HY_CUDA_JIT_THREADS", 0)) {
+        // A trajectory is one long indivisible job of a thread: with B trajectories on n_sm * T thread slots
+        // the last "wave" is partly empty (125 000 trajectories on 148 x 512 slots: 1.65 waves, 82 % of the
+        // slots busy).  Throughput grows like sqrt(T) between 256 and 512 threads (measured on config 4):
+        // pick the CTA size that maximises sqrt(T) x slot efficiency.
+        double best = -1;
+        for (uint32_t t = 256; t <= 512; t += 32) {
+            const double slots = (double)n_sm * t, waves = std::ceil((double)B / slots);
+            const double score = std::sqrt((double)t) * (double)B / (waves * slots);
+            if (score > best * 1.0001) {
+                best = score;
+                T = t;
+            }
+        }
+    }
     // do not keep more trajectories resident than the batch can feed
     const uint32_t need = std::max(1u, (B + n_sm - 1) / n_sm);
     T = std::max(32u, std::min(T, (need + 31u) & ~31u));
