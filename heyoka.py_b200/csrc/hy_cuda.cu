@@ -99,6 +99,7 @@ struct hy_ctx {
     std::vector<int32_t> h_ev_dir;
     std::vector<double> h_ev_cd;
     uint32_t *d_srow = nullptr;
+    uint32_t *d_recoff = nullptr; // register-resident kernels: record element -> column offset
     int32_t *d_ssp = nullptr;
     void *d_gjet = nullptr;
     // lanes (device)
@@ -582,6 +583,18 @@ int upload_program(hy_ctx *c)
             if (p) cudaFree(p);
         CU(cudaMalloc(&c->d_srow, d.n_state * 4));
         CU(cudaMemcpy(c->d_srow, c->prog.state_row.data(), d.n_state * 4, cudaMemcpyHostToDevice));
+        if (c->d_recoff) cudaFree(c->d_recoff);
+        c->d_recoff = nullptr;
+        if (li.kernel_variant && li.kernel_variant != HY_VARIANT_JIT) {
+            // order stride of the state jets in the column of the matched kernel
+            const bool crb = li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
+            const uint32_t xs = crb ? (uint32_t)hy::CRB_XS : (uint32_t)hy::NBR_JS, P1 = d.order + 1;
+            std::vector<uint32_t> tab((size_t)d.n_state * P1);
+            for (uint32_t i = 0; i < d.n_state; ++i)
+                for (uint32_t k = 0; k < P1; ++k) tab[(size_t)i * P1 + k] = c->prog.state_row[i] + k * xs;
+            CU(cudaMalloc(&c->d_recoff, tab.size() * 4));
+            CU(cudaMemcpy(c->d_recoff, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&c->d_ssp, d.n_state * 4));
         CU(cudaMemcpy(c->d_ssp, c->prog.state_spill.data(), d.n_state * 4, cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_ev, std::max<size_t>(1, d.n_events) * 4));
@@ -806,6 +819,7 @@ template <typename R> hy::KParams<R> make_params(hy_ctx *c, const RunArgs &a)
     P.resume = a.resume;
     P.pause_on_nt = a.pause_on_nt;
     P.launch_steps = a.launch_steps;
+    P.rec_off = c->d_recoff;
     P.red_idx = c->d_red;
     P.n_red = c->n_red;
     P.rec = rec_dev<R>(c->rec, a.rec_on, a.rec_append);
@@ -1176,7 +1190,8 @@ int hy_destroy(hy_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet, c->d_state, c->d_pars,
                     c->d_thi /* block of the per-lane vectors */, c->d_tc, c->d_gws, c->d_tmp_in, c->d_tmp_out,
-                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt, c->d_evstats};
+                    c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt, c->d_evstats,
+                    c->d_recoff};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     hy::jit::unload(c->jit_k);

@@ -164,6 +164,7 @@ template <typename R> struct KParams {
     int resume;                  // lanes continue from the counters / grid index of the previous launch
     int pause_on_nt;             // stop a lane (PAUSED) after a step that logged a non-terminal event
     unsigned long long launch_steps; // per-launch step budget (0: none): the lane stops with PAUSED
+    const uint32_t *rec_off;     // [n (p+1)] register-resident kernels: column offset of record element (i, k)
     const uint32_t *red_idx;     // [n_red] state variables reduced to [0, 2 pi) after every step
     uint32_t n_red;
     RecDev<R> rec;               // continuous-output recorder (rec.on)
@@ -1796,6 +1797,25 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 }
             }
 
+            // ---- continuous-output record on the register-resident kernels: the WARP copies the step
+            // records of its trajectories one after the other, 32 consecutive elements per store (full
+            // 256-byte segments; the per-group loop below writes 8 G bytes per trajectory and store)
+            if constexpr (FX && NB != 0) {
+                if (P.rec.on) {
+                    R *my_dst = nullptr;
+                    if (stepping) my_dst = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
+                    const uint32_t nP = n * P1;
+#pragma unroll 1
+                    for (uint32_t g = 0; g < 32u / G; ++g) {
+                        R *dst = reinterpret_cast<R *>(__shfl_sync(TM_FULL, (unsigned long long)my_dst, (int)(g * G)));
+                        if (!dst) continue; // (warp-uniform)
+                        const R *wg = w + ((int)g - (int)(lane / G)) * (int)RS; // column of group g of this warp
+                        // (P.rec_off: the [variable][order] -> column offset table, L1-resident)
+                        for (uint32_t e = lane; e < nP; e += 32u) dst[e] = wg[__ldg(&P.rec_off[e])];
+                    }
+                    __syncwarp();
+                }
+            }
             // ---- optional tc write, then the state update ----
             if (stepping && (P.write_tc || (FX && P.rec.on) || P.mode == MODE_GRID)) {
                 if (P.write_tc && P.tc) {
@@ -1804,7 +1824,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         for (uint32_t k_ = sub; k_ < P1; k_ += G) P.tc[(size_t)(v_ * P1 + k_) * P.B + traj] = XJ(v_, k_);
                     if (G > 1) __syncwarp(gmask);
                 }
-                if ((FX && P.rec.on)) {
+                if ((FX && P.rec.on) && NB == 0) {
                     // step record: [n][p+1] coefficients (the end time follows after the time update)
                     R *dstc = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     for (uint32_t v_ = 0; v_ < n; ++v_) {
