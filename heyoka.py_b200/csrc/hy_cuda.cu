@@ -517,10 +517,15 @@ int choose_geometry(hy_ctx *c)
     if (li.smem_bytes > (uint32_t)smem_optin) return fail("tape does not fit in shared memory");
     // Events on a register-resident kernel: rebuild the kernel (FX build) with the event functions as
     // generated code (hy_jit.hpp, EvtGen; NVRTC compiles the one instantiation in 5-7 s).
-    // HY_CUDA_JIT_EVT = 0: never (the event tape is interpreted), 1 (default): always.  A failed
-    // compilation leaves the interpreted event tape in place.
+    // HY_CUDA_JIT_EVT = 0: never (the event tape is interpreted), 1 (default): for batches of at least
+    // HY_CUDA_JIT_EVT_MIN_BATCH lanes, 2: always.  A failed compilation leaves the interpreted event tape
+    // in place.
     if (c->use_evt && li.kernel_variant != HY_VARIANT_JIT && !c->no_jit) {
-        const uint32_t ej = env_u32("HY_CUDA_JIT_EVT", 1);
+        // (the 5-7 s of compilation pay for themselves on large ensembles only: below
+        //  HY_CUDA_JIT_EVT_MIN_BATCH lanes - default 4096 - the event tape is interpreted; HY_CUDA_JIT_EVT=2
+        //  generates the code whatever the batch)
+        uint32_t ej = env_u32("HY_CUDA_JIT_EVT", 1);
+        if (ej == 1 && c->B < env_u32("HY_CUDA_JIT_EVT_MIN_BATCH", 4096)) ej = 0;
         const bool crb = li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
         std::string kname;
         const char *R = c->fp_bits == 64 ? "double" : "float";
