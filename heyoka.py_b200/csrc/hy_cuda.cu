@@ -133,6 +133,11 @@ struct hy_ctx {
     // run-time compiled kernel (hy_jit.hpp; li.kernel_variant == HY_VARIANT_JIT)
     hy::jit::Image jit_img;
     hy::jit::Loaded jit_k;
+    // N-body tapes with parametric masses: the register-resident kernel built at hy_create time with
+    // HY_NBR_PAR - the plain build (jit_img / jit_k hold the FX build)
+    hy::jit::Image jit_img_plain;
+    hy::jit::Loaded jit_k_plain;
+    std::string jit_defs; // macro definitions every run-time build of this context's kernel starts with
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0;
@@ -152,8 +157,11 @@ cudaError_t launch_g(const hy::KParams<R> &P, const hy_launch_info &li, cudaStre
 }
 
 template <typename R>
-cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx, const hy::jit::Loaded *jk)
+cudaError_t launch(const hy::KParams<R> &P, const hy_launch_info &li, cudaStream_t s, bool fx, const hy::jit::Loaded *jk,
+                   const hy::jit::Loaded *jkp = nullptr)
 {
+    if (!fx && jkp && jkp->func && li.kernel_variant != HY_VARIANT_JIT)
+        return hy::jit::launch(*jkp, P, li.ctas, li.threads, li.smem_bytes, s);
     // register-resident N-body kernels (hy_nbody_reg.cuh)
     // a register-resident kernel rebuilt at hy_create time with its event functions as generated code
     if (fx && jk && jk->func && li.kernel_variant != HY_VARIANT_JIT)
@@ -355,9 +363,40 @@ int choose_geometry(hy_ctx *c)
         return true;
     };
     hy::NbMatch nbm;
-    if (!force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
-        hy::match_nbody(md, mops, mterms, nbm) &&
-        hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits)) {
+    c->jit_defs.clear();
+    c->jit_img_plain = hy::jit::Image();
+    auto nbody_kname = [&](uint32_t variant, bool fxb) {
+        const char *R = c->fp_bits == 64 ? "double" : "float";
+        if (variant == (uint32_t)hy::NBR_VARIANT_P22)
+            return std::string("hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, ") + (fxb ? "true>" : "false>");
+        return std::string("hy::propagate_kernel<") + R + ", 16, true, " + std::to_string(variant) + ", false, hy::NBR_PMAX, " +
+               (fxb ? "true>" : "false>");
+    };
+    bool nb_ok = !force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
+                 hy::match_nbody(md, mops, mterms, nbm) && hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits);
+    if (nb_ok && nbm.has_par) {
+        // Masses scaled by runtime parameters: no precompiled kernel reads parameters - build the matched
+        // kernel now (NVRTC, ~6 s per build, cached) with HY_NBR_PAR.  No compiler: the tape goes the general way.
+        nb_ok = !c->no_jit && env_u32("HY_CUDA_JIT", 2) != 0 && env_u32("HY_CUDA_WGX", 0) == 0;
+        if (nb_ok) {
+            const uint32_t v = hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits);
+            const std::string defs = "#define HY_NBR_PAR 1\n";
+            const std::string src = defs + "#include \"hy_kernels.cuh\"\n";
+            hy::jit::Image fxi;
+            std::string e1 = hy::jit::build(src, nbody_kname(v, false), c->jit_img_plain);
+            if (e1.empty()) e1 = hy::jit::build(src, nbody_kname(v, true), fxi);
+            if (e1.empty()) {
+                c->jit_img = fxi;
+                c->jit_defs = defs;
+            } else {
+                nb_ok = false;
+                c->jit_img_plain = hy::jit::Image();
+                if (env_u32("HY_CUDA_JIT_VERBOSE", 0))
+                    std::fprintf(stderr, "hy_cuda: N-body kernel with parametric masses not built: %s\n", e1.c_str());
+            }
+        }
+    }
+    if (nb_ok) {
         hy::Program pr;
         pr.G = 16;
         pr.n_phases = 0;
@@ -374,6 +413,11 @@ int choose_geometry(hy_ctx *c)
         pr.n_clusters = nbm.n_pairs;
         pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
         const bool ev_att = attach_events(pr) && !(wgx && evt_ok);
+        if (nbm.has_par) { // parameter rows of the trajectory, after everything else in the column
+            pr.par_off = pr.ws_len;
+            pr.ws_len += d.n_par;
+            pr.one_off = pr.ws_len;
+        }
         // column stride: even (16-byte aligned vectors); + 2 spreads the two trajectories of a warp over the banks
         const uint32_t RS = (pr.ws_len + 1u) / 2u * 2u + 2u;
         hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
@@ -391,6 +435,12 @@ int choose_geometry(hy_ctx *c)
                 li.kernel_variant = 106;
             }
         }
+    }
+    if (!li.kernel_variant && !c->jit_img_plain.cubin.empty()) {
+        // (built for parametric masses, but the column did not fit: the builds are not used)
+        c->jit_img_plain = hy::jit::Image();
+        c->jit_img = hy::jit::Image();
+        c->jit_defs.clear();
     }
     // Register-resident CR3BP kernel (hy_cr3bp_reg.cuh): two lanes per trajectory, state jets
     // [order][variable] in shared memory.
@@ -538,7 +588,7 @@ int choose_geometry(hy_ctx *c)
         else if (!crb && ej >= 1 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
             kname = "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
         if (!kname.empty()) {
-            const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order);
+            const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order, c->jit_defs);
             hy::jit::Image img;
             std::string jerr = hy::jit::build(src, kname, img);
             if (jerr.empty()) {
@@ -550,6 +600,13 @@ int choose_geometry(hy_ctx *c)
             if (!jerr.empty() && env_u32("HY_CUDA_JIT_VERBOSE", 0))
                 std::fprintf(stderr, "hy_cuda: event code generation failed, the event tape is interpreted: %s\n", jerr.c_str());
         }
+    }
+    hy::jit::unload(c->jit_k_plain);
+    if (!c->jit_img_plain.cubin.empty() && li.kernel_variant != HY_VARIANT_JIT) {
+        CU(cudaSetDevice(c->device));
+        std::string lerr = hy::jit::load(c->jit_img_plain, li.smem_bytes, false, c->jit_k_plain);
+        if (lerr.empty() && !c->jit_k.func) lerr = hy::jit::load(c->jit_img, li.smem_bytes, false, c->jit_k);
+        if (!lerr.empty()) return fail("hy_create: " + lerr);
     }
     if (li.kernel_variant == HY_VARIANT_JIT) {
         CU(cudaSetDevice(c->device));
@@ -903,9 +960,9 @@ int launch_once(hy_ctx *c, const RunArgs &a)
     const bool fx = a.rec_on || a.use_active || a.resume || a.pause_on_nt || a.launch_steps || c->n_red || c->use_evt;
     cudaError_t e;
     if (c->fp_bits == 64)
-        e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx, &c->jit_k);
+        e = launch<double>(make_params<double>(c, a), c->li, c->stream, fx, &c->jit_k, &c->jit_k_plain);
     else
-        e = launch<float>(make_params<float>(c, a), c->li, c->stream, fx, &c->jit_k);
+        e = launch<float>(make_params<float>(c, a), c->li, c->stream, fx, &c->jit_k, &c->jit_k_plain);
     if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
     ++c->last_launches;
     return 0;
@@ -1140,6 +1197,8 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
     c->evt_prog = src->evt_prog;
     c->no_jit = src->no_jit;
     c->jit_img = src->jit_img;
+    c->jit_img_plain = src->jit_img_plain;
+    c->jit_defs = src->jit_defs;
     if (common_init(c)) return 1;
     if (alloc_lanes(c)) return 1;
     {
@@ -1153,6 +1212,10 @@ int hy_clone(const hy_ctx *src, hy_ctx **out, int device)
     if (!c->jit_img.cubin.empty()) {
         const bool whole = c->li.kernel_variant == HY_VARIANT_JIT;
         const std::string lerr = hy::jit::load(c->jit_img, c->li.smem_bytes, whole && !c->li.ws_in_smem, c->jit_k);
+        if (!lerr.empty()) return fail("hy_clone: " + lerr);
+    }
+    if (!c->jit_img_plain.cubin.empty()) {
+        const std::string lerr = hy::jit::load(c->jit_img_plain, c->li.smem_bytes, false, c->jit_k_plain);
         if (!lerr.empty()) return fail("hy_clone: " + lerr);
     }
     if (upload_program(c)) return 1;
@@ -1200,6 +1263,7 @@ int hy_destroy(hy_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     hy::jit::unload(c->jit_k);
+    hy::jit::unload(c->jit_k_plain);
     rec_free(c->rec);
     rec_free(c->rec_spare);
     if (c->ev0) cudaEventDestroy(c->ev0);

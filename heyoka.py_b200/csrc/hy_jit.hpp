@@ -529,10 +529,11 @@ struct EvtGen {
 };
 
 // Translation unit of a register-resident kernel (FX build) with generated event functions.
-inline std::string evt_kernel_source(const EvtProgram &ep, const std::vector<uint32_t> &state_row, uint32_t order)
+inline std::string evt_kernel_source(const EvtProgram &ep, const std::vector<uint32_t> &state_row, uint32_t order,
+                                     const std::string &defs = "")
 {
     EvtGen g(ep, state_row, order);
-    std::string s = "#define HY_JIT_EVT 1\n#include \"hy_kernels.cuh\"\nnamespace hy {\n";
+    std::string s = defs + "#define HY_JIT_EVT 1\n#include \"hy_kernels.cuh\"\nnamespace hy {\n";
     s += g.source();
     s += "} // namespace hy\n";
     return s;

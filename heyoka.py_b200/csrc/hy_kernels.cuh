@@ -1403,7 +1403,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     w[s_srow[i]] = x0;
                     if (s_ssp[i] >= 0) gj[(uint32_t)s_ssp[i] * P1] = x0;
                 }
-                for (uint32_t i = sub; i < d.n_par; i += G) w[par_off + i * XS] = P.pars[(size_t)i * P.B + traj];
+                // (register-resident kernels keep the parameters as unit-stride rows after the state jets)
+                for (uint32_t i = sub; i < d.n_par; i += G)
+                    w[par_off + i * (NB == 0 ? XS : 1u)] = P.pars[(size_t)i * P.B + traj];
                 hi = P.t_hi[traj];
                 lo = P.t_lo[traj];
                 mdt = P.mdt ? P.mdt[traj] : r_inf<R>();
@@ -1518,7 +1520,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #ifdef HY_WGX_PROF
                     const long long c1 = clock64();
 #endif
-                    nbr_jets<R, NB, PM, true, true>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, true, true>(w, s_imm + nl.coef, nl, p, par_off);
 #ifdef HY_WGX_PROF
                     const long long c2 = clock64();
 #endif
@@ -1534,14 +1536,14 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #ifdef HY_WGX_PROF
                     const long long c1 = clock64();
 #endif
-                    nbr_jets<R, NB, PM, true>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, true>(w, s_imm + nl.coef, nl, p, par_off);
 #ifdef HY_WGX_PROF
                     prof_c = clock64();
                     prof_jets += prof_c - c1;
                     ++prof_n;
 #endif
                 } else
-                    nbr_jets<R, NB, PM, false>(w, s_imm + nl.coef, nl, p);
+                    nbr_jets<R, NB, PM, false>(w, s_imm + nl.coef, nl, p, par_off);
             } else if constexpr (NB < 0) {
                 // (PM = NBR_PMAX: the standard builds; PM = CRB_PMAX_HI: the FP64 order-22 build)
                 constexpr int CPM = PM == NBR_PMAX ? CrbPmax<R>::value : PM;

@@ -28,6 +28,8 @@ namespace hy {
 
 struct NbMatch {
     uint32_t nb = 0, n_pairs = 0;
+    bool has_par = false; // masses (acceleration coefficients) scaled by runtime parameters: the kernel is
+                          // built at hy_create time with HY_NBR_PAR (hy_jit.hpp), not one of the precompiled ones
     std::vector<double> imm; // NBR_NIMM entries (layout in hy_nbody_reg.cuh)
 };
 
@@ -45,7 +47,7 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
 {
     const uint32_t P1 = d.order + 1, n = d.n_state;
     // (orders NBR_PMAX + 1 .. NBR_LMAX: only the 6-body FP64 build has a kernel - the caller checks)
-    if (d.n_events || d.n_par || n % 6 || d.order > (uint32_t)NBR_LMAX || d.order < 2) return false;
+    if (d.n_events || n % 6 || d.order > (uint32_t)NBR_LMAX || d.order < 2) return false;
     const uint32_t NB = n / 6;
     if (NB < 2 || NB > (uint32_t)NBR_MAXB) return false;
     const uint32_t NP = NB * (NB - 1) / 2;
@@ -69,7 +71,12 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
     };
     std::vector<Pair> pairs;
     std::vector<char> have_x(n, 0), have_v(n, 0);
-    std::vector<std::vector<std::pair<int, double>>> acc(n); // v variable -> (pair, coef) in term order
+    struct Term {
+        int first;     // pair
+        double second; // coefficient
+        int par;       // runtime parameter multiplying it, or -1
+    };
+    std::vector<std::vector<Term>> acc(n); // v variable -> (pair, coef, par) in term order
     for (uint32_t i = 0; i < d.n_ops; ++i) {
         const hy_op &o = ops[i];
         if (o.flags & HY_OPF_EVENT) return false;
@@ -123,12 +130,12 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
             have_v[v] = 1;
             for (uint32_t q = 0; q < o.n; ++q) {
                 const hy_term &t = terms[o.b + q];
-                if (t.par >= 0) return false;
+                if (t.par >= (int32_t)d.n_par) return false;
                 auto it = tout.find(t.src & 0x7fffffffu);
                 if (it == tout.end() || it->second.second != v % 6 - 3) return false;
                 const Pair &p = pairs[it->second.first];
                 if (p.a != v / 6 && p.b != v / 6) return false;
-                acc[v].push_back({it->second.first, t.coef});
+                acc[v].push_back(Term{it->second.first, t.coef, t.par});
             }
         } break;
         case HY_OP_SVD: {
@@ -150,13 +157,14 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
     out.nb = NB;
     out.n_pairs = NP;
     out.imm.assign(NBR_NIMM, 0.0);
+    out.has_par = d.n_par != 0; // (parameters that no term uses still travel with the trajectory)
     std::vector<int> qa(NP, -1), qb(NP, -1);
     for (uint32_t b = 0; b < NB; ++b) {
         const auto &r0 = acc[6 * b + 3];
         for (int c = 1; c < 3; ++c) {
             const auto &rc = acc[6 * b + 3 + c];
             for (uint32_t q = 0; q + 1 < NB; ++q)
-                if (rc[q].first != r0[q].first || rc[q].second != r0[q].second) return false;
+                if (rc[q].first != r0[q].first || rc[q].second != r0[q].second || rc[q].par != r0[q].par) return false;
         }
         for (uint32_t q = 0; q + 1 < NB; ++q) {
             const int pr = r0[q].first;
@@ -164,8 +172,9 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
             if (slot >= 0) return false; // the same pair twice in one sum
             slot = (int)q;
             out.imm[b * NBR_CS + q] = r0[q].second;
-            // pair slot (= lane) whose products feed this term
-            const uint32_t src[2] = {(uint32_t)pr, 0u};
+            // pair slot (= lane) whose products feed this term; second word: parameter index + 1 (0: none)
+            const uint32_t src[2] = {(uint32_t)pr, (uint32_t)(r0[q].par + 1)};
+            if (r0[q].par >= 0) out.has_par = true;
             std::memcpy(&out.imm[NBR_OFF0 + b * NBR_CS + q], src, 8);
         }
     }

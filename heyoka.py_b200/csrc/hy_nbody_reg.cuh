@@ -306,7 +306,7 @@ template <typename R, int NB, int PMAX, bool FULL, bool WGX, int K> struct NbrOr
 // hold the state (visible to the whole group); on exit rows 0..p are complete.
 template <typename R, int NB, int PMAX, bool FULL, bool WGX = false>
 __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__restrict__ coef, const NbrLane<NB> &L,
-                                         const uint32_t p)
+                                         const uint32_t p, const uint32_t par_off = 0)
 {
     constexpr int JS = NBR_JS;
     R d0[PMAX], d1[PMAX], d2[PMAX], r2[PMAX], c[PMAX], inv = 0;
@@ -314,6 +314,21 @@ __device__ __forceinline__ void nbr_jets(R *__restrict__ w, const double *__rest
     R cf[NB - 1];
 #pragma unroll
     for (int q = 0; q < NB - 1; ++q) cf[q] = (R)coef[q];
+#ifdef HY_NBR_PAR
+    // Masses as runtime parameters (a build made at hy_create time, hy_jit.hpp): term q of the body's sums is
+    // coef[q] * par[pidx - 1] - the tape's LINCOMB multiplies the two before the FMA, and so does this.  The
+    // parameter rows sit at par_off in the column of the trajectory this body lane serves.
+    {
+        const int col = L.xbody - (L.coef / NBR_CS) * NBR_BS; // 0, or the neighbouring column
+#pragma unroll
+        for (int q = 0; q < NB - 1; ++q) {
+            const uint32_t pi = reinterpret_cast<const uint2 *>(coef + NBR_OFF0 + q)->y;
+            if (pi) cf[q] = cf[q] * w[col + (int)par_off + (int)pi - 1];
+        }
+    }
+#else
+    (void)par_off;
+#endif
     // the body lanes read the other trajectory's state: make the whole warp's updates visible
     __syncwarp();
     // x[1] = v[0]

@@ -144,30 +144,53 @@ def test_events_bitwise_and_high_accuracy():
     assert (a.propagate_res_arrays[0] > -10).any()  # some lanes stopped on the terminal event
 
 
-def test_parametric_masses_nbody_compiled_matches_oracle():
-    # an N-body system with the masses as runtime parameters is NOT matched by the register-resident
-    # kernel (hy_nbody_match.hpp).  Its tape is wide and regular: by default it stays on the
-    # interpreter (16-lane groups, 94 % lane utilisation - faster than one thread per trajectory);
-    # forced onto the compiled kernel it reproduces the oracle (the interpreter's fused pair op sums
-    # in another order: the two GPU paths agree to rounding, not bit for bit)
+def test_parametric_masses_nbody_gets_the_register_kernel():
+    # An N-body system with the masses as runtime parameters (model.nbody(masses=[par[i], ...])): the
+    # matcher accepts parameter-scaled acceleration terms and hy_create BUILDS the register-resident
+    # kernel for it (NVRTC, HY_NBR_PAR: the body lanes multiply their coefficients by the trajectory's
+    # parameters).  Bit for bit the tape interpreter's result, the oracle's to 1e-12 - and every lane has
+    # its own masses.
     from hy_b200 import model
 
     sys_ = model.nbody(6, masses=[hy.par[i] for i in range(6)], Gconst=W.OSS_G)
     B = 64
     ic = W.oss_ensemble(B)
-    pars = W.OSS_MASSES[:, None] * np.ones((1, B))
-    d = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
-    assert d._ctx.launch_info()["kernel_variant"] == 0 and d._ctx.launch_info()["group"] == 16
-    a, b = _pair(sys_, ic, pars=pars)
+    pars = W.OSS_MASSES[:, None] * (1.0 + 0.01 * np.linspace(-1, 1, B))[None, :]
+    a = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
+    assert a._ctx.launch_info()["kernel_variant"] == 6, a._ctx.launch_info()
+    os.environ["HY_CUDA_NO_NBODY_REG"] = "1"
+    try:
+        b = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
+        b._ctx
+    finally:
+        del os.environ["HY_CUDA_NO_NBODY_REG"]
+    assert b._ctx.launch_info()["kernel_variant"] == 0 and b._ctx.launch_info()["group"] == 16
     for ta in (a, b):
         ta.propagate_until(30.0)
-    assert np.array_equal(a.propagate_res_arrays[3], b.propagate_res_arrays[3])
-    assert np.max(np.abs(a.state - b.state) / np.maximum(1.0, np.abs(b.state))) < 1e-12
+    _same(a, b)
+    # the FX build too (continuous output) and a copy on the same kernel
+    import copy
+
+    c = copy.deepcopy(a)
+    ca, _ = a.propagate_for(5.0, c_output=True)
+    cb, _ = b.propagate_for(5.0, c_output=True)
+    c.propagate_for(5.0)
+    _same(a, b)
+    _same(c, b)
+    tq = np.linspace(30.5, 34.5, 5)[:, None] * np.ones((1, B))
+    assert np.array_equal(ca(tq), cb(tq))
     orc = COracle(D.decompose(sys_, a.order), ic, pars=pars)
-    oc, mn, mx, ns, _ = orc.propagate_until(30.0)
-    assert list(a.propagate_res_arrays[3]) == list(ns)
+    oc, mn, mx, ns, _ = orc.propagate_until(35.0)
     err = np.max(np.abs(a.state - orc.state) / np.maximum(1.0, np.abs(orc.state)))
     assert err < 1e-12, err
+    # changing a lane's masses changes that lane only
+    a2 = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
+    a3 = hy.taylor_adaptive_batch(sys_, ic, pars=pars)
+    a2.pars[1, 7] *= 1.5
+    a2.propagate_until(35.0)
+    a3.propagate_until(35.0)
+    diff = np.abs(a2.state - a3.state).max(axis=0)
+    assert diff[7] > 1e-9 and np.all(np.delete(diff, 7) == 0.0)
 
 
 def test_compiled_kernel_in_shared_memory_and_clone():

@@ -44,6 +44,17 @@ def test_non_matching_tapes_keep_the_interpreter():
     assert _variant(hy.model.nbody(6, masses=[1.0, 1e-3, 1e-3, 1e-3, 1e-3, 0.0])) == 0
 
 
+def test_parametric_masses_match():
+    # masses as runtime parameters (the reference's model.nbody accepts expressions): the acceleration
+    # terms carry par[j]; the matcher accepts them (the kernel is then built at hy_create time with
+    # HY_NBR_PAR: tests/test_gpu_jit.py)
+    sys_ = hy.model.nbody(6, masses=[hy.par[i] for i in range(6)], Gconst=0.5)
+    assert D.decompose(sys_, 20).n_par == 6
+    assert _variant(sys_) == 6
+    mixed = hy.model.nbody(4, masses=[1.0, hy.par[0], 1e-3, hy.par[1]])
+    assert _variant(mixed) == 4
+
+
 def test_perturbed_nbody_is_rejected():
     # an extra force term / a different exponent must not be swallowed by the matcher
     sys_ = common.oss_sys()
