@@ -520,7 +520,14 @@ int choose_geometry(hy_ctx *c)
     if (jit_mode == 2 && (env_u32("HY_CUDA_NO_NBODY_REG", 0) || env_u32("HY_CUDA_NO_CR3BP_REG", 0) ||
                           env_u32("HY_CUDA_NO_REG_EVENTS", 0)))
         jit_mode = 0;
-    const bool interp_weak = !bestG || !best_smem || best_score < (double)env_u32("HY_CUDA_JIT_MAX_SCORE", 200);
+    // (central-force tapes - N-body problems beyond the six bodies of the register kernels, fixed centres -
+    //  run mostly on the fused, order-specialised pair op: the interpreter beats one thread per trajectory
+    //  there whatever the score says - 7 / 8 bodies: 1.98e7 / 1.84e7 vs 1.66e7 / 1.25e7 steps/s)
+    uint32_t n_pair_ops = 0;
+    for (const hy::DOp &q : best.ops) n_pair_ops += q.opcode == hy::DOP_PAIR;
+    const bool pair_dominated = bestG && best_smem && 4u * n_pair_ops >= best.n_clusters && n_pair_ops >= 3;
+    const bool interp_weak = !bestG || !best_smem ||
+                             (best_score < (double)env_u32("HY_CUDA_JIT_MAX_SCORE", 200) && !pair_dominated);
     if (!li.kernel_variant && !force_global && !Genv && (jit_mode == 1 || (jit_mode == 2 && interp_weak))) {
         hy::Program pr;
         std::string jerr;

@@ -562,9 +562,13 @@ struct Nvrtc {
     int (*Version)(int *, int *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     std::string err;
+    std::mutex mtx; // (contexts are created from several host threads: ensembles, the lane-sharded integrator)
+    bool loaded = false;
     bool load()
     {
-        if (h) return true;
+        std::lock_guard<std::mutex> lk(mtx);
+        if (loaded) return true;
+        if (h) return false; // (an earlier attempt found the library but not every symbol)
         if (const char *e = std::getenv("HY_CUDA_NVRTC_LIB")) { // (explicit library; also how the tests take NVRTC away)
             h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
         } else {
@@ -595,6 +599,7 @@ struct Nvrtc {
         HY_NVRTC_SYM(Version)
         HY_NVRTC_SYM(GetErrorString)
 #undef HY_NVRTC_SYM
+        loaded = true;
         return true;
     }
 };
@@ -783,9 +788,11 @@ struct Driver {
     int (*FuncGetAttribute)(int *, int, void *) = nullptr;
     int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
     std::string err;
+    std::mutex mtx;
     bool ok = false;
     bool load()
     {
+        std::lock_guard<std::mutex> lk(mtx);
         if (ok) return true;
         auto get = [&](const char *nm, void **fp) {
             cudaDriverEntryPointQueryResult qr;
