@@ -369,18 +369,20 @@ int choose_geometry(hy_ctx *c)
         const char *R = c->fp_bits == 64 ? "double" : "float";
         if (variant == (uint32_t)hy::NBR_VARIANT_P22)
             return std::string("hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, ") + (fxb ? "true>" : "false>");
-        return std::string("hy::propagate_kernel<") + R + ", 16, true, " + std::to_string(variant) + ", false, hy::NBR_PMAX, " +
-               (fxb ? "true>" : "false>");
+        return std::string("hy::propagate_kernel<") + R + (variant > 6 ? ", 32, true, " : ", 16, true, ") + std::to_string(variant) +
+               ", false, hy::NBR_PMAX, " + (fxb ? "true>" : "false>");
     };
     bool nb_ok = !force_global && !Genv && env_u32("HY_CUDA_NO_NBODY_REG", 0) == 0 &&
                  hy::match_nbody(md, mops, mterms, nbm) && hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits);
-    if (nb_ok && nbm.has_par) {
-        // Masses scaled by runtime parameters: no precompiled kernel reads parameters - build the matched
-        // kernel now (NVRTC, ~6 s per build, cached) with HY_NBR_PAR.  No compiler: the tape goes the general way.
+    if (nb_ok && (nbm.has_par || nbm.g32)) {
+        // Masses scaled by runtime parameters (no precompiled kernel reads parameters), or 7 / 8 bodies (21 / 28
+        // pairs: 32-lane groups, one trajectory per warp): build the matched kernel now (NVRTC, ~6 s per build,
+        // cached) with HY_NBR_PAR / HY_NBR_G32.  No compiler: the tape goes the general way.
         nb_ok = !c->no_jit && env_u32("HY_CUDA_JIT", 2) != 0 && env_u32("HY_CUDA_WGX", 0) == 0;
         if (nb_ok) {
             const uint32_t v = hy::nbody_kernel_variant(nbm.nb, d.order, c->fp_bits);
-            const std::string defs = "#define HY_NBR_PAR 1\n";
+            const std::string defs = std::string(nbm.has_par ? "#define HY_NBR_PAR 1\n" : "") +
+                                     (nbm.g32 ? "#define HY_NBR_G32 1\n" : "");
             const std::string src = defs + "#include \"hy_kernels.cuh\"\n";
             hy::jit::Image fxi;
             std::string e1 = hy::jit::build(src, nbody_kname(v, false), c->jit_img_plain);
@@ -398,20 +400,21 @@ int choose_geometry(hy_ctx *c)
     }
     if (nb_ok) {
         hy::Program pr;
-        pr.G = 16;
+        const uint32_t NG = nbm.g32 ? 32u : 16u; // lanes of a group
+        pr.G = NG;
         pr.n_phases = 0;
         pr.phase_slot = {0};
         pr.imm = nbm.imm;
         // experimental: warpgroup rotation (24 trajectories per SM, registers traded between warpgroups)
         const bool wgx = env_u32("HY_CUDA_WGX", 0) != 0 && nbm.nb == 6 && c->fp_bits == 64 &&
                          d.order == (uint32_t)hy::NBR_PMAX && c->B >= 24u * li.n_sm;
-        pr.ws_len = (uint32_t)hy::nbr_ws(wgx);
+        pr.ws_len = nbm.g32 ? (uint32_t)hy::NbrHostLayout(true).ws : (uint32_t)hy::nbr_ws(wgx);
         pr.par_off = pr.one_off = pr.ws_len;
         pr.n_spill = 0;
         for (uint32_t i = 0; i < d.n_state; ++i) pr.state_row.push_back((uint32_t)hy::nbr_state_off((int)i));
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = nbm.n_pairs;
-        pr.lane_utilisation = (double)nbm.n_pairs / 16.0;
+        pr.lane_utilisation = (double)nbm.n_pairs / (double)NG;
         const bool ev_att = attach_events(pr) && !(wgx && evt_ok);
         if (nbm.has_par) { // parameter rows of the trajectory, after everything else in the column
             pr.par_off = pr.ws_len;
@@ -420,12 +423,12 @@ int choose_geometry(hy_ctx *c)
         }
         // column stride: even (16-byte aligned vectors); + 2 spreads the two trajectories of a warp over the banks
         const uint32_t RS = (pr.ws_len + 1u) / 2u * 2u + 2u;
-        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 16, 0, RS, (uint32_t)c->rb, 0);
+        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), NG, 0, RS, (uint32_t)c->rb, 0);
         const uint32_t fixed = L0.total + 64;
         if (ev_att && fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 2) {
             c->use_evt = evt_ok;
-            bestG = 16;
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), (wgx ? 384u : max_threads) / 16u) & ~1u;
+            bestG = NG;
+            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), (wgx ? 384u : max_threads) / NG) & ~1u;
             bestRS = RS;
             best_smem = true;
             best = pr;
@@ -589,9 +592,9 @@ int choose_geometry(hy_ctx *c)
         if (crb && ej >= 1)
             kname = std::string("hy::propagate_kernel<") + R + ", 2, true, -1, false, " +
                     (li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22 ? "hy::CRB_PMAX_HI" : "hy::NBR_PMAX") + ", true>";
-        else if (!crb && ej >= 1 && li.kernel_variant >= 3 && li.kernel_variant <= 6)
-            kname = std::string("hy::propagate_kernel<") + R + ", 16, true, " + std::to_string(li.kernel_variant) +
-                    ", false, hy::NBR_PMAX, true>";
+        else if (!crb && ej >= 1 && li.kernel_variant >= 3 && li.kernel_variant <= 8)
+            kname = std::string("hy::propagate_kernel<") + R + (li.kernel_variant > 6 ? ", 32, true, " : ", 16, true, ") +
+                    std::to_string(li.kernel_variant) + ", false, hy::NBR_PMAX, true>";
         else if (!crb && ej >= 1 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
             kname = "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
         if (!kname.empty()) {
@@ -614,6 +617,8 @@ int choose_geometry(hy_ctx *c)
         std::string lerr = hy::jit::load(c->jit_img_plain, li.smem_bytes, false, c->jit_k_plain);
         if (lerr.empty() && !c->jit_k.func) lerr = hy::jit::load(c->jit_img, li.smem_bytes, false, c->jit_k);
         if (!lerr.empty()) return fail("hy_create: " + lerr);
+        li.regs_per_thread = (uint32_t)c->jit_k_plain.regs;
+        return upload_program(c);
     }
     if (li.kernel_variant == HY_VARIANT_JIT) {
         CU(cudaSetDevice(c->device));

@@ -1331,11 +1331,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         // (a 64-bit shared access costs one wavefront per active half-warp).
         // (trajectory 0: lanes 0..NB-1, trajectory 1: lanes 8..8+NB-1 - one quarter-warp each, so the
         // 128-bit accesses of the two trajectories never meet in one wavefront)
-        nl.body = lane < 16u && (lane & 7u) < (uint32_t)NB;
+        nl.body = G == 32 ? lane < (uint32_t)NB : (lane < 16u && (lane & 7u) < (uint32_t)NB);
         // (every lane gets valid body addresses - the loads of the body phase are not predicated:
         // lanes 16..31 mirror lanes 0..15, the spare lanes of a quarter-warp mirror its first bodies)
-        const uint32_t bt = (lane >> 3) & 1u, bd = (lane & 7u) % (uint32_t)NB;
-        const int32_t col = (bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
+        // (G = 32: one trajectory per warp - its bodies on lanes 0..NB-1, the other lanes mirror them)
+        const uint32_t bt = G == 32 ? 0u : (lane >> 3) & 1u, bd = (G == 32 ? lane : (lane & 7u)) % (uint32_t)NB;
+        const int32_t col = (G != 32 && bt != (lane >> 4)) ? (bt ? (int32_t)RS : -(int32_t)RS) : 0; // the other trajectory's column
         nl.xbody = col + (int32_t)(NBR_BS * bd);
         nl.coef = (int32_t)(NBR_CS * bd);
 #pragma unroll
@@ -1928,7 +1929,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             if constexpr (NB > 0) {
                 // one full-mask ballot, each half-warp looks at its own 16 bits
                 const unsigned bad = __ballot_sync(TM_FULL, !finite);
-                finite = ((bad >> (lane & 16u)) & 0xffffu) == 0u;
+                finite = G == 32 ? bad == 0u : ((bad >> (lane & 16u)) & 0xffffu) == 0u;
             } else if constexpr (NB < 0) {
                 __syncwarp();
                 const unsigned bad = __ballot_sync(TM_FULL, !finite);

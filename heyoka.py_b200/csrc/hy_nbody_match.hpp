@@ -26,8 +26,20 @@
 
 namespace hy {
 
+// Host view of the immediate-table / column layout of hy_nbody_reg.cuh for the two group sizes (the device
+// constants NBR_MAXB, NBR_NLANES, NBR_LANE0, NBR_OFF0, NBR_NIMM, NBR_TB0 with and without HY_NBR_G32).
+struct NbrHostLayout {
+    int maxb, lanes, lane0, off0, nimm, ws;
+    explicit NbrHostLayout(bool g32)
+        : maxb(g32 ? 8 : 6), lanes(g32 ? 32 : 16), lane0(maxb * NBR_CS), off0(lane0 + lanes), nimm(off0 + maxb * NBR_CS),
+          ws(maxb * NBR_BS)
+    {
+    }
+};
+
 struct NbMatch {
     uint32_t nb = 0, n_pairs = 0;
+    bool g32 = false; // 7 or 8 bodies: 32-lane groups, one trajectory per warp (built at hy_create time, HY_NBR_G32)
     bool has_par = false; // masses (acceleration coefficients) scaled by runtime parameters: the kernel is
                           // built at hy_create time with HY_NBR_PAR (hy_jit.hpp), not one of the precompiled ones
     std::vector<double> imm; // NBR_NIMM entries (layout in hy_nbody_reg.cuh)
@@ -35,9 +47,12 @@ struct NbMatch {
 
 // body counts with a compiled register-resident kernel (hy_nb3.cu ... hy_nb6.cu)
 inline bool nbody_kernel_compiled(uint32_t nb) { return nb >= 3 && nb <= 6; }
+// body counts served by a kernel built at hy_create time on 32-lane groups
+inline bool nbody_kernel_g32(uint32_t nb) { return nb == 7 || nb == 8; }
 // kernel variant for a matched tape of nb bodies at Taylor order p (0: none compiled)
 inline uint32_t nbody_kernel_variant(uint32_t nb, uint32_t order, int fp_bits)
 {
+    if (nbody_kernel_g32(nb)) return order <= (uint32_t)NBR_PMAX ? nb : 0u;
     if (!nbody_kernel_compiled(nb)) return 0;
     if (order <= (uint32_t)NBR_PMAX) return nb;
     return (nb == 6 && fp_bits == 64 && order <= (uint32_t)NBR_LMAX) ? (uint32_t)NBR_VARIANT_P22 : 0u;
@@ -49,7 +64,9 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
     // (orders NBR_PMAX + 1 .. NBR_LMAX: only the 6-body FP64 build has a kernel - the caller checks)
     if (d.n_events || n % 6 || d.order > (uint32_t)NBR_LMAX || d.order < 2) return false;
     const uint32_t NB = n / 6;
-    if (NB < 2 || NB > (uint32_t)NBR_MAXB) return false;
+    if (NB < 2 || NB > 8u) return false;
+    const bool g32 = NB > 6;
+    const NbrHostLayout HL(g32);
     const uint32_t NP = NB * (NB - 1) / 2;
     if (d.n_ops != 3 * NP + 3 * NP + 6 * NB) return false;
     // state variable index of a jet reference (or -1)
@@ -146,7 +163,7 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
         default: return false;
         }
     }
-    if (pairs.size() != NP || NP > 16) return false;
+    if (pairs.size() != NP || NP > (uint32_t)HL.lanes) return false;
     for (const Pair &p : pairs)
         if (!p.has_pow || !p.has_mul) return false;
     for (uint32_t b = 0; b < NB; ++b)
@@ -156,7 +173,8 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
     out = NbMatch();
     out.nb = NB;
     out.n_pairs = NP;
-    out.imm.assign(NBR_NIMM, 0.0);
+    out.g32 = g32;
+    out.imm.assign(HL.nimm, 0.0);
     out.has_par = d.n_par != 0; // (parameters that no term uses still travel with the trajectory)
     std::vector<int> qa(NP, -1), qb(NP, -1);
     for (uint32_t b = 0; b < NB; ++b) {
@@ -175,14 +193,14 @@ inline bool match_nbody(const hy_dims &d, const hy_op *ops, const hy_term *terms
             // pair slot (= lane) whose products feed this term; second word: parameter index + 1 (0: none)
             const uint32_t src[2] = {(uint32_t)pr, (uint32_t)(r0[q].par + 1)};
             if (r0[q].par >= 0) out.has_par = true;
-            std::memcpy(&out.imm[NBR_OFF0 + b * NBR_CS + q], src, 8);
+            std::memcpy(&out.imm[HL.off0 + b * NBR_CS + q], src, 8);
         }
     }
-    for (uint32_t s = 0; s < 16; ++s) {
+    for (uint32_t s = 0; s < (uint32_t)HL.lanes; ++s) {
         const uint32_t pr = s < NP ? s : 0; // idle lanes mirror pair 0
         if (qa[pr] < 0 || qb[pr] < 0) return false;
         const uint32_t rec[2] = {(uint32_t)pairs[pr].a, (uint32_t)pairs[pr].b}; // lane record
-        std::memcpy(&out.imm[NBR_LANE0 + s], rec, 8);
+        std::memcpy(&out.imm[HL.lane0 + s], rec, 8);
     }
     return true;
 }

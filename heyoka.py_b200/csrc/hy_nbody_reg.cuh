@@ -44,7 +44,16 @@ constexpr int NBR_PMAX = 20;   // Taylor order of the fully unrolled register-re
 constexpr int NBR_LMAX = 22;   // rows of the column layout; also the order of the 6-body FP64 high-accuracy
                                // build (tol = 1e-18: the reference's own benchmark, ensemble_batch_perf.ipynb)
 constexpr int NBR_VARIANT_P22 = 226; // hy_launch_info.kernel_variant of that build
+// bodies / lanes of a group: 6 bodies (15 pairs) on 16-lane groups, two trajectories per warp - the precompiled
+// kernels; with HY_NBR_G32 (a build made at hy_create time, hy_jit.hpp) 7 or 8 bodies (21 / 28 pairs) on the 32 lanes
+// of a warp, one trajectory per warp.  The host mirrors these numbers in NbrHostLayout (hy_nbody_match.hpp).
+#ifdef HY_NBR_G32
+constexpr int NBR_MAXB = 8;
+constexpr int NBR_NLANES = 32;
+#else
 constexpr int NBR_MAXB = 6;    // bodies (pairs <= 15 fit one 16-lane group)
+constexpr int NBR_NLANES = 16;
+#endif
 
 // Trajectory column (shared memory, elements):
 //   body b, order k:  [x, y, z, -, vx, vy, vz, -]  at  b * NBR_BS + k * NBR_JS   (16-byte aligned
@@ -77,7 +86,7 @@ __host__ __device__ constexpr int nbr_state_off(int i) { return (i / 6) * NBR_BS
 //   imm[NBR_OFF0 + body * NBR_CS + q]  uint32: pair slot index feeding term q of the body's sums
 constexpr int NBR_CS = 9; // odd stride: the body lanes read their rows conflict-free
 constexpr int NBR_LANE0 = NBR_MAXB * NBR_CS;
-constexpr int NBR_OFF0 = NBR_LANE0 + 16;
+constexpr int NBR_OFF0 = NBR_LANE0 + NBR_NLANES;
 constexpr int NBR_NIMM = NBR_OFF0 + NBR_MAXB * NBR_CS;
 
 // ---- one order of one pair, everything in registers ----

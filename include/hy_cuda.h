@@ -337,6 +337,9 @@ typedef struct hy_launch_info {
     uint32_t regs_per_thread;
     uint32_t kernel_variant; /* 0: tape interpreter; 3..6: register-resident
                                 N-body kernel for N bodies (hy_nbody_reg.cuh);
+                                7, 8: the same kernel on 32-lane groups, built at
+                                hy_create time (NVRTC), as are the builds for
+                                parametric masses; 1000: HY_VARIANT_JIT;
                                 226: the 6-body FP64 build unrolled to order 22
                                 (tol = 1e-18, orders 21..22);
                                 222: the FP64 CR3BP build unrolled to order 22;

@@ -193,6 +193,89 @@ def test_parametric_masses_nbody_gets_the_register_kernel():
     assert diff[7] > 1e-9 and np.all(np.delete(diff, 7) == 0.0)
 
 
+def _nbody_ic(nb, B, fp=np.float64):
+    """The outer Solar System plus nb - 6 light bodies on wide orbits."""
+    extra = nb - 6
+    masses = list(W.OSS_MASSES) + [1e-9 * (1 + e) for e in range(extra)]
+    add = []
+    for e in range(extra):
+        r = 45.0 + 7.0 * e
+        add.append(np.array([r, 0.0, 0.3, 0.0, 2 * np.pi / np.sqrt(r), 0.0])[:, None] * np.ones((1, B)))
+    ic = np.concatenate([W.oss_ensemble(B)] + add, axis=0).astype(fp)
+    from hy_b200 import model
+
+    return model.nbody(nb, masses=masses, Gconst=W.OSS_G), ic
+
+
+@pytest.mark.parametrize("nb,fp", [(7, np.float64), (8, np.float64), (8, np.float32)])
+def test_seven_and_eight_bodies_on_32_lane_groups(nb, fp):
+    # 21 / 28 pairs do not fit a 16-lane group: hy_create builds the register-resident kernel on
+    # 32-lane groups (one trajectory per warp; NVRTC, HY_NBR_G32).  Same arithmetic as the interpreter's
+    # fused pair op + LINCOMB + SVD: bit for bit, every API feature that runs in the kernel included.
+    B = 37
+    sys_, ic = _nbody_ic(nb, B, fp)
+    a = hy.taylor_adaptive_batch(sys_, ic, fp_type=fp)
+    li = a._ctx.launch_info()
+    assert li["kernel_variant"] == nb and li["group"] == 32, li
+    os.environ["HY_CUDA_NO_NBODY_REG"] = "1"
+    try:
+        b = hy.taylor_adaptive_batch(sys_, ic, fp_type=fp)
+        b._ctx
+    finally:
+        del os.environ["HY_CUDA_NO_NBODY_REG"]
+    assert b._ctx.launch_info()["kernel_variant"] == 0
+    for ta in (a, b):
+        ta.step(write_tc=True)
+    assert np.array_equal(a.tc, b.tc)
+    tf = np.linspace(20.0, 40.0, B).astype(fp)
+    for ta in (a, b):
+        ta.propagate_until(tf)
+    _same(a, b)
+    grid = (np.linspace(40.0, 44.0, 5)[:, None] * np.ones((1, B))).astype(fp)
+    assert np.array_equal(a.propagate_grid(grid)[1], b.propagate_grid(grid)[1])
+    ca, _ = a.propagate_for(fp(3.0), c_output=True)
+    cb, _ = b.propagate_for(fp(3.0), c_output=True)
+    _same(a, b)
+    tq = (np.linspace(44.2, 46.8, 4)[:, None] * np.ones((1, B))).astype(fp)
+    assert np.array_equal(ca(tq), cb(tq))
+    if fp == np.float64:
+        orc = COracle(D.decompose(sys_, a.order), ic)
+        c = hy.taylor_adaptive_batch(sys_, ic)
+        c.propagate_until(25.0)
+        oc, mn, mx, ns, _ = orc.propagate_until(25.0)
+        assert list(c.propagate_res_arrays[3]) == list(ns)
+        err = np.max(np.abs(c.state - orc.state) / np.maximum(1.0, np.abs(orc.state)))
+        assert err < 1e-12, err
+
+
+def test_eight_bodies_with_parametric_masses_and_an_event():
+    # both build switches at once (HY_NBR_PAR + HY_NBR_G32), plus a terminal event on the event tape
+    from hy_b200 import model
+
+    B = 20
+    _, ic = _nbody_ic(8, B)
+    masses = list(W.OSS_MASSES) + [1e-9, 2e-9]
+    sys_ = model.nbody(8, masses=[hy.par[i] for i in range(8)], Gconst=W.OSS_G)
+    pars = np.array(masses)[:, None] * np.ones((1, B))
+    x6 = sys_[36][0]  # x of body 6
+    ev = lambda: [hy.t_event_batch(x6 - 44.0, direction=hy.event_direction.negative)]
+    a = hy.taylor_adaptive_batch(sys_, ic, pars=pars, t_events=ev())
+    assert a._ctx.launch_info()["kernel_variant"] == 8
+    os.environ["HY_CUDA_NO_NBODY_REG"] = "1"
+    try:
+        b = hy.taylor_adaptive_batch(sys_, ic, pars=pars, t_events=ev())
+        b._ctx
+    finally:
+        del os.environ["HY_CUDA_NO_NBODY_REG"]
+    assert b._ctx.launch_info()["kernel_variant"] == 0
+    for ta in (a, b):
+        ta.propagate_until(60.0)
+    assert np.array_equal(a.propagate_res_arrays[0], b.propagate_res_arrays[0])
+    assert (a.propagate_res_arrays[0] > -10).all()          # every lane stops on the event
+    assert np.max(np.abs(a.time - b.time)) < 1e-9
+    assert np.max(np.abs(a.state - b.state) / np.maximum(1.0, np.abs(b.state))) < 1e-9
+
+
 def test_compiled_kernel_in_shared_memory_and_clone():
     # a small tape: the interleaved workspace of a whole CTA fits in shared memory
     sys_ = W.forced_pendulum_sys()
