@@ -418,6 +418,9 @@ def main():
     K = cfgd["grid_eval"]
     tq = np.repeat(np.linspace(0.0, cfgd["horizon"], K), B).reshape(K, B) if K else None
     gout = np.empty((K, n, B)) if K else None
+    # (device-resident arm: the query times and the evaluated grid stay in HBM)
+    d_tq = torch.from_numpy(tq).to(dev) if K else None
+    d_gout = torch.empty((K, n, B), dtype=torch.float64, device=dev) if K else None
 
     def reset_dev():
         _cabi.check(_cabi.lib().hy_upload_dev(
@@ -439,7 +442,7 @@ def main():
         launches[0] += nl
         if cfgd["c_output"]:
             rec = ctx.cout_detach()
-            rec.eval(tq, K, gout)          # K x B dense evaluations (one more launch)
+            rec.eval_dev(d_tq.data_ptr(), K, d_gout.data_ptr())  # K x B dense evaluations (one more launch)
             launches[0] += 2               # chunk directory + evaluation kernels
             rec.close()                    # the pool goes back to the context
         return int(nst.sum()), ms

@@ -1679,6 +1679,30 @@ int hy_cout_eval(hy_cout *r, const void *t, size_t k, void *out)
     return 0;
 }
 
+/* hy_cout_eval with device-resident query times / output (same layouts): the evaluation of a
+ * continuous output whose consumers live on the GPU. */
+int hy_cout_eval_dev(hy_cout *r, const void *d_t, size_t k, void *d_out)
+{
+    if (!r || !d_t || !d_out) return fail("hy_cout_eval_dev: null argument");
+    CU(cudaSetDevice(r->device));
+    const size_t B = r->B, rb = r->rb, n = r->n;
+    if (B == 0 || k == 0) return 0;
+    if (rec_index(r)) return 1;
+    const unsigned th = 128;
+    const unsigned bl = (unsigned)((k * B + th - 1) / th);
+    if (rb == 8)
+        hy::cout_eval_kernel<double><<<bl, th, 0, r->stream>>>(rec_dev<double>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                               (const double *)d_t, (double *)d_out, (uint32_t)n, r->P1 - 1,
+                                                               (uint32_t)B, (uint32_t)k);
+    else
+        hy::cout_eval_kernel<float><<<bl, th, 0, r->stream>>>(rec_dev<float>(r, 1, 0), r->d_dir_off, r->d_dir,
+                                                              (const float *)d_t, (float *)d_out, (uint32_t)n, r->P1 - 1,
+                                                              (uint32_t)B, (uint32_t)k);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
 int hy_events_count(hy_ctx *c, uint64_t *n)
 {
     if (!c || !n) return fail("null argument");

@@ -1808,13 +1808,29 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     R *my_dst = nullptr;
                     if (stepping) my_dst = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     const uint32_t nP = n * P1;
+                    // (P.rec_off: the [variable][order] -> column offset table; records of up to 128 elements -
+                    //  the CR3BP's 126 - keep this lane's four offsets in registers: per trajectory four
+                    //  independent load / store pairs instead of a chain of dependent table look-ups)
+                    const bool small_rec = nP <= 128u;
+                    uint32_t ro[4];
+#pragma unroll
+                    for (int m_ = 0; m_ < 4; ++m_)
+                        ro[m_] = (small_rec && lane + 32u * m_ < nP) ? __ldg(&P.rec_off[lane + 32u * m_]) : 0u;
 #pragma unroll 1
                     for (uint32_t g = 0; g < 32u / G; ++g) {
                         R *dst = reinterpret_cast<R *>(__shfl_sync(TM_FULL, (unsigned long long)my_dst, (int)(g * G)));
                         if (!dst) continue; // (warp-uniform)
                         const R *wg = w + ((int)g - (int)(lane / G)) * (int)RS; // column of group g of this warp
-                        // (P.rec_off: the [variable][order] -> column offset table, L1-resident)
-                        for (uint32_t e = lane; e < nP; e += 32u) dst[e] = wg[__ldg(&P.rec_off[e])];
+                        if (small_rec) {
+                            R v_[4];
+#pragma unroll
+                            for (int m_ = 0; m_ < 4; ++m_) v_[m_] = wg[ro[m_]];
+#pragma unroll
+                            for (int m_ = 0; m_ < 4; ++m_)
+                                if (lane + 32u * m_ < nP) dst[lane + 32u * m_] = v_[m_];
+                        } else {
+                            for (uint32_t e = lane; e < nP; e += 32u) dst[e] = wg[__ldg(&P.rec_off[e])];
+                        }
                     }
                     __syncwarp();
                 }

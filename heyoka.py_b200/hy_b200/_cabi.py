@@ -144,6 +144,7 @@ SYMBOLS = [
     "hy_cout_info",
     "hy_cout_get",
     "hy_cout_eval",
+    "hy_cout_eval_dev",
     "hy_events_count",
     "hy_events_drain",
     "hy_get_cooldowns",
@@ -455,6 +456,10 @@ class CoutRecord:
 
     def eval(self, t, k, out):
         check(lib().hy_cout_eval(self._h, ptr(t), C.c_size_t(int(k)), ptr(out)))
+
+    def eval_dev(self, d_t, k, d_out):
+        """hy_cout_eval_dev: query times and output are device pointers (ints)."""
+        check(lib().hy_cout_eval_dev(self._h, C.c_void_p(int(d_t)), C.c_size_t(int(k)), C.c_void_p(int(d_out))))
 
     def close(self):
         if self._h is not None and self._h.value:

@@ -304,6 +304,8 @@ int hy_cout_free(hy_cout *rec, hy_ctx *recycle_into);
 int hy_cout_info(hy_cout *rec, uint64_t *n_steps, uint64_t *max_steps);
 int hy_cout_get(hy_cout *rec, void *tcs, void *times_hi, void *times_lo, uint64_t S);
 int hy_cout_eval(hy_cout *rec, const void *t, size_t k, void *out);
+/* the same with device pointers (t [k, B] and out [k, n, B] in device memory) */
+int hy_cout_eval_dev(hy_cout *rec, const void *d_t, size_t k, void *d_out);
 
 /* Events (taylor_expose_events.cpp:185-317; integrator side
  * expose_batch_integrators.cpp:651-656).  The device appends one record per

@@ -357,3 +357,28 @@ def test_angle_reducer_runs_on_the_device(fp):
     e = hy.taylor_adaptive_batch(sys_, ic, fp_type=fp)
     e.propagate_until(fp(20.0), callback=[hy.callback.angle_reducer([x]), _CountCb()])
     assert _rel(e.state.astype(np.float64), a.state.astype(np.float64)) < tol
+
+
+def test_cout_eval_with_device_pointers_matches_host_path():
+    # hy_cout_eval_dev: query times / output in device memory (what a GPU-resident consumer uses;
+    # bench.py's device arm) - the same numbers as the host-pointer call
+    import torch
+
+    B = 300
+    sys_, ic = W.cr3bp_sys(0.01), W.cr3bp_ensemble(B)
+    ta = hy.taylor_adaptive_batch(sys_, ic)
+    ta._push()
+    oc = np.zeros(B, dtype=np.int64)
+    ns = np.zeros(B, dtype=np.uint64)
+    ta._ctx.propagate(np.full(B, 5.0), 0, 0, None, 0, 1, oc, None, None, ns)
+    rec = ta._ctx.cout_detach()
+    K = 7
+    tq = np.repeat(np.linspace(0.3, 4.7, K), B).reshape(K, B)
+    out_h = np.empty((K, 6, B))
+    rec.eval(tq, K, out_h)
+    d_tq = torch.from_numpy(tq).cuda()
+    d_out = torch.empty((K, 6, B), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    rec.eval_dev(d_tq.data_ptr(), K, d_out.data_ptr())
+    assert np.array_equal(d_out.cpu().numpy(), out_h)
+    rec.close()
