@@ -308,6 +308,21 @@ int jit_plan(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uin
     return 1;
 }
 
+// Name of the FX build of a register-resident kernel that carries generated event functions ("" for a
+// variant that has none).
+static std::string evt_kernel_name(uint32_t variant, int fp_bits)
+{
+    const char *R = fp_bits == 64 ? "double" : "float";
+    if (variant == (uint32_t)hy::CRB_VARIANT || variant == (uint32_t)hy::CRB_VARIANT_P22)
+        return std::string("hy::propagate_kernel<") + R + ", 2, true, -1, false, " +
+               (variant == (uint32_t)hy::CRB_VARIANT_P22 ? "hy::CRB_PMAX_HI" : "hy::NBR_PMAX") + ", true>";
+    if (variant >= 3 && variant <= 8)
+        return std::string("hy::propagate_kernel<") + R + (variant > 6 ? ", 32, true, " : ", 16, true, ") + std::to_string(variant) +
+               ", false, hy::NBR_PMAX, true>";
+    if (variant == (uint32_t)hy::NBR_VARIANT_P22) return "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
+    return "";
+}
+
 int upload_program(hy_ctx *c);
 
 // Choose the launch geometry for a tape: group size G (threads cooperating on
@@ -586,19 +601,10 @@ int choose_geometry(hy_ctx *c)
         //  generates the code whatever the batch)
         uint32_t ej = env_u32("HY_CUDA_JIT_EVT", 1);
         if (ej == 1 && c->B < env_u32("HY_CUDA_JIT_EVT_MIN_BATCH", 4096)) ej = 0;
-        const bool crb = li.kernel_variant == (uint32_t)hy::CRB_VARIANT || li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
-        std::string kname;
-        const char *R = c->fp_bits == 64 ? "double" : "float";
-        if (crb && ej >= 1)
-            kname = std::string("hy::propagate_kernel<") + R + ", 2, true, -1, false, " +
-                    (li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22 ? "hy::CRB_PMAX_HI" : "hy::NBR_PMAX") + ", true>";
-        else if (!crb && ej >= 1 && li.kernel_variant >= 3 && li.kernel_variant <= 8)
-            kname = std::string("hy::propagate_kernel<") + R + (li.kernel_variant > 6 ? ", 32, true, " : ", 16, true, ") +
-                    std::to_string(li.kernel_variant) + ", false, hy::NBR_PMAX, true>";
-        else if (!crb && ej >= 1 && li.kernel_variant == (uint32_t)hy::NBR_VARIANT_P22)
-            kname = "hy::propagate_kernel<double, 16, true, 6, false, hy::NBR_LMAX, true>";
+        const std::string kname = ej >= 1 ? evt_kernel_name(li.kernel_variant, c->fp_bits) : std::string();
         if (!kname.empty()) {
-            const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order, c->jit_defs);
+            const std::string src = hy::jit::evt_kernel_source(c->evt_prog, c->prog.state_row, d.order, c->jit_defs, G,
+                                                               2u * (d.n_state + c->evt_prog.n_slots));
             hy::jit::Image img;
             std::string jerr = hy::jit::build(src, kname, img);
             if (jerr.empty()) {
@@ -1842,6 +1848,50 @@ int hy_jit_precompile(int fp_bits, const hy_tape *full, uint32_t batch, int *fro
                            env_u32("HY_CUDA_JIT", 2) == 1, pr, smem, T, img, err);
     if (r < 0) return fail("hy_jit_precompile: " + err);
     if (from_cache) *from_cache = r == 0 ? -1 : (img.from_cache ? 1 : 0);
+    if (compile_s) *compile_s = img.compile_s;
+    return 0;
+}
+
+/* The same for the event functions of a system served by a register-resident kernel: match the ODE
+ * tape, lower the event tape, generate and compile the kernel that hy_create2 would build for it
+ * (*from_cache = -1: the system gets no such kernel - its events run on the interpreter). */
+int hy_jit_precompile_events(int fp_bits, const hy_tape *full, const hy_tape *ode, const hy_event_tape *evt, int *from_cache,
+                             double *compile_s)
+{
+    if (!full || !full->dims || !ode || !ode->dims || !ode->ops || !evt || !evt->ops)
+        return fail("hy_jit_precompile_events: null argument");
+    if (fp_bits != 32 && fp_bits != 64) return fail("hy_jit_precompile_events: fp_bits must be 32 or 64");
+    const hy_dims &d = *full->dims;
+    if (from_cache) *from_cache = -1;
+    if (compile_s) *compile_s = 0;
+    uint32_t variant = 0, G = 0;
+    std::vector<uint32_t> state_row;
+    std::string defs;
+    hy::NbMatch nbm;
+    hy::CrbMatch crm;
+    if (hy::match_nbody(*ode->dims, ode->ops, ode->terms, nbm) && (variant = hy::nbody_kernel_variant(nbm.nb, d.order, fp_bits))) {
+        G = nbm.g32 ? 32u : 16u;
+        for (uint32_t i = 0; i < d.n_state; ++i) state_row.push_back((uint32_t)hy::nbr_state_off((int)i));
+        defs = std::string(nbm.has_par ? "#define HY_NBR_PAR 1\n" : "") + (nbm.g32 ? "#define HY_NBR_G32 1\n" : "");
+    } else if (hy::match_cr3bp(*ode->dims, ode->ops, ode->terms, fp_bits, crm)) {
+        variant = hy::cr3bp_kernel_variant(d.order, fp_bits);
+        G = 2;
+        for (uint32_t i = 0; i < d.n_state; ++i) state_row.push_back(i);
+    }
+    const std::string kname = evt_kernel_name(variant, fp_bits);
+    if (kname.empty()) return 0;
+    hy::EvtProgram ep;
+    const std::vector<hy_op> ops(evt->ops, evt->ops + evt->n_ops);
+    const std::vector<hy_term> terms(evt->terms, evt->terms + evt->n_terms);
+    const std::vector<uint32_t> ev_ref(evt->ev_ref, evt->ev_ref + evt->n_events);
+    const std::vector<uint32_t> op_start(evt->op_start, evt->op_start + evt->n_events + 1);
+    const std::string err = hy::build_event_program(d.n_state, d.order, ops, terms, ev_ref, op_start, evt->n_rows, ep);
+    if (!err.empty()) return 0; // (hy_create2 keeps such a system on the interpreter)
+    const std::string src = hy::jit::evt_kernel_source(ep, state_row, d.order, defs, G, 2u * (d.n_state + ep.n_slots));
+    hy::jit::Image img;
+    const std::string jerr = hy::jit::build(src, kname, img);
+    if (!jerr.empty()) return fail("hy_jit_precompile_events: " + jerr);
+    if (from_cache) *from_cache = img.from_cache ? 1 : 0;
     if (compile_s) *compile_s = img.compile_s;
     return 0;
 }

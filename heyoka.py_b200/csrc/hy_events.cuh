@@ -303,11 +303,14 @@ static __device__ __noinline__ void detect_events(const R *w, const uint32_t *ev
     }
 }
 
-// Advance the cooldown clocks of a trajectory by |h| (run by one lane).
+// Advance the cooldown clocks of a trajectory by |h| (run by one lane).  Returns whether any cooldown
+// is still running (a caller that tracks this skips the call - three global loads per step - until
+// the next terminal event starts a cooldown).
 template <typename R>
-__device__ inline void advance_cooldowns(uint32_t traj, uint32_t n_tevents, R h, const EvParams<R> E)
+__device__ inline bool advance_cooldowns(uint32_t traj, uint32_t n_tevents, R h, const EvParams<R> E)
 {
     const R ah = h < 0 ? -h : h;
+    bool live = false;
     for (uint32_t e = 0; e < n_tevents; ++e) {
         const size_t ci = (size_t)traj * n_tevents + e;
         const R tot = E.cd_total[ci];
@@ -318,9 +321,11 @@ __device__ inline void advance_cooldowns(uint32_t traj, uint32_t n_tevents, R h,
                 E.cd_elapsed[ci] = 0;
             } else {
                 E.cd_elapsed[ci] = el;
+                live = true;
             }
         }
     }
+    return live;
 }
 
 } // namespace hy

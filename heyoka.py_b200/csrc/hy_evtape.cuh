@@ -135,6 +135,64 @@ __device__ __forceinline__ R evt_conv_ct(const R *__restrict__ pa, const R *__re
     return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
+// ---- product units of the generated event code (hy_jit.hpp, EvtGen): ONE lane computes orders 0, p-1
+// and p of a square / product from a single pass over its operands' coefficients (registers), and the
+// lanes of a trajectory's group work on different products at the same time - same code, operand
+// addresses selected by lane.  `al`: the operand is (jet + c), i.e. a LINCOMB "1 * x + c" that nobody
+// else reads (it differs from x at order 0 only, so its jet is never materialised).  The sums are
+// chained exactly like evt_exec's SQUARE / MUL (term u on chain u mod 4, folded (s0 + s1) + (s2 + s3)).
+template <typename R, int K> __device__ __forceinline__ R evt_sq_at(const R *v)
+{
+    constexpr int half = (K + 1) >> 1;
+    R s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < half; ++u) s[u & 3] = evt_fma(v[u], v[K - u], s[u & 3]);
+    R acc = (s[0] + s[1]) + (s[2] + s[3]);
+    acc = acc + acc;
+    if ((K & 1) == 0) acc = evt_fma(v[K >> 1], v[K >> 1], acc);
+    return acc;
+}
+template <typename R, int K> __device__ __forceinline__ R evt_mul_at(const R *a, const R *b)
+{
+    R s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u <= K; ++u) s[u & 3] = evt_fma(a[u], b[K - u], s[u & 3]);
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+template <typename R, int S, int P>
+__device__ __forceinline__ void evt_unit_sq(const R *__restrict__ a, bool al, R c, R *__restrict__ out, bool on)
+{
+    R v[P + 1];
+#pragma unroll
+    for (int u = 0; u <= P; ++u) v[u] = a[u * S];
+    if (al) v[0] = v[0] + c;
+    const R o0 = evt_sq_at<R, 0>(v), o1 = evt_sq_at<R, (P > 0 ? P - 1 : 0)>(v), o2 = evt_sq_at<R, P>(v);
+    if (on) {
+        out[0] = o0;
+        out[1] = o1;
+        out[2] = o2;
+    }
+}
+template <typename R, int SA, int SB, int P>
+__device__ __forceinline__ void evt_unit_mul(const R *__restrict__ a, bool ala, R ca, const R *__restrict__ b, bool alb,
+                                             R cb, R *__restrict__ out, bool on)
+{
+    R va[P + 1], vb[P + 1];
+#pragma unroll
+    for (int u = 0; u <= P; ++u) {
+        va[u] = a[u * SA];
+        vb[u] = b[u * SB];
+    }
+    if (ala) va[0] = va[0] + ca;
+    if (alb) vb[0] = vb[0] + cb;
+    const R o0 = evt_mul_at<R, 0>(va, vb), o1 = evt_mul_at<R, (P > 0 ? P - 1 : 0)>(va, vb), o2 = evt_mul_at<R, P>(va, vb);
+    if (on) {
+        out[0] = o0;
+        out[1] = o1;
+        out[2] = o2;
+    }
+}
+
 // sum_{j = j0}^{j1} (wk + j wj) * pa[j sa] * pb[(k - j) sb]  (the recurrences of pow / exp / log / sincos)
 template <typename R>
 static __device__ __noinline__ R evt_wconv(const R *__restrict__ pa, int sa, const R *__restrict__ pb, int sb, int k,
@@ -393,6 +451,27 @@ template <typename R, int S, int P> __device__ __forceinline__ Ival<R> iv_taylor
     const R d1 = c[S] * h, c0 = c[0];
     const R lo = c0 + fmin(d1, (R)0) - r, hi = c0 + fmax(d1, (R)0) + r;
     return iv_widen<R>(lo, hi);
+}
+
+// Pieces of evt_interval for the generated straight-line form (intervals in registers, literal coefficients).
+template <typename R> __device__ __forceinline__ Ival<R> iv_fix(Ival<R> v)
+{
+    if (!(v.lo == v.lo) || !(v.hi == v.hi)) v = iv_all<R>();
+    return v;
+}
+template <typename R> __device__ __forceinline__ void iv_lin_term(R &lo, R &hi, R c, Ival<R> x)
+{
+    lo += c >= (R)0 ? c * x.lo : c * x.hi;
+    hi += c >= (R)0 ? c * x.hi : c * x.lo;
+}
+template <typename R> __device__ __forceinline__ Ival<R> iv_lin_finish(R lo, R hi, int n)
+{
+    const R e = (R)(4 + 2 * n);
+    Ival<R> r = iv_widen<R>(lo, hi);
+    const R m = (fabs(lo) + fabs(hi)) * e * (sizeof(R) == 8 ? (R)2.3e-16 : (R)1.2e-07f);
+    r.lo -= m;
+    r.hi += m;
+    return iv_fix<R>(r);
 }
 
 // Interval image of one op given the intervals of its operands in iv[] (slot-indexed: slots

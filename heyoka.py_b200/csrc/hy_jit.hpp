@@ -24,6 +24,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,7 @@
 #include <numeric>
 #include <sstream>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/hy_cuda.h"
@@ -495,44 +497,430 @@ struct EvtGen {
         default: os << "      evt_exec<R, XS>(" << eop(o) << ", terms, C, " << Ks << "u);\n"; break;
         }
     }
+    // ------------------------------------------------------------------------------------------
+    // Plan of the lane-parallel form.  Three-order squares / products ("units") read only state jets and
+    // jets of every-order ops, never each other; they are de-duplicated (events often share y^2, z^2, ...),
+    // spread over the lanes of the trajectory's group and computed from ONE pass over the operands'
+    // coefficients; a LINCOMB "1 * x + c" that only units read is folded into their operand (alias).
+    // The three orders of every unit go to a scratch area (the interval scratch, unused at that
+    // point); lane 0 then runs the remaining three-order ops (LINCOMB / ADDSUB as literal code).
+    // ------------------------------------------------------------------------------------------
+    struct Opnd {
+        bool state = false; // C.w + off, stride XS;  else C.ews + off, stride 1
+        uint32_t off = 0;
+        bool al = false;
+        double c = 0;
+        bool operator<(const Opnd &o) const
+        {
+            uint64_t a, b;
+            std::memcpy(&a, &c, 8);
+            std::memcpy(&b, &o.c, 8);
+            return std::tie(state, off, al, a) < std::tie(o.state, o.off, o.al, b);
+        }
+    };
+    struct Unit {
+        int kind; // 0: square, 1: product
+        Opnd a, b;
+    };
+    uint32_t group = 2, scratch_len = 0;
+    std::vector<Unit> units;            // unique units
+    std::map<uint32_t, uint32_t> unit_of; // ews offset of a unit op's output -> unit
+    std::vector<char> alias;            // per op: folded into its consumers
+    std::vector<Opnd> alias_op;         // per op (alias): the operand it stands for
+    bool plan_ok = false;
+
+    static std::string lit(double v)
+    {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%a", v);
+        return std::string("(R)") + buf;
+    }
+    static bool is_ews(uint16_t ref) { return (ref & ER_KIND) == ER_CUR || (ref & ER_KIND) == ER_JET; }
+    bool plan()
+    {
+        const size_t n_ops = ep.ops.size();
+        alias.assign(n_ops, 0);
+        alias_op.assign(n_ops, Opnd());
+        std::map<uint32_t, size_t> prod; // ews offset -> producing op
+        for (size_t i = 0; i < n_ops; ++i) {
+            const EOp &o = ep.ops[i];
+            if (o.opcode == HY_OP_MULSH) {
+                for (uint32_t j = 0; j < o.n; ++j) prod[ep.terms[o.b + j].dst & 0x3fff] = i;
+            } else {
+                prod[o.dst & 0x3fff] = i;
+                if (o.opcode == HY_OP_SINCOS) prod[o.dst2 & 0x3fff] = i;
+            }
+        }
+        auto is_term = [](uint8_t oc) { return oc == HY_OP_LINCOMB || oc == HY_OP_SUMSQ || oc == HY_OP_MULSH; };
+        auto unit_op = [](const EOp &o) {
+            return !(o.flags & EOF_ALL) && (o.opcode == HY_OP_SQUARE || o.opcode == HY_OP_MUL || o.opcode == HY_OP_MULSH);
+        };
+        // alias candidates
+        for (size_t i = 0; i < n_ops; ++i) {
+            const EOp &o = ep.ops[i];
+            if (!(o.flags & EOF_ALL) || o.opcode != HY_OP_LINCOMB || (o.dst & ER_KIND) != ER_JET) continue;
+            int n_var = 0, n_one = 0;
+            Opnd q;
+            bool ok = true;
+            for (uint32_t j = 0; j < o.n; ++j) {
+                const ETerm &t = ep.terms[o.b + j];
+                if ((t.src & ER_KIND) == ER_ONE) {
+                    ++n_one;
+                    q.c = t.coef;
+                } else if ((t.src & ER_KIND) == ER_STATE && t.coef == 1.0) {
+                    ++n_var;
+                    q.state = true;
+                    q.off = state_row[t.src & 0x3fff];
+                } else
+                    ok = false;
+            }
+            if (!ok || n_var != 1 || n_one > 1) continue;
+            q.al = n_one == 1;
+            // every reader must be a unit
+            bool only_units = true;
+            const uint16_t me = o.dst & 0x3fff;
+            auto reads = [&](uint16_t ref) { return is_ews(ref) && (ref & 0x3fff) == me; };
+            for (size_t j = 0; j < n_ops && only_units; ++j) {
+                const EOp &c = ep.ops[j];
+                bool r = false;
+                if (is_term(c.opcode)) {
+                    for (uint32_t u = 0; u < c.n; ++u) r = r || reads(ep.terms[c.b + u].src);
+                    if (c.opcode == HY_OP_MULSH) r = r || reads(c.a);
+                } else if (c.opcode != HY_OP_TIME) {
+                    r = reads(c.a);
+                    if (c.opcode == HY_OP_MUL || c.opcode == HY_OP_DIV || c.opcode == HY_OP_ADDSUB) r = r || reads(c.b);
+                }
+                if (r && !unit_op(c)) only_units = false;
+            }
+            for (uint32_t off : ep.ev_off)
+                if (off == me) only_units = false; // (an event function itself)
+            if (!only_units) continue;
+            alias[i] = 1;
+            alias_op[i] = q;
+        }
+        // units
+        bool ok = true;
+        auto opnd = [&](uint16_t ref) -> Opnd {
+            Opnd q;
+            const uint16_t kind = ref & ER_KIND, off = ref & 0x3fff;
+            if (kind == ER_STATE) {
+                q.state = true;
+                q.off = state_row[off];
+            } else if (kind == ER_JET) {
+                auto it = prod.find(off);
+                if (it != prod.end() && alias[it->second])
+                    q = alias_op[it->second];
+                else
+                    q.off = off;
+            } else
+                ok = false; // (a product reading a single row or the unit jet: the serial form handles it)
+            return q;
+        };
+        std::map<std::tuple<int, Opnd, Opnd>, uint32_t> seen;
+        auto add = [&](int kind, Opnd a, Opnd b, uint16_t dst) {
+            auto key = std::make_tuple(kind, a, b);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (uint32_t)units.size()).first;
+                units.push_back(Unit{kind, a, b});
+            }
+            unit_of[dst & 0x3fff] = it->second;
+        };
+        for (size_t i = 0; i < n_ops; ++i) {
+            const EOp &o = ep.ops[i];
+            if (!unit_op(o)) continue;
+            if (o.opcode == HY_OP_SQUARE)
+                add(0, opnd(o.a), Opnd(), o.dst);
+            else if (o.opcode == HY_OP_MUL)
+                add(1, opnd(o.a), opnd(o.b), o.dst);
+            else
+                for (uint32_t j = 0; j < o.n; ++j) add(1, opnd(ep.terms[o.b + j].src), opnd(o.a), ep.terms[o.b + j].dst);
+        }
+        // a reader of a unit's output other than LINCOMB / ADDSUB (none is generated by the front end)
+        for (size_t i = 0; i < n_ops && ok; ++i) {
+            const EOp &o = ep.ops[i];
+            if (o.opcode == HY_OP_LINCOMB || o.opcode == HY_OP_ADDSUB || o.opcode == HY_OP_TIME) continue;
+            auto bad = [&](uint16_t ref) { return is_ews(ref) && unit_of.count(ref & 0x3fff); };
+            if (is_term(o.opcode)) {
+                for (uint32_t u = 0; u < o.n; ++u)
+                    if (bad(ep.terms[o.b + u].src)) ok = false;
+                if (o.opcode == HY_OP_MULSH && bad(o.a)) ok = false;
+            } else {
+                if (bad(o.a)) ok = false;
+                if ((o.opcode == HY_OP_MUL || o.opcode == HY_OP_DIV) && bad(o.b)) ok = false;
+            }
+        }
+        if (p < 2 || units.empty() || 3u * units.size() > scratch_len) ok = false;
+        plan_ok = ok;
+        if (!ok) {
+            alias.assign(n_ops, 0);
+            units.clear();
+            unit_of.clear();
+        }
+        return ok;
+    }
+    // "sub == 0 ? v0 : sub == 1 ? v1 : ... : v_last"
+    static std::string sel(const std::vector<std::string> &v)
+    {
+        bool same = true;
+        for (const auto &x : v) same = same && x == v[0];
+        if (same) return v[0];
+        std::string s;
+        for (size_t i = 0; i + 1 < v.size(); ++i) s += "sub == " + std::to_string(i) + "u ? " + v[i] + " : ";
+        return s + v.back();
+    }
+    // value of an operand of a three-order LINCOMB / ADDSUB at the literal order K (q = 0, 1, 2)
+    std::string val(uint16_t ref, uint32_t K, uint32_t q) const
+    {
+        const uint16_t kind = ref & ER_KIND, off = ref & 0x3fff;
+        if (kind == ER_ONE) return K == 0 ? "(R)1" : "(R)0";
+        if (kind == ER_STATE) return "C.w[" + std::to_string(state_row[off] ) + " + " + std::to_string(K) + " * XS]";
+        auto it = unit_of.find(off);
+        if (it != unit_of.end()) return "scr[" + std::to_string(3 * it->second + q) + "]";
+        return "C.ews[" + std::to_string(off + (kind == ER_JET ? K : 0u)) + "]";
+    }
+    void emit_units()
+    {
+        const uint32_t NL = std::min<uint32_t>(group, 8u);
+        // group by signature: same code on every lane of a round
+        std::map<std::tuple<int, bool, bool>, std::vector<uint32_t>> sig;
+        for (uint32_t u = 0; u < units.size(); ++u) sig[std::make_tuple(units[u].kind, units[u].a.state, units[u].b.state)].push_back(u);
+        for (const auto &g : sig) {
+            const int kind = std::get<0>(g.first);
+            const std::vector<uint32_t> &us = g.second;
+            for (size_t r0 = 0; r0 < us.size(); r0 += NL) {
+                const size_t cnt = std::min<size_t>(NL, us.size() - r0);
+                std::vector<std::string> oa, ala, ca, ob, alb, cb, so;
+                bool any_ala = false, any_alb = false;
+                for (size_t l = 0; l < cnt; ++l) {
+                    const Unit &U = units[us[r0 + l]];
+                    oa.push_back(std::to_string(U.a.off) + "u");
+                    ala.push_back(U.a.al ? "true" : "false");
+                    ca.push_back(lit(U.a.al ? U.a.c : 0.0));
+                    ob.push_back(std::to_string(U.b.off) + "u");
+                    alb.push_back(U.b.al ? "true" : "false");
+                    cb.push_back(lit(U.b.al ? U.b.c : 0.0));
+                    so.push_back(std::to_string(3 * us[r0 + l]) + "u");
+                    any_ala = any_ala || U.a.al;
+                    any_alb = any_alb || U.b.al;
+                }
+                const Unit &U0 = units[us[r0]];
+                const std::string sa = U0.a.state ? "XS" : "1", sb = U0.b.state ? "XS" : "1";
+                const std::string ba = U0.a.state ? "C.w" : "C.ews", bb = U0.b.state ? "C.w" : "C.ews";
+                os << "    { // " << cnt << (kind ? " product(s)" : " square(s)") << "\n";
+                os << "      const bool on = sub < " << cnt << "u;\n";
+                os << "      const R *a = " << ba << " + (" << sel(oa) << ");\n";
+                if (any_ala) os << "      const bool ala = " << sel(ala) << "; const R ca = " << sel(ca) << ";\n";
+                if (kind) {
+                    os << "      const R *b = " << bb << " + (" << sel(ob) << ");\n";
+                    if (any_alb) os << "      const bool alb = " << sel(alb) << "; const R cb = " << sel(cb) << ";\n";
+                }
+                os << "      R *out = scr + (" << sel(so) << ");\n";
+                if (kind)
+                    os << "      evt_unit_mul<R, " << sa << ", " << sb << ", " << p << ">(a, " << (any_ala ? "ala, ca" : "false, (R)0")
+                       << ", b, " << (any_alb ? "alb, cb" : "false, (R)0") << ", out, on);\n";
+                else
+                    os << "      evt_unit_sq<R, " << sa << ", " << p << ">(a, " << (any_ala ? "ala, ca" : "false, (R)0") << ", out, on);\n";
+                os << "    }\n";
+            }
+        }
+    }
+    // lane 0: the three-order ops that are not units, at the literal order K
+    void emit_rest_at(const EOp &o, uint32_t K, uint32_t q)
+    {
+        const ETerm *t = ep.terms.data() + o.b;
+        switch (o.opcode) {
+        case HY_OP_SQUARE:
+        case HY_OP_MUL:
+            if ((o.dst & ER_KIND) == ER_JET) os << "      C.st(" << o.dst << ", " << K << ", " << val(o.dst, K, q) << ");\n";
+            break;
+        case HY_OP_MULSH:
+            for (uint32_t j = 0; j < o.n; ++j)
+                if ((t[j].dst & ER_KIND) == ER_JET) os << "      C.st(" << t[j].dst << ", " << K << ", " << val(t[j].dst, K, q) << ");\n";
+            break;
+        case HY_OP_LINCOMB:
+            os << "      { R acc = 0;\n";
+            for (uint32_t j = 0; j < o.n; ++j) os << "        acc = evt_fma(" << lit(t[j].coef) << ", " << val(t[j].src, K, q) << ", acc);\n";
+            os << "        C.st(" << o.dst << ", " << K << ", acc); }\n";
+            break;
+        case HY_OP_ADDSUB:
+            os << "      C.st(" << o.dst << ", " << K << ", " << ((o.flags & EOF_NEGA) ? "-" : "") << val(o.a, K, q) << " + "
+               << ((o.flags & EOF_NEGB) ? "-" : "") << val(o.b, K, q) << ");\n";
+            break;
+        default: emit_at(o, K); break;
+        }
+    }
     std::string source()
     {
-        os << "// event functions: " << ep.ops.size() << " ops, " << ep.ev_slot.size() << " events, order " << p << "\n";
-        os << "template <typename R, int XS> __device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm *terms)\n{\n";
-        for (const EOp &o : ep.ops)
-            if (o.flags & EOF_ALL) os << "    evt_exec_all<R, XS>(" << eop(o) << ", terms, C, " << p << "u);\n";
-        for (uint32_t K : {0u, p - 1u, p}) {
-            os << "    { // order " << K << "\n";
-            for (const EOp &o : ep.ops)
-                if (!(o.flags & EOF_ALL)) emit_at(o, K);
+        plan();
+        const uint32_t P3[3] = {0u, p - 1u, p};
+        os << "// event functions: " << ep.ops.size() << " ops, " << ep.ev_slot.size() << " events, order " << p << "; "
+           << (plan_ok ? std::to_string(units.size()) + " product units on the lanes of the group" : std::string("serial form")) << "\n";
+        os << "template <typename R, int XS>\n__device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm "
+              "*terms, R *scr, uint32_t sub)\n{\n    (void)terms; (void)scr;\n";
+        if (plan_ok) {
+            bool any_all = false;
+            for (size_t i = 0; i < ep.ops.size(); ++i) any_all = any_all || ((ep.ops[i].flags & EOF_ALL) && !alias[i]);
+            if (any_all) {
+                os << "    if (sub == 0) {\n";
+                for (size_t i = 0; i < ep.ops.size(); ++i)
+                    if ((ep.ops[i].flags & EOF_ALL) && !alias[i])
+                        os << "      evt_exec_all<R, XS>(" << eop(ep.ops[i]) << ", terms, C, " << p << "u);\n";
+                os << "    }\n    __syncwarp();\n";
+            }
+            emit_units();
+            os << "    __syncwarp();\n    if (sub == 0) {\n";
+            for (uint32_t q = 0; q < 3; ++q) {
+                os << "    { // order " << P3[q] << "\n";
+                for (const EOp &o : ep.ops)
+                    if (!(o.flags & EOF_ALL)) emit_rest_at(o, P3[q], q);
+                os << "    }\n";
+            }
             os << "    }\n";
+        } else {
+            os << "    if (sub != 0) return;\n";
+            for (const EOp &o : ep.ops)
+                if (o.flags & EOF_ALL) os << "    evt_exec_all<R, XS>(" << eop(o) << ", terms, C, " << p << "u);\n";
+            for (uint32_t K : P3) {
+                os << "    { // order " << K << "\n";
+                for (const EOp &o : ep.ops)
+                    if (!(o.flags & EOF_ALL)) emit_at(o, K);
+                os << "    }\n";
+            }
         }
         os << "}\n";
+        // the remaining orders (rare: an event may happen in this step), lane 0
         os << "template <typename R, int XS>\n__device__ __forceinline__ void hy_gen_evt_order(const EvtCtx<R, XS> &C, const ETerm *terms, uint32_t k)\n{\n";
         os << "    (void)C; (void)terms; (void)k;\n";
+        bool any_alias = false;
+        for (size_t i = 0; i < ep.ops.size(); ++i) any_alias = any_alias || alias[i];
+        if (any_alias) {
+            os << "    if (k == 1u) { // (the folded operands as jets: the generic ops below read them)\n";
+            for (size_t i = 0; i < ep.ops.size(); ++i)
+                if (alias[i]) os << "      evt_exec_all<R, XS>(" << eop(ep.ops[i]) << ", terms, C, " << p << "u);\n";
+            os << "    }\n";
+        }
         for (const EOp &o : ep.ops)
             if (!(o.flags & EOF_ALL)) os << "    evt_exec<R, XS>(" << eop(o) << ", terms, C, k);\n";
         os << "}\n";
-        os << "template <typename R, int XS>\n__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, "
-              "const double *imm, R t0, R h)\n{\n    (void)terms; (void)imm; (void)t0;\n";
-        for (size_t i = 0; i < ep.state_used.size(); ++i)
-            if (ep.state_used[i])
-                os << "    { const Ival<R> v = iv_taylor_abs<R, XS, " << p << ">(w + " << state_row[i] << ", h); iv[" << 2 * i
-                   << "] = v.lo; iv[" << 2 * i + 1 << "] = v.hi; }\n";
-        for (const EOp &o : ep.ops) os << "    evt_interval<R>(" << eop(o) << ", terms, iv, imm, t0, h);\n";
-        os << "    bool maybe = false;\n";
-        for (uint32_t sl : ep.ev_slot)
-            os << "    { const R glo = iv[" << 2 * sl << "], ghi = iv[" << 2 * sl + 1 << "]; if (!(glo > (R)0 || ghi < (R)0)) maybe = true; }\n";
-        os << "    return maybe;\n}\n";
+        emit_interval();
         return os.str();
+    }
+    // Interval pass: the state enclosures on the lanes of the group, then the tape on lane 0 - intervals in
+    // registers and literal coefficients when every op is algebraic, the generic evt_interval otherwise.
+    void emit_interval()
+    {
+        os << "template <typename R, int XS>\n__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, "
+              "const double *imm, R t0, R h, uint32_t sub)\n{\n    (void)terms; (void)imm; (void)t0;\n";
+        std::vector<uint32_t> used;
+        for (size_t i = 0; i < ep.state_used.size(); ++i)
+            if (ep.state_used[i]) used.push_back((uint32_t)i);
+        const uint32_t NL = std::min<uint32_t>(group, 8u);
+        for (size_t r0 = 0; r0 < used.size(); r0 += NL) {
+            const size_t cnt = std::min<size_t>(NL, used.size() - r0);
+            std::vector<std::string> row, slot;
+            for (size_t l = 0; l < cnt; ++l) {
+                row.push_back(std::to_string(state_row[used[r0 + l]]) + "u");
+                slot.push_back(std::to_string(2 * used[r0 + l]) + "u");
+            }
+            os << "    { const Ival<R> v = iv_taylor_abs<R, XS, " << p << ">(w + (" << sel(row) << "), h);\n";
+            os << "      if (sub < " << cnt << "u) { R *o = iv + (" << sel(slot) << "); o[0] = v.lo; o[1] = v.hi; } }\n";
+        }
+        os << "    __syncwarp();\n    bool maybe = false;\n    if (sub == 0) {\n";
+        bool simple = true;
+        for (const EOp &o : ep.ops)
+            simple = simple && (o.opcode == HY_OP_LINCOMB || o.opcode == HY_OP_ADDSUB || o.opcode == HY_OP_MUL ||
+                                o.opcode == HY_OP_SQUARE || o.opcode == HY_OP_SUMSQ || o.opcode == HY_OP_MULSH);
+        if (simple) {
+            std::map<uint32_t, std::string> name; // slot -> variable
+            for (uint32_t i : used) {
+                name[i] = "s" + std::to_string(i);
+                os << "      const Ival<R> s" << i << " = {iv[" << 2 * i << "], iv[" << 2 * i + 1 << "]};\n";
+            }
+            std::map<std::tuple<int, std::string, std::string>, std::string> seen;
+            auto get = [&](uint16_t ref, uint16_t slot) -> std::string {
+                if ((ref & ER_KIND) == ER_ONE) return "Ival<R>{(R)1, (R)1}";
+                auto it = name.find(slot);
+                return it == name.end() ? std::string("iv_all<R>()") : it->second;
+            };
+            auto def = [&](uint16_t slot, int kind, const std::string &a, const std::string &b, const std::string &expr) {
+                auto key = std::make_tuple(kind, a, b);
+                if (kind >= 0) {
+                    auto it = seen.find(key);
+                    if (it != seen.end()) {
+                        name[slot] = it->second;
+                        return;
+                    }
+                }
+                const std::string nm = "s" + std::to_string(slot);
+                os << "      const Ival<R> " << nm << " = iv_fix<R>(" << expr << ");\n";
+                name[slot] = nm;
+                if (kind >= 0) seen[key] = nm;
+            };
+            for (const EOp &o : ep.ops) {
+                const ETerm *t = ep.terms.data() + o.b;
+                switch (o.opcode) {
+                case HY_OP_SQUARE: {
+                    const std::string a = get(o.a, o.sa);
+                    def(o.sd, 0, a, "", "iv_sqr<R>(" + a + ")");
+                } break;
+                case HY_OP_MUL: {
+                    const std::string a = get(o.a, o.sa), b = get(o.b, o.sb);
+                    def(o.sd, 1, a, b, "iv_mul<R>(" + a + ", " + b + ")");
+                } break;
+                case HY_OP_MULSH: {
+                    const std::string b = get(o.a, o.sa);
+                    for (uint32_t j = 0; j < o.n; ++j) {
+                        const std::string a = get(t[j].src, t[j].ssrc);
+                        def(t[j].sdst, 1, a, b, "iv_mul<R>(" + a + ", " + b + ")");
+                    }
+                } break;
+                case HY_OP_ADDSUB: {
+                    const std::string a = get(o.a, o.sa), b = get(o.b, o.sb);
+                    const std::string alo = (o.flags & EOF_NEGA) ? "-" + a + ".hi" : a + ".lo", ahi = (o.flags & EOF_NEGA) ? "-" + a + ".lo" : a + ".hi";
+                    const std::string blo = (o.flags & EOF_NEGB) ? "-" + b + ".hi" : b + ".lo", bhi = (o.flags & EOF_NEGB) ? "-" + b + ".lo" : b + ".hi";
+                    def(o.sd, -1, "", "", "iv_widen<R>(" + alo + " + " + blo + ", " + ahi + " + " + bhi + ")");
+                } break;
+                case HY_OP_SUMSQ: {
+                    os << "      R l" << o.sd << " = 0, h" << o.sd << " = 0;\n";
+                    for (uint32_t j = 0; j < o.n; ++j)
+                        os << "      { const Ival<R> q = iv_sqr<R>(" << get(t[j].src, t[j].ssrc) << "); l" << o.sd << " += q.lo; h" << o.sd
+                           << " += q.hi; }\n";
+                    def(o.sd, -1, "", "", "iv_widen<R>(l" + std::to_string(o.sd) + ", h" + std::to_string(o.sd) + ")");
+                } break;
+                default: { // LINCOMB
+                    os << "      R l" << o.sd << " = 0, h" << o.sd << " = 0;\n";
+                    for (uint32_t j = 0; j < o.n; ++j)
+                        os << "      iv_lin_term<R>(l" << o.sd << ", h" << o.sd << ", " << lit(t[j].coef) << ", " << get(t[j].src, t[j].ssrc)
+                           << ");\n";
+                    os << "      const Ival<R> s" << o.sd << " = iv_lin_finish<R>(l" << o.sd << ", h" << o.sd << ", " << o.n << ");\n";
+                    name[o.sd] = "s" + std::to_string(o.sd);
+                } break;
+                }
+            }
+            for (uint32_t sl : ep.ev_slot) {
+                const std::string g = name.count(sl) ? name[sl] : std::string("iv_all<R>()");
+                os << "      { const Ival<R> g = " << g << "; if (!(g.lo > (R)0 || g.hi < (R)0)) maybe = true; }\n";
+            }
+        } else {
+            for (const EOp &o : ep.ops) os << "      evt_interval<R>(" << eop(o) << ", terms, iv, imm, t0, h);\n";
+            for (uint32_t sl : ep.ev_slot)
+                os << "      { const R glo = iv[" << 2 * sl << "], ghi = iv[" << 2 * sl + 1
+                   << "]; if (!(glo > (R)0 || ghi < (R)0)) maybe = true; }\n";
+        }
+        os << "    }\n    return maybe;\n}\n";
     }
 };
 
 // Translation unit of a register-resident kernel (FX build) with generated event functions.
+// `group`: lanes per trajectory of the kernel; `scratch_len`: elements of the interval scratch (it doubles as
+// the exchange area of the lane-parallel products).
 inline std::string evt_kernel_source(const EvtProgram &ep, const std::vector<uint32_t> &state_row, uint32_t order,
-                                     const std::string &defs = "")
+                                     const std::string &defs = "", uint32_t group = 1, uint32_t scratch_len = 0)
 {
     EvtGen g(ep, state_row, order);
+    g.group = group;
+    g.scratch_len = scratch_len;
     std::string s = defs + "#define HY_JIT_EVT 1\n#include \"hy_kernels.cuh\"\nnamespace hy {\n";
     s += g.source();
     s += "} // namespace hy\n";

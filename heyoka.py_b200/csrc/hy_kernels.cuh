@@ -47,11 +47,13 @@ namespace hy {
 // first lane of the trajectory's group.  norms: the ops needed at every order over all orders, the
 // rest at orders 0, p-1, p; order: the rest at one more order (rare path: an event may happen);
 // interval: enclosures of the event functions over the step, true if one of them contains 0.
-template <typename R, int XS> __device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm *terms);
+template <typename R, int XS>
+__device__ __forceinline__ void hy_gen_evt_norms(const EvtCtx<R, XS> &C, const ETerm *terms, R *scr, uint32_t sub);
 template <typename R, int XS>
 __device__ __forceinline__ void hy_gen_evt_order(const EvtCtx<R, XS> &C, const ETerm *terms, uint32_t k);
 template <typename R, int XS>
-__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, const double *imm, R t0, R h);
+__device__ __forceinline__ bool hy_gen_evt_interval(const R *w, R *iv, const ETerm *terms, const double *imm, R t0, R h,
+                                                    uint32_t sub);
 #endif
 #ifdef HY_JIT
 // generated per tape: orders 0 .. p-1 of every op / the event-function ops at order p
@@ -1379,6 +1381,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
     R hi = 0, lo = 0, mdt = 0, tf_hi = 0, tf_lo = 0;
     uint32_t gi = 0; // next grid point to emit (MODE_GRID)
     uint32_t cc = 0; // recorded continuous-output steps
+    bool cd_live = true; // (register kernels with events) a terminal-event cooldown may be running
     // (recorder state other than the step count `cc` is NOT kept in registers across the jets: the id of
     //  the lane's last chunk is re-read from P.rec.tail once per recorded step; the per-launch step
     //  budget is checked against the step count at fetch time, kept in shared memory)
@@ -1421,6 +1424,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 }
                 gi = (FX && P.resume) ? P.gidx[traj] : 0u;
                 cc = 0;
+                cd_live = true;
                 if (P.mode == MODE_GRID && !(FX && P.resume)) {
                     // Grid points at (or before) the starting time take the current state.
                     const R dir = tf_hi - hi;
@@ -1588,7 +1592,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 if (reg_events) {
                     const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
 #ifdef HY_JIT_EVT
-                    if (sub == 0) hy_gen_evt_norms<R, (int)XS>(ec, s_eterms);
+                    // (every lane of the group: the products are spread over the lanes; the interval scratch
+                    //  is free here and carries their results to lane 0)
+                    hy_gen_evt_norms<R, (int)XS>(ec, s_eterms, w + P.evt.eiv_off, sub);
 #else
                     for (uint32_t e = sub; e < P.evt.n_events; e += G) {
                         const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
@@ -1737,7 +1743,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     R *iv = w + P.evt.eiv_off;
                     bool maybe = false;
 #ifdef HY_JIT_EVT
-                    if (sub == 0) maybe = hy_gen_evt_interval<R, (int)XS>(w, iv, s_eterms, s_eimm, hi, h);
+                    maybe = hy_gen_evt_interval<R, (int)XS>(w, iv, s_eterms, s_eimm, hi, h, sub);
 #else
                     for (uint32_t i = sub; i < n; i += G) {
                         if (!s_eused[i]) continue; // (no event reads this state variable)
@@ -1795,7 +1801,9 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                             so = -(long long)term_ev - 1;
                         }
                     }
-                    if (stepping && sub == 0 && d.n_tevents) advance_cooldowns<R>(traj, d.n_tevents, h, P.ev);
+                    // (cd_live: a cooldown may be running - after the fetch, and from a terminal event on)
+                    if (term_ev >= 0) cd_live = true;
+                    if (stepping && sub == 0 && d.n_tevents && cd_live) cd_live = advance_cooldowns<R>(traj, d.n_tevents, h, P.ev);
                     __syncwarp();
                 }
             }

@@ -153,6 +153,7 @@ SYMBOLS = [
     "hy_get_launch_info",
     "hy_tape_kernel_variant",
     "hy_jit_precompile",
+    "hy_jit_precompile_events",
     "hy_measure_fma_peak",
 ]
 
@@ -195,6 +196,22 @@ def jit_precompile(dc, fp_bits=64, batch=1 << 20, n_tevents=0):
     full = tape_t(C.addressof(dims), _vp(dc.ops), _vp(dc.terms), _vp(dc.level_start), _vp(dc.ev_ref))
     fc, cs = C.c_int(0), C.c_double(0.0)
     check(lib().hy_jit_precompile(C.c_int(fp_bits), C.byref(full), C.c_uint32(batch), C.byref(fc), C.byref(cs)))
+    return fc.value, cs.value
+
+
+def jit_precompile_events(dc, dc_ode, evt, fp_bits=64, n_tevents=0):
+    """hy_jit_precompile_events: the generated event functions of a system that a register-resident
+    kernel serves (same tapes as hy_create2), compiled without a device.  Returns (from_cache,
+    compile_seconds); from_cache is -1 when the system gets no such kernel."""
+    dims = _dims_of(dc, n_tevents)
+    d_ode = _dims_of(dc_ode, 0, 0)
+    full = tape_t(C.addressof(dims), _vp(dc.ops), _vp(dc.terms), _vp(dc.level_start), _vp(dc.ev_ref))
+    ode = tape_t(C.addressof(d_ode), _vp(dc_ode.ops), _vp(dc_ode.terms), _vp(dc_ode.level_start), None)
+    et = event_tape_t(len(evt.ops), len(evt.terms), evt.n_rows, evt.n_events, _vp(evt.ops), _vp(evt.terms),
+                      _vp(evt.ev_ref), _vp(evt.op_start))
+    fc, cs = C.c_int(0), C.c_double(0.0)
+    check(lib().hy_jit_precompile_events(C.c_int(fp_bits), C.byref(full), C.byref(ode), C.byref(et), C.byref(fc),
+                                         C.byref(cs)))
     return fc.value, cs.value
 
 

@@ -368,6 +368,11 @@ int hy_tape_kernel_variant(const hy_dims *dims, const hy_op *ops, const hy_term 
  * *from_cache: 1 the kernel was already cached, 0 it was compiled now (*compile_s seconds), -1 the
  * tape is served by the interpreter (no kernel is generated for it). */
 int hy_jit_precompile(int fp_bits, const hy_tape *full, uint32_t batch, int *from_cache, double *compile_s);
+/* The same for the generated event functions of a system that a register-resident kernel serves
+ * (`ode`: the ODE-only tape, `evt`: the event tape, as for hy_create2).  *from_cache = -1: no such
+ * kernel exists for the system (its events run on the tape interpreter). */
+int hy_jit_precompile_events(int fp_bits, const hy_tape *full, const hy_tape *ode, const hy_event_tape *evt,
+                             int *from_cache, double *compile_s);
 
 /* DFMA/FFMA peak microbenchmark used as the compute roof (no peak for
  * FP64/FP32 FMA is in MEASURED_PEAKS.json): returns TFLOP/s. */

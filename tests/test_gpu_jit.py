@@ -329,3 +329,24 @@ print("fallback ok", li["group"])
                PYTHONPATH=os.pathsep.join(sys.path))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_thread_ensemble_on_a_compiled_kernel():
+    # ensemble iterations clone the template's context (hy_clone loads the compiled image again) and
+    # run concurrently from a thread pool: same results as serial runs of the same initial conditions
+    vs = hy.var_ode_sys(W.kepler_j2_sys(), hy.var_args.vars)
+    B, n_iter = 32, 6
+    ics = [W.kepler_j2_ensemble(B, seed=100 + i) for i in range(n_iter)]
+    tmpl = hy.taylor_adaptive_batch(vs, ics[0])
+    assert tmpl._ctx.launch_info()["kernel_variant"] == JIT
+
+    def gen(ta, i):
+        ta.state[:6] = ics[i]
+        return ta
+
+    res = hy.ensemble_propagate_until_batch(tmpl, 2500.0, n_iter, gen)
+    for i, r in enumerate(res):
+        ref = hy.taylor_adaptive_batch(vs, ics[i])
+        ref.propagate_until(2500.0)
+        assert np.array_equal(r[0].state, ref.state), i
+        assert np.array_equal(r[0].propagate_res_arrays[3], ref.propagate_res_arrays[3])

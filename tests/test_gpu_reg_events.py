@@ -187,3 +187,59 @@ def test_generated_event_code_vs_interpreted_event_tape():
     calm = ds < 1e-7
     assert calm.mean() > 0.95 and np.max(dt[calm]) < 1e-7
     assert np.array_equal(a.propagate_res_arrays[3][same & calm], b.propagate_res_arrays[3][same & calm])
+
+
+def _gen_vs_interp_events(sys_, ic, evs, variant, T):
+    """The same event-carrying system with the event tape interpreted (HY_CUDA_JIT_EVT=0) and as generated
+    code (=2: products spread over the lanes of the group, shared sub-expressions computed once, "x + c"
+    folded into its readers).  The generated code chains every sum like the interpreter: bit for bit."""
+    logs = {}
+
+    def mk(key, mode):
+        logs[key] = []
+
+        def cb(ta, t, d_sgn, bidx):
+            logs[key].append((bidx, float(t), d_sgn))
+
+        os.environ["HY_CUDA_JIT_EVT"] = mode
+        try:
+            ta = hy.taylor_adaptive_batch(sys_, ic, nt_events=[hy.nt_event_batch(e, cb) for e in evs])
+            ta._ctx
+        finally:
+            del os.environ["HY_CUDA_JIT_EVT"]
+        assert ta._ctx.launch_info()["kernel_variant"] == variant
+        return ta
+
+    a, b = mk("a", "0"), mk("b", "2")
+    a.propagate_until(T)
+    b.propagate_until(T)
+    ka = sorted(logs["a"], key=lambda r: (r[0], r[1]))
+    kb = sorted(logs["b"], key=lambda r: (r[0], r[1]))
+    assert len(ka) > 2 * ic.shape[1]
+    assert ka == kb
+    assert np.array_equal(a.state, b.state) and np.array_equal(a.time, b.time)
+    assert np.array_equal(a.propagate_res_arrays[3], b.propagate_res_arrays[3])
+
+
+def test_generated_events_nbody_lane_parallel_products():
+    # 16 lanes per trajectory: squares of every-order differences (unit-stride operands), products of
+    # state jets, products of folded "x + c" operands, a repeated square
+    sys_ = W.oss_sys()
+    ic = W.oss_ensemble(8)
+    v = lambda s: hy.expression(s)
+    dx, dy, dz = v("x_1") - v("x_2"), v("y_1") - v("y_2"), v("z_1") - v("z_2")
+    evs = [dx * dx + dy * dy + dz * dz - 60.0,
+           v("x_1") * v("vy_1") - v("y_1") * v("vx_1") - 2.0,
+           (v("x_1") + 0.5) * (v("y_1") - 0.25),
+           v("y_1"),
+           v("vx_5") * v("vx_5") - 1e-2,
+           dx * dx - 4.0]
+    _gen_vs_interp_events(sys_, ic, evs, 6, 60.0)
+
+
+def test_generated_events_cr3bp_recurrences_and_products():
+    # recurrent ops (sqrt, sin(time)) keep the generic interval pass and the every-order pass on lane 0
+    sys_ = W.cr3bp_sys(0.01)
+    x, y, z, px = hy.make_vars("x", "y", "z", "px")
+    evs = [hy.sqrt(x * x + y * y) - (0.9 + 0.05 * hy.sin(hy.time)), px, (x - 0.3) * (y + 0.1), (x - 0.3) ** 2 + y * y - 0.5]
+    _gen_vs_interp_events(sys_, W.cr3bp_ensemble(32), evs, 203, 10.0)

@@ -72,3 +72,36 @@ def test_order_blocking_variant_compiles(jit_cache, monkeypatch):
     monkeypatch.setenv("HY_CUDA_JIT_BLOCK", "4")
     assert _cabi.jit_precompile(dc, 64, batch=64)[0] == 0
     assert len(_images(jit_cache)) == 2
+
+
+def test_event_code_generation_without_a_device(tmp_path, monkeypatch):
+    # hy_jit_precompile_events: the event functions of a system on a register-resident kernel, generated
+    # and compiled device-less.  The source shows the lane-parallel plan: config 5's nine squares are five
+    # distinct ones ((x - mu)^2, (x - mu + 1)^2, x^2, y^2, z^2), "x - mu" never becomes a jet of its own.
+    import hy_b200 as hy
+    from hy_b200 import _cabi, decompose as D, workloads as W
+
+    monkeypatch.setenv("HY_CUDA_JIT_CACHE", str(tmp_path / "cache"))
+    monkeypatch.setenv("HY_CUDA_JIT_DUMP", str(tmp_path))
+    mu, order = 0.01, 20
+    x, y, z = hy.make_vars("x", "y", "z")
+    evs = [(x - mu) ** 2 + y * y + z * z - 0.012 ** 2, (x - mu + 1.0) ** 2 + y * y + z * z - 0.012 ** 2,
+           x * x + y * y + z * z - 25.0]
+    sys5 = W.cr3bp_sys(mu)
+    args = (D.decompose(sys5, order, events=evs), D.decompose(sys5, order),
+            D.decompose_event_tape(evs, [l.name for l, _ in sys5], order))
+    fc, secs = _cabi.jit_precompile_events(*args, 64, n_tevents=3)
+    assert fc == 0 and secs > 0
+    src = "".join(p.read_text() for p in tmp_path.glob("hy_jit_*.cu"))
+    assert "5 product units on the lanes of the group" in src
+    assert src.count("evt_unit_sq<R, XS, 20>") == 3            # 5 squares on 2 lanes: 3 rounds
+    norms = src.split("hy_gen_evt_order")[0]
+    assert "evt_exec_all" not in norms                         # the folded operands are not materialised ...
+    assert src.split("hy_gen_evt_order")[1].count("evt_exec_all") == 2   # ... unless the root finder runs
+    assert _cabi.jit_precompile_events(*args, 64, n_tevents=3)[0] == 1     # second time: from the cache
+    # a system with no register-resident kernel has no such build
+    xx, vv = hy.make_vars("x", "v")
+    pend = [(xx, vv), (vv, -9.8 * hy.sin(xx))]
+    pe = [xx - 0.1]
+    assert _cabi.jit_precompile_events(D.decompose(pend, order, events=pe), D.decompose(pend, order),
+                                       D.decompose_event_tape(pe, ["x", "v"], order), 64, n_tevents=1)[0] == -1
