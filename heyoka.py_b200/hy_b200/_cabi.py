@@ -246,6 +246,71 @@ class PinnedArray:
             pass
 
 
+class _PinnedBlock:
+    """One pinned buffer of the output pool handed out as an ndarray (np.asarray(block)): the array's
+    base keeps the block alive, the block goes back to the pool with the last view."""
+
+    def __init__(self, pool, p, cap, shape, dtype):
+        self._pool, self._p, self._cap = pool, p, cap
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str, "data": (p, False),
+                                    "version": 3}
+
+    def __del__(self):
+        try:
+            self._pool._give(self._p, self._cap)
+        except Exception:
+            pass
+
+
+class PinnedPool:
+    """Recycled page-locked result buffers.  A large result (the [k, n, B] array of a continuous-output
+    evaluation) written into fresh pageable memory costs a page fault per 4 KiB and a staged copy - several
+    times the kernel that produced it; a pinned buffer that a previous, dropped result has released takes
+    the DMA directly.  Arrays the caller keeps stay valid (their buffer is not reused while referenced)."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self, keep_bytes=4 << 30):
+        import threading
+
+        self._lock = threading.Lock()
+        self._free = []  # (cap, ptr)
+        self._kept = 0
+        self._keep_bytes = keep_bytes
+
+    def array(self, shape, dtype):
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        if nbytes < self.MIN_BYTES:
+            return np.zeros(shape, dtype=dtype)
+        p = None
+        with self._lock:
+            best = None
+            for i, (cap, _) in enumerate(self._free):
+                if nbytes <= cap <= 2 * nbytes and (best is None or cap < self._free[best][0]):
+                    best = i
+            if best is not None:
+                cap, p = self._free.pop(best)
+                self._kept -= cap
+        if p is None:
+            cap = (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)
+            q = C.c_void_p()
+            if lib().hy_host_alloc(C.byref(q), C.c_size_t(cap)) != 0 or not q.value:
+                return np.zeros(shape, dtype=dtype)  # (no page-locked memory left: an ordinary array)
+            p = q.value
+        return np.asarray(_PinnedBlock(self, p, cap, shape, dtype))
+
+    def _give(self, p, cap):
+        with self._lock:
+            if self._kept + cap <= self._keep_bytes:
+                self._free.append((cap, p))
+                self._kept += cap
+                return
+        lib().hy_host_free(C.c_void_p(p))
+
+
+OUT_POOL = PinnedPool()
+
+
 def _vp(a):
     return None if a is None else a.ctypes.data
 

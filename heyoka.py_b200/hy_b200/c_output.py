@@ -81,9 +81,10 @@ class continuous_output_batch_impl:
                         "number of columns must be {} but it is {} instead".format(B, arr.shape[1])
                     )
                 k = arr.shape[0]
-                out = np.zeros((k, n, B), dtype=fp)
+                # (large results land in a recycled page-locked buffer: _cabi.PinnedPool)
+                out = _cabi.OUT_POOL.array((k, n, B), fp)
                 if k:
-                    tt = np.ascontiguousarray(arr.astype(fp))
+                    tt = np.ascontiguousarray(arr, dtype=fp)
                     self._rec.eval(tt, k, out)
                 return out
             raise ValueError(

@@ -382,3 +382,27 @@ def test_cout_eval_with_device_pointers_matches_host_path():
     rec.eval_dev(d_tq.data_ptr(), K, d_out.data_ptr())
     assert np.array_equal(d_out.cpu().numpy(), out_h)
     rec.close()
+
+
+def test_large_dense_output_lands_in_recycled_pinned_buffers():
+    # c_out(t) with a [k, B] time grid: results of a MiB and more are written into page-locked buffers of
+    # _cabi.OUT_POOL; a buffer is reused only after the array that holds it is gone
+    sys_ = W.cr3bp_sys(0.01)
+    B, K = 2048, 16
+    ta = hy.taylor_adaptive_batch(sys_, W.cr3bp_ensemble(B))
+    c_out, _ = ta.propagate_until(2.0, c_output=True)
+    tq = np.linspace(0.0, 2.0, K)[:, None] * np.ones((1, B))
+    a = c_out(tq)
+    pa = a.ctypes.data
+    assert a.shape == (K, 6, B) and a.flags.writeable and type(a.base).__name__ == "_PinnedBlock"
+    b = c_out(tq[::-1].copy())
+    assert b.ctypes.data != pa                       # `a` is alive: its buffer is not handed out again
+    assert np.array_equal(a, b[::-1])
+    assert np.allclose(a[-1], ta.state, rtol=0, atol=1e-12)   # t = 2: the final state
+    keep = a.copy()
+    del a
+    c = c_out(tq)
+    assert c.ctypes.data == pa and np.array_equal(c, keep)   # the released buffer, reused
+    small = c_out(tq[:1])                            # below a MiB: an ordinary array
+    assert small.base is None or type(small.base).__name__ != "_PinnedBlock"
+    assert np.array_equal(small[0], keep[0])
