@@ -112,6 +112,7 @@ struct hy_ctx {
     unsigned char *d_active = nullptr;
     uint32_t *d_gidx = nullptr;
     void *d_gws = nullptr;
+    void *d_evws = nullptr; // event workspace slab of the register-resident kernels (EvtDev::gws)
     // events
     int32_t *d_ev_dir = nullptr;
     double *d_ev_cd = nullptr;
@@ -358,25 +359,33 @@ int choose_geometry(hy_ctx *c)
     c->use_evt = false;
     std::string evt_err;
     // Append the event workspace / interval scratch to the column of a matched tape.
-    auto attach_events = [&](hy::Program &pr) -> bool {
+    // (in_global: the workspace goes to a slab in global memory instead - the column keeps the state jets
+    //  only, more trajectories fit in shared memory; see EvtDev::gws)
+    auto attach_events = [&](hy::Program &pr, bool in_global) -> bool {
         if (!evt_ok) return true;
         hy::EvtProgram ep;
         evt_err = hy::build_event_program(d.n_state, d.order, c->h_evt_ops, c->h_evt_terms, c->h_evt_ref,
                                           c->h_evt_start, c->evt_rows, ep);
         if (!evt_err.empty()) return false;
-        const uint32_t ews_off = (pr.ws_len + 1u) & ~1u;
+        const uint32_t ews_off = in_global ? 0u : (pr.ws_len + 1u) & ~1u;
         const uint32_t eiv_off = ews_off + ((c->evt_rows + 1u) & ~1u);
-        pr.ws_len = eiv_off + 2u * (d.n_state + ep.n_slots);
-        pr.par_off = pr.one_off = pr.ws_len;
+        const uint32_t end = eiv_off + 2u * (d.n_state + ep.n_slots);
+        if (!in_global) {
+            pr.ws_len = end;
+            pr.par_off = pr.one_off = pr.ws_len;
+        }
         pr.ev_ref.clear();
         for (uint32_t off : ep.ev_off) pr.ev_ref.push_back(ews_off + off);
         pr.evt_bytes = (uint32_t)ep.blob.size();
         c->evt_blob = ep.blob;
         c->evt_prog = ep;
         c->evt_dev = hy::EvtDev{nullptr, ep.n_ops, ep.n_terms, ep.n_imm, d.n_events, ews_off, eiv_off, ep.n_slots,
-                                (uint32_t)ep.blob.size()};
+                                (uint32_t)ep.blob.size(), nullptr, nullptr, in_global ? (end + 3u) & ~3u : 0u};
         return true;
     };
+    // HY_CUDA_EVT_GLOBAL_WS = 0: always inside the column, 1: always the global slab, 2 (default): the slab when
+    // it lets more trajectories be resident
+    const uint32_t evt_gws_mode = env_u32("HY_CUDA_EVT_GLOBAL_WS", 2);
     hy::NbMatch nbm;
     c->jit_defs.clear();
     c->jit_img_plain = hy::jit::Image();
@@ -430,7 +439,7 @@ int choose_geometry(hy_ctx *c)
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = nbm.n_pairs;
         pr.lane_utilisation = (double)nbm.n_pairs / (double)NG;
-        const bool ev_att = attach_events(pr) && !(wgx && evt_ok);
+        const bool ev_att = attach_events(pr, evt_gws_mode == 1) && !(wgx && evt_ok);
         if (nbm.has_par) { // parameter rows of the trajectory, after everything else in the column
             pr.par_off = pr.ws_len;
             pr.ws_len += d.n_par;
@@ -477,18 +486,32 @@ int choose_geometry(hy_ctx *c)
         pr.state_spill.assign(d.n_state, -1);
         pr.n_clusters = 2;
         pr.lane_utilisation = 1.0;
-        const bool ev_att = attach_events(pr);
         // column stride = 2 * odd: the 16 lanes of a half-warp (8 trajectories x 2 lanes, three
         // elements apart) hit 16 different 64-bit banks
-        uint32_t RS = pr.ws_len;
-        while (RS % 4u != 2u) ++RS;
-        hy::SmemLayout L0 = hy::make_layout(d, prog_dims(pr), 2, 0, RS, (uint32_t)c->rb, 0);
-        const uint32_t fixed = L0.total + 64;
-        if (ev_att && fixed < (uint32_t)smem_optin && ((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u) >= 16) {
+        const uint32_t mt = (uint32_t)hy::hy_max_threads(2, true, -1, (int)c->rb);
+        uint32_t RS = 0, fixed = 0;
+        // trajectories per CTA of a column layout (0: does not fit)
+        auto crb_fit = [&](const hy::Program &q) -> uint32_t {
+            RS = q.ws_len;
+            while (RS % 4u != 2u) ++RS;
+            hy::SmemLayout L0 = hy::make_layout(d, prog_dims(q), 2, 0, RS, (uint32_t)c->rb, 0);
+            fixed = L0.total + 64;
+            if (fixed >= (uint32_t)smem_optin) return 0u;
+            return std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), mt / 2u) & ~15u;
+        };
+        // event workspace: inside the column, or - when that keeps fewer trajectories resident - a global slab
+        bool ev_att = true, ev_glob = evt_gws_mode == 1;
+        if (evt_ok && evt_gws_mode == 2) {
+            hy::Program a = pr, b = pr;
+            ev_att = attach_events(a, false) && attach_events(b, true);
+            if (ev_att) ev_glob = crb_fit(b) > crb_fit(a);
+        }
+        ev_att = ev_att && attach_events(pr, ev_glob);
+        const uint32_t crbT = ev_att ? crb_fit(pr) : 0u;
+        if (crbT >= 16) {
             c->use_evt = evt_ok;
             bestG = 2;
-            const uint32_t mt = (uint32_t)hy::hy_max_threads(2, true, -1, (int)c->rb);
-            bestT = std::min(((uint32_t)smem_optin - fixed) / (RS * (uint32_t)c->rb + 4u), mt / 2u) & ~15u;
+            bestT = crbT;
             bestRS = RS;
             best_smem = true;
             best = pr;
@@ -694,6 +717,15 @@ int upload_program(hy_ctx *c)
         CU(cudaMemcpy(c->d_evt, c->evt_blob.data(), c->evt_blob.size(), cudaMemcpyHostToDevice));
         c->evt_dev.blob = c->d_evt;
         c->evt_dev.stats = nullptr;
+        if (c->d_evws) cudaFree(c->d_evws);
+        c->d_evws = nullptr;
+        c->evt_dev.gws = nullptr;
+        if (c->evt_dev.gstride) {
+            const size_t bytes = (size_t)li.ctas * T * c->evt_dev.gstride * c->rb;
+            CU(cudaMalloc(&c->d_evws, bytes));
+            CU(cudaMemset(c->d_evws, 0, bytes));
+            c->evt_dev.gws = c->d_evws;
+        }
         if (env_u32("HY_CUDA_EVENT_STATS", 0)) {
             if (!c->d_evstats) CU(cudaMalloc((void **)&c->d_evstats, 16));
             CU(cudaMemset(c->d_evstats, 0, 16));
@@ -1277,7 +1309,7 @@ int hy_destroy(hy_ctx *c)
     void *ptrs[] = {c->d_prog, c->d_phase, c->d_ev, c->d_srow, c->d_ssp, c->d_gjet, c->d_state, c->d_pars,
                     c->d_thi /* block of the per-lane vectors */, c->d_tc, c->d_gws, c->d_tmp_in, c->d_tmp_out,
                     c->d_ev_dir, c->d_ev_cd, c->d_cd_elapsed, c->d_cd_total, c->d_log, c->d_log_count, c->d_red, c->d_evt, c->d_evstats,
-                    c->d_recoff};
+                    c->d_recoff, c->d_evws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     hy::jit::unload(c->jit_k);

@@ -60,6 +60,12 @@ struct EvtDev {
     uint32_t bytes;        // size of the blob
     unsigned long long *stats; // optional counters (HY_CUDA_EVENT_STATS=1): [0] steps, [1] steps whose
                                // enclosure contained 0 (remaining orders + root finder run)
+    // The event workspace + interval scratch outside the trajectory column: a global slab, gstride elements
+    // per resident trajectory (ews_off = 0 then).  A step touches a few dozen of its elements (L1 / L2
+    // hits), and the shared memory it frees holds more trajectories - the register-resident kernels are
+    // latency bound, their rate follows the resident warps.  gws = null: inside the column.
+    void *gws;
+    uint32_t gstride;
 };
 
 template <typename R, int XS> struct EvtCtx {

@@ -1311,6 +1311,11 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
 #endif
     // global scratch of this trajectory slot's spilled state jets
     R *gj = P.gjet + ((size_t)blockIdx.x * P.T + slot) * (size_t)P.pd.n_spill * P1;
+    // event workspace of the register-resident kernels (hy_evtape.cuh): inside the column, or a slab in
+    // global memory; wev: the base that the event-jet references (s_ev, relative to the column) apply to
+    R *const ews = P.evt.gws ? reinterpret_cast<R *>(P.evt.gws) + ((size_t)blockIdx.x * P.T + slot) * P.evt.gstride
+                             : w + P.evt.ews_off;
+    R *const wev = ews - P.evt.ews_off;
     // order j of state variable i (resident jet or spilled copy; .cg: written by other lanes of the group)
 // (NB > 0: the orders of a state variable are NBR_JS elements apart, see hy_nbody_reg.cuh)
     // (HY_JIT: the rows of the interleaved workspace are HY_WS elements apart; state_row, ev_ref, par_off
@@ -1590,11 +1595,11 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // whose history nobody reads at orders 0, p-1, p (all the step-size norms need).
             if constexpr (FX && NB != 0) {
                 if (reg_events) {
-                    const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+                    const EvtCtx<R, (int)XS> ec{w, s_srow, ews, s_rk, s_eimm, hi};
 #ifdef HY_JIT_EVT
                     // (every lane of the group: the products are spread over the lanes; the interval scratch
                     //  is free here and carries their results to lane 0)
-                    hy_gen_evt_norms<R, (int)XS>(ec, s_eterms, w + P.evt.eiv_off, sub);
+                    hy_gen_evt_norms<R, (int)XS>(ec, s_eterms, ews + (P.evt.eiv_off - P.evt.ews_off), sub);
 #else
                     for (uint32_t e = sub; e < P.evt.n_events; e += G) {
                         const uint32_t o0 = s_estart[e], o1 = s_estart[e + 1];
@@ -1652,7 +1657,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 if constexpr (FX) {
                     if (reg_events) // the event functions take part in the norms
                         for (uint32_t e = sub; e < P.evt.n_events; e += G) {
-                            const R *x = &w[s_ev[e]];
+                            const R *x = &wev[s_ev[e]];
                             n0 = nan_max(n0, r_abs(x[0]));
                             n1 = nan_max(n1, r_abs(x[p - 1]));
                             n2 = nan_max(n2, r_abs(x[p]));
@@ -1666,7 +1671,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         x1 = XJ(i, p - 1);
                         x2 = XJ(i, p);
                     } else {
-                        const R *x = &w[s_ev[i - n]];
+                        const R *x = &wev[s_ev[i - n]];
                         x0 = x[0];
                         x1 = x[(p - 1) * ES];
                         x2 = x[p * ES];
@@ -1740,7 +1745,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 if (reg_events) {
                     // ---- can an event happen in [0, h] at all?  Interval Horner enclosures of the state
                     // polynomials over the step, pushed through the event tape in interval arithmetic.
-                    R *iv = w + P.evt.eiv_off;
+                    R *iv = ews + (P.evt.eiv_off - P.evt.ews_off);
                     bool maybe = false;
 #ifdef HY_JIT_EVT
                     maybe = hy_gen_evt_interval<R, (int)XS>(w, iv, s_eterms, s_eimm, hi, h, sub);
@@ -1769,7 +1774,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                     }
                     if (gmaybe) {
                         // ---- rare: the remaining orders of the event jets, then the root finder ----
-                        const EvtCtx<R, (int)XS> ec{w, s_srow, w + P.evt.ews_off, s_rk, s_eimm, hi};
+                        const EvtCtx<R, (int)XS> ec{w, s_srow, ews, s_rk, s_eimm, hi};
 #ifdef HY_JIT_EVT
                         if (sub == 0) {
 #pragma unroll 1
@@ -1790,7 +1795,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                         __syncwarp(gmask);
                         R h_eff = h;
                         if (sub == 0)
-                            detect_events<R>(w, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
+                            detect_events<R>(wev, s_ev, d.n_events, d.n_tevents, (int)p, h, hi, lo, traj, ns, P.ev, h_eff,
                                              term_ev, nt_fired);
                         h_eff = __shfl_sync(gmask, h_eff, 0, G);
                         term_ev = __shfl_sync(gmask, term_ev, 0, G);
