@@ -47,7 +47,7 @@ struct hy_cout {
     uint32_t B = 0, n = 0, P1 = 0;
     std::vector<void *> segs; // pool segments (device)
     void **d_seg = nullptr;   // device copy of the segment table (HY_REC_MAXSEG entries)
-    uint32_t seg_chunks = 0, rec_len = 0, chunk_len = 0;
+    uint32_t seg_chunks = 0, rec_len = 0, chunk_len = 0, si = 0, sk = 1;
     void *d_lane = nullptr; // one allocation: next | dir_next | head | tail | count | nchunks | dir_off | t0_hi | t0_lo
     unsigned int *d_next = nullptr, *d_dir_next = nullptr;
     uint32_t *d_head = nullptr, *d_tail = nullptr, *d_count = nullptr, *d_nch = nullptr, *d_dir_off = nullptr;
@@ -777,6 +777,15 @@ int rec_create(hy_ctx *c, hy_cout **out)
     r->P1 = c->d.order + 1;
     r->rec_len = r->n * r->P1 + 2u;
     r->chunk_len = 2u + hy::HY_REC_CH * r->rec_len;
+    // record layout (RecDev::si, sk): order-major for the FP64 CR3BP kernel - its column in shared memory is the
+    // record, copied out by TMA (HY_CUDA_REC_BULK=0: element copies into the tc layout, as on every other kernel)
+    r->si = r->P1;
+    r->sk = 1;
+    const bool crb = c->li.kernel_variant == (uint32_t)hy::CRB_VARIANT || c->li.kernel_variant == (uint32_t)hy::CRB_VARIANT_P22;
+    if (crb && c->rb == 8 && env_u32("HY_CUDA_REC_BULK", 1)) {
+        r->si = 1;
+        r->sk = r->n;
+    }
     const size_t chunk_bytes = (size_t)r->chunk_len * r->rb;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -830,6 +839,8 @@ template <typename R> hy::RecDev<R> rec_dev(const hy_cout *r, int on, int append
     d.t0_lo = (R *)r->d_t0lo;
     d.rec_len = r->rec_len;
     d.chunk_len = r->chunk_len;
+    d.si = r->si;
+    d.sk = r->sk;
     d.on = on;
     d.append = append;
     return d;

@@ -140,6 +140,10 @@ template <typename R> struct RecDev {
     uint32_t *count;        // [B] recorded steps
     R *t0_hi, *t0_lo;       // [B] time at which the lane's record starts
     uint32_t rec_len, chunk_len;
+    // element (variable i, order k) of a record is at i * si + k * sk: (p + 1, 1) - the reference's tc
+    // layout - or (1, n), order-major: the layout of the CR3BP kernel's column in shared memory, whose
+    // FP64 records leave the SM as ONE bulk copy (TMA) per step instead of 126 element copies
+    uint32_t si, sk;
     int on, append;
     __device__ __forceinline__ R *chunk(uint32_t cid) const
     {
@@ -1517,6 +1521,13 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         }
         const bool stepping = have && !fin;
 
+        if constexpr (FX && NB < 0 && sizeof(R) == 8) {
+            // (the bulk copy of the previous step's record must have READ the column before the jets rewrite it)
+            if (P.rec.on && P.rec.sk != 1u) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+        }
         if (NB != 0 || stepping) {
             // ---- jets: orders 0..p-1 of every op (the state recurrence is part of the program) ----
             if constexpr (NB > 0) {
@@ -1634,6 +1645,12 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
         if (NB != 0 || stepping) {
             constexpr unsigned TM_FULL = 0xffffffffu;
             const unsigned tmask = NB != 0 ? TM_FULL : gmask;
+            // (recorder: the id of the lane's last chunk, asked for now - an L2 round trip - and needed only
+            //  after the step size is known; not kept in a register across the jets)
+            uint32_t rec_tail = HY_REC_NONE;
+            if constexpr (FX) {
+                if (P.rec.on && stepping) rec_tail = __ldcg(&P.rec.tail[traj]);
+            }
             // ---- step size ----
             R n0 = 0, n1 = 0, n2 = 0;
             // NB > 0: lane `sub` < 2 NB owns one 3-vector of the state (position or velocity of a body;
@@ -1816,10 +1833,31 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             // ---- continuous-output record on the register-resident kernels: the WARP copies the step
             // records of its trajectories one after the other, 32 consecutive elements per store (full
             // 256-byte segments; the per-group loop below writes 8 G bytes per trajectory and store)
+            if constexpr (FX && NB < 0 && sizeof(R) == 8) {
+                if (P.rec.on && P.rec.sk != 1u) {
+                    // order-major records: orders 1..p of the trajectory's column ARE the record - one bulk copy
+                    // shared -> global (TMA) issued by lane 0; order 0 (which the state update below rewrites) goes
+                    // by ordinary stores.  The copy is waited for at the top of the next step, before the jets
+                    // overwrite the column.
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (stepping) {
+                        R *dst = P.rec.chunk(rec_tail) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
+                        for (uint32_t i = sub; i < n; i += G) dst[i] = w[i];
+                        if (sub == 0) {
+                            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(w + n);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + n), "r"(sa),
+                                         "r"((uint32_t)(n * p * 8u))
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
+            }
             if constexpr (FX && NB != 0) {
-                if (P.rec.on) {
+                if (P.rec.on && !(NB < 0 && sizeof(R) == 8 && P.rec.sk != 1u)) {
                     R *my_dst = nullptr;
-                    if (stepping) my_dst = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
+                    if (stepping) my_dst = P.rec.chunk(rec_tail) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     const uint32_t nP = n * P1;
                     // (P.rec_off: the [variable][order] -> column offset table; records of up to 128 elements -
                     //  the CR3BP's 126 - keep this lane's four offsets in registers: per trajectory four
@@ -1850,7 +1888,16 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             }
             // ---- optional tc write, then the state update ----
             if (stepping && (P.write_tc || (FX && P.rec.on) || P.mode == MODE_GRID)) {
-                if (P.write_tc && P.tc) {
+                // tc: only the coefficients of the lane's LAST step of this launch can be observed (every step
+                // overwrites them; callbacks that read them run between launches) - time limit reached, terminal
+                // event, step / launch budget, pause for a callback, or a single step.  (A step that ends in a
+                // non-finite state is found out after the update: its coefficients are not written.)
+                const bool last_step =
+                    P.mode == MODE_STEP || term_ev >= 0 || (so == HY_OUTCOME_TIME_LIMIT && h == rem) ||
+                    (P.max_steps && ns + 1 >= P.max_steps) ||
+                    ((FX && P.launch_steps) && (uint32_t)(ns + 1) - s_ns0[slot] >= (uint32_t)P.launch_steps) ||
+                    (FX && P.pause_on_nt && nt_fired);
+                if (P.write_tc && P.tc && last_step) {
                     // (variable-major loops: no division per element)
                     for (uint32_t v_ = 0; v_ < n; ++v_)
                         for (uint32_t k_ = sub; k_ < P1; k_ += G) P.tc[(size_t)(v_ * P1 + k_) * P.B + traj] = XJ(v_, k_);
@@ -1858,7 +1905,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 }
                 if ((FX && P.rec.on) && NB == 0) {
                     // step record: [n][p+1] coefficients (the end time follows after the time update)
-                    R *dstc = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
+                    R *dstc = P.rec.chunk(rec_tail) + 2u + (cc % HY_REC_CH) * P.rec.rec_len;
                     for (uint32_t v_ = 0; v_ < n; ++v_) {
                         R *dv = dstc + v_ * P1;
                         for (uint32_t k_ = sub; k_ < P1; k_ += G) dv[k_] = XJ(v_, k_);
@@ -2001,7 +2048,7 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
                 if ((FX && P.rec.on)) {
                     if (sub == 0) {
                         const bool fin_ = (P.mode != MODE_STEP) && so == HY_OUTCOME_TIME_LIMIT && h == rem;
-                        R *dstt = P.rec.chunk(__ldcg(&P.rec.tail[traj])) + 2u + (cc % HY_REC_CH) * P.rec.rec_len + n * P1;
+                        R *dstt = P.rec.chunk(rec_tail) + 2u + (cc % HY_REC_CH) * P.rec.rec_len + n * P1;
                         dstt[0] = fin_ ? tf_hi : hi;
                         dstt[1] = fin_ ? tf_lo : lo;
                     }
@@ -2060,6 +2107,8 @@ __global__ void __launch_bounds__(WGX ? 384 : hy_max_threads(G, SMEM, NB, (int)s
             if (G > 1) __syncwarp(gmask);
         }
     }
+    // (bulk copies of continuous-output records still in flight: complete before the thread exits)
+    if constexpr (FX && NB < 0 && sizeof(R) == 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef HY_WGX_PROF
     if constexpr (NB > 0) {
         if (blockIdx.x == 0 && lane == 0 && prof_n)
@@ -2171,10 +2220,27 @@ __global__ void cout_eval_kernel(const RecDev<R> rec, const uint32_t *__restrict
     }
     const R tau = (tq - t0h) - t0l;
     const R *base = rec_step(rec, dir, off, sidx);
+    const uint32_t si = rec.si, sk = rec.sk;
+    if (sk != 1u && n <= 8u) {
+        // order-major record: all variables advance together, every order one contiguous read
+        R acc[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i) acc[i] = i < n ? base[p * sk + i] : (R)0;
+        for (uint32_t k = p; k-- > 0;) {
+            const R *x = base + k * sk;
+#pragma unroll
+            for (uint32_t i = 0; i < 8u; ++i)
+                if (i < n) acc[i] = r_fma(acc[i], tau, x[i]);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+            if (i < n) out[((size_t)q * n + i) * B + l] = acc[i];
+        return;
+    }
     for (uint32_t i = 0; i < n; ++i) {
-        const R *x = base + i * P1;
-        R acc = x[p];
-        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k]);
+        const R *x = base + i * si;
+        R acc = x[p * sk];
+        for (uint32_t k = p; k-- > 0;) acc = r_fma(acc, tau, x[k * sk]);
         out[((size_t)q * n + i) * B + l] = acc;
     }
 }
@@ -2198,7 +2264,9 @@ __global__ void rec_gather_kernel(const RecDev<R> rec, const uint32_t *__restric
     if (s < S) {
         const R *src = s < cnt ? rec_step(rec, dir, dir_off[l], s) : nullptr;
         if (tcs)
-            for (uint32_t i = 0; i < nP; ++i) tcs[((size_t)s * nP + i) * B + l] = src ? src[i] : nan;
+            for (uint32_t v_ = 0, i = 0; v_ < n; ++v_)
+                for (uint32_t k_ = 0; k_ <= p; ++k_, ++i)
+                    tcs[((size_t)s * nP + i) * B + l] = src ? src[v_ * rec.si + k_ * rec.sk] : nan;
         thi[(size_t)(s + 1) * B + l] = src ? src[nP] : nan;
         tlo[(size_t)(s + 1) * B + l] = src ? src[nP + 1] : nan;
     }

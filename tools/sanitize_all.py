@@ -67,6 +67,16 @@ for fp in (np.float64, np.float32):
 xx, yy, zz = hy.make_vars("x", "y", "z")
 cev = [hy.t_event_batch((xx - 0.01) ** 2 + yy * yy + zz * zz - 0.2 ** 2), hy.t_event_batch(xx * xx + yy * yy + zz * zz - 1.3 ** 2)]
 drive("CR3BP register kernel + event tape", hy.taylor_adaptive_batch(W.cr3bp_sys(0.01), W.cr3bp_ensemble(B), t_events=cev), 1.5, 2.0)
+with env(HY_CUDA_JIT_EVT=2):   # events as generated code on both lanes, workspace in the global slab (T = 128 layout)
+    drive("CR3BP register kernel + generated event code", hy.taylor_adaptive_batch(W.cr3bp_sys(0.01), W.cr3bp_ensemble(B), t_events=cev), 1.5, 2.0)
+    with env(HY_CUDA_EVT_GLOBAL_WS=0):
+        drive("CR3BP register kernel + generated event code, workspace in the column",
+              hy.taylor_adaptive_batch(W.cr3bp_sys(0.01), W.cr3bp_ensemble(B), t_events=cev), 1.5, 2.0)
+    v_ = lambda s_: hy.expression(s_)
+    nev = [hy.nt_event_batch((v_("x_1") - v_("x_2")) ** 2 + (v_("y_1") - v_("y_2")) ** 2 - 60.0, lambda ta, t, d, i: None),
+           hy.nt_event_batch((v_("x_1") + 0.5) * (v_("y_1") - 0.25), lambda ta, t, d, i: None)]
+    drive("N-body register kernel + generated event code (16 lanes)",
+          hy.taylor_adaptive_batch(W.oss_sys(), W.oss_ensemble(B, amp=1e-3), nt_events=nev), 3.0, 4.0)
 # 3. run-time compiled kernels
 with env(HY_CUDA_JIT=1):
     drive("compiled kernel, shared-memory workspace + events", hy.taylor_adaptive_batch(pend, pic, **evs()), 2.0, 3.0)
