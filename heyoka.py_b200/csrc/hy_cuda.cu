@@ -262,6 +262,10 @@ int jit_plan(const hy_dims &d, const hy_op *ops, const hy_term *terms, const uin
     gen.pf_dist = env_u32("HY_CUDA_JIT_PF_DIST", 0);
     gen.pf_level = env_u32("HY_CUDA_JIT_PF_LEVEL", 1);
     gen.batch = env_u32("HY_CUDA_JIT_BATCH", 64);
+    // Products / quotients of a level that share an operand load it once (convn_wide, jop_divsh; bit-identical).
+    // Measured on config 4 (10^6 lanes, 512-thread CTAs = 128 registers): 30 % fewer operand loads but 12-term blocks
+    // instead of whole convolutions in flight - 1.09e7 against 1.51e7 steps/s.  Off by default.
+    gen.div_group = env_u32("HY_CUDA_JIT_SHARE", 0) != 0;
     const size_t col_bytes = (size_t)pr.ws_len * rb;
     if (!force && col_bytes <= env_u32("HY_CUDA_JIT_MIN_BYTES", 3072)) return 0;
     hy::ProgDims pd0 = prog_dims(pr);

@@ -59,6 +59,7 @@ struct Gen {
     uint32_t M = 0;
     uint32_t pf_dist = 0, pf_level = 1; // software prefetch: ops ahead (0: off), cache level
     uint32_t batch = 0;                  // loads per batch of independent linear ops (0: program order, no batches)
+    bool div_group = true;               // quotients of a level by the same denominator as groups (jop_divsh)
     std::vector<int64_t> qbase;
     uint32_t q_rows = 0;
     Gen(const hy_dims &d_, const Program &p_, uint32_t blk) : d(d_), pr(p_)
@@ -250,9 +251,12 @@ struct Gen {
         std::vector<uint32_t> idx(pr.n_slots);
         std::iota(idx.begin(), idx.end(), 0u);
         auto cls = [&](uint32_t i) { return is_linear(pr.ops[i]) ? 0u : 1u + pr.ops[i].opcode; };
+        // (the quotients of a level next to each other by denominator: they are emitted as groups, jop_divsh)
+        auto den = [&](uint32_t i) { return pr.ops[i].opcode == HY_OP_DIV ? pr.ops[i].b : 0u; };
         std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
             if (lvl[a] != lvl[b]) return lvl[a] < lvl[b];
-            return cls(a) < cls(b);
+            if (cls(a) != cls(b)) return cls(a) < cls(b);
+            return den(a) < den(b);
         });
         levels_ = lvl;
         return idx;
@@ -344,6 +348,7 @@ struct Gen {
         os << "// generated by hy_jit.hpp: " << d.n_state << " state variables, order " << d.order << ", " << pr.n_slots
            << " ops, " << pr.ws_len << " workspace rows\n";
         os << "#define HY_JIT 1\n#define HY_WS " << WS << "\n#define HY_JIT_THREADS " << threads << "\n";
+        if (!div_group) os << "#define HY_JIT_NOSHARE 1\n";
         os << "#include \"hy_kernels.cuh\"\n";
         os << "#define W(r) w[(r) * HY_WS]\n";
         os << "namespace hy {\n";
@@ -366,6 +371,25 @@ struct Gen {
             while (i < ord.size()) {
                 const DOp &o = pr.ops[ord[i]];
                 if (!is_linear(o)) {
+                    // quotients of this level by the same denominator: groups of up to four share its loads
+                    size_t g = i;
+                    if (o.opcode == HY_OP_DIV && !M && div_group)
+                        while (g < ord.size() && g - i < (threads > 256 ? 2u : 4u) && pr.ops[ord[g]].opcode == HY_OP_DIV && pr.ops[ord[g]].b == o.b &&
+                               levels_[ord[g]] == levels_[ord[i]])
+                            ++g;
+                    if (g - i >= 2) {
+                        const size_t nt = g - i;
+                        os << "      { // " << nt << " quotients by row " << o.b << "\n        const JDivRows<" << nt << "> r = {{";
+                        for (size_t q = i; q < g; ++q)
+                            os << (q > i ? ", " : "") << row(pr.ops[ord[q]].a, pr.ops[ord[q]].flags & DF_JA);
+                        os << "}, {";
+                        for (size_t q = i; q < g; ++q) os << (q > i ? ", " : "") << pr.ops[ord[q]].dst;
+                        os << "}, {";
+                        for (size_t q = i; q < g; ++q) os << (q > i ? ", " : "") << pr.ops[ord[q]].dst2;
+                        os << "}};\n        jop_divsh<R, HY_WS, " << nt << ">(w, k, " << o.b << ", r);\n      }\n";
+                        i = g;
+                        continue;
+                    }
                     if (!emit_op(o, ord[i], true)) return "";
                     ++i;
                     continue;

@@ -370,6 +370,43 @@ __device__ __noinline__ void conv3_wide(const R *__restrict__ a0, const R *__res
 #endif
 
 #ifdef HY_JIT
+// NT convolutions that share one operand, every element of it loaded ONCE: o_t = sum_{j<n} ps[+-j] * pt[t][-+j]
+// (FWD: the shared operand is the one read forwards).  Each sum is chained exactly like conv_wide / conv():
+// term j on chain j mod 4, folded (s0 + s1) + (s2 + s3) - the results are bit-identical to NT separate calls.
+// Blocks of 24 (NT <= 2) or 12 terms: all loads of a block are in flight before its first FMA.
+// (CTAs of more than 256 threads have 128 registers per thread: at most two products per call, 12-term blocks)
+#if defined(HY_JIT_THREADS) && HY_JIT_THREADS > 256
+#define HY_JIT_SMALLREG 1
+#else
+#define HY_JIT_SMALLREG 0
+#endif
+template <typename R, int S, int NT, bool FWD>
+__device__ __forceinline__ void convn_wide(const R *__restrict__ ps, const R *const (&pt)[NT], int n, R (&o)[NT])
+{
+    constexpr int BL = (NT <= 2 && !HY_JIT_SMALLREG) ? 24 : 12;
+    R s[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += BL) {
+        R sv[BL], tv[NT][BL];
+        const int m = n - j0;
+#pragma unroll
+        for (int u = 0; u < BL; ++u) {
+            const bool v = u < m;
+            sv[u] = v ? ps[(FWD ? (j0 + u) : -(j0 + u)) * S] : (R)0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) tv[t][u] = v ? pt[t][(FWD ? -(j0 + u) : (j0 + u)) * S] : (R)0;
+        }
+#pragma unroll
+        for (int u = 0; u < BL; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) s[t][u & 3] = r_fma(tv[t][u], sv[u], s[t][u & 3]);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) o[t] = (s[t][0] + s[t][1]) + (s[t][2] + s[t][3]);
+}
+
 // Software prefetch of the rows an upcoming op will read (rows [0, n) of a jet): needs no
 // registers, so the memory round trip of op i + D overlaps the arithmetic of ops i .. i + D - 1.
 template <typename R, int S, int LVL> __device__ __forceinline__ void pf_rows(const R *p, int n)
@@ -545,6 +582,29 @@ __device__ __noinline__ void jop_mulsh(R *__restrict__ w, uint32_t k, uint32_t b
             w[r.dst[0] * S] = s0;
             w[r.dst[1] * S] = s1;
             w[r.dst[2 % NT] * S] = s2;
+#ifndef HY_JIT_NOSHARE
+        } else if (NT == 2 || NT == 4) {
+            // (the shared operand's elements are loaded once for the NT products)
+            const R *pt[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) pt[t] = w + r.a[t] * S;
+            R o[NT];
+            if (NT == 4 && HY_JIT_SMALLREG) {
+                // (two pairs: the register budget of a 512-thread CTA)
+                const R *p0[2] = {pt[0], pt[1]}, *p1[2] = {pt[2 % NT], pt[3 % NT]};
+                R o0[2], o1[2];
+                convn_wide<R, S, 2, false>(pb + k * S, p0, (int)k + 1, o0);
+                convn_wide<R, S, 2, false>(pb + k * S, p1, (int)k + 1, o1);
+                o[0] = o0[0];
+                o[1] = o0[1];
+                o[2 % NT] = o1[0];
+                o[3 % NT] = o1[1];
+            } else {
+                convn_wide<R, S, NT, false>(pb + k * S, pt, (int)k + 1, o);
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) w[r.dst[t] * S] = o[t];
+#endif
         } else {
 #pragma unroll
             for (int t = 0; t < NT; ++t) w[r.dst[t] * S] = conv_wide<R, S>(w + r.a[t] * S, pb + k * S, (int)k + 1);
@@ -593,6 +653,36 @@ __device__ __noinline__ void jop_div(R *__restrict__ w, uint32_t k, uint32_t bi,
     } else {
         const R s = (w[(q + bi - 1) * S] + shortsum<R, S, M>(pb + S, pc + (k - 1) * S, bi)) + shortsum<R, S, M>(pc, pb + k * S, bi);
         pc[k * S] = (w[num * S] - s) * w[inv * S];
+    }
+}
+// NT quotients by the same denominator b (grouped by the generator: DIV ops of one dependency level): b's
+// coefficients are loaded once.  Per quotient the arithmetic is jop_div's, statement by statement.
+template <int NT> struct JDivRows {
+    uint32_t num[NT], c[NT], inv[NT];
+};
+template <typename R, int S, int NT>
+__device__ __noinline__ void jop_divsh(R *__restrict__ w, uint32_t k, uint32_t b, const JDivRows<NT> r)
+{
+    const R *pb = w + b * S;
+    if (k == 0) {
+        const R iv = (R)1 / pb[0];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) w[r.inv[t] * S] = iv;
+    }
+    R cv[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) cv[t] = 0;
+    if (k > 0) {
+        const R *pt[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) pt[t] = w + (r.c[t] + k - 1) * S;
+        convn_wide<R, S, NT, true>(pb + S, pt, (int)k, cv);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        R acc = w[r.num[t] * S];
+        if (k > 0) acc -= cv[t];
+        w[(r.c[t] + k) * S] = acc * w[r.inv[t] * S];
     }
 }
 template <typename R, int S> __device__ __noinline__ void jop_square(R *__restrict__ w, uint32_t k, uint32_t a, uint32_t dst)
