@@ -406,3 +406,38 @@ def test_large_dense_output_lands_in_recycled_pinned_buffers():
     small = c_out(tq[:1])                            # below a MiB: an ordinary array
     assert small.base is None or type(small.base).__name__ != "_PinnedBlock"
     assert np.array_equal(small[0], keep[0])
+
+
+@pytest.mark.parametrize("devs", [[0, 0], "all"])
+def test_lane_sharded_cr3bp_with_events_and_c_output(devs):
+    # the CR3BP register kernel with terminal events (event workspace in its global slab, one per context)
+    # and with continuous output (order-major records, TMA bulk copy), split over several contexts / cloned
+    mu = 0.01
+    x, y, z = hy.make_vars("x", "y", "z")
+    evs = [(x - mu) ** 2 + y * y + z * z - 0.2 ** 2, x * x + y * y + z * z - 1.3 ** 2]
+    B = 150
+    rng = np.random.default_rng(3)
+    ic = np.array([-0.80, 0.0, 0.0, 0.0, -0.6276410653920693, 0.0])[:, None] * np.ones((1, B))
+    ic[0] += rng.uniform(-1e-2, 1e-2, B)
+    ic[4] += rng.uniform(-1e-2, 1e-2, B)
+    mk = lambda **kw: hy.taylor_adaptive_batch(W.cr3bp_sys(mu), ic, t_events=[hy.t_event_batch(e) for e in evs], **kw)
+    a, b = mk(), mk(device=devs)
+    assert a._ctx.launch_info()["kernel_variant"] == 203
+    a.propagate_until(12.0)
+    b.propagate_until(12.0)
+    assert (a.propagate_res_arrays[0] > -10).sum() > 5          # some lanes stopped at an event
+    assert np.array_equal(a.state, b.state) and np.array_equal(a.time, b.time)
+    for u, v in zip(a.propagate_res_arrays, b.propagate_res_arrays):
+        assert np.array_equal(u, v)
+    c = copy.deepcopy(a)                                        # hy_clone: its own slab
+    a.propagate_until(14.0)
+    c.propagate_until(14.0)
+    assert np.array_equal(a.state, c.state)
+    # continuous output of the event-free system on the same split
+    p, q = hy.taylor_adaptive_batch(W.cr3bp_sys(mu), ic), hy.taylor_adaptive_batch(W.cr3bp_sys(mu), ic, device=devs)
+    cp, _ = p.propagate_until(3.0, c_output=True)
+    cq, _ = q.propagate_until(3.0, c_output=True)
+    tq = np.repeat(np.linspace(0.0, 3.0, 9), B).reshape(9, B)
+    assert np.array_equal(cp(tq), cq(tq))
+    assert np.array_equal(np.array(cp.tcs), np.array(cq.tcs), equal_nan=True)   # (NaN past a lane's own step count)
+    assert np.array_equal(np.array(p.tc), np.array(q.tc))       # tc: the last step's coefficients
