@@ -151,19 +151,20 @@ class ClockSampler:
         }
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel from the committed
-    `ncu --set full` capture of the SAME kernel on a smaller launch (profiles/r01_ncu_full_bench_kernel.txt,
-    a 6.4 ms launch over 125 000 trajectories x 1 step-segment) - a file read, not a measurement of the
-    timed launch; HBM traffic of this kernel is the state in/out only, so it does not grow with the
-    number of steps.  None if the summary is missing."""
+def ncu_traffic(trajectories):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the propagate kernel, from the committed
+    `ncu --set full` capture of the SAME kernel at the bench geometry (profiles/r02_ncu_full_cfg2.txt:
+    10^6 trajectories, 148 CTAs x 256 threads, one 400-yr segment) - a file read, not a measurement of the
+    timed launch.  The kernel's HBM traffic is the per-lane state / time / result vectors in and out: it
+    does not grow with the number of steps and is proportional to the trajectories of the launch (scaled
+    here when a rank holds fewer than 10^6).  None if the summary is missing."""
     try:
         tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_kernel.txt")):
+        for ln in open(os.path.join(ROOT, "profiles", "r02_ncu_full_cfg2.txt")):
             if ln.startswith("dram__bytes_read.sum [") or ln.startswith("dram__bytes_write.sum ["):
                 unit = ln.split("[")[1].split("]")[0]
                 tot += float(ln.split("=")[1]) * mult[unit]
-        return tot or None
+        return tot * trajectories / 1e6 if tot else None
     except Exception:
         return None
 
@@ -584,10 +585,11 @@ def main():
             "kernel": "hy::propagate_kernel<double,{},true,{}>{}".format(li["group"], variant, kname),
             "kernel_ms_per_launch": kern_ms / args.steps,
             "flops_per_trajectory_step": fl,
-            "traffic": ncu_traffic() if args.config == 2 else None,
-            "traffic_note": "ncu --set full capture of the same kernel on a 125 000-trajectory, 6.4 ms launch "
-                            "(profiles/r01_ncu_full_bench_kernel.txt); the kernel's HBM traffic is the state "
-                            "in/out and does not depend on the number of steps" if args.config == 2 else None,
+            "traffic": ncu_traffic(B) if args.config == 2 else None,
+            "traffic_note": "ncu --set full capture of the same kernel at the bench geometry (10^6 trajectories, "
+                            "profiles/r02_ncu_full_cfg2.txt: 691 MB per launch), scaled to this rank's trajectories; "
+                            "the kernel's HBM traffic is the per-lane vectors in/out and does not depend on the "
+                            "number of steps" if args.config == 2 else None,
             "hbm": {
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_gbs": alg_bytes * args.steps / k_s / 1e9,
