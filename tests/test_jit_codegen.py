@@ -105,3 +105,31 @@ def test_event_code_generation_without_a_device(tmp_path, monkeypatch):
     pe = [xx - 0.1]
     assert _cabi.jit_precompile_events(D.decompose(pend, order, events=pe), D.decompose(pend, order),
                                        D.decompose_event_tape(pe, ["x", "v"], order), 64, n_tevents=1)[0] == -1
+
+
+def test_event_code_generation_for_a_16_lane_group(tmp_path, monkeypatch):
+    # N-body register kernel (16 lanes per trajectory): differences of state jets are every-order ops (lane 0,
+    # then a warp sync), their squares / the products of state jets are spread over up to 8 lanes per round,
+    # "x + c" operands of a product are folded, the event function that IS a product is stored as a jet
+    import hy_b200 as hy
+    from hy_b200 import _cabi, decompose as D, workloads as W
+
+    monkeypatch.setenv("HY_CUDA_JIT_CACHE", str(tmp_path / "cache"))
+    monkeypatch.setenv("HY_CUDA_JIT_DUMP", str(tmp_path))
+    sys_ = W.oss_sys()
+    v = lambda s: hy.expression(s)
+    dx, dy = v("x_1") - v("x_2"), v("y_1") - v("y_2")
+    evs = [dx * dx + dy * dy - 60.0, v("x_1") * v("vy_1") - v("y_1") * v("vx_1") - 2.0, (v("x_1") + 0.5) * (v("y_1") - 0.25)]
+    order = 20
+    fc, secs = _cabi.jit_precompile_events(D.decompose(sys_, order, events=evs), D.decompose(sys_, order),
+                                           D.decompose_event_tape(evs, [l.name for l, _ in sys_], order), 64)
+    assert fc == 0
+    src = "".join(p.read_text() for p in tmp_path.glob("hy_jit_*.cu"))
+    assert "propagate_kernel" not in src.split("namespace hy {")[1].split("hy_gen_evt_norms")[0]
+    assert "5 product units on the lanes of the group" in src
+    norms = src.split("hy_gen_evt_order")[0]
+    assert norms.count("evt_exec_all") == 2 and "__syncwarp();" in norms      # dx, dy: every-order ADDSUBs on lane 0
+    assert "evt_unit_sq<R, 1, 20>" in norms                                   # squares of unit-stride jets (dx, dy)
+    assert "evt_unit_mul<R, XS, XS, 20>" in norms and "sub == 2u ?" not in norms.split("evt_unit_sq")[0]
+    assert "const bool ala = " in norms and "const bool alb = " in norms      # (x_1 + 0.5) * (y_1 - 0.25): both folded
+    assert "sub < 3u" in norms                                                # three products in one round
