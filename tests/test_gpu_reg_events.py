@@ -163,9 +163,9 @@ def test_register_events_with_recurrences_and_time():
 
 def test_generated_event_code_vs_interpreted_event_tape():
     # Large batches get the event functions as generated code (csrc/hy_jit.hpp, EvtGen: NVRTC build of the
-    # FX kernel); small ones the interpreted event tape.  Same trajectories, same events: the two agree
-    # (different summation order of the three-order convolutions and a looser state enclosure, so the
-    # comparison is to rounding / chaotic amplification, not bit for bit).
+    # FX kernel); small ones the interpreted event tape.  Same trajectories, same events.  The generated code
+    # chains every sum like the interpreted tape and its (different, cheaper) enclosure test is conservative
+    # as well, so config 5's chaotic family comes out bit for bit - outcomes, event times, states, step counts.
     B = 1024
     sys_, evs, ic = _cfg5(B, 123, 0.2, 1.3)
     mk = lambda: hy.taylor_adaptive_batch(sys_, ic, t_events=[hy.t_event_batch(e) for e in evs])
@@ -179,14 +179,10 @@ def test_generated_event_code_vs_interpreted_event_tape():
     assert a._ctx.launch_info()["kernel_variant"] == 203 and b._ctx.launch_info()["kernel_variant"] == 203
     a.propagate_until(30.0)
     b.propagate_until(30.0)
-    oa, ob = a.propagate_res_arrays[0], b.propagate_res_arrays[0]
-    same = oa == ob
-    assert same.mean() > 0.995 and (oa > -10).sum() > 50
-    dt = np.abs(a.time - b.time)[same]
-    ds = np.abs(a.state - b.state).max(axis=0)[same]
-    calm = ds < 1e-7
-    assert calm.mean() > 0.95 and np.max(dt[calm]) < 1e-7
-    assert np.array_equal(a.propagate_res_arrays[3][same & calm], b.propagate_res_arrays[3][same & calm])
+    assert (a.propagate_res_arrays[0] > -10).sum() > 50
+    for u, v in zip(a.propagate_res_arrays, b.propagate_res_arrays):
+        assert np.array_equal(u, v)
+    assert np.array_equal(a.time, b.time) and np.array_equal(a.state, b.state)
 
 
 def _gen_vs_interp_events(sys_, ic, evs, variant, T):
