@@ -277,3 +277,93 @@ def test_high_accuracy_and_backward():
     ta.propagate_until(2.0)
     assert all(r[0] in (hy.taylor_outcome.err_nf_state, hy.taylor_outcome.time_limit)
                for r in ta.propagate_res)
+
+
+@pytest.mark.parametrize("fp", [np.float32, np.float64])
+def test_propagate_grid_reference_scenarios(fp):
+    # /root/reference/heyoka/_test_batch_integrator.py:692-857, scenario by scenario (the scalar integrator of the
+    # comparison there is replaced by one-lane batch integrators)
+    from copy import deepcopy
+
+    x, v = hy.make_vars("x", "v")
+    eqns = [(x, v), (v, -9.8 * hy.sin(x))]
+    x_ic = np.array([0.06, 0.07, 0.08, 0.09], dtype=fp)
+    v_ic = np.array([0.025, 0.026, 0.027, 0.028], dtype=fp)
+    ta = hy.taylor_adaptive_batch(eqns, [x_ic, v_ic], fp_type=fp)
+
+    with pytest.raises(ValueError) as cm:
+        ta.propagate_grid(np.array([], dtype=fp))
+    assert ("Invalid grid passed to the propagate_grid() method of a batch integrator: the expected number of "
+            "dimensions is 2, but the input array has a dimension of 1") in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.propagate_grid(np.array([[1, 2], [3, 4]], dtype=fp))
+    assert ("Invalid grid passed to the propagate_grid() method of a batch integrator: the shape must be (n, 4) "
+            "but the number of columns is 2 instead") in str(cm.value)
+
+    grid = np.array([[-0.1, -0.2, -0.3, -0.4], [0.01, 0.02, 0.03, 0.9], [1.0, 1.1, 1.2, 1.3],
+                     [11.0, 11.1, 11.2, 11.3]], dtype=fp)
+    ta.propagate_until(grid[0, :])
+    bres = ta.propagate_grid(grid)
+    assert bres[0] is None and bres[1].shape == (4, 2, 4)
+    for idx in range(4):
+        one = hy.taylor_adaptive_batch(eqns, [x_ic[idx:idx + 1], v_ic[idx:idx + 1]], fp_type=fp)
+        one.propagate_until(grid[0, idx:idx + 1])
+        sres = one.propagate_grid(grid[:, idx:idx + 1].copy())
+        assert np.max(np.abs(sres[1][:, :, 0] - bres[1][:, :, idx])) < np.finfo(fp).eps * 100
+
+    # vector / scalar max_delta_t
+    def restart():
+        ta.set_time(fp(0.0))
+        ta.state[:] = [x_ic, v_ic]
+        ta.propagate_until(grid[0, :])
+
+    restart()
+    b1 = ta.propagate_grid(grid, max_delta_t=[fp(1e-3)] * 4)
+    res = deepcopy(ta.propagate_res)
+    restart()
+    b2 = ta.propagate_grid(grid, max_delta_t=fp(1e-3))
+    assert np.all(b1[1] == b2[1]) and ta.propagate_res == res
+
+    # dynamic attributes through the callback; no copies of the callback
+    def cb(t):
+        t.counter = t.counter + 1 if hasattr(t, "counter") else 0
+        return True
+
+    restart()
+    ta.propagate_grid(grid, callback=cb)
+    assert ta.counter > 0
+
+    class cb_id:
+        def __call__(self_, t):
+            assert id(self_) == self_.orig_id
+            return True
+
+    inst = cb_id()
+    inst.orig_id = id(inst)
+    restart()
+    ta.propagate_grid(grid, callback=inst)
+
+    with pytest.raises(TypeError) as cm:
+        restart()
+        ta.propagate_grid(grid, callback="hello world")
+    assert "cannot be used as a step callback because it is not callable" in str(cm.value)
+
+    class broken_cb:
+        def __call__(self_, t):
+            return []
+
+    with pytest.raises(TypeError) as cm:
+        restart()
+        ta.propagate_grid(grid, callback=broken_cb())
+    assert "The call operator of a step callback is expected to return a boolean, but a value of type" in str(cm.value)
+
+    class cb_hook:
+        def __call__(self_, t):
+            return True
+
+        def pre_hook(self_, t):
+            t.foo = True
+
+    restart()
+    ta.propagate_grid(grid, callback=cb_hook())
+    assert ta.foo
