@@ -29,7 +29,8 @@ class _llvm_state_stub:
     """Inert stand-in for ``ta.llvm_state`` (the reference exposes the JIT
     state, expose_batch_integrators.cpp:670; there is no LLVM here)."""
 
-    def __init__(self, kw):
+    def __init__(self, kw, ta=None):
+        self._ta = ta  # (the reference's llvm_state property keeps the integrator alive)
         self.opt_level = kw.get("opt_level", 3)
         self.force_avx512 = kw.get("force_avx512", False)
         self.slp_vectorize = kw.get("slp_vectorize", False)
@@ -42,6 +43,19 @@ class _llvm_state_stub:
 
     def __repr__(self):
         return "<llvm_state stub: libhy_cuda does not JIT>"
+
+
+class _view_owner:
+    """Base object of the numpy views of an integrator's buffers: holds the integrator, so that a view
+    outlives `del ta` - the buffers are page-locked memory the integrator frees when it goes.  (The
+    reference's views hold a reference to the integrator in the same way,
+    expose_batch_integrators.cpp:394-518: `sys.getrefcount(ta)` grows by one per live view.)"""
+
+    def __init__(self, ta, a, writeable):
+        self._ta = ta
+        ai = dict(a.__array_interface__)
+        ai["data"] = (ai["data"][0], not writeable)
+        self.__array_interface__ = ai
 
 
 def _check_scalar_type(x, fp_t, what):
@@ -111,6 +125,10 @@ class taylor_adaptive_batch_impl:
             sys_list = list(sys)
         self._sys = [(l, _E._wrap(r)) for l, r in sys_list]
         n = len(self._sys)
+        if state_.shape[0] == 0:
+            # an empty initial state: zeros (the C++ constructor value-initialises a missing state;
+            # /root/reference/heyoka/_test_batch_integrator.py:530-539)
+            state_ = np.zeros((n, B), dtype=fp)
         if state_.shape[0] != n:
             raise ValueError(
                 "Inconsistent sizes detected in the initialization of an adaptive Taylor "
@@ -313,25 +331,30 @@ class taylor_adaptive_batch_impl:
         v.flags.writeable = False
         return v
 
+    def _view(self, a, writeable=False):
+        if a.size == 0:
+            return a if writeable else self._ro(a)
+        return np.asarray(_view_owner(self, a, writeable))
+
     @property
     def state(self):
-        return self._p_state.array
+        return self._view(self._p_state.array, True)
 
     @property
     def pars(self):
-        return self._p_pars.array
+        return self._view(self._p_pars.array, True)
 
     @property
     def time(self):
-        return self._ro(self._p_thi.array)
+        return self._view(self._p_thi.array)
 
     @property
     def dtime(self):
-        return (self._ro(self._p_thi.array), self._ro(self._p_tlo.array))
+        return (self._view(self._p_thi.array), self._view(self._p_tlo.array))
 
     @property
     def last_h(self):
-        return self._ro(self._p_lasth.array)
+        return self._view(self._p_lasth.array)
 
     @property
     def tc(self):
@@ -343,13 +366,13 @@ class taylor_adaptive_batch_impl:
             elif self._ctx_obj is not None or self._tc_written:
                 self._ctx.get_tc(self._p_tc.array)
             self._tc_valid = True
-        return self._ro(self._p_tc.array)
+        return self._view(self._p_tc.array)
 
     @property
     def d_output(self):
         if self._p_dout is None:
             self._p_dout = _devctx.host_array((self._n, self._B), self._fp)
-        return self._ro(self._p_dout.array)
+        return self._view(self._p_dout.array)
 
     def set_time(self, tm):
         fp, B = self._fp, self._B
@@ -442,7 +465,7 @@ class taylor_adaptive_batch_impl:
 
     @property
     def llvm_state(self):
-        return _llvm_state_stub(self._llvm_kw)
+        return _llvm_state_stub(self._llvm_kw, self)
 
     @property
     def step_res(self):

@@ -367,3 +367,120 @@ def test_propagate_grid_reference_scenarios(fp):
     restart()
     ta.propagate_grid(grid, callback=cb_hook())
     assert ta.foo
+
+
+@pytest.mark.parametrize("fp", [np.float32, np.float64])
+def test_reference_scenarios_d_output_time_dtime_basic(fp):
+    # /root/reference/heyoka/_test_batch_integrator.py:340-553 (test_update_d_output, test_set_time, test_dtime,
+    # test_basic), scenario by scenario
+    from copy import deepcopy
+    from sys import getrefcount
+
+    x, v = hy.make_vars("x", "v")
+    sys_ = [(x, v), (v, -9.8 * hy.sin(x))]
+
+    # ---- update_d_output (:340-413)
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1, 0.2, 0.3], [0.25, 0.26, 0.27, 0.28]], dtype=fp),
+                                  fp_type=fp)
+    ta.step(write_tc=True)
+    with pytest.raises(ValueError):
+        ta.update_d_output(fp(0.3))[0] = fp(0.5)
+    d_out = ta.update_d_output(fp(0.3))
+    assert d_out.shape == (2, 4)
+    rc = getrefcount(ta)
+    tmp_out = ta.update_d_output(fp(0.2))
+    assert getrefcount(ta) == rc + 1
+    with pytest.raises(ValueError):
+        ta.update_d_output(np.array([0.3, 0.4, 0.45, 0.46], dtype=fp))[0] = fp(0.5)
+    d_out2 = ta.update_d_output(np.array([0.3, 0.4, 0.45, 0.46], dtype=fp))
+    assert d_out2.shape == (2, 4)
+    rc = getrefcount(ta)
+    tmp_out2 = ta.update_d_output(np.array([0.31, 0.41, 0.66, 0.67], dtype=fp))
+    assert getrefcount(ta) == rc + 1
+    cp = deepcopy(ta.update_d_output(fp(0.3)))
+    assert np.all(cp == ta.update_d_output([fp(0.3)] * 4))
+    ta.set_time(fp(0.0))
+    ta.state[:] = [[0.0, 0.01, 0.02, 0.03], [0.205, 0.206, 0.207, 0.208]]
+    ta.step(write_tc=True)
+    ta.update_d_output(ta.time)
+    eps10 = np.finfo(fp).eps * 10
+    assert np.allclose(ta.d_output, ta.state, rtol=eps10, atol=eps10)
+    ta.update_d_output(fp(0.0), rel_time=True)
+    assert np.allclose(ta.d_output, ta.state, rtol=eps10, atol=eps10)
+    del tmp_out, tmp_out2
+
+    # ---- set_time (:415-438), dtime (:440-488)
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=fp), fp_type=fp)
+    assert np.all(ta.time == [0, 0])
+    ta.set_time([fp(-1.0), fp(1.0)])
+    assert np.all(ta.time == [-1, 1])
+    ta.set_time(fp(5.0))
+    assert np.all(ta.time == [5, 5])
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=fp), fp_type=fp)
+    assert np.all(ta.dtime[0] == [0, 0]) and np.all(ta.dtime[1] == [0, 0])
+    with pytest.raises(ValueError):
+        ta.dtime[0][0] = 0.5
+    with pytest.raises(ValueError):
+        ta.dtime[1][0] = 0.5
+    ta.step()
+    ta.propagate_for(fp(1000.1))
+    assert not np.all(ta.dtime[1] == [0, 0])
+    ta.set_dtime(fp(1.0), fp(0.5))
+    assert np.all(ta.dtime[0] == [1.5, 1.5]) and np.all(ta.dtime[1] == [0, 0])
+    ta.set_dtime([fp(1.0), fp(2.0)], [fp(0.5), fp(0.25)])
+    assert np.all(ta.dtime[0] == [1.5, 2.25]) and np.all(ta.dtime[1] == [0, 0])
+    with pytest.raises(TypeError) as cm:
+        ta.set_dtime([fp(1.0), fp(2.0)], fp(0.5))
+    assert "The two arguments to the set_dtime() method must be of the same type" in str(cm.value)
+
+    # ---- basic (:490-553)
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=fp),
+                                  t_events=[hy.t_event_batch(v, fp_type=fp)], fp_type=fp)
+    assert ta.with_events and not ta.compact_mode and not ta.high_accuracy and ta.sys == sys_
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=fp), compact_mode=True,
+                                  high_accuracy=True, fp_type=fp)
+    assert not ta.with_events and ta.compact_mode and ta.high_accuracy
+    assert not ta.llvm_state.fast_math and not ta.llvm_state.force_avx512 and ta.llvm_state.opt_level == 3
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.empty((0, 2), dtype=fp), compact_mode=True, high_accuracy=True,
+                                  fp_type=fp)
+    assert np.all(ta.state == np.zeros((2, 2), dtype=fp))
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=fp), compact_mode=True,
+                                  high_accuracy=True, force_avx512=True, fast_math=True, opt_level=0, fp_type=fp)
+    assert ta.llvm_state.fast_math and ta.llvm_state.force_avx512 and ta.llvm_state.opt_level == 0
+
+
+def test_views_keep_the_integrator_alive():
+    # _test_batch_integrator.py:13-50 (llvm_state reference counting) and the view semantics of
+    # expose_batch_integrators.cpp:394-518: every live view holds the integrator, whose page-locked buffers it aliases
+    import gc
+    from sys import getrefcount
+
+    x, v = hy.make_vars("x", "v")
+    sys_ = [(x, v), (v, -9.8 * hy.sin(x))]
+    ta = hy.taylor_adaptive_batch(sys_, [[0.0, 0.0], [0.0, 0.0]])
+    rc = getrefcount(ta)
+    tmp = ta.llvm_state
+    assert getrefcount(ta) == rc + 1
+    assert not ta.llvm_state.force_avx512 and not ta.llvm_state.slp_vectorize
+    tb = hy.taylor_adaptive_batch(sys_, [[0.0, 0.0], [0.0, 0.0]], force_avx512=True, slp_vectorize=True, parjit=True,
+                                  compact_mode=True, code_model=hy.code_model.large)
+    rc = getrefcount(tb)
+    tmp = tb.llvm_state
+    assert getrefcount(tb) == rc + 1
+    assert tb.llvm_state.force_avx512 and tb.llvm_state.slp_vectorize and tb.llvm_state.code_model == hy.code_model.large
+    # views outlive `del ta`
+    tc_ = hy.taylor_adaptive_batch(sys_, [[0.1, 0.2], [0.3, 0.4]])
+    tc_.step(write_tc=True)
+    st, tm, lh, tcs = tc_.state, tc_.time, tc_.last_h, tc_.tc
+    keep = [np.array(a) for a in (st, tm, lh, tcs)]
+    st[0, 0] = 5.0                                   # state is writable and aliases the integrator's buffer
+    assert tc_.state[0, 0] == 5.0
+    keep[0][0, 0] = 5.0
+    with pytest.raises(ValueError):
+        tm[0] = 1.0
+    del tc_
+    gc.collect()
+    junk = [hy.taylor_adaptive_batch(sys_, [[1.0, 2.0], [3.0, 4.0]]) for _ in range(4)]   # would reuse freed buffers
+    for a, k in zip((st, tm, lh, tcs), keep):
+        assert np.array_equal(a, k)
+    del junk
