@@ -1,0 +1,192 @@
+"""GPU: the scenarios of the reference's own batch-integrator tests, one by one
+(/root/reference/heyoka/_test_batch_integrator.py; the line ranges are cited per test), run against
+`hy_b200` - same calls, same expectations, same error messages."""
+
+import pickle
+from copy import copy, deepcopy
+
+import numpy as np
+import pytest
+
+import hy_b200 as hy
+
+pytestmark = pytest.mark.gpu
+
+FP = [np.float32, np.float64]
+
+
+def _pend():
+    x, v = hy.make_vars("x", "v")
+    return x, v, [(x, v), (v, -9.8 * hy.sin(x))]
+
+
+def test_type_conversions():
+    # :51-87
+    x, v, sys_ = _pend()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=((0.0, 0.1), (0.25, 0.26)), tol=1e-4)
+    assert np.all(ta.state == ((0.0, 0.1), (0.25, 0.26)))
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]]), tol=1e-4)
+    assert np.all(ta.state == ((0.0, 0.1), (0.25, 0.26)))
+    if np.finfo(np.double).nmant == np.finfo(np.longdouble).nmant:
+        return
+    ld = np.longdouble
+    with pytest.raises(TypeError):
+        hy.taylor_adaptive_batch(sys=sys_, state=((ld(0.0), ld(0.1)), (ld(0.25), ld(0.26))), tol=1e-4)
+    with pytest.raises(TypeError):
+        hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.1], [0.25, 0.26]], dtype=ld), tol=1e-4)
+
+
+def test_copy():
+    # :89-126
+    x, v, sys_ = _pend()
+
+    def cb0(ta, t, d_sgn, bidx):
+        pass
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0, 0.01], [0.25, 0.26]],
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-10, cb0)])
+    for _ in range(4):
+        ta.step()
+
+    class foo:
+        pass
+
+    ta.bar = foo()
+    assert id(ta.bar) == id(copy(ta).bar)
+    assert id(ta.bar) != id(deepcopy(ta).bar)
+    assert np.all(ta.state == copy(ta).state)
+    assert np.all(ta.state == deepcopy(ta).state)
+    ta_dc = deepcopy(ta)
+    assert ta_dc.state[0, 0] == ta.state[0, 0]
+    ta.state[0, 0] += 1
+    assert ta_dc.state[0, 0] != ta.state[0, 0]
+
+
+@pytest.mark.parametrize("fp", FP)
+@pytest.mark.parametrize("which", ["for", "until"])
+def test_propagate_for_until(fp, which):
+    # :128-338 (propagate_for and propagate_until run the same scenarios)
+    ic = np.array([[0.0, 0.1, 0.2, 0.3], [0.25, 0.26, 0.27, 0.28]], dtype=fp)
+    x, v, sys_ = _pend()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=ic, fp_type=fp)
+    prop = lambda *a, **k: getattr(ta, "propagate_" + which)(*a, **k)
+
+    def restart():
+        ta.set_time(fp(0.0))
+        ta.state[:] = ic
+
+    prop([fp(10.0)] * 4)
+    st, res = deepcopy(ta.state), deepcopy(ta.propagate_res)
+    restart()
+    prop(fp(10.0))
+    assert np.all(ta.state == st) and res == ta.propagate_res
+    restart()
+    prop([fp(10.0)] * 4, max_delta_t=[fp(1e-4)] * 4)
+    st, res = deepcopy(ta.state), deepcopy(ta.propagate_res)
+    restart()
+    prop(fp(10.0), max_delta_t=fp(1e-4))
+    assert np.all(ta.state == st) and res == ta.propagate_res
+
+    def cb(t):
+        t.counter = t.counter + 1 if hasattr(t, "counter") else 0
+        return True
+
+    tgt = fp(10.0) if which == "for" else fp(20.0)
+    prop(tgt, callback=cb)
+    assert ta.counter > 0
+
+    class cb_id:
+        def __call__(self_, t):
+            assert id(self_) == self_.orig_id
+            return True
+
+    inst = cb_id()
+    inst.orig_id = id(inst)
+    prop(fp(10.0) if which == "for" else fp(30.0), callback=inst)
+    with pytest.raises(TypeError) as cm:
+        restart()
+        prop(fp(10.0), callback="hello world")
+    assert "cannot be used as a step callback because it is not callable" in str(cm.value)
+
+    class broken_cb:
+        def __call__(self_, t):
+            return []
+
+    with pytest.raises(TypeError) as cm:
+        restart()
+        prop(fp(10.0), callback=broken_cb())
+    assert "The call operator of a step callback is expected to return a boolean, but a value of type" in str(cm.value)
+
+    class cb_hook:
+        def __call__(self_, t):
+            return True
+
+        def pre_hook(self_, t):
+            t.foo = True
+
+    restart()
+    prop(fp(10.0), callback=cb_hook())
+    assert ta.foo
+
+
+@pytest.mark.parametrize("fp", FP)
+def test_events(fp):
+    # :555-600
+    x, v, sys_ = _pend()
+
+    def cb0(ta, t, d_sgn, bidx):
+        pass
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0.0, 0.001], [0.25, 0.2501]], dtype=fp),
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-6, cb0, fp_type=fp)],
+                                  t_events=[hy.t_event_batch(v, fp_type=fp)], fp_type=fp)
+    assert ta.with_events and len(ta.t_events) == 1 and len(ta.nt_events) == 1
+    ta.propagate_until([fp(1e9), fp(1e9)])
+    assert all(int(_[0]) == -1 for _ in ta.propagate_res)
+    assert ta.te_cooldowns[0][0] is not None and ta.te_cooldowns[1][0] is not None
+    ta.reset_cooldowns(0)
+    assert ta.te_cooldowns[0][0] is None and ta.te_cooldowns[1][0] is not None
+    ta.reset_cooldowns()
+    assert ta.te_cooldowns[0][0] is None and ta.te_cooldowns[1][0] is None
+
+
+def _s11n_cb0(ta, t, d_sgn, bidx):
+    pass
+
+
+class _s11n_cb1:
+    def __init__(self):
+        self.n = 0
+
+    def __call__(self, ta, d_sgn, bidx):
+        self.n = self.n + 1
+        return True
+
+
+@pytest.mark.parametrize("fp", FP)
+def test_s11n(fp):
+    # :602-690
+    x, v, sys_ = _pend()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0, 0.01], [0.25, 0.26]], dtype=fp),
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-6, _s11n_cb0, fp_type=fp)], fp_type=fp)
+    for _ in range(4):
+        ta.step()
+    ta2 = pickle.loads(pickle.dumps(ta))
+    assert np.all(ta.state == ta2.state) and np.all(ta.time == ta2.time)
+    assert len(ta.t_events) == len(ta2.t_events) and len(ta.nt_events) == len(ta2.nt_events)
+    ta.step()
+    ta2.step()
+    assert np.all(ta.state == ta2.state) and np.all(ta.time == ta2.time)
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0, 0.01], [0.25, 0.26]], dtype=fp), tol=fp(1e-6), fp_type=fp)
+    assert ta.tol == fp(1e-6)
+    ta.foo = "hello world"
+    ta = pickle.loads(pickle.dumps(ta))
+    assert ta.foo == "hello world"
+    clb = _s11n_cb1()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=np.array([[0, 0.01], [0.25, 0.26]], dtype=fp),
+                                  t_events=[hy.t_event_batch(v, callback=clb, fp_type=fp)], fp_type=fp)
+    assert id(clb) != id(ta.t_events[0].callback)
+    assert ta.t_events[0].callback.n == 0
+    ta.propagate_until([fp(100.0), fp(100.0)])
+    ta2 = pickle.loads(pickle.dumps(ta))
+    assert ta.t_events[0].callback.n == ta2.t_events[0].callback.n
