@@ -190,3 +190,114 @@ def test_s11n(fp):
     ta.propagate_until([fp(100.0), fp(100.0)])
     ta2 = pickle.loads(pickle.dumps(ta))
     assert ta.t_events[0].callback.n == ta2.t_events[0].callback.n
+
+
+@pytest.mark.parametrize("fp", FP)
+def test_step_callback(fp):
+    # :859-921
+    from hy_b200.callback import angle_reducer
+
+    x, v, sys_ = _pend()
+
+    class cb_hook:
+        def __call__(self_, ta):
+            return True
+
+        def pre_hook(self_, ta):
+            ta.foo = True
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[fp(0.0), fp(0.01)], [fp(10.0), fp(10.01)]], fp_type=fp)
+    cb1, cb2 = cb_hook(), cb_hook()
+    res = ta.propagate_for(fp(10.0), callback=[cb1, cb2])
+    assert isinstance(res[1], list) and isinstance(res[1][0], cb_hook) and isinstance(res[1][1], cb_hook)
+    assert id(res[1][0]) == id(cb1) and id(res[1][1]) == id(cb2)
+    assert hasattr(ta, "foo")
+    res = ta.propagate_until(fp(20.0), callback=[cb1, angle_reducer([x]), cb2])
+    assert isinstance(res[1], list) and isinstance(res[1][0], cb_hook)
+    assert isinstance(res[1][1], angle_reducer) and isinstance(res[1][2], cb_hook)
+    assert id(res[1][0]) == id(cb1) and id(res[1][2]) == id(cb2)
+    assert 0 <= ta.state[0, 0] < fp(6.29) and 0 <= ta.state[0, 1] < fp(6.29)
+    res = ta.propagate_grid([[fp(20.0), fp(20.0)], [fp(30.0), fp(30.1)]], callback=cb1)
+    assert isinstance(res[0], cb_hook) and id(res[0]) == id(cb1)
+    res = ta.propagate_for(fp(10.0), callback=angle_reducer([x]))
+    assert isinstance(res[1], angle_reducer)
+    assert 0 <= ta.state[0, 0] < fp(6.29) and 0 <= ta.state[0, 1] < fp(6.29)
+
+
+def test_ensemble_batch():
+    # /root/reference/heyoka/_test_ensemble.py:13-236 (thread algorithm throughout; the process algorithm for the
+    # first scenario and for the serialisation of callbacks - every worker process creates its own CUDA context)
+    from hy_b200.callback import angle_reducer
+
+    x, v, sys_ = _pend()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0] * 4] * 2)
+    ics = np.zeros((10, 2, 4))
+    for i in range(10):
+        ics[i, 0] = [0.05 + i / 100, 0.051 + i / 100, 0.052 + i / 100, 0.053 + i / 100.0]
+        ics[i, 0] = [0.025 + i / 100, 0.026 + i / 100, 0.027 + i / 100, 0.028 + i / 100.0]
+
+    def gen(t, idx):
+        t.set_time(0.0)
+        t.state[:] = ics[idx]
+        return t
+
+    for algo in ("thread", "process"):
+        kw = dict(algorithm=algo, max_workers=8) if algo == "thread" else dict(algorithm=algo, max_workers=2, chunksize=3)
+        ret = hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, **kw)
+        assert len(ret) == 10
+        for i in range(10):
+            ta.set_time(0.0)
+            ta.state[:] = ics[i]
+            ta.propagate_until(20.0)
+            assert all(abs(ret[i][0].time[j] - 20.0) < 1e-7 for j in range(4))
+            assert np.all(ta.state == ret[i][0].state) and ret[i][1] is None
+            assert np.all(ta.time == ret[i][0].time) and ta.propagate_res == ret[i][0].propagate_res
+        if algo == "process":
+            continue
+        ret = hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, c_output=True, **kw)
+        for i in range(10):
+            ta.set_time(0.0)
+            ta.state[:] = ics[i]
+            loc = ta.propagate_until(20.0, c_output=True)
+            assert np.all(ta.state == ret[i][0].state) and ret[i][1] is not None
+            assert ta.propagate_res == ret[i][0].propagate_res
+            assert np.all(loc[0](5.0) == ret[i][1](5.0))
+
+    def gen10(t, idx):
+        t.set_time(10.0)
+        t.state[:] = ics[idx]
+        return t
+
+    ret = hy.ensemble_propagate_for_batch(ta, 20.0, 10, gen10, algorithm="thread", max_workers=8)
+    for i in range(10):
+        ta.set_time(10.0)
+        ta.state[:] = ics[i]
+        ta.propagate_for(20.0)
+        assert all(abs(ret[i][0].time[j] - 30.0) < 1e-7 for j in range(4))
+        assert np.all(ta.state == ret[i][0].state) and ret[i][1] is None
+        assert ta.propagate_res == ret[i][0].propagate_res
+
+    grid = np.linspace(0.0, 20.0, 80)
+    splat = np.repeat(grid, 4).reshape(-1, 4)
+    ret = hy.ensemble_propagate_grid_batch(ta, grid, 10, gen, algorithm="thread", max_workers=8)
+    for i in range(10):
+        ta.set_time(0.0)
+        ta.state[:] = ics[i]
+        loc = ta.propagate_grid(splat)
+        assert np.all(loc[1] == ret[i][2])
+        assert np.all(ta.state == ret[i][0].state) and ta.propagate_res == ret[i][0].propagate_res
+
+    class step_cb:
+        def __call__(self_, t):
+            assert id(self_) != self_.orig_id      # callbacks are deep-copied per iteration
+            return True
+
+    cb = step_cb()
+    cb.orig_id = id(cb)
+    ret = hy.ensemble_propagate_for_batch(ta, 20.0, 10, gen, algorithm="thread", max_workers=8, callback=cb)
+    assert all(isinstance(r[2], step_cb) for r in ret)
+    ret = hy.ensemble_propagate_for_batch(ta, 20.0, 10, gen, algorithm="thread", max_workers=8,
+                                          callback=[cb, angle_reducer([x])])
+    for r in ret:
+        assert isinstance(r[2], list) and len(r[2]) == 2
+        assert isinstance(r[2][0], step_cb) and isinstance(r[2][1], angle_reducer)
