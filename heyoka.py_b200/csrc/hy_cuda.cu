@@ -1652,6 +1652,113 @@ int hy_cout_detach(hy_ctx *c, hy_cout **out)
     return 0;
 }
 
+extern "C++" {
+namespace {
+// host image of a record pool: per lane a run of consecutive chunks, records in the tc layout
+template <typename R>
+void build_pool_image(std::vector<R> &buf, std::vector<uint32_t> &head, std::vector<uint32_t> &tail, uint32_t n, uint32_t P1,
+                      uint32_t B, const uint64_t *ns, const R *tcs, const R *thi, const R *tlo, uint32_t rec_len,
+                      uint32_t chunk_len)
+{
+    const uint32_t nP = n * P1;
+    uint32_t cid = 0;
+    for (uint32_t l = 0; l < B; ++l) {
+        const uint32_t cnt = (uint32_t)ns[l], nch = (cnt + hy::HY_REC_CH - 1u) / hy::HY_REC_CH;
+        head[l] = nch ? cid : hy::HY_REC_NONE;
+        tail[l] = nch ? cid + nch - 1u : hy::HY_REC_NONE;
+        for (uint32_t j = 0; j < nch; ++j) {
+            const uint32_t next = j + 1u < nch ? cid + j + 1u : hy::HY_REC_NONE;
+            std::memcpy(&buf[(size_t)(cid + j) * chunk_len], &next, 4);
+        }
+        for (uint32_t s = 0; s < cnt; ++s) {
+            R *dst = &buf[(size_t)(cid + s / hy::HY_REC_CH) * chunk_len + 2u + (s % hy::HY_REC_CH) * rec_len];
+            for (uint32_t i = 0; i < nP; ++i) dst[i] = tcs[((size_t)s * nP + i) * B + l];
+            dst[nP] = thi[(size_t)(s + 1) * B + l];
+            dst[nP + 1] = tlo[(size_t)(s + 1) * B + l];
+        }
+        cid += nch;
+    }
+}
+} // namespace
+} // extern "C++"
+
+int hy_cout_from_host(hy_cout **out, int device, int fp_bits, uint32_t n_state, uint32_t order, uint32_t batch,
+                      const uint64_t *n_steps, const void *tcs, const void *times_hi, const void *times_lo, uint64_t S)
+{
+    if (!out || !n_steps || !times_hi || !times_lo || (S && !tcs)) return fail("hy_cout_from_host: null argument");
+    if (fp_bits != 32 && fp_bits != 64) return fail("hy_cout_from_host: fp_bits must be 32 or 64");
+    if (!batch || !n_state) return fail("hy_cout_from_host: empty record");
+    *out = nullptr;
+    size_t total = 0;
+    for (uint32_t l = 0; l < batch; ++l) {
+        if (n_steps[l] > S) return fail("hy_cout_from_host: a lane holds more steps than the arrays");
+        total += (n_steps[l] + hy::HY_REC_CH - 1u) / hy::HY_REC_CH;
+    }
+    if (total >= 0x7fffffffu) return fail("hy_cout_from_host: the record is too large");
+    CU(cudaSetDevice(device));
+    hy_cout *r = new hy_cout();
+    r->device = device;
+    r->rb = fp_bits == 64 ? 8 : 4;
+    r->B = batch;
+    r->n = n_state;
+    r->P1 = order + 1;
+    r->rec_len = r->n * r->P1 + 2u;
+    r->chunk_len = 2u + hy::HY_REC_CH * r->rec_len;
+    r->si = r->P1; // the reference's tc layout
+    r->sk = 1;
+    r->seg_chunks = (uint32_t)std::max<size_t>(16, total);
+    auto bail = [&](int rc) {
+        rec_free(r);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("hy_cout_from_host: no stream"));
+    if (cudaMalloc((void **)&r->d_seg, HY_REC_MAXSEG * sizeof(void *)) != cudaSuccess ||
+        cudaMemset(r->d_seg, 0, HY_REC_MAXSEG * sizeof(void *)) != cudaSuccess)
+        return bail(fail("hy_cout_from_host: out of device memory"));
+    const size_t B = r->B;
+    const size_t lane_bytes = 16 + 5 * B * 4 + 2 * B * 8;
+    if (cudaMalloc(&r->d_lane, lane_bytes) != cudaSuccess || cudaMemset(r->d_lane, 0, lane_bytes) != cudaSuccess)
+        return bail(fail("hy_cout_from_host: out of device memory"));
+    char *q = (char *)r->d_lane;
+    r->d_next = (unsigned int *)q;
+    r->d_dir_next = (unsigned int *)(q + 8);
+    q += 16;
+    r->d_t0hi = q, q += B * 8;
+    r->d_t0lo = q, q += B * 8;
+    r->d_head = (uint32_t *)q, q += B * 4;
+    r->d_tail = (uint32_t *)q, q += B * 4;
+    r->d_count = (uint32_t *)q, q += B * 4;
+    r->d_nch = (uint32_t *)q, q += B * 4;
+    r->d_dir_off = (uint32_t *)q;
+    if (rec_add_segment(r)) return bail(1);
+    std::vector<uint32_t> head(B), tail(B), count(B);
+    for (size_t l = 0; l < B; ++l) count[l] = (uint32_t)n_steps[l];
+    const size_t elems = (size_t)r->seg_chunks * r->chunk_len;
+    cudaError_t e = cudaSuccess;
+    if (r->rb == 8) {
+        std::vector<double> buf(elems, 0.0);
+        build_pool_image<double>(buf, head, tail, r->n, r->P1, r->B, n_steps, (const double *)tcs, (const double *)times_hi,
+                                 (const double *)times_lo, r->rec_len, r->chunk_len);
+        e = cudaMemcpy(r->segs[0], buf.data(), elems * 8, cudaMemcpyHostToDevice);
+    } else {
+        std::vector<float> buf(elems, 0.0f);
+        build_pool_image<float>(buf, head, tail, r->n, r->P1, r->B, n_steps, (const float *)tcs, (const float *)times_hi,
+                                (const float *)times_lo, r->rec_len, r->chunk_len);
+        e = cudaMemcpy(r->segs[0], buf.data(), elems * 4, cudaMemcpyHostToDevice);
+    }
+    const unsigned int used = (unsigned int)total;
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_next, &used, 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_t0hi, times_hi, B * r->rb, cudaMemcpyHostToDevice); // row 0: the start times
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_t0lo, times_lo, B * r->rb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_head, head.data(), B * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_tail, tail.data(), B * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_count, count.data(), B * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail(std::string("hy_cout_from_host: ") + cudaGetErrorString(e)));
+    r->indexed = false;
+    *out = r;
+    return 0;
+}
+
 int hy_cout_free(hy_cout *r, hy_ctx *recycle_into)
 {
     if (!r) return 0;

@@ -127,6 +127,7 @@ SYMBOLS = [
     "hy_propagate_ex",
     "hy_set_angle_reducer",
     "hy_cout_detach",
+    "hy_cout_from_host",
     "hy_cout_free",
     "hy_host_alloc",
     "hy_host_free",
@@ -526,7 +527,7 @@ class CoutRecord:
         import weakref
 
         self._h = handle
-        self._ctx_ref = weakref.ref(ctx)
+        self._ctx_ref = weakref.ref(ctx) if ctx is not None else (lambda: None)
 
     def info(self, n_steps):
         mx = C.c_uint64(0)
@@ -562,6 +563,20 @@ class CoutRecord:
             self.close()
         except Exception:
             pass
+
+
+def cout_from_host(fp, n, order, B, n_steps, tcs, thi, tlo, S, device=0):
+    """hy_cout_from_host (include/hy_cuda_cout.h): a record rebuilt from the arrays hy_cout_get exports -
+    how a copied / unpickled continuous_output_batch gets its device record back."""
+    h = C.c_void_p()
+    ns = np.ascontiguousarray(n_steps, dtype=np.uint64)
+    tcs = np.ascontiguousarray(tcs, dtype=fp)
+    thi = np.ascontiguousarray(thi, dtype=fp)
+    tlo = np.ascontiguousarray(tlo, dtype=fp)
+    check(lib().hy_cout_from_host(C.byref(h), C.c_int(int(device)), C.c_int(64 if np.dtype(fp) == np.float64 else 32),
+                                  C.c_uint32(int(n)), C.c_uint32(int(order)), C.c_uint32(int(B)), ptr(ns), ptr(tcs),
+                                  ptr(thi), ptr(tlo), C.c_uint64(int(S))))
+    return CoutRecord(h, None)
 
 
 def tape_kernel_variant(dc):

@@ -1,5 +1,5 @@
-"""CPU: the C-ABI library loads and exports every symbol include/hy_cuda.h
-declares (no compute calls without a GPU); the product fails loudly without a
+"""CPU: the C-ABI library loads and exports every symbol include/*.h
+declare (no compute calls without a GPU); the product fails loudly without a
 device."""
 
 import ctypes
@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    txt = open(os.path.join(ROOT, "include", "hy_cuda.h")).read()
+    inc = os.path.join(ROOT, "include")
+    txt = "".join(open(os.path.join(inc, f)).read() for f in sorted(os.listdir(inc)) if f.endswith(".h"))
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(hy_[a-z_0-9]+)\s*\(", txt)))
 

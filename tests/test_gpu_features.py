@@ -102,7 +102,7 @@ def test_continuous_output_vs_oracle_ragged():
     assert c_out.n_steps == max(ns)
     times = c_out.times
     for l in range(4):
-        assert np.all(np.isnan(times[ns[l] + 1:, l])) and not np.any(np.isnan(times[: ns[l] + 1, l]))
+        assert np.all(times[ns[l] + 1:, l] == times[ns[l], l]) and np.all(np.isfinite(times[:, l]))   # end time repeated
         assert np.all(np.isnan(c_out.tcs[ns[l]:, :, :, l]))
     tq = np.array([[0.5, 0.5, 0.5, 0.5], [2.9, 4.9, 6.9, 8.9], [1.0, 2.0, 3.0, 4.0]])
     out = c_out(tq)

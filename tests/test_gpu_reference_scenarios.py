@@ -226,7 +226,8 @@ def test_step_callback(fp):
 
 def test_ensemble_batch():
     # /root/reference/heyoka/_test_ensemble.py:13-236 (thread algorithm throughout; the process algorithm for the
-    # first scenario and for the serialisation of callbacks - every worker process creates its own CUDA context)
+    # propagate_until scenarios, with and without c_output - every worker process creates its own CUDA context and
+    # the continuous outputs travel back pickled)
     from hy_b200.callback import angle_reducer
 
     x, v, sys_ = _pend()
@@ -252,8 +253,6 @@ def test_ensemble_batch():
             assert all(abs(ret[i][0].time[j] - 20.0) < 1e-7 for j in range(4))
             assert np.all(ta.state == ret[i][0].state) and ret[i][1] is None
             assert np.all(ta.time == ret[i][0].time) and ta.propagate_res == ret[i][0].propagate_res
-        if algo == "process":
-            continue
         ret = hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, c_output=True, **kw)
         for i in range(10):
             ta.set_time(0.0)
@@ -301,3 +300,138 @@ def test_ensemble_batch():
     for r in ret:
         assert isinstance(r[2], list) and len(r[2]) == 2
         assert isinstance(r[2][0], step_cb) and isinstance(r[2][1], angle_reducer)
+
+
+@pytest.mark.parametrize("fp,c_out_t", [(np.float32, "continuous_output_batch_flt"), (np.float64, "continuous_output_batch_dbl")])
+def test_c_output_batch(fp, c_out_t):
+    # /root/reference/heyoka/test.py:1414-1771 (the scalar integrators of the comparison are one-lane batch integrators)
+    from pickle import dumps, loads
+    from sys import getrefcount
+
+    x, v, sys_ = _pend()
+    c_out = getattr(hy, c_out_t)()
+    msg = "Cannot use a default-constructed continuous_output_batch object"
+
+    def check_default(c):
+        with pytest.raises(ValueError) as cm:
+            c.n_steps
+        assert msg in str(cm.value)
+        assert c.batch_size == 0 and "forward" not in repr(c) and c.llvm_state.ir != ""
+
+    for arg in (np.zeros((0,), dtype=fp), fp(1)):
+        with pytest.raises(ValueError) as cm:
+            c_out(arg)
+        assert msg in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        c_out(time=[fp(0), fp(0)])
+    assert msg in str(cm.value)
+    assert c_out.output is None and c_out.times is None and c_out.tcs is None
+    with pytest.raises(ValueError) as cm:
+        c_out.bounds
+    assert msg in str(cm.value)
+    check_default(c_out)
+    check_default(copy(c_out))
+    check_default(deepcopy(c_out))
+    check_default(loads(dumps(c_out)))
+
+    ic = [[fp(0), fp(0.01), fp(0.02), fp(0.03)], [fp(0.25), fp(0.26), fp(0.27), fp(0.28)]]
+    arr_ic = np.array(ic)
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=ic, fp_type=fp)
+
+    def reset():
+        ta.state[:] = ic
+        ta.set_time([fp(0)] * 4)
+
+    final_tm = [fp(10), fp(10.4), fp(10.5), fp(11.0)]
+    check_tm = [fp(0.1), fp(1.3), fp(5.6), fp(9.1)]
+    c_out, cb = ta.propagate_until(final_tm)
+    assert cb is None and c_out is None
+    reset()
+    c_out, cb = ta.propagate_until(final_tm, c_output=False)
+    assert cb is None and c_out is None
+    reset()
+    c_out, cb = ta.propagate_until(final_tm, c_output=True)
+    assert cb is None and c_out is not None
+    assert c_out(check_tm).shape == (2, 4)
+    with pytest.raises(ValueError):
+        c_out(check_tm)[0] = 0.5
+    rc = getrefcount(c_out)
+    tmp_out = c_out(check_tm)
+    assert getrefcount(c_out) == rc + 1
+    with pytest.raises(ValueError) as cm:
+        c_out(np.zeros((1, 1, 1), dtype=fp))
+    assert ("Invalid time array passed to a continuous_output_batch object: the number of dimensions must be 1 or 2, "
+            "but it is 3 instead") in str(cm.value)
+    for n_ in (1, 0, 5):
+        with pytest.raises(ValueError) as cm:
+            c_out(np.zeros((n_,), dtype=fp))
+        assert ("Invalid time array passed to a continuous_output_batch object: the length must be 4 but it is {} "
+                "instead".format(n_)) in str(cm.value)
+
+    # one-lane integrators for comparison
+    eps10 = np.finfo(fp).eps * 10
+    scal = []
+    for idx in range(4):
+        one = hy.taylor_adaptive_batch(sys=sys_, state=arr_ic[:, idx:idx + 1], fp_type=fp)
+        scal.append(one.propagate_until(final_tm[idx:idx + 1], c_output=True)[0])
+    c_out(check_tm)
+    for idx in range(4):
+        scal[idx](check_tm[idx:idx + 1])
+        assert np.allclose(scal[idx].output[:, 0], c_out.output[:, idx], rtol=eps10, atol=eps10)
+    rc = getrefcount(c_out)
+    tmp_out2 = c_out(check_tm)
+    assert getrefcount(c_out) == rc + 1
+    scal_res = deepcopy(c_out(fp(0.42)))
+    assert np.all(scal_res == c_out([fp(0.42)] * 4))
+    nc_check_tm = np.vstack([check_tm, np.zeros((4,), dtype=fp)]).T.flatten()[::2]
+    c_out(nc_check_tm)
+    for idx in range(4):
+        assert np.allclose(scal[idx].output[:, 0], c_out.output[:, idx], rtol=eps10, atol=eps10)
+    with pytest.raises(ValueError) as cm:
+        c_out(np.zeros((5, 3), dtype=fp))
+    assert ("Invalid time array passed to a continuous_output_batch object: the number of columns must be 4 but it is 3 "
+            "instead") in str(cm.value)
+    b_check_tm = np.repeat(check_tm, 5, axis=0).reshape((4, 5)).T
+    out_b = c_out(b_check_tm)
+    assert out_b.shape == (5, 2, 4)
+    for idx in range(4):
+        scal[idx](check_tm[idx:idx + 1])
+        for j in range(5):
+            assert np.allclose(scal[idx].output[:, 0], out_b[j, :, idx], rtol=eps10, atol=eps10)
+    assert c_out(np.zeros((0, 4), dtype=fp)).shape == (0, 2, 4)
+
+    assert c_out.times.shape == (c_out.n_steps + 1, 4) and np.all(np.isfinite(c_out.times))
+    with pytest.raises(ValueError):
+        c_out.times[0] = 0.5
+    rc = getrefcount(c_out)
+    tmp_out3 = c_out.times
+    assert getrefcount(c_out) == rc + 1
+    assert c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4)
+    with pytest.raises(ValueError):
+        c_out.tcs[0] = 0.5
+    rc = getrefcount(c_out)
+    tmp_out4 = c_out.tcs
+    assert getrefcount(c_out) == rc + 1
+    assert np.all(c_out.bounds[0] == [0.0] * 4)
+    assert np.allclose(c_out.bounds[1], final_tm, rtol=eps10, atol=eps10)
+    assert c_out.batch_size == 4 and "forward" in repr(c_out) and c_out.llvm_state.ir != ""
+    c_out = copy(c_out)
+    assert c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4) and c_out.llvm_state.ir != ""
+    c_out = deepcopy(c_out)
+    assert c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4)
+    c_out = loads(dumps(c_out))
+    assert c_out.llvm_state.ir != "" and c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4)
+
+    class foo:
+        pass
+
+    c_out_copy = deepcopy(c_out)
+    c_out_copy.bar = foo()
+    assert id(c_out_copy.bar) == id(copy(c_out_copy).bar)
+    assert id(c_out_copy.bar) != id(deepcopy(c_out_copy).bar)
+    assert np.all(c_out_copy(fp(0.1)) == copy(c_out_copy)(fp(0.1)))
+    assert np.all(c_out_copy(fp(0.1)) == deepcopy(c_out_copy)(fp(0.1)))
+    c_out.foo = []
+    c_out = loads(dumps(c_out))
+    assert c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4) and c_out.foo == []
+    del tmp_out, tmp_out2, tmp_out3, tmp_out4
