@@ -133,10 +133,12 @@ def dispatch(ta):
         lane = int(r["lane"])
         if ev >= nte:
             cb = ta._nt_events[ev - nte].callback
+            # (errors raised while the reference's C++ loop calls back into Python surface as RuntimeError:
+            #  /root/reference/heyoka/test.py:836-846, :968-999)
             try:
                 cb(ta, ta._fp(r["t"]), int(r["d_sgn"]), lane)
             except TypeError as e:
-                raise TypeError(
+                raise RuntimeError(
                     "The call operator of a non-terminal event callback has an incompatible "
                     "signature: {}".format(e)
                 )
@@ -144,13 +146,18 @@ def dispatch(ta):
             cb = ta._t_events[ev].callback
             keep = False
             if cb is not None:
-                keep = cb(ta, int(r["d_sgn"]), lane)
+                try:
+                    keep = cb(ta, int(r["d_sgn"]), lane)
+                except TypeError as e:
+                    raise RuntimeError(
+                        "The call operator of a terminal event callback has an incompatible "
+                        "signature: {}".format(e)
+                    )
                 if not isinstance(keep, (bool, np.bool_)):
-                    raise TypeError(
-                        "The call operator of a terminal event callback is expected to return a "
-                        "boolean, but a value of type \"{}\" was returned instead".format(
-                            type(keep).__name__
-                        )
+                    # (taylor_expose_events.cpp:128-134)
+                    raise RuntimeError(
+                        "Unable to convert a Python object of type '{}' to the C++ type 'bool' in the "
+                        "construction of the return value of an event callback".format(type(keep))
                     )
             term[lane] = (ev, bool(keep))
     return term

@@ -181,5 +181,5 @@ def test_continuing_terminal_event_callback():
 
     ta = hy.taylor_adaptive_batch(common.pendulum_sys(), np.array([[0.05, 0.05], [0.025, 0.025]]),
                                   t_events=[hy.t_event_batch(v, callback=bad)])
-    with pytest.raises(TypeError):
+    with pytest.raises(RuntimeError, match="in the construction of the return value of an event callback"):
         ta.propagate_until(10.0)

@@ -435,3 +435,135 @@ def test_c_output_batch(fp, c_out_t):
     c_out = loads(dumps(c_out))
     assert c_out.tcs.shape == (c_out.n_steps, 2, ta.order + 1, 4) and c_out.foo == []
     del tmp_out, tmp_out2, tmp_out3, tmp_out4
+
+
+def test_event_detection_batch():
+    # /root/reference/heyoka/test.py:694-999
+
+    x, v, sys_ = _pend()
+    counter, cur_time = [0] * 2, [0.0] * 2
+    ta_id = [None]
+
+    def cb0(ta, t, d_sgn, bidx):
+        assert t > cur_time[bidx]
+        assert counter[bidx] % 3 == 0 or counter[bidx] % 3 == 2
+        assert ta_id[0] == id(ta)
+        counter[bidx] += 1
+        cur_time[bidx] = t
+
+    def cb1(ta, t, d_sgn, bidx):
+        assert t > cur_time[bidx]
+        assert counter[bidx] % 3 == 1
+        assert ta_id[0] == id(ta)
+        counter[bidx] += 1
+        cur_time[bidx] = t
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-10, cb0), hy.nt_event_batch(v, cb1)])
+    ta_id[0] = id(ta)
+    ta.propagate_until([4.0, 4.0])
+    assert all(_[0] == hy.taylor_outcome.time_limit for _ in ta.propagate_res)
+    assert counter == [12, 12]
+
+    class ccb0:
+        def __init__(self):
+            self.lst = []
+
+        def __call__(self, ta, t, d_sgn, bidx):
+            pass
+
+    class ccb1(ccb0):
+        pass
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-10, ccb0()), hy.nt_event_batch(v, ccb1()),
+                                             hy.nt_event_batch(v, ccb1())])
+    # (the reference's event objects alias storage inside the C++ integrator and therefore hold it -
+    #  getrefcount(ta) grows by 3 there; here they are plain Python objects owned by the integrator)
+    nt_list = ta.nt_events
+    assert len(nt_list) == 3
+    for i in range(3):
+        assert id(ta.nt_events[i].callback) == id(ta.nt_events[i].callback)
+        assert id(ta.nt_events[i].callback.lst) == id(ta.nt_events[i].callback.lst)
+    ta_copy = deepcopy(ta)
+    for i in range(3):
+        assert id(ta_copy.nt_events[i].callback) != id(ta.nt_events[i].callback)
+        assert id(ta_copy.nt_events[i].callback.lst) != id(ta.nt_events[i].callback.lst)
+    del nt_list
+
+    def cb2(ta, t):
+        pass
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-10, cb2)])
+    with pytest.raises(RuntimeError):
+        ta.propagate_until([4.0, 4.0])
+
+    # terminal events
+    counter_t, counter_nt, cur_time = [0] * 2, [0] * 2, [0.0] * 2
+
+    def ncb(ta, t, d_sgn, bidx):
+        assert t > cur_time[bidx] and ta_id[0] == id(ta)
+        counter_nt[bidx] += 1
+        cur_time[bidx] = t
+
+    def tcb(ta, d_sgn, bidx):
+        assert ta.time[bidx] > cur_time[bidx] and ta_id[0] == id(ta)
+        counter_t[bidx] += 1
+        cur_time[bidx] = ta.time[bidx]
+        return True
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  nt_events=[hy.nt_event_batch(v * v - 1e-10, ncb)],
+                                  t_events=[hy.t_event_batch(v, callback=tcb)])
+    ta_id[0] = id(ta)
+    while True:
+        ta.step()
+        if all(_[0] > hy.taylor_outcome.success for _ in ta.step_res):
+            break
+    assert all(int(_[0]) == 0 for _ in ta.step_res) and all(_ < 1 for _ in ta.time)
+    assert all(_ == 1 for _ in counter_nt) and all(_ == 1 for _ in counter_t)
+    while True:
+        ta.step()
+        if all(_[0] > hy.taylor_outcome.success for _ in ta.step_res):
+            break
+    assert all(int(_[0]) == 0 for _ in ta.step_res) and all(_ > 1 for _ in ta.time)
+    assert all(_ == 3 for _ in counter_nt) and all(_ == 2 for _ in counter_t)
+
+    class tcb0:
+        def __init__(self):
+            self.lst = []
+
+        def __call__(self, ta, d_sgn, bidx):
+            pass
+
+    class tcb1(tcb0):
+        pass
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  t_events=[hy.t_event_batch(v * v - 1e-10, callback=tcb0()),
+                                            hy.t_event_batch(v, callback=tcb1()), hy.t_event_batch(v, callback=tcb1())])
+    t_list = ta.t_events
+    assert len(t_list) == 3
+    for i in range(3):
+        assert id(ta.t_events[i].callback) == id(ta.t_events[i].callback)
+        assert id(ta.t_events[i].callback.lst) == id(ta.t_events[i].callback.lst)
+    ta_copy = deepcopy(ta)
+    for i in range(3):
+        assert id(ta_copy.t_events[i].callback) != id(ta.t_events[i].callback)
+        assert id(ta_copy.t_events[i].callback.lst) != id(ta.t_events[i].callback.lst)
+    del t_list
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  t_events=[hy.t_event_batch(v * v - 1e-10, callback=cb2)])
+    with pytest.raises(RuntimeError):
+        ta.propagate_until([4.0, 4.0])
+
+    def cb3(ta, d_sgn, bidx):
+        return "hello"
+
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0, 0.001], [0.25, 0.2501]],
+                                  t_events=[hy.t_event_batch(v * v - 1e-10, callback=cb3)])
+    with pytest.raises(RuntimeError) as cm:
+        ta.propagate_until([4.0, 4.0])
+    assert "in the construction of the return value of an event callback" in str(cm.value)
