@@ -29,47 +29,82 @@ def _check_dir(direction):
     return direction
 
 
-class nt_event_batch_impl:
+_OWN = ("expression", "callback", "direction", "cooldown")
+
+
+class _event_base:
+    """Copy / pickle semantics of the reference's event classes (copy_wrapper / deepcopy_wrapper,
+    common_utils.hpp; pickle_wrappers.hpp:35-73): the callback is always deep-copied (value semantics of the
+    C++ wrapper, taylor_expose_events.cpp:83), dynamic attributes are shared by `copy` and deep-copied by
+    `deepcopy`; the callback is serialised with the active backend (cloudpickle by default, so lambdas and
+    local classes travel: `set_serialization_backend`)."""
+
+    def _extras(self):
+        return {k: v for k, v in self.__dict__.items() if k not in _OWN}
+
+    def __copy__(self):
+        new = self._clone()
+        new.__dict__.update(self._extras())
+        return new
+
+    def __deepcopy__(self, memo):
+        new = self._clone()
+        new.__dict__.update(_copy.deepcopy(self._extras(), memo))
+        return new
+
+    def __getstate__(self):
+        from .ensemble import get_serialization_backend
+
+        d = dict(self.__dict__)
+        d["callback"] = None if self.callback is None else get_serialization_backend().dumps(self.callback)
+        return d
+
+    def __setstate__(self, d):
+        from .ensemble import get_serialization_backend
+
+        d = dict(d)
+        if d.get("callback") is not None:
+            d["callback"] = get_serialization_backend().loads(d["callback"])
+        self.__dict__.update(d)
+
+
+def _not_callable(callback):
+    return TypeError("An object of type '{}' cannot be used as an event callback because it is not "
+                     "callable".format(str(type(callback))))
+
+
+class nt_event_batch_impl(_event_base):
     _fp = np.float64
 
     def __init__(self, ex, callback, direction=event_direction.any):
         if not isinstance(ex, _E.expression):
             raise TypeError("An event needs an expression as first argument")
         if callback is None or not callable(callback):
-            raise TypeError(
-                "An object of type '{}' cannot be used as an event callback because it is not "
-                "callable".format(type(callback).__name__)
-            )
+            raise _not_callable(callback)
         self.expression = ex
         self.callback = _copy.deepcopy(callback)
         self.direction = _check_dir(direction)
 
     def __repr__(self):
         return (
-            "C++ datatype   : {}\nEvent type     : non-terminal\nEvent direction: "
+            "C++ datatype   : {}\nEvent type     : non-terminal\nEvent expression: {}\nEvent direction: "
             "event_direction::{}\nBatch mode     : true\n".format(
-                "double" if self._fp == np.float64 else "float", self.direction.name
+                "double" if self._fp == np.float64 else "float", self.expression, self.direction.name
             )
         )
 
-    def __deepcopy__(self, memo):
+    def _clone(self):
         return type(self)(self.expression, self.callback, direction=self.direction)
 
-    def __copy__(self):
-        return self.__deepcopy__({})
 
-
-class t_event_batch_impl:
+class t_event_batch_impl(_event_base):
     _fp = np.float64
 
     def __init__(self, ex, callback=None, direction=event_direction.any, cooldown=-1):
         if not isinstance(ex, _E.expression):
             raise TypeError("An event needs an expression as first argument")
         if callback is not None and not callable(callback):
-            raise TypeError(
-                "An object of type '{}' cannot be used as an event callback because it is not "
-                "callable".format(type(callback).__name__)
-            )
+            raise _not_callable(callback)
         self.expression = ex
         self.callback = _copy.deepcopy(callback) if callback is not None else None
         self.direction = _check_dir(direction)
@@ -80,20 +115,16 @@ class t_event_batch_impl:
 
     def __repr__(self):
         return (
-            "C++ datatype   : {}\nEvent type     : terminal\nEvent direction: "
+            "C++ datatype   : {}\nEvent type     : terminal\nEvent expression: {}\nEvent direction: "
             "event_direction::{}\nWith callback  : {}\nCooldown       : {}\nBatch mode     : true\n".format(
-                "double" if self._fp == np.float64 else "float", self.direction.name,
+                "double" if self._fp == np.float64 else "float", self.expression, self.direction.name,
                 "yes" if self.callback is not None else "no",
                 "auto" if self.cooldown < 0 else self.cooldown,
             )
         )
 
-    def __deepcopy__(self, memo):
-        return type(self)(self.expression, self.callback, direction=self.direction,
-                          cooldown=self.cooldown)
-
-    def __copy__(self):
-        return self.__deepcopy__({})
+    def _clone(self):
+        return type(self)(self.expression, self.callback, direction=self.direction, cooldown=self.cooldown)
 
 
 class nt_event_batch_dbl(nt_event_batch_impl):
