@@ -528,7 +528,7 @@ class taylor_adaptive_batch_impl:
         self._need_var()
         if not hasattr(self, "_tstate"):
             self._tstate = np.zeros((self.n_orig_sv, self._B), dtype=self._fp)
-        return self._ro(self._tstate)
+        return self._view(self._tstate)
 
     def eval_taylor_map(self, inputs):
         """Reference: expose_batch_integrators.cpp:573-649 (argument checks and messages)."""

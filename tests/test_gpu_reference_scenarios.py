@@ -567,3 +567,54 @@ def test_event_detection_batch():
     with pytest.raises(RuntimeError) as cm:
         ta.propagate_until([4.0, 4.0])
     assert "in the construction of the return value of an event callback" in str(cm.value)
+
+
+def test_var_integrator_batch():
+    # /root/reference/heyoka/_test_var_integrator.py:143-258
+    from sys import getrefcount
+
+    x, v = hy.make_vars("x", "v")
+    orig_sys = [(x, v), (v, hy.cos(hy.time) - hy.par[0] * v - hy.sin(x))]
+    vsys = hy.var_ode_sys(orig_sys, hy.var_args.vars, order=2)
+    ta = hy.taylor_adaptive_batch(vsys, [[0.2, 0.21], [0.3, 0.31]], pars=[[0.4, 0.41]], time=[0.5, 0.51],
+                                  compact_mode=True)
+    assert ta.dim > 2 and ta.n_orig_sv == 2 and ta.is_variational and ta.vorder == 2 and ta.vargs == [x, v]
+    rc = getrefcount(ta)
+    ts = ta.tstate
+    assert getrefcount(ta) == rc + 1
+    assert ts.shape == (2, 2) and np.all(ts == [[0.0, 0.0], [0.0, 0.0]])
+    with pytest.raises(ValueError):
+        ta.tstate[0] = 0.5
+    assert ta.get_vslice(order=0) == slice(0, 2, None) and ta.get_vslice(order=0, component=1) == slice(1, 2, None)
+    assert ta.get_vslice(order=1) == slice(2, 6, None) and ta.get_vslice(order=1, component=1) == slice(4, 6, None)
+    assert ta.get_mindex(0) == [0, 0, 0] and ta.get_mindex(1) == [1, 0, 0] and ta.get_mindex(2) == [0, 1, 0]
+    assert ta.get_mindex(3) == [0, 0, 1] and ta.get_mindex(4) == [1, 1, 0] and ta.get_mindex(i=5) == [1, 0, 1]
+    ta.propagate_until(3.0)
+    ts2 = ta.eval_taylor_map([[0.0, 0.0], [0.0, 0.0]])
+    assert getrefcount(ta) == rc + 2
+    assert np.shares_memory(ts, ts2) and np.all(ts2 == ta.state[:2])
+    ts2 = ta.eval_taylor_map(np.array([[0.0, 0.0], [0.0, 0.0]]))
+    assert np.shares_memory(ts, ts2) and np.all(ts2 == ta.state[:2])
+    with pytest.raises(TypeError) as cm:
+        ta.eval_taylor_map(np.array([0.0, 0.0], dtype=np.int32))
+    assert "Invalid dtype detected for the inputs of a Taylor map evaluation:" in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(np.array([0.0, 0.0, 0.0, 0.0])[::2])
+    assert "Invalid inputs array detected in a Taylor map evaluation: the array is not C-style contiguous, please " in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(np.array([0.0, 0.0]))
+    assert "The array of inputs provided for the evaluation of a Taylor map has 1 dimension(s), " in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(np.array([[0.0, 0.0]]))
+    assert ("The array of inputs provided for the evaluation of a Taylor map has 1 row(s), but it must have 2 row(s) "
+            "instead") in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(np.array([[0.0], [0.0]]))
+    assert ("The array of inputs provided for the evaluation of a Taylor map has 1 column(s), but it must have 2 "
+            "column(s) instead") in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(ta.state[:2])
+    assert "may overlap" in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        ta.eval_taylor_map(ta.tstate)
+    assert "may overlap" in str(cm.value)
