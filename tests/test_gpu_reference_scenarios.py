@@ -618,3 +618,35 @@ def test_var_integrator_batch():
     with pytest.raises(ValueError) as cm:
         ta.eval_taylor_map(ta.tstate)
     assert "may overlap" in str(cm.value)
+
+
+def test_ensemble_argument_errors():
+    # /root/reference/heyoka/_test_ensemble.py:394-438 (the checks are shared by the scalar and the batch functions)
+    x, v, sys_ = _pend()
+    ta = hy.taylor_adaptive_batch(sys=sys_, state=[[0.0] * 4] * 2)
+
+    def gen(t, idx):
+        return t
+
+    with pytest.raises(TypeError) as cm:
+        hy.ensemble_propagate_until_batch(ta, 20.0, "a", gen)
+    assert "The n_iter parameter must be an integer, but an object of type" in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        hy.ensemble_propagate_until_batch(ta, 20.0, -1, gen)
+    assert "The n_iter parameter must be non-negative" in str(cm.value)
+    for fn in (hy.ensemble_propagate_until_batch, hy.ensemble_propagate_for_batch):
+        with pytest.raises(TypeError) as cm:
+            fn(ta, [20.0], 10, gen)
+        assert ("Cannot perform an ensemble propagate_until/for(): the final epoch/time interval must be a scalar, "
+                "not an iterable object") in str(cm.value)
+    with pytest.raises(ValueError) as cm:
+        hy.ensemble_propagate_grid_batch(ta, [[20.0, 20.0]], 10, gen)
+    assert ("Cannot perform an ensemble propagate_grid(): the input time grid must be one-dimensional, but instead it "
+            "has 2 dimensions") in str(cm.value)
+    with pytest.raises(TypeError) as cm:
+        hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, max_delta_t=[10])
+    assert ('Cannot perform an ensemble propagate_until/for/grid(): the "max_delta_t" argument must be a scalar, '
+            "not an iterable object") in str(cm.value)
+    with pytest.raises(TypeError):
+        hy.ensemble_propagate_until_batch(ta, 20.0, 10, gen, chunksize=1)   # not recognised in threaded mode
+    assert hy.ensemble_propagate_until_batch(ta, 20.0, 0, gen) == []
