@@ -480,13 +480,15 @@ def diff(e, x):
     """Symbolic derivative of ``e`` w.r.t. variable or parameter ``x``
     (reference: expose_expression.cpp ``diff``)."""
     x = _wrap(x)
-    if x.kind not in (_VAR, _PAR):
+    if x.kind not in (_VAR, _PAR, _TIME):
         raise ValueError("diff() requires a variable or a parameter")
     d = {}
     for n in topo_order([e]):
         k = n.kind
-        if k in (_NUM, _TIME):
+        if k == _NUM:
             r = _num(0.0)
+        elif k == _TIME:
+            r = _num(1.0 if x.kind == _TIME else 0.0)  # (the explicit partial derivative w.r.t. time)
         elif k in (_VAR, _PAR):
             r = _num(1.0 if n is x else 0.0)
         else:

@@ -111,6 +111,8 @@ class taylor_adaptive_batch_impl:
             raise ValueError("The batch size in a batch integrator cannot be zero")
 
         self._vsys = None
+        auto_var_ic = False
+        n_orig = 0
         if isinstance(sys, _var_ode_sys):
             self._vsys = sys
             sys_list = sys.sys
@@ -121,6 +123,7 @@ class taylor_adaptive_batch_impl:
                 full[:n_orig] = state_
                 full[n_orig:] = sys._initial_var_state(fp)[:, None]
                 state_ = full
+                auto_var_ic = True
         else:
             sys_list = list(sys)
         self._sys = [(l, _E._wrap(r)) for l, r in sys_list]
@@ -203,6 +206,10 @@ class taylor_adaptive_batch_impl:
         else:
             time_ = np.zeros(B, dtype=fp)
 
+        if self._vsys is not None and getattr(self._vsys, "_ic_sym", None) is not None and auto_var_ic:
+            # the initial time is a variational argument: its initial conditions depend on the initial state,
+            # the parameters and the time (var_ode_sys.py)
+            state_[n_orig:] = self._vsys._initial_var_state_at(state_[:n_orig], pars_, time_, fp)
         self._B = B
         self._n = n
         self._alloc(state_, pars_, time_, np.zeros(B, dtype=fp))

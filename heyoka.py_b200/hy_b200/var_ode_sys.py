@@ -72,13 +72,13 @@ class var_ode_sys:
         if isinstance(args, var_args):
             if int(args) == 0 or int(args) > 7:
                 raise ValueError("Invalid var_args enumerator detected")
-            if args & var_args.time:
-                raise NotImplementedError("var_ode_sys: derivatives w.r.t. the initial time")
             al = []
             if args & var_args.vars:
                 al += [E.expression(nm) for nm in names]
             if args & var_args.params:
                 al += [E.par[i] for i in range(npar)]
+            if args & var_args.time:
+                al += [E.time]
             if not al:
                 raise ValueError("Cannot formulate the variational equations with an empty list of arguments")
         else:
@@ -86,13 +86,13 @@ class var_ode_sys:
             if not al:
                 raise ValueError("Cannot formulate the variational equations with an empty list of arguments")
             for a in al:
-                if not isinstance(a, E.expression) or a.kind not in ("var", "par"):
+                if not isinstance(a, E.expression) or a.kind not in ("var", "par", "time"):
                     raise ValueError(
-                        "var_ode_sys: the arguments must be state variables or parameters"
+                        "var_ode_sys: the arguments must be state variables, parameters or the time"
                     )
                 if a.kind == "var" and a.name not in names:
                     raise ValueError("var_ode_sys: '{}' is not a state variable".format(a.name))
-            if len(set(id(a) for a in al)) != len(al):
+            if len(set(("time",) if a.kind == "time" else (a.kind, a.name if a.kind == "var" else a.value) for a in al)) != len(al):
                 raise ValueError("Duplicate entries detected in the list of variational arguments")
         self.vargs_list = al
         self.n_orig_sv = n
@@ -142,6 +142,43 @@ class var_ode_sys:
                     eq[(i, al_)] = total_diff(eq[(i, tuple(lower))], j)
                     eqs.append((sym[(i, al_)], eq[(i, al_)]))
         self.sys = eqs
+        # ---- the initial time as an argument (var_args.time): d^beta x / ... d t0^m of the flow x(t; x0, alpha, t0).
+        # The equations need nothing new - the right-hand side does not depend on t0, so only the chain terms above
+        # appear - but the initial conditions do: differentiating the identity x(t0; x0, alpha, t0) = x0 gives, for a
+        # multi-index gamma and beta = gamma + e_t0,
+        #     IC_beta = d/dt0 [IC_gamma](x0, alpha, t0)  -  (equation of gamma, evaluated on the initial conditions)
+        # e.g. dx/dt0 = -f(x0, alpha, t0), d2x/dt0 dx0_j = -df/dx_j, d2x/dt0^2 = -f_t + f_x f.  They are built here as
+        # expressions of the original state symbols, the parameters and the time, and evaluated by the integrator's
+        # constructor on its initial state (`_initial_var_state_at`).  (Derived from the definition of the flow in
+        # var_ode_sys.ipynb; the reference holds no numerical value for a time argument to pin this against - the
+        # test checks it against finite differences of the flow.)
+        self._jt = [j for j, a in enumerate(al) if a.kind == "time"]
+        self._ic_sym = None
+        if self._jt:
+            jt = self._jt[0]
+            ic = {}
+            for m in range(1, order + 1):
+                for i in range(n):
+                    for al_ in self._mi[m]:
+                        if al_[jt] == 0:
+                            # no time component: identity for d x_i / d x_i(0), zero otherwise
+                            one = m == 1 and al[al_.index(1)].kind == "var" and al[al_.index(1)].name == names[i]
+                            ic[(i, al_)] = E.expression(1.0 if one else 0.0)
+            smap_names = {}
+            for m in range(1, order + 1):
+                for i in range(n):
+                    for al_ in self._mi[m]:
+                        if al_[jt] == 0:
+                            continue
+                        g = list(al_)
+                        g[jt] -= 1
+                        g = tuple(g)
+                        lower = E.expression(names[i]) if g == zero else ic[(i, g)]
+                        rhs_g = eq[(i, g)]
+                        sub = {sym[k].name: v for k, v in ic.items()}
+                        val = E.diff(lower, E.time) - (E.subs(rhs_g, sub) if sub else rhs_g)
+                        ic[(i, al_)] = val
+            self._ic_sym = ic
 
     @property
     def vargs(self):
@@ -155,6 +192,27 @@ class var_ode_sys:
                 if a.kind == "var" and a.name == self._names[i]:
                     ic[i * na + j] = 1  # order 1: d x_i / d x_i(0) = 1; every higher order starts at 0
         return ic
+
+    def _initial_var_state_at(self, x0, pars, t0, fp):
+        """Initial conditions of the variational variables for the given initial state [n, B], parameters
+        [m, B] and times [B] (they depend on them only when the initial time is an argument)."""
+        B = x0.shape[1]
+        out = np.repeat(self._initial_var_state(fp)[:, None], B, axis=1)
+        if self._ic_sym is None:
+            return out
+        n = self.n_orig_sv
+        vv = {nm: np.asarray(x0[i], dtype=np.float64) for i, nm in enumerate(self._names)}
+        pp = [np.asarray(p, dtype=np.float64) for p in pars]
+        tt = np.asarray(t0, dtype=np.float64)
+        for m in range(1, self.order + 1):
+            nm_ = len(self._mi[m])
+            for i in range(n):
+                for q, al_ in enumerate(self._mi[m]):
+                    if al_[self._jt[0]] == 0:
+                        continue
+                    v = E.eval_numpy(self._ic_sym[(i, al_)], vv, pars=pp, tm=tt)
+                    out[self._off[m] - n + i * nm_ + q] = np.broadcast_to(np.asarray(v, dtype=fp), (B,))
+        return out
 
     def get_vslice(self, order, component=None):
         n = self.n_orig_sv
